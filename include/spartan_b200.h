@@ -1,0 +1,246 @@
+/* spartan_b200 -- C ABI of the B200 (sm_100a) tile evaluator.
+ *
+ * This is the drop-in boundary for Spartan's per-tile hot path.  The reference
+ * has no C ABI: its seam is the Python kernel contract
+ *   mapper_fn(ex, **kw) -> LocalKernelResult        (spartan/core.pyx:159-169)
+ * invoked per tile by Worker._run_kernel             (spartan/worker.py:232-304)
+ * plus the tile store BlobCtx.create/get/update      (spartan/blob_ctx.py:18-284).
+ * Every entry point below names the reference code it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; device pointers are raw CUDA addresses
+ *     (the Python host obtains them from torch tensors, any allocator works);
+ *   - every function returns 0 (SP_OK) or a negative sp_status; the message of
+ *     the last failure on the calling thread is sp_last_error();
+ *   - launches are asynchronous on `stream` (a cudaStream_t passed as void*;
+ *     NULL = legacy default stream); nothing here synchronises the device;
+ *   - there is NO CPU fallback: without a CUDA device the compute entry points
+ *     fail with SP_ERR_CUDA.  The extent algebra (sp_extent_*) is host-only.
+ */
+#ifndef SPARTAN_B200_H_
+#define SPARTAN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  SP_OK = 0,
+  SP_ERR_INVALID = -1,      /* bad argument */
+  SP_ERR_CUDA = -2,         /* CUDA runtime / driver error */
+  SP_ERR_UNSUPPORTED = -3,  /* expression not mappable to the device evaluator */
+  SP_ERR_NOMEM = -4
+} sp_status;
+
+typedef enum {
+  SP_F32 = 0,
+  SP_F64 = 1,
+  SP_I32 = 2,
+  SP_I64 = 3,
+  SP_U8 = 4,
+  SP_BOOL = 5 /* numpy bool_: one byte, 0 or 1 */
+} sp_dtype;
+
+#define SP_MAX_DIM 32 /* spartan/array/extent.pyx:20-21 MAX_DIM */
+
+const char* sp_last_error(void);
+int sp_version(void);
+/* Device properties of the current CUDA device (fails without a GPU). */
+int sp_device_info(int* n_sms, int64_t* hbm_bytes, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------
+ * Extent algebra (host only, int64, bit-exact with spartan/array/extent.pyx).
+ * An extent is (ul[ndim], lr[ndim]) inside an array of shape array_shape.
+ * Functions that can produce an empty result return 1 when the result is
+ * valid and 0 when it is "None" in the reference (any ul >= lr), <0 on error.
+ * ------------------------------------------------------------------------ */
+/* extent.pyx:367-387 intersection */
+int sp_extent_intersection(int ndim, const int64_t* a_ul, const int64_t* a_lr, const int64_t* b_ul,
+                           const int64_t* b_lr, int64_t* out_ul, int64_t* out_lr);
+/* extent.pyx:207-219 ravelled_pos (C order) */
+int64_t sp_extent_ravelled_pos(int ndim, const int64_t* idx, const int64_t* array_shape);
+/* extent.pyx:196-205 unravelled_pos */
+int sp_extent_unravelled_pos(int64_t idx, int ndim, const int64_t* array_shape, int64_t* out_idx);
+/* extent.pyx:411-432 drop_axis; axis < 0 wraps; axis == SP_AXIS_NONE gives the 0-d extent (out_ndim = 0). */
+#define SP_AXIS_NONE (-1000)
+int sp_extent_drop_axis(int ndim, const int64_t* ul, const int64_t* lr, const int64_t* array_shape, int axis,
+                        int64_t* out_ul, int64_t* out_lr, int64_t* out_shape, int* out_ndim);
+/* extent.pyx:121-127 TileExtent.to_global */
+int64_t sp_extent_to_global(int ndim, const int64_t* ul, const int64_t* lr, const int64_t* array_shape,
+                            int64_t idx, int axis);
+/* extent.pyx:501-570 change_partition_axis, one-dimensional target (the grid
+ * branch :545-552 is a reference defect, SURVEY.md section 9 Q1: it is NOT
+ * reproduced -- grid-tiled input returns SP_ERR_UNSUPPORTED).  1 = valid, 0 = None. */
+int sp_extent_change_partition_axis(int ndim, const int64_t* ul, const int64_t* lr, const int64_t* array_shape,
+                                    int axis, int64_t* out_ul, int64_t* out_lr);
+/* distarray.py:26-48 good_tile_shape (Python-2 floor division semantics) */
+int sp_good_tile_shape(int ndim, const int64_t* shape, int64_t num_shards, int64_t* out_tile_shape);
+/* distarray.py:51-110 compute_splits + compute_extents: enumerates tiles in
+ * itertools.product (row-major) order.  Call with out_ul == NULL to get the
+ * tile count; otherwise fills out_ul/out_lr [n_tiles * ndim] and
+ * out_worker[n_tiles] = index % num_shards (index if num_shards == -1). */
+int64_t sp_compute_extents(int ndim, const int64_t* shape, const int64_t* tile_hint /* may be NULL */,
+                           int64_t num_shards, int64_t* out_ul, int64_t* out_lr, int64_t* out_worker);
+
+/* ------------------------------------------------------------------------
+ * Tile fill (creation.py:67-106 _make_zeros/_make_ones, :135-141 _arange_mapper,
+ * srandom.py:40-47 _make_rand/_make_randn) -- written straight into HBM.
+ * ------------------------------------------------------------------------ */
+typedef enum {
+  SP_FILL_CONST = 0, /* dst[i] = a */
+  SP_FILL_IOTA = 1,  /* dst[i] = a + b * (offset + i)   (arange: a=start, b=step) */
+  SP_FILL_RAND = 2,  /* uniform [0,1): Philox4x32-10 keyed by seed, counter = offset + i */
+  SP_FILL_RANDN = 3  /* standard normal (Box-Muller over the same Philox stream) */
+} sp_fill_kind;
+int sp_fill(void* dst, int dtype, int64_t n, int kind, double a, double b, uint64_t seed, int64_t offset,
+            void* stream);
+
+/* ------------------------------------------------------------------------
+ * Fused element-wise map (local.py:115-127 FnCallExpr.evaluate over the tree
+ * MapMapFusion builds, optimize.py:133-187) and fused map+reduce
+ * (reduce.py:21-70 _reduce_mapper with ReduceMapFusion, optimize.py:190-227).
+ *
+ * A program is the postfix bytecode of the LocalExpr tree.  Operands are
+ * addressed through a common 3-D iteration space (d0, d1, d2), d2 innermost;
+ * each operand has element strides (s0, s1, s2) with 0 = broadcast
+ * (broadcast.py:28-158).  Scalars are SP_OP_CONST immediates.
+ * ------------------------------------------------------------------------ */
+typedef enum {
+  /* leaves */
+  SP_OP_IN = 0,    /* push operand #arg */
+  SP_OP_CONST = 1, /* push immediate #arg (sp_program.consts[arg]) */
+  /* binary: pop b, pop a, push f(a, b)      (base.py:331-388, mathematics.py, logic.py) */
+  SP_OP_ADD = 8,
+  SP_OP_SUB = 9,
+  SP_OP_MUL = 10,
+  SP_OP_DIV = 11,   /* np.divide on floats (true division); floor division on ints */
+  SP_OP_MOD = 12,   /* np.mod (sign of divisor) */
+  SP_OP_POW = 13,
+  SP_OP_MAX = 14,   /* np.maximum (NaN propagating) */
+  SP_OP_MIN = 15,
+  SP_OP_EQ = 16,
+  SP_OP_NE = 17,
+  SP_OP_LT = 18,
+  SP_OP_LE = 19,
+  SP_OP_GT = 20,
+  SP_OP_GE = 21,
+  SP_OP_AND = 22,   /* logical_and */
+  SP_OP_OR = 23,
+  SP_OP_XOR = 24,
+  SP_OP_FMOD = 25,  /* np.fmod (sign of dividend) */
+  SP_OP_FLOORDIV = 26,
+  /* unary: pop a, push f(a) */
+  SP_OP_NEG = 40,
+  SP_OP_ABS = 41,
+  SP_OP_SQRT = 42,
+  SP_OP_EXP = 43,
+  SP_OP_LOG = 44,
+  SP_OP_SQUARE = 45,
+  SP_OP_RECIP = 46,
+  SP_OP_NOT = 47,
+  SP_OP_NONZERO = 48, /* x != 0 -> 1/0  (count_nonzero, np.all/any inputs) */
+  SP_OP_ISZERO = 49,
+  /* casts to a narrower type inside a wider compute type (arrays.py:26-35 astype and
+   * NumPy per-ufunc result dtypes): value := (compute_t)(target_t)value */
+  SP_OP_CAST_F32 = 56,
+  SP_OP_CAST_I64 = 57,
+  SP_OP_CAST_I32 = 58,
+  SP_OP_CAST_BOOL = 59,
+  SP_OP_CAST_U8 = 60
+} sp_opcode;
+
+#define SP_MAX_PROGRAM 64
+#define SP_MAX_OPERANDS 8
+#define SP_MAX_CONSTS 16
+#define SP_MAX_STACK 8
+
+typedef struct {
+  int32_t n_ops;
+  int32_t compute_dtype; /* SP_F32, SP_F64 or SP_I64: the register type of the evaluation stack */
+  uint8_t op[SP_MAX_PROGRAM];
+  uint8_t arg[SP_MAX_PROGRAM];
+  double consts[SP_MAX_CONSTS];   /* used when compute_dtype is SP_F32 / SP_F64 */
+  int64_t iconsts[SP_MAX_CONSTS]; /* used when compute_dtype is SP_I64 */
+} sp_program;
+
+typedef struct {
+  const void* ptr; /* device pointer to element (0,0,0) of this operand's view */
+  int32_t dtype;
+  int32_t pad;
+  int64_t stride[3]; /* in elements; 0 = broadcast along that dim */
+} sp_operand;
+
+/* out[d0,d1,d2] = program(in...), out written with strides out->stride, cast to out->dtype. */
+int sp_map(const sp_program* prog, int n_in, const sp_operand* in, const sp_operand* out, const int64_t dims[3],
+           void* stream);
+
+typedef enum {
+  SP_RED_SUM = 0,  /* mathematics.py:126 _sum_local;  combiner np.add */
+  SP_RED_MIN = 1,  /* statistics.py:59;               combiner np.minimum */
+  SP_RED_MAX = 2,  /* statistics.py:40;               combiner np.maximum */
+  SP_RED_PROD = 3, /* mathematics.py:146 _prod_local; combiner np.multiply */
+  SP_RED_ALL = 4,  /* logic.py:25 (value != 0 folded with AND) */
+  SP_RED_ANY = 5   /* logic.py:37 */
+} sp_reduce_op;
+
+/* Reduce program(in...) over d1 of the iteration space (d0 = outer, d1 = reduced
+ * axis, d2 = inner):  out[d0, d2] = op_{d1} program(...)[d0, d1, d2].
+ * axis=None is expressed as dims = (1, n, 1).  `out` strides are (s_outer, ignored, s_inner).
+ * If accumulate != 0 the result is combined into the existing out values with the same
+ * op (Tile.merge "reducer(old, new)", tile.pyx:263-283); otherwise it replaces them
+ * (first write).  scratch: device buffer of at least sp_map_reduce_scratch_bytes(). */
+int64_t sp_map_reduce_scratch_bytes(const int64_t dims[3], int compute_dtype);
+int sp_map_reduce(const sp_program* prog, int n_in, const sp_operand* in, const sp_operand* out,
+                  const int64_t dims[3], int reduce_op, int accumulate, void* scratch, int64_t scratch_bytes,
+                  void* stream);
+
+/* Cross-tile combiner on one device: dst = op(dst, src) element-wise over n contiguous
+ * elements (Tile.merge dense path, tile.pyx:250-283).  Across GPUs the host uses
+ * ncclAllReduce with the matching op instead. */
+int sp_combine(void* dst, const void* src, int dtype, int64_t n, int reduce_op, void* stream);
+
+/* Strided rectangle copy between tiles (DistArrayImpl.fetch stitching, distarray.py:294-367,
+ * and update splitting, :372-422): copies dims[0..2] elements; strides in elements. */
+int sp_copy_rect(void* dst, const int64_t dst_stride[3], const void* src, const int64_t src_stride[3],
+                 const int64_t dims[3], int dtype, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Dense contraction (dot.py:195-238 dot_map2_mapper / dot_outer_mapper:
+ * `tiles[0].dot(tiles[1])`, partials merged with np.add).
+ * ------------------------------------------------------------------------ */
+typedef enum {
+  SP_GEMM_TF32X1 = 0, /* one tcgen05 kind::tf32 pass over RN-rounded operands */
+  SP_GEMM_TF32X3 = 1, /* hi/lo split, 3 passes: ~fp32-faithful (error ~2^-21 per product) */
+  SP_GEMM_SIMT = 2    /* CUDA-core reference path, exact per-dtype arithmetic (also f64 / i64 / i32) */
+} sp_gemm_precision;
+
+#define SP_GEMM_MAX_TERMS 24
+
+typedef struct {
+  const float* A; /* [M, K] row-major, leading dimension lda */
+  int64_t lda;
+  const float* B; /* [K, N] row-major, leading dimension ldb */
+  int64_t ldb;
+  int64_t K;
+} sp_gemm_segment;
+
+/* C[M,N] (+)= sum_s A_s[M,K_s] * B_s[K_s,N]: one launch for a whole strip-joined dot
+ * (join_mapper, map.py:243-286).  accumulate != 0 adds into C (np.add combiner). */
+int64_t sp_gemm_f32_workspace_bytes(int64_t M, int64_t N, int n_seg, const int64_t* seg_k, int precision);
+int sp_gemm_f32_segments(int n_seg, const sp_gemm_segment* segs, float* C, int64_t ldc, int64_t M, int64_t N,
+                         int accumulate, int precision, void* workspace, int64_t workspace_bytes, void* stream);
+int sp_gemm_f32(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
+                int64_t N, int64_t K, int accumulate, int precision, void* workspace, int64_t workspace_bytes,
+                void* stream);
+/* CUDA-core GEMM for dtypes the tensor path does not carry exactly (reference tests use
+ * float64 / int64 operands: tests/test_dot.py:8-103, tests/test_matmul.py:12-22). */
+int sp_gemm_simt(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t M, int64_t N,
+                 int64_t K, int dtype, int accumulate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPARTAN_B200_H_ */

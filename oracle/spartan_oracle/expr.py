@@ -1,0 +1,985 @@
+"""ORACLE (test infrastructure only) -- expression graph, fusion passes and per-tile evaluator.
+
+Restates, for the hot path only:
+  spartan/expr/operator/base.py        Expr / AsArray / Val / ListExpr / TupleExpr, evaluate, glom
+  spartan/expr/operator/local.py       LocalInput / FnCallExpr / LocalMapExpr / LocalMapLocationExpr / LocalReduceExpr
+  spartan/expr/operator/map.py         tile_mapper, MapExpr, map(), join_mapper, Map2Expr, map2()
+  spartan/expr/operator/reduce.py      _reduce_mapper, ReduceExpr, reduce()
+  spartan/expr/operator/outer.py       outer_mapper, OuterProductExpr, outer()
+  spartan/expr/operator/ndarray.py     NdArrayExpr
+  spartan/expr/operator/map_with_location.py
+  spartan/expr/operator/optimize.py    MapMapFusion (:133-187), ReduceMapFusion (:190-227), optimize (:1072)
+  spartan/expr/{creation,mathematics,statistics,logic,sorting,arrays,srandom,dot}.py builders
+  spartan/expr/operator/write_array.py from_numpy (:424-445)
+
+NumPy-1 value-based casting is emulated in ``_call_ufunc``: a 0-d operand
+never widens an array operand of the same or a higher kind.
+"""
+import collections
+import itertools
+
+import numpy as np
+
+from . import distarray, extent
+from .distarray import Broadcast, broadcast
+
+# ----------------------------------------------------------------------------------- local.py
+_var_id = itertools.count()
+_expr_id = itertools.count()
+
+
+def make_var():
+  return 'key_%d' % next(_var_id)
+
+
+class LocalExpr(object):
+  def __init__(self, deps=None):
+    self.deps = list(deps or [])
+
+  def add_dep(self, v):
+    self.deps.append(v)
+
+
+class LocalInput(LocalExpr):
+  def __init__(self, idx):
+    LocalExpr.__init__(self)
+    assert idx != ''
+    self.idx = idx
+
+  def evaluate(self, ctx):
+    return ctx[self.idx]
+
+
+_KIND_RANK = {'b': 0, 'u': 1, 'i': 1, 'f': 2, 'c': 3}
+
+
+def legacy_result_type(args):
+  """np.result_type as NumPy 1.x computed it for ufunc operands (value-based scalar casting)."""
+  arrs = [np.asarray(a) for a in args]
+  arrays = [a for a in arrs if a.ndim > 0]
+  scalars = [a for a in arrs if a.ndim == 0]
+  if not arrays or not scalars:
+    return np.result_type(*[a.dtype for a in arrs])
+  max_arr = max(_KIND_RANK[a.dtype.kind] for a in arrays)
+  max_sc = max(_KIND_RANK[a.dtype.kind] for a in scalars)
+  if max_sc <= max_arr:
+    dts = [a.dtype for a in arrays] + [np.min_scalar_type(a[()]) for a in scalars]
+    return np.result_type(*dts)
+  return np.result_type(*[a.dtype for a in arrs])
+
+
+def _call_ufunc(fn, deps, kw):
+  if len(deps) >= 2 and any(np.ndim(d) == 0 for d in deps) and any(np.ndim(d) > 0 for d in deps):
+    dt = legacy_result_type(deps)
+    deps = [np.asarray(d, dtype=dt) if np.ndim(d) == 0 else d for d in deps]
+  return fn(*deps, **kw)
+
+
+class FnCallExpr(LocalExpr):
+  # local.py:73-127
+  def __init__(self, fn, kw=None, deps=None, pretty_fn=None):
+    LocalExpr.__init__(self, deps)
+    assert fn is not None
+    self.fn = fn
+    self.kw = kw if kw is not None else {}
+    self.pretty_fn = pretty_fn
+
+  def evaluate(self, ctx):
+    deps = [d.evaluate(ctx) for d in self.deps]
+    if isinstance(self.fn, np.ufunc):
+      return _call_ufunc(self.fn, deps, self.kw)
+    return self.fn(*deps, **self.kw)
+
+
+class LocalMapExpr(FnCallExpr):
+  pass
+
+
+class LocalMapLocationExpr(LocalMapExpr):
+  # local.py:136-149
+  def evaluate(self, ctx):
+    deps = []
+    for d in self.deps:
+      if isinstance(d, LocalInput) and d.idx == 'extent':
+        deps.append(d.evaluate(ctx).to_tuple())
+      else:
+        deps.append(d.evaluate(ctx))
+    return self.fn(*deps, **self.kw)
+
+
+class LocalReduceExpr(FnCallExpr):
+  pass
+
+
+# ----------------------------------------------------------------------------------- base.py
+class NotShapeable(Exception):
+  pass
+
+
+class EvalCache(object):
+  # base.py:73-114 (reference counting elided: oracle expressions are short-lived)
+  def __init__(self):
+    self.cache = {}
+
+  def set(self, exprid, value):
+    self.cache[exprid] = value
+
+  def get(self, exprid):
+    return self.cache.get(exprid, None)
+
+  def clear(self):
+    self.cache.clear()
+
+
+eval_cache = EvalCache()
+_not_idempotent = set()
+
+
+class Expr(object):
+  needs_cache = True
+  members = ()
+
+  def __init__(self, expr_id=None, **kw):
+    self.expr_id = next(_expr_id) if expr_id is None else expr_id
+    self.shape_cache = kw.pop('shape_cache', None)
+    self.optimized_expr = None
+    for k in self.members:
+      setattr(self, k, kw.pop(k, None))
+    assert not kw, kw
+
+  def cache(self):
+    return eval_cache.get(self.expr_id)
+
+  def dependencies(self):
+    return dict((k, getattr(self, k)) for k in self.members)
+
+  def compute_shape(self):
+    raise NotShapeable
+
+  def visit(self, visitor):
+    deps = dict((k, visitor.visit(getattr(self, k))) for k in self.members)
+    return expr_like(self, **deps)
+
+  def evaluate(self):
+    # base.py:272-313 -- note: evaluate() does NOT optimise
+    cache = self.cache()
+    if cache is not None:
+      return cache
+    deps = {}
+    for k, vs in self.dependencies().items():
+      deps[k] = vs.evaluate() if isinstance(vs, Expr) else vs
+    value = self._evaluate(distarray.get_ctx(), deps)
+    if self.needs_cache:
+      eval_cache.set(self.expr_id, value)
+    return value
+
+  def __hash__(self):
+    return self.expr_id
+
+  @property
+  def shape(self):
+    cache = self.cache()
+    if cache is not None:
+      return cache.shape
+    if self.shape_cache is None:
+      try:
+        self.shape_cache = self.compute_shape()
+      except NotShapeable:
+        self.shape_cache = evaluate(self).shape
+    return self.shape_cache
+
+  @property
+  def ndim(self):
+    return len(self.shape)
+
+  def optimized(self):
+    if self.optimized_expr is None:
+      self.optimized_expr = optimize(self)
+      self.optimized_expr.optimized_expr = self.optimized_expr
+    return self.optimized_expr
+
+  def glom(self):
+    return glom(self)
+
+  # operator overloads, base.py:331-388
+  def __add__(self, o): return map((self, o), np.add)
+  def __sub__(self, o): return map((self, o), np.subtract)
+  def __mul__(self, o): return map((self, o), np.multiply)
+  def __mod__(self, o): return map((self, o), np.mod)
+  def __truediv__(self, o): return map((self, o), np.divide)
+  def __eq__(self, o): return map((self, o), np.equal)
+  def __ne__(self, o): return map((self, o), np.not_equal)
+  def __lt__(self, o): return map((self, o), np.less)
+  def __gt__(self, o): return map((self, o), np.greater)
+  def __and__(self, o): return map((self, o), np.logical_and)
+  def __or__(self, o): return map((self, o), np.logical_or)
+  def __pow__(self, o): return map((self, o), np.power)
+  def __neg__(self): return map((self,), np.negative)
+  def __rsub__(self, o): return map((o, self), np.subtract)
+  def __radd__(self, o): return map((o, self), np.add)
+  def __rmul__(self, o): return map((o, self), np.multiply)
+  def __rtruediv__(self, o): return map((o, self), np.divide)
+
+  def sum(self, axis=None, tile_hint=None): return sum(self, axis, tile_hint)
+  def min(self, axis=None): return min(self, axis)
+  def max(self, axis=None): return max(self, axis)
+  def prod(self, axis=None): return prod(self, axis)
+  def argmin(self, axis=None): return argmin(self, axis)
+  def argmax(self, axis=None): return argmax(self, axis)
+  def astype(self, dtype): return astype(self, dtype)
+  def dot(self, other): return dot(self, other)
+
+
+def expr_like(expr, **kw):
+  # base.py:49-68
+  kw['expr_id'] = expr.expr_id
+  kw['shape_cache'] = expr.shape_cache
+  return expr.__class__(**kw)
+
+
+class AsArray(Expr):
+  members = ('val',)
+
+  def visit(self, visitor):
+    return self
+
+  def compute_shape(self):
+    if hasattr(self.val, 'shape'):
+      return self.val.shape
+    if np.isscalar(self.val):
+      return ()
+    raise NotShapeable
+
+  def _evaluate(self, ctx, deps):
+    return distarray.as_array(deps['val'])
+
+
+class Val(Expr):
+  members = ('val',)
+  needs_cache = False
+
+  def visit(self, visitor):
+    return self
+
+  def dependencies(self):
+    return {}
+
+  def compute_shape(self):
+    return self.val.shape
+
+  def _evaluate(self, ctx, deps):
+    return self.val
+
+
+class ListExpr(Expr):
+  members = ('vals',)
+  needs_cache = False
+
+  def dependencies(self):
+    return dict(('v%d' % i, v) for i, v in enumerate(self.vals))
+
+  def _evaluate(self, ctx, deps):
+    return [deps['v%d' % i] for i in range(len(self.vals))]
+
+  def visit(self, visitor):
+    return ListExpr(vals=[visitor.visit(v) for v in self.vals])
+
+  def __iter__(self): return iter(self.vals)
+  def __getitem__(self, i): return self.vals[i]
+  def __len__(self): return len(self.vals)
+
+
+class TupleExpr(ListExpr):
+  def _evaluate(self, ctx, deps):
+    return tuple(deps['v%d' % i] for i in range(len(self.vals)))
+
+  def visit(self, visitor):
+    return TupleExpr(vals=tuple(visitor.visit(v) for v in self.vals))
+
+
+def glom(value):
+  if isinstance(value, Expr):
+    value = evaluate(value)
+  if isinstance(value, np.ndarray):
+    return value
+  return value.glom()
+
+
+def evaluate(node):
+  return node.evaluate() if isinstance(node, Expr) else node
+
+
+def as_array(v):
+  return v if isinstance(v, Expr) else AsArray(val=v)
+
+
+def lazify(val):
+  return val if isinstance(val, Expr) else Val(val=val)
+
+
+# ----------------------------------------------------------------------------------- ndarray.py
+class NdArrayExpr(Expr):
+  members = ('_shape', 'dtype', 'tile_hint', 'reduce_fn', 'sparse')
+
+  def visit(self, visitor):
+    return self
+
+  def dependencies(self):
+    return {}
+
+  def compute_shape(self):
+    return tuple(self._shape)
+
+  def _evaluate(self, ctx, deps):
+    return distarray.create(self._shape, self.dtype, reducer=self.reduce_fn, tile_hint=self.tile_hint)
+
+
+def ndarray(shape, dtype=np.float64, tile_hint=None, reduce_fn=None, sparse=False):
+  return NdArrayExpr(_shape=tuple(shape), dtype=dtype, tile_hint=tile_hint, reduce_fn=reduce_fn, sparse=sparse)
+
+
+# ----------------------------------------------------------------------------------- map.py
+def get_local_values(ex, children, child_to_var):
+  # map.py:33-45
+  local_values = {}
+  for child, childv in zip(children, child_to_var):
+    if isinstance(child, Broadcast):
+      local_values[childv] = child.fetch_base_tile(ex)
+    else:
+      local_values[childv] = child.fetch(ex)
+  return local_values
+
+
+def tile_mapper(ex, children, child_to_var, op):
+  # map.py:48-88
+  local_values = get_local_values(ex, children, child_to_var)
+  local_values['extent'] = ex
+  result = op.evaluate(local_values)
+  if result is local_values[child_to_var[0]]:
+    return [(ex, children[0].tiles[ex])]
+  result = np.asarray(result)
+  assert ex.shape == result.shape, 'Bad shape -- source = %s, result = %s' % (ex.shape, result.shape)
+  tile_id = distarray.get_ctx().create(distarray.from_data(result))
+  return [(ex, tile_id)]
+
+
+class MapExpr(Expr):
+  members = ('children', 'child_to_var', 'op')
+
+  def compute_shape(self):
+    # map.py:104-128
+    orig_shapes = [list(x.shape) for x in self.children]
+    max_dim = max(len(s) for s in orig_shapes)
+    new_shapes = [[1] * (max_dim - len(s)) + s for s in orig_shapes]
+    out = collections.defaultdict(int)
+    for s in new_shapes:
+      for i, v in enumerate(s):
+        out[i] = v if v > out[i] else out[i]
+    return tuple(out[i] for i in range(len(out)))
+
+  def _evaluate(self, ctx, deps):
+    # map.py:149-169
+    children = list(deps['children'])
+    child_to_var = list(deps['child_to_var'])
+    children = broadcast(children)
+    largest = distarray.largest_value(children)
+    i = children.index(largest)
+    children[0], children[i] = children[i], children[0]
+    child_to_var[0], child_to_var[i] = child_to_var[i], child_to_var[0]
+    return largest.map_to_array(tile_mapper, kw={'children': children, 'child_to_var': child_to_var,
+                                                 'op': self.op})
+
+
+def _is_iterable(x):
+  return isinstance(x, (list, tuple))
+
+
+def map(inputs, fn, numpy_expr=None, fn_kw=None):
+  # map.py:172-205
+  assert fn is not None
+  if not _is_iterable(inputs):
+    inputs = [inputs]
+  op_deps, children, child_to_var = [], [], []
+  for v in inputs:
+    v = as_array(v)
+    varname = make_var()
+    children.append(v)
+    child_to_var.append(varname)
+    op_deps.append(LocalInput(idx=varname))
+  op = LocalMapExpr(fn=fn, kw=fn_kw, pretty_fn=numpy_expr, deps=op_deps)
+  return MapExpr(children=ListExpr(vals=children), child_to_var=child_to_var, op=op)
+
+
+def map_with_location(inputs, fn, numpy_expr=None, fn_kw=None):
+  # map_with_location.py:22-60
+  if not _is_iterable(inputs):
+    inputs = [inputs]
+  op_deps, children, child_to_var = [], [], []
+  for v in inputs:
+    v = as_array(v)
+    varname = make_var()
+    children.append(v)
+    child_to_var.append(varname)
+    op_deps.append(LocalInput(idx=varname))
+  op_deps += [LocalInput(idx='extent')]
+  op = LocalMapLocationExpr(fn=fn, kw=fn_kw, pretty_fn=numpy_expr, deps=op_deps)
+  return MapExpr(children=ListExpr(vals=children), child_to_var=child_to_var, op=op)
+
+
+def join_mapper(ex, arrays, axes, local_user_fn, local_user_fn_kw, target):
+  # map.py:243-286
+  if len(axes) == 0:
+    tiles = [a.fetch(ex) for a in arrays]
+    join_extents = ex
+  else:
+    first_extent = extent.change_partition_axis(ex, axes[0])
+    if first_extent is None:
+      return []
+    keys = (first_extent.ul[axes[0]], first_extent.lr[axes[0]])
+    join_extents = [first_extent]
+    for i in range(1, len(arrays)):
+      ul = [0] * len(arrays[i].shape)
+      lr = list(arrays[i].shape)
+      ul[axes[i]] = keys[0]
+      lr[axes[i]] = keys[1]
+      join_extents.append(extent.create(ul, lr, arrays[i].shape))
+    tiles = [arrays[i].fetch(join_extents[i]) for i in range(len(arrays))]
+  result = local_user_fn(join_extents, tiles, **(local_user_fn_kw or {}))
+  if result is not None:
+    for rex, v in result:
+      target.update(rex, v, wait=False)
+  return []
+
+
+class Map2Expr(Expr):
+  members = ('arrays', 'axes', 'fn', 'fn_kw', 'out_shape', 'tile_hint', 'dtype', 'reducer')
+
+  def compute_shape(self):
+    return self.out_shape
+
+  def _evaluate(self, ctx, deps):
+    # map.py:306-334
+    arrays = deps['arrays']
+    dtype = deps['dtype'] if deps['dtype'] is not None else arrays[0].dtype
+    target = distarray.create(deps['out_shape'], dtype, reducer=deps['reducer'], tile_hint=deps['tile_hint'])
+    arrays[0].foreach_tile(mapper_fn=join_mapper,
+                           kw=dict(arrays=arrays, axes=deps['axes'], local_user_fn=deps['fn'],
+                                   local_user_fn_kw=deps['fn_kw'], target=target))
+    return target
+
+
+def map2(arrays, axes=(), fn=None, fn_kw=None, shape=None, tile_hint=None, dtype=None, reducer=None):
+  # map.py:337-375
+  if not _is_iterable(arrays): arrays = [arrays]
+  if not _is_iterable(axes): axes = [axes]
+  assert fn is not None and shape is not None
+  assert len(axes) == 0 or len(arrays) == len(axes)
+  arrays = TupleExpr(vals=tuple(as_array(a) if not isinstance(a, Expr) else a for a in arrays))
+  return Map2Expr(arrays=arrays, axes=tuple(axes), fn=fn, fn_kw=fn_kw, out_shape=tuple(shape),
+                  tile_hint=tile_hint, dtype=dtype, reducer=reducer)
+
+
+# ----------------------------------------------------------------------------------- outer.py
+def outer_mapper(ex, arrays, axes, local_user_fn, local_user_fn_kw, target):
+  # outer.py:12-59
+  first_extent = extent.change_partition_axis(ex, axes[0])
+  first_tile = arrays[0].fetch(first_extent)
+  kw = local_user_fn_kw or {}
+  if axes[1] is None:
+    outer_extent = extent.from_shape(arrays[1].shape)
+    outer_tile = arrays[1].fetch(outer_extent)
+    for rex, v in (local_user_fn(first_extent, first_tile, outer_extent, outer_tile, **kw) or []):
+      target.update(rex, v, wait=False)
+  else:
+    done = {}
+    for key in arrays[1].tiles.keys():
+      outer_extent = extent.change_partition_axis(key, axes[1])
+      if outer_extent is None or done.get(outer_extent) is not None:
+        continue
+      outer_tile = arrays[1].fetch(outer_extent)
+      for rex, v in (local_user_fn(first_extent, first_tile, outer_extent, outer_tile, **kw) or []):
+        target.update(rex, v, wait=False)
+      done[outer_extent] = True
+  return []
+
+
+class OuterProductExpr(Expr):
+  members = ('arrays', 'axes', 'fn', 'fn_kw', 'out_shape', 'tile_hint', 'dtype', 'reducer')
+
+  def compute_shape(self):
+    return self.out_shape
+
+  def _evaluate(self, ctx, deps):
+    # outer.py:62-99
+    arrays = deps['arrays']
+    dtype = deps['dtype'] if deps['dtype'] is not None else arrays[0].dtype
+    target = distarray.create(deps['out_shape'], dtype, reducer=deps['reducer'], tile_hint=deps['tile_hint'])
+    arrays[0].foreach_tile(mapper_fn=outer_mapper,
+                           kw=dict(arrays=arrays, axes=deps['axes'], local_user_fn=deps['fn'],
+                                   local_user_fn_kw=deps['fn_kw'], target=target))
+    return target
+
+
+def outer(arrays, axes, fn, fn_kw=None, shape=None, tile_hint=None, reducer=None, dtype=None):
+  assert fn is not None and shape is not None
+  arrays = TupleExpr(vals=tuple(arrays))
+  return OuterProductExpr(arrays=arrays, axes=tuple(axes), fn=fn, fn_kw=fn_kw, out_shape=tuple(shape),
+                          tile_hint=tile_hint, dtype=dtype, reducer=reducer)
+
+
+# ----------------------------------------------------------------------------------- reduce.py
+def _reduce_mapper(ex, children, child_to_var, op, axis, output):
+  # reduce.py:21-70
+  local_values = {}
+  for i in range(len(children)):
+    if isinstance(children[i], Broadcast):
+      lv = children[i].fetch_base_tile(ex)
+    else:
+      lv = children[i].fetch(ex)
+    local_values[child_to_var[i]] = lv
+  local_values['extent'] = ex
+  local_values['axis'] = axis
+  local_reduction = op.evaluate(local_values)
+  dst_extent = extent.index_for_reduction(ex, axis)
+  local_reduction = np.asarray(local_reduction)
+  assert local_reduction.size == dst_extent.size
+  local_reduction = local_reduction.reshape(dst_extent.shape)
+  output.update(dst_extent, local_reduction)
+  return []
+
+
+class ReduceExpr(Expr):
+  members = ('children', 'child_to_var', 'axis', 'dtype_fn', 'op', 'accumulate_fn', 'tile_hint')
+
+  def compute_shape(self):
+    # reduce.py:87-94
+    shapes = [i.shape for i in self.children]
+    child_shape = collections.defaultdict(int)
+    for s in shapes:
+      for i, v in enumerate(s):
+        child_shape[i] = v if v > child_shape[i] else child_shape[i]
+    input_shape = tuple(child_shape[i] for i in range(len(child_shape)))
+    return tuple(extent.shape_for_reduction(input_shape, self.axis))
+
+  def _evaluate(self, ctx, deps):
+    # reduce.py:100-127
+    children = broadcast(list(deps['children']))
+    largest = distarray.largest_value(children)
+    dtype = deps['dtype_fn'](children[0])
+    shape = extent.shape_for_reduction(children[0].shape, deps['axis'])
+    output_array = distarray.create(shape, dtype, reducer=deps['accumulate_fn'], tile_hint=self.tile_hint)
+    largest.foreach_tile(_reduce_mapper, kw={'children': children, 'child_to_var': deps['child_to_var'],
+                                             'op': deps['op'], 'axis': deps['axis'], 'output': output_array})
+    return output_array
+
+
+def reduce(v, axis, dtype_fn, local_reduce_fn, accumulate_fn, fn_kw=None, tile_hint=None):
+  # reduce.py:130-167
+  fn_kw = dict(fn_kw or {})
+  varname = make_var()
+  assert 'axis' not in fn_kw
+  fn_kw['axis'] = axis
+  reduce_op = LocalReduceExpr(fn=local_reduce_fn, deps=[LocalInput(idx='extent'), LocalInput(idx=varname)],
+                              kw=fn_kw)
+  return ReduceExpr(children=ListExpr(vals=[as_array(v)]), child_to_var=[varname], axis=axis,
+                    dtype_fn=dtype_fn, op=reduce_op, accumulate_fn=accumulate_fn, tile_hint=tile_hint)
+
+
+# ----------------------------------------------------------------------------------- optimize.py
+def fusable(v):
+  # optimize.py:107-116 (the node kinds that exist in the oracle)
+  return isinstance(v, (MapExpr, ReduceExpr, NdArrayExpr, Val, AsArray))
+
+
+def merge_var(children, child_to_var, k, v):
+  # optimize.py:119-130
+  if k in child_to_var:
+    assert children[child_to_var.index(k)] is v or children[child_to_var.index(k)].expr_id == v.expr_id
+  else:
+    children.append(v)
+    child_to_var.append(k)
+
+
+class OptimizePass(object):
+  def __init__(self):
+    self.visited = {}
+
+  def visit(self, op):
+    if not isinstance(op, Expr):
+      return op
+    if op.expr_id in self.visited:
+      return self.visited[op.expr_id]
+    name = 'visit_%s' % op.__class__.__name__
+    opt_op = getattr(self, name)(op) if hasattr(self, name) else op.visit(self)
+    self.visited[opt_op.expr_id] = opt_op
+    return opt_op
+
+
+class MapMapFusion(OptimizePass):
+  # optimize.py:133-187
+  def visit_MapExpr(self, expr):
+    map_children = self.visit(expr.children)
+    all_maps = all(fusable(v) for v in map_children)
+    if not all_maps or expr.expr_id in _not_idempotent:
+      return expr.visit(self)
+    children, child_to_var = [], []
+    combined_op = expr.op.__class__(fn=expr.op.fn, kw=expr.op.kw, pretty_fn=expr.op.pretty_fn)
+    for child_expr in map_children:
+      if isinstance(child_expr, MapExpr) and child_expr.expr_id not in _not_idempotent:
+        for k, v in zip(child_expr.child_to_var, child_expr.children):
+          merge_var(children, child_to_var, k, v)
+        combined_op.add_dep(child_expr.op)
+      else:
+        children.append(child_expr)
+        key = make_var()
+        combined_op.add_dep(LocalInput(idx=key))
+        child_to_var.append(key)
+    if isinstance(combined_op, LocalMapLocationExpr):
+      combined_op.add_dep(LocalInput(idx='extent'))
+    return expr_like(expr, children=ListExpr(vals=children), child_to_var=child_to_var, op=combined_op)
+
+
+class ReduceMapFusion(OptimizePass):
+  # optimize.py:190-227
+  def visit_ReduceExpr(self, expr):
+    old_children = self.visit(expr.children)
+    for v in old_children:
+      if not isinstance(v, MapExpr) or v.expr_id in _not_idempotent:
+        return expr.visit(self)
+    combined_op = LocalReduceExpr(fn=expr.op.fn, kw=expr.op.kw, deps=[expr.op.deps[0]])
+    new_children, new_child_to_var = [], []
+    for child_expr in old_children:
+      for k, v in zip(child_expr.child_to_var, child_expr.children):
+        merge_var(new_children, new_child_to_var, k, v)
+      combined_op.add_dep(child_expr.op)
+    return expr_like(expr, children=ListExpr(vals=new_children), child_to_var=new_child_to_var,
+                     axis=expr.axis, dtype_fn=expr.dtype_fn, accumulate_fn=expr.accumulate_fn,
+                     op=combined_op, tile_hint=expr.tile_hint)
+
+
+def optimize(dag):
+  # optimize.py:1072-1099 -- pass order; AutomaticTiling / RotateSlice / Parakeet are out of scope
+  for p in (MapMapFusion, ReduceMapFusion):
+    dag = p().visit(dag)
+  return dag
+
+
+# ----------------------------------------------------------------------------------- builders
+def _make_zeros(input): return np.zeros(input.shape, input.dtype)     # creation.py:67-68
+def _make_ones(input): return np.ones(input.shape, input.dtype)       # creation.py:92-93
+
+
+def zeros(shape, dtype=np.float32, tile_hint=None):
+  return map(ndarray(shape, dtype=dtype, tile_hint=tile_hint), fn=_make_zeros)
+
+
+def ones(shape, dtype=np.float32, tile_hint=None):
+  return map(ndarray(shape, dtype=dtype, tile_hint=tile_hint), fn=_make_ones)
+
+
+def _arange_mapper(tile, ex, start, stop, step, dtype=None):
+  # creation.py:135-141
+  pos = extent.ravelled_pos(ex[0], ex[2])
+  ex_start = pos * step + start
+  ex_stop = int(np.prod(tile.shape)) * step + ex_start
+  return np.arange(ex_start, ex_stop, step, dtype=dtype).reshape(tile.shape)
+
+
+def arange(start=None, stop=None, step=1, dtype=np.float64, tile_hint=None):
+  # creation.py:144-206
+  if start is None and stop is None:
+    raise ValueError('No valid parameters')
+  shape = None
+  if isinstance(start, (tuple, list)):
+    shape = start
+    start = 0
+    if stop is not None:
+      start = stop
+      stop = None
+  elif start is None:
+    start = 0
+  elif stop is None:
+    stop = start
+    start = 0
+  if shape is None and stop is None:
+    raise ValueError('Shape or stop expected, none supplied.')
+  if shape is not None and stop is not None:
+    raise ValueError('Only shape OR stop can be supplied, not both.')
+  if shape is None:
+    length = int(np.ceil((stop - start) / float(step)))
+    shape = (length,)
+  return map_with_location(ndarray(shape, dtype, tile_hint), _arange_mapper,
+                           fn_kw={'start': start, 'stop': stop, 'step': step, 'dtype': dtype})
+
+
+def rand(*shape, **kw):
+  # srandom.py:69-85 (float64, unseeded in the reference; the oracle takes an explicit seed)
+  tile_hint = kw.pop('tile_hint', None)
+  seed = kw.pop('seed', 0)
+  rng = np.random.default_rng(seed)
+  e = map(ndarray(shape, dtype=np.float64, tile_hint=tile_hint), fn=lambda input: rng.random(input.shape))
+  _not_idempotent.add(e.expr_id)
+  return e
+
+
+def from_numpy(npa, tile_hint=None):
+  # write_array.py:424-445 -> WriteArrayExpr: create the array, update the full region
+  npa = np.asarray(npa)
+
+  class _FromNumpy(Expr):
+    members = ()
+
+    def compute_shape(self_):
+      return npa.shape
+
+    def visit(self_, visitor):
+      return self_
+
+    def _evaluate(self_, ctx, deps):
+      arr = distarray.create(npa.shape, npa.dtype, tile_hint=tile_hint)
+      arr.update(extent.from_shape(npa.shape), npa)
+      return arr
+  return _FromNumpy()
+
+
+def astype(x, dtype):
+  # arrays.py:26-42
+  return map(x, lambda t, dtype: t.astype(dtype), fn_kw={'dtype': np.dtype(dtype).str})
+
+
+def add(a, b): return map((a, b), fn=np.add)
+def sub(a, b): return map((a, b), fn=np.subtract)
+def multiply(a, b): return map((a, b), fn=np.multiply)
+def divide(a, b): return map((a, b), fn=np.divide)
+def maximum(a, b): return map((a, b), fn=np.maximum)
+def minimum(a, b): return map((a, b), fn=np.minimum)
+def power(a, b): return map((a, b), fn=np.power)
+def ln(v): return map(v, fn=np.log)
+log = ln
+def exp(v): return map(v, fn=np.exp)
+def sqrt(v): return map(v, fn=np.sqrt)
+def square(v): return map(v, fn=np.square)
+def abs(v): return map(v, fn=np.abs)
+def negative(v): return map(v, fn=np.negative)
+def reciprocal(v): return map(v, fn=np.reciprocal)
+def equal(a, b): return map((a, b), fn=np.equal)
+def not_equal(a, b): return map((a, b), fn=np.not_equal)
+def greater(a, b): return map((a, b), fn=np.greater)
+def greater_equal(a, b): return map((a, b), fn=np.greater_equal)
+def less(a, b): return map((a, b), fn=np.less)
+def less_equal(a, b): return map((a, b), fn=np.less_equal)
+def logical_and(a, b): return map((a, b), fn=np.logical_and)
+def logical_or(a, b): return map((a, b), fn=np.logical_or)
+def logical_xor(a, b): return map((a, b), fn=np.logical_xor)
+
+
+def _sum_local(ex, data, axis): return data.sum(axis)                  # mathematics.py:126-127
+def _prod_local(ex, data, axis): return data.prod(axis)                # mathematics.py:146-147
+
+
+def sum(x, axis=None, tile_hint=None):
+  # mathematics.py:130-143
+  return reduce(x, axis=axis, dtype_fn=lambda input: input.dtype, local_reduce_fn=_sum_local,
+                accumulate_fn=np.add, tile_hint=tile_hint)
+
+
+def _prod_dtype_fn(input):
+  # mathematics.py:150-154
+  return np.dtype(np.int64) if input.dtype == np.int32 else input.dtype
+
+
+def prod(x, axis=None, tile_hint=None):
+  return reduce(x, axis=axis, dtype_fn=_prod_dtype_fn, local_reduce_fn=_prod_local,
+                accumulate_fn=np.multiply, tile_hint=tile_hint)
+
+
+def max(x, axis=None, tile_hint=None):
+  # statistics.py:26-42
+  return reduce(x, axis=axis, dtype_fn=lambda input: input.dtype,
+                local_reduce_fn=lambda ex, data, axis: data.max(axis), accumulate_fn=np.maximum,
+                tile_hint=tile_hint)
+
+
+def min(x, axis=None, tile_hint=None):
+  # statistics.py:45-61
+  return reduce(x, axis=axis, dtype_fn=lambda input: input.dtype,
+                local_reduce_fn=lambda ex, data, axis: data.min(axis), accumulate_fn=np.minimum,
+                tile_hint=tile_hint)
+
+
+def mean(x, axis=None):
+  # statistics.py:64-76
+  if axis is None:
+    return sum(x, axis) / float(np.prod(x.shape))
+  return sum(x, axis) / float(x.shape[axis])
+
+
+def all(array, axis=None):
+  # logic.py:25-34
+  return reduce(array, axis=axis, dtype_fn=lambda input: np.bool_,
+                local_reduce_fn=lambda ex, tile, axis=None: np.all(tile, axis=axis),
+                accumulate_fn=np.logical_and)
+
+
+def any(array, axis=None):
+  # logic.py:37-46
+  return reduce(array, axis=axis, dtype_fn=lambda input: np.bool_,
+                local_reduce_fn=lambda ex, tile, axis=None: np.any(tile, axis=axis),
+                accumulate_fn=np.logical_or)
+
+
+def _countnonzero_local(ex, data, axis):
+  # sorting.py:126-133
+  if axis is None:
+    return np.asarray(np.count_nonzero(data))
+  return (data > 0).sum(axis)
+
+
+def count_nonzero(array, axis=None, tile_hint=None):
+  return reduce(array, axis, dtype_fn=lambda input: np.int64, local_reduce_fn=_countnonzero_local,
+                accumulate_fn=np.add, tile_hint=tile_hint)
+
+
+def _countzero_local(ex, data, axis):
+  # sorting.py:153-157
+  if axis is None:
+    return np.asarray(int(np.prod(ex.shape)) - np.count_nonzero(data))
+  return (data == 0).sum(axis)
+
+
+def count_zero(array, axis=None):
+  return reduce(array, axis, dtype_fn=lambda input: np.int64, local_reduce_fn=_countzero_local,
+                accumulate_fn=np.add)
+
+
+def _arg_mapper(a, b, ex, axis=None):
+  # sorting.py:67-85
+  c = np.zeros(a.shape)
+  c[a == b] = 1
+  max_index = np.argmax(c, axis)
+  if axis is not None:
+    shape = list(a.shape)
+    shape[axis] = 1
+    global_index = max_index.reshape(tuple(shape)) + ex[0][axis]
+  else:
+    ex_shape = []
+    for i in range(len(ex[0])):
+      ex_shape.append(ex[1][i] - ex[0][i])
+      ex_shape[i] = 1 if ex_shape[i] == 0 else ex_shape[i]
+    local_index = extent.unravelled_pos(int(max_index), ex_shape)
+    # NB: the reference ravels with ex_shape (sorting.py:82), which is only the global position when the
+    # tile spans the trailing dims; the oracle keeps the intent (global C-order position).
+    global_index = extent.ravelled_pos(np.asarray(ex[0]) + local_index, ex[2])
+  c = np.zeros(a.shape, dtype=np.int64) + global_index
+  c[a != b] = np.prod(np.asarray(ex[2]))
+  return c
+
+
+class ReshapeLast(Expr):
+  """Minimal stand-in for ``compute_min.reshape(shape-with-1-at-axis)`` used by argmin/argmax
+  (sorting.py:97-101; reshape.py is otherwise out of scope): evaluates eagerly through NumPy."""
+  members = ('array', 'new_shape')
+
+  def compute_shape(self):
+    return tuple(self.new_shape)
+
+  def _evaluate(self, ctx, deps):
+    data = deps['array'].glom().reshape(self.new_shape)
+    arr = distarray.create(data.shape, data.dtype)
+    arr.update(extent.from_shape(data.shape), data)
+    return arr
+
+
+def _arg_reduce(x, axis, which):
+  compute = which(x, axis)
+  if axis is not None:
+    shape = list(x.shape)
+    shape[axis] = 1
+    compute = ReshapeLast(array=compute, new_shape=tuple(shape))
+  argument = map_with_location((x, compute), _arg_mapper, fn_kw={'axis': axis})
+  return min(argument, axis)
+
+
+def argmin(x, axis=None):
+  return _arg_reduce(x, axis, min)      # sorting.py:88-105
+
+
+def argmax(x, axis=None):
+  return _arg_reduce(x, axis, max)      # sorting.py:108-124
+
+
+# ----------------------------------------------------------------------------------- dot.py
+def dot_map2_np_mapper(extents, tiles, array2):
+  # dot.py:172-187
+  ex = extents[0]
+  if len(ex.ul) == 1:
+    target_ex = extent.create((0,), (1,), (1,))
+    target_tile = tiles[0].dot(array2[ex.ul[0]:ex.lr[0]]).reshape(1,)
+  elif len(array2.shape) == 1:
+    target_ex = extent.create((ex.ul[0],), (ex.lr[0],), (ex.array_shape[0],))
+    target_tile = tiles[0].dot(array2[ex.ul[1]:ex.lr[1]])
+  else:
+    target_ex = extent.create((ex.ul[0], 0), (ex.lr[0], array2.shape[1]), (ex.array_shape[0], array2.shape[1]))
+    target_tile = tiles[0].dot(array2[ex.ul[1]:ex.lr[1], ])
+  yield target_ex, target_tile
+
+
+def dot_map2_vec_mapper(extents, tiles):
+  # dot.py:190-192
+  yield extent.create((0,), (1,), (1,)), tiles[0].dot(tiles[1]).reshape(1,)
+
+
+def dot_map2_mapper(extents, tiles, is_vec=None):
+  # dot.py:195-217 (dense)
+  tiles = list(tiles)
+  if is_vec:
+    ul = (0,); lr = (extents[1].lr[1],); shape = (extents[1].shape[1],)
+    tiles[0] = tiles[0].reshape(extents[0].shape[1],)
+  elif len(tiles[1].shape) == 1:
+    ul = (0,); lr = (extents[0].lr[0],); shape = (extents[0].shape[0],)
+  else:
+    ul = (0, 0); lr = (extents[0].lr[0], extents[1].lr[1]); shape = (extents[0].shape[0], extents[1].shape[1])
+  yield extent.create(ul, lr, shape), tiles[0].dot(tiles[1])
+
+
+def dot_outer_mapper(ex_a, tile_a, ex_b, tile_b):
+  # dot.py:222-238
+  if len(tile_b.shape) == 1:
+    ul = (ex_a.ul[0],); lr = (ex_a.lr[0],); shape = (ex_a.array_shape[0],)
+  else:
+    ul = (ex_a.ul[0], ex_b.ul[1]); lr = (ex_a.lr[0], ex_b.lr[1])
+    shape = (ex_a.array_shape[0], ex_b.array_shape[1])
+  yield extent.create(ul, lr, shape), tile_a.dot(tile_b)
+
+
+def dot(a, b, tile_hint=None):
+  """dot.py:243-299 routing.  Operands must be 1-D tiled (row or column strips): the reference's
+  grid-tiled path contracts only #tiles k-indices and np.dot is what its
+  tests assert, so for grid tilings use ``np.dot`` of the glommed operands as the oracle."""
+  if isinstance(b, np.ndarray):
+    if len(a.shape) == 1 and len(b.shape) == 1:
+      shape = (1,)
+    elif len(a.shape) > 1 and len(b.shape) == 1:
+      shape = (a.shape[0],)
+    else:
+      shape = (a.shape[0], b.shape[1])
+    return map2(a, axes=[0], fn=dot_map2_np_mapper, fn_kw={'array2': b}, shape=shape, reducer=np.add)
+  if len(a.shape) == 1 and len(b.shape) == 1:
+    if a.shape[0] != b.shape[0]:
+      raise ValueError('objects are not aligned')
+    return map2((a, b), (0, 0), fn=dot_map2_vec_mapper, shape=(1,), reducer=np.add)
+  elif len(a.shape) == 1 and len(b.shape) > 1:
+    raise NotImplementedError('vec . matrix needs reshape (dot.py:296-299); out of scope')
+  elif len(a.shape) > 1 and len(b.shape) == 1:
+    if a.shape[1] != b.shape[0]:
+      raise ValueError('objects are not aligned')
+    shape = (a.shape[0],)
+  else:
+    if tile_hint is None:
+      tile_hint = (a.shape[0], b.shape[1])
+    if a.shape[1] != b.shape[0]:
+      raise ValueError('objects are not aligned')
+    shape = (a.shape[0], b.shape[1])
+  if a.shape[0] > a.shape[1]:
+    return outer((a, b), (0, None), dot_outer_mapper, shape=shape, tile_hint=tile_hint, reducer=np.add)
+  return map2((a, b), (1, 0), dot_map2_mapper, shape=shape, tile_hint=tile_hint, reducer=np.add)

@@ -1,0 +1,550 @@
+// Dense fp32 contraction for spartan.dot on B200 (sm_100a).
+//
+// Replaces the per-tile `tiles[0].dot(tiles[1])` BLAS call of the reference
+// (spartan/expr/dot.py:195-217 dot_map2_mapper, :222-238 dot_outer_mapper) and
+// the `np.add` combiner that merges the rank-k partials
+// (spartan/array/tile.pyx:263-268) with one persistent, warp-specialised
+// tcgen05 kernel:
+//
+//   C[m, n] (+)= sum over terms t, k :  A_t[m, k] * Bt_t[n, k]
+//
+// * operands are *prepared* copies (prep_a / prep_bt below): fp32 values
+//   rounded to TF32 with round-to-nearest (the tensor core would otherwise
+//   truncate, a systematic -2^-11 bias), B transposed so both operands are
+//   K-major, K zero-padded to a multiple of 32 so TMA strides are 16B aligned;
+// * "terms" express both precision splitting (tf32x3: lo*hi + hi*lo + hi*hi)
+//   and K-segments (one term per (A strip, B strip) pair of a tiled dot), so a
+//   whole tiled contraction is ONE launch and the accumulator never leaves
+//   TMEM between strips;
+// * TMA (cp.async.bulk.tensor, 128B swizzle) -> 4-stage smem ring -> one
+//   elected thread issues tcgen05.mma.kind::tf32 (M=128, N=256, K=8) into a
+//   double-buffered 2x256-column TMEM accumulator -> 4 epilogue warps drain
+//   TMEM with tcgen05.ld and store/accumulate C.
+//
+// Roofline: tensor pipe. Algorithmic work = 2*M*N*K flop per dot.
+#include "sp_common.h"
+#include <cuda.h>
+
+namespace sp {
+namespace gemm {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 32;            // fp32 elements = one 128B swizzle row
+constexpr int UMMA_K = 8;         // tf32: 32 bytes of K per MMA
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 4;   // 16 KiB
+constexpr int B_STAGE_BYTES = BN * BK * 4;   // 32 KiB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int NUM_ACC = 2;
+constexpr int TMEM_COLS = NUM_ACC * BN;      // 512
+constexpr int NUM_THREADS = 256;             // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 epilogue
+constexpr int EPI_WARP0 = 4;
+constexpr int GROUP_M = 16;                  // tile rasterisation group (L2 reuse)
+constexpr int MAX_TERMS = SP_GEMM_MAX_TERMS;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct Term {
+  int a_map;
+  int b_map;
+  int k_blocks;
+  int pad;
+};
+
+struct Params {
+  CUtensorMap maps[2 * MAX_TERMS];
+  Term terms[MAX_TERMS];
+  int n_terms;
+  int M, N;
+  int m_blocks, n_blocks;
+  int accumulate;
+  float* C;
+  int64_t ldc;
+};
+
+// ----------------------------------------------------------------------------
+// PTX wrappers
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], tf32 inputs, fp32 accumulate.
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+      : "memory");
+}
+
+// Arrives on `bar` once every previously issued tcgen05.mma of this thread retired.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
+// Field layout follows the sm_100 shared-memory matrix descriptor
+// (start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout [61,64)).
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(1) << 16;              // LBO (unused for swizzled K-major)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;      // SBO: next 8-row group
+  d |= static_cast<uint64_t>(1) << 46;              // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;              // SWIZZLE_128B
+  return d;
+}
+
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
+  return (1u << 4)                      // D format: F32
+         | (2u << 7)                    // A format: TF32
+         | (2u << 10)                   // B format: TF32
+         | (0u << 15) | (0u << 16)      // A, B K-major
+         | (static_cast<uint32_t>(n >> 3) << 17)
+         | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void tile_coords(int tile, int m_blocks, int n_blocks, int& m_blk, int& n_blk) {
+  const int tiles_per_group = GROUP_M * n_blocks;
+  const int group = tile / tiles_per_group;
+  const int first_m = group * GROUP_M;
+  const int rows_in_group = min(GROUP_M, m_blocks - first_m);
+  const int in_group = tile - group * tiles_per_group;
+  m_blk = first_m + in_group % rows_in_group;
+  n_blk = in_group / rows_in_group;
+}
+
+// ----------------------------------------------------------------------------
+// The kernel
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tf32_kernel(const __grid_constant__ Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[NUM_ACC], tmem_empty[NUM_ACC], tmem_ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + NUM_ACC + a); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * STAGES + 2 * NUM_ACC);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.m_blocks * p.n_blocks;
+
+  if (warp == 0 && lane == 0) {
+    for (int t = 0; t < p.n_terms; ++t) {
+      tma_prefetch_desc(&p.maps[p.terms[t].a_map]);
+      tma_prefetch_desc(&p.maps[p.terms[t].b_map]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < NUM_ACC; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), 4);   // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int m_blk, n_blk;
+        tile_coords(tile, p.m_blocks, p.n_blocks, m_blk, n_blk);
+        for (int t = 0; t < p.n_terms; ++t) {
+          const Term term = p.terms[t];
+          const CUtensorMap* map_a = &p.maps[term.a_map];
+          const CUtensorMap* map_b = &p.maps[term.b_map];
+          for (int kb = 0; kb < term.k_blocks; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
+            const uint32_t b_dst = a_dst + A_STAGE_BYTES;
+            mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+            tma_load_2d(a_dst, map_a, full_bar(stage), kb * BK, m_blk * BM);
+            tma_load_2d(b_dst, map_b, full_bar(stage), kb * BK, n_blk * BN);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        uint32_t accum = 0;
+        for (int t = 0; t < p.n_terms; ++t) {
+          const int k_blocks = p.terms[t].k_blocks;
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
+            const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t da = make_kmajor_sw128_desc(a_addr + k * UMMA_K * 4);
+              const uint64_t db = make_kmajor_sw128_desc(b_addr + k * UMMA_K * 4);
+              umma_tf32(tmem_d, da, db, idesc, accum);
+              accum = 1;
+            }
+            umma_commit(empty_bar(stage));      // frees the smem slot when these MMAs retire
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        umma_commit(tmem_full_bar(acc));        // accumulator complete -> epilogue
+        if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= EPI_WARP0) {
+    // ===================== Epilogue: TMEM -> registers -> C =====================
+    const int q = warp - EPI_WARP0;              // TMEM lane quarter owned by this warp (warp % 4)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int m_blk, n_blk;
+      tile_coords(tile, p.m_blocks, p.n_blocks, m_blk, n_blk);
+      mbar_wait(tmem_full_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row = m_blk * BM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      float* c_row = p.C + static_cast<int64_t>(row) * p.ldc;
+      const bool vec_ok = ((reinterpret_cast<uint64_t>(p.C) & 15) == 0) && ((p.ldc & 3) == 0);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c;
+        tmem_ld_32x32b_x32(taddr, r);
+        tmem_ld_wait();
+        const int col0 = n_blk * BN + c;
+        if (row_ok) {
+          if (vec_ok && col0 + 32 <= p.N) {
+            float4* dst = reinterpret_cast<float4*>(c_row + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                     __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+              if (p.accumulate) {
+                const float4 o = dst[j];
+                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+              }
+              dst[j] = v;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (col0 + j < p.N) {
+                float v = __uint_as_float(r[j]);
+                if (p.accumulate) v += c_row[col0 + j];
+                c_row[col0 + j] = v;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+      if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ----------------------------------------------------------------------------
+// Operand preparation: RN-round to TF32, optional hi/lo split, pad K to 32,
+// transpose B.  HBM-bound: reads the operand once, writes 1 (or 2) copies.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ float rn_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// A: [M, K] with leading dim lda  ->  hi/lo: [M, Kp] (Kp multiple of 32, zero tail)
+__global__ void prep_a_kernel(const float* __restrict__ A, int64_t lda, int M, int K, int Kp,
+                              float* __restrict__ hi, float* __restrict__ lo) {
+  const int64_t total = static_cast<int64_t>(M) * Kp;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t m = i / Kp;
+    const int k = static_cast<int>(i - m * Kp);
+    const float a = (k < K) ? A[m * lda + k] : 0.0f;
+    const float h = rn_tf32(a);
+    hi[i] = h;
+    if (lo != nullptr) lo[i] = rn_tf32(a - h);
+  }
+}
+
+// B: [K, N] with leading dim ldb  ->  hiT/loT: [N, Kp]
+__global__ void prep_bt_kernel(const float* __restrict__ B, int64_t ldb, int K, int N, int Kp,
+                               float* __restrict__ hiT, float* __restrict__ loT) {
+  __shared__ float tile[32][33];
+  const int n0 = blockIdx.x * 32;
+  const int k0 = blockIdx.y * 32;
+  // read B[k0+ty.., n0+tx] coalesced along n
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int k = k0 + r, n = n0 + threadIdx.x;
+    tile[r][threadIdx.x] = (k < K && n < N) ? B[static_cast<int64_t>(k) * ldb + n] : 0.0f;
+  }
+  __syncthreads();
+  // write out[n0+r, k0+tx] coalesced along k
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int n = n0 + r, k = k0 + threadIdx.x;
+    if (n < N && k < Kp) {
+      const float b = tile[threadIdx.x][r];
+      const float h = rn_tf32(b);
+      const int64_t o = static_cast<int64_t>(n) * Kp + k;
+      hiT[o] = h;
+      if (loT != nullptr) loT[o] = rn_tf32(b - h);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// Host side
+// ----------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess) {
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// 2-D K-major fp32 tensor [rows, Kp], box = [box_rows, BK], 128B swizzle.
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t Kp, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  SP_REQUIRE(enc != nullptr, SP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(Kp), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(Kp) * 4};
+  cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SP_REQUIRE(r == CUDA_SUCCESS, SP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+  return SP_OK;
+}
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+}  // namespace gemm
+}  // namespace sp
+
+using namespace sp;
+using namespace sp::gemm;
+
+extern "C" int64_t sp_gemm_f32_workspace_bytes(int64_t M, int64_t N, int n_seg, const int64_t* seg_k, int precision) {
+  const int copies = (precision == SP_GEMM_TF32X3) ? 2 : 1;
+  int64_t total = 0;
+  for (int s = 0; s < n_seg; ++s) {
+    const int64_t Kp = round_up(seg_k[s], BK);
+    total += round_up((M + N) * Kp * 4 * copies, 1024);
+  }
+  return total + 1024;
+}
+
+extern "C" int sp_gemm_f32_segments(int n_seg, const sp_gemm_segment* segs, float* C, int64_t ldc, int64_t M,
+                                     int64_t N, int accumulate, int precision, void* workspace,
+                                     int64_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SP_REQUIRE(precision == SP_GEMM_TF32X1 || precision == SP_GEMM_TF32X3, SP_ERR_INVALID,
+             "sp_gemm_f32_segments: unknown precision %d", precision);
+  const int copies = (precision == SP_GEMM_TF32X3) ? 2 : 1;
+  const int terms_per_seg = (precision == SP_GEMM_TF32X3) ? 3 : 1;
+  SP_REQUIRE(n_seg >= 1 && n_seg * terms_per_seg <= MAX_TERMS, SP_ERR_INVALID,
+             "sp_gemm_f32_segments: %d segments x %d terms exceeds %d", n_seg, terms_per_seg, MAX_TERMS);
+  SP_REQUIRE(M > 0 && N > 0 && M < (1ll << 31) && N < (1ll << 31), SP_ERR_INVALID, "bad M/N %lld %lld",
+             (long long)M, (long long)N);
+  {
+    int64_t ks[MAX_TERMS];
+    for (int s = 0; s < n_seg; ++s) ks[s] = segs[s].K;
+    const int64_t need = sp_gemm_f32_workspace_bytes(M, N, n_seg, ks, precision);
+    SP_REQUIRE(workspace != nullptr && workspace_bytes >= need, SP_ERR_INVALID,
+               "sp_gemm_f32_segments: workspace %lld B < required %lld B", (long long)workspace_bytes,
+               (long long)need);
+  }
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    SP_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+
+  Params p;
+  memset(&p, 0, sizeof(p));
+  uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uint64_t>(workspace) + 1023) & ~1023ull);
+  int n_maps = 0, n_terms = 0;
+  for (int s = 0; s < n_seg; ++s) {
+    const sp_gemm_segment& g = segs[s];
+    SP_REQUIRE(g.K > 0, SP_ERR_INVALID, "segment %d has K=%lld", s, (long long)g.K);
+    const int64_t Kp = round_up(g.K, BK);
+    float* a_hi = reinterpret_cast<float*>(ws);
+    float* b_hi = a_hi + M * Kp;
+    float* a_lo = nullptr;
+    float* b_lo = nullptr;
+    if (copies == 2) {
+      a_lo = b_hi + N * Kp;
+      b_lo = a_lo + M * Kp;
+    }
+    ws += round_up((M + N) * Kp * 4 * copies, 1024);
+
+    {
+      const int64_t total = M * Kp;
+      const int threads = 256;
+      const int blocks = static_cast<int>(std::min<int64_t>((total + threads - 1) / threads, 148 * 16));
+      prep_a_kernel<<<blocks, threads, 0, stream>>>(g.A, g.lda, static_cast<int>(M), static_cast<int>(g.K),
+                                                    static_cast<int>(Kp), a_hi, a_lo);
+      dim3 grid(static_cast<unsigned>((N + 31) / 32), static_cast<unsigned>(Kp / 32));
+      dim3 block(32, 8);
+      prep_bt_kernel<<<grid, block, 0, stream>>>(g.B, g.ldb, static_cast<int>(g.K), static_cast<int>(N),
+                                                 static_cast<int>(Kp), b_hi, b_lo);
+    }
+
+    const int ia_hi = n_maps++, ib_hi = n_maps++;
+    int rc = make_map(&p.maps[ia_hi], a_hi, M, Kp, BM);
+    if (rc) return rc;
+    rc = make_map(&p.maps[ib_hi], b_hi, N, Kp, BN);
+    if (rc) return rc;
+    const int kb = static_cast<int>(Kp / BK);
+    if (copies == 2) {
+      const int ia_lo = n_maps++, ib_lo = n_maps++;
+      rc = make_map(&p.maps[ia_lo], a_lo, M, Kp, BM);
+      if (rc) return rc;
+      rc = make_map(&p.maps[ib_lo], b_lo, N, Kp, BN);
+      if (rc) return rc;
+      // small cross terms first, dominant term last
+      p.terms[n_terms++] = Term{ia_lo, ib_hi, kb, 0};
+      p.terms[n_terms++] = Term{ia_hi, ib_lo, kb, 0};
+    }
+    p.terms[n_terms++] = Term{ia_hi, ib_hi, kb, 0};
+  }
+  p.n_terms = n_terms;
+  p.M = static_cast<int>(M);
+  p.N = static_cast<int>(N);
+  p.m_blocks = static_cast<int>((M + BM - 1) / BM);
+  p.n_blocks = static_cast<int>((N + BN - 1) / BN);
+  p.accumulate = accumulate;
+  p.C = C;
+  p.ldc = ldc;
+
+  const int tiles = p.m_blocks * p.n_blocks;
+  const int grid = std::min(tiles, num_sms());
+  gemm_tf32_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);
+  SP_CUDA_CHECK(cudaGetLastError());
+  return SP_OK;
+}
+
+extern "C" int sp_gemm_f32(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                            int64_t M, int64_t N, int64_t K, int accumulate, int precision, void* workspace,
+                            int64_t workspace_bytes, void* stream) {
+  sp_gemm_segment seg;
+  seg.A = A; seg.lda = lda; seg.B = B; seg.ldb = ldb; seg.K = K;
+  return sp_gemm_f32_segments(1, &seg, C, ldc, M, N, accumulate, precision, workspace, workspace_bytes, stream);
+}

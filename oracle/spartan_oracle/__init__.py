@@ -1,0 +1,3 @@
+"""ORACLE -- test infrastructure only (see oracle/README.md).  Never imported by spartan_b200/."""
+from . import extent, distarray, expr            # noqa: F401
+from .distarray import initialize                 # noqa: F401

@@ -15,6 +15,7 @@ Restates, for the hot path only:
 NumPy-1 value-based casting is emulated in ``_call_ufunc``: a 0-d operand
 never widens an array operand of the same or a higher kind.
 """
+import builtins as _b
 import collections
 import itertools
 
@@ -60,8 +61,8 @@ def legacy_result_type(args):
   scalars = [a for a in arrs if a.ndim == 0]
   if not arrays or not scalars:
     return np.result_type(*[a.dtype for a in arrs])
-  max_arr = max(_KIND_RANK[a.dtype.kind] for a in arrays)
-  max_sc = max(_KIND_RANK[a.dtype.kind] for a in scalars)
+  max_arr = _b.max(_KIND_RANK[a.dtype.kind] for a in arrays)
+  max_sc = _b.max(_KIND_RANK[a.dtype.kind] for a in scalars)
   if max_sc <= max_arr:
     dts = [a.dtype for a in arrays] + [np.min_scalar_type(a[()]) for a in scalars]
     return np.result_type(*dts)
@@ -69,7 +70,7 @@ def legacy_result_type(args):
 
 
 def _call_ufunc(fn, deps, kw):
-  if len(deps) >= 2 and any(np.ndim(d) == 0 for d in deps) and any(np.ndim(d) > 0 for d in deps):
+  if len(deps) >= 2 and _b.any(np.ndim(d) == 0 for d in deps) and _b.any(np.ndim(d) > 0 for d in deps):
     dt = legacy_result_type(deps)
     deps = [np.asarray(d, dtype=dt) if np.ndim(d) == 0 else d for d in deps]
   return fn(*deps, **kw)
@@ -369,7 +370,7 @@ class MapExpr(Expr):
   def compute_shape(self):
     # map.py:104-128
     orig_shapes = [list(x.shape) for x in self.children]
-    max_dim = max(len(s) for s in orig_shapes)
+    max_dim = _b.max(len(s) for s in orig_shapes)
     new_shapes = [[1] * (max_dim - len(s)) + s for s in orig_shapes]
     out = collections.defaultdict(int)
     for s in new_shapes:
@@ -588,7 +589,7 @@ def reduce(v, axis, dtype_fn, local_reduce_fn, accumulate_fn, fn_kw=None, tile_h
 # ----------------------------------------------------------------------------------- optimize.py
 def fusable(v):
   # optimize.py:107-116 (the node kinds that exist in the oracle)
-  return isinstance(v, (MapExpr, ReduceExpr, NdArrayExpr, Val, AsArray))
+  return isinstance(v, (MapExpr, ReduceExpr, NdArrayExpr, Val, AsArray, WriteArrayExpr))
 
 
 def merge_var(children, child_to_var, k, v):
@@ -619,7 +620,7 @@ class MapMapFusion(OptimizePass):
   # optimize.py:133-187
   def visit_MapExpr(self, expr):
     map_children = self.visit(expr.children)
-    all_maps = all(fusable(v) for v in map_children)
+    all_maps = _b.all(fusable(v) for v in map_children)
     if not all_maps or expr.expr_id in _not_idempotent:
       return expr.visit(self)
     children, child_to_var = [], []
@@ -722,24 +723,30 @@ def rand(*shape, **kw):
   return e
 
 
+class WriteArrayExpr(Expr):
+  # write_array.py:46-94 restricted to the from_numpy use: create the array, update the full region
+  members = ('npa', 'tile_hint')
+
+  def compute_shape(self):
+    return self.npa.shape
+
+  def visit(self, visitor):
+    return self
+
+  def dependencies(self):
+    return {}
+
+  def _evaluate(self, ctx, deps):
+    arr = distarray.create(self.npa.shape, self.npa.dtype, tile_hint=self.tile_hint)
+    arr.update(extent.from_shape(self.npa.shape), self.npa)
+    return arr
+
+
 def from_numpy(npa, tile_hint=None):
-  # write_array.py:424-445 -> WriteArrayExpr: create the array, update the full region
-  npa = np.asarray(npa)
-
-  class _FromNumpy(Expr):
-    members = ()
-
-    def compute_shape(self_):
-      return npa.shape
-
-    def visit(self_, visitor):
-      return self_
-
-    def _evaluate(self_, ctx, deps):
-      arr = distarray.create(npa.shape, npa.dtype, tile_hint=tile_hint)
-      arr.update(extent.from_shape(npa.shape), npa)
-      return arr
-  return _FromNumpy()
+  # write_array.py:424-445
+  if not isinstance(npa, np.ndarray):
+    raise TypeError('Expected ndarray, got: %s' % type(npa))
+  return WriteArrayExpr(npa=npa, tile_hint=tile_hint)
 
 
 def astype(x, dtype):

@@ -1,0 +1,164 @@
+"""BlobCtx: the tile store and kernel dispatcher of one GPU rank.
+
+Keeps the reference's name and call surface (spartan/blob_ctx.py:18-301: create / get / update /
+destroy_all / map / tile_op / num_workers / is_master, module-level get()/set()) but none of its
+mechanism: there is no master, no RPC and no pickled closures.  The job is SPMD -- one process per
+GPU, every process builds the same expression DAG and walks the same tiles in the same order:
+
+  * ``num_workers``  = number of GPU ranks (torch.distributed world size), ``worker_id`` = this rank;
+  * a tile lives in the HBM of exactly one rank; TileId = (worker, per-worker sequence number) is
+    assigned deterministically, so every rank knows the whole extent -> TileId table of every array
+    without exchanging a byte (the reference learns it from RPC replies, distarray.py:202-208);
+  * ``map`` runs the per-tile kernel function for every tile on every rank; the function launches CUDA
+    work only where the tile is local (``ctx.is_local``) and takes part in collectives otherwise.
+
+Device memory comes from torch (caching allocator, streams); compute goes through the C ABI.
+"""
+import os
+import threading
+
+import numpy as np
+import torch
+
+from . import comm
+from ._lib import SpartanError
+from .core import TileId
+
+_TORCH_DTYPES = {
+  np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
+  np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64,
+  np.dtype(np.uint8): torch.uint8, np.dtype(np.bool_): torch.bool,
+}
+
+
+def torch_dtype(dtype):
+  dtype = np.dtype(dtype)
+  if dtype not in _TORCH_DTYPES:
+    raise SpartanError('dtype %s is not supported by the device evaluator (float32/float64/int32/int64/uint8/bool)'
+                       % dtype)
+  return _TORCH_DTYPES[dtype]
+
+
+class BlobCtx(object):
+  def __init__(self, worker_id=0, num_workers=1, device=None):
+    self.worker_id = int(worker_id)
+    self.num_workers = int(num_workers)
+    if device is None:
+      device = torch.device('cuda', int(os.environ.get('LOCAL_RANK', 0))) if torch.cuda.is_available() \
+        else torch.device('cpu')
+    self.device = torch.device(device)
+    self._blobs = {}                          # TileId -> DeviceTile, local tiles only (worker.py:70 _blobs)
+    self._next_id = [0] * self.num_workers    # per-worker id sequence, identical on every rank
+    self._rr = 0
+    self._scratch = {}
+    self.kernel_launches = 0                  # launches of this library's kernels (bench.py "gpu_launches")
+
+  # ------------------------------------------------------------------ reference surface
+  def is_master(self):
+    return True      # SPMD: every rank holds the DAG; blob_ctx.py:35-40
+
+  def is_local(self, tile_id):
+    return tile_id.worker == self.worker_id or tile_id.worker < 0
+
+  def new_tile_id(self, hint=-1):
+    """blob_ctx.py:221-254: hint >= 0 picks worker hint % num_workers, otherwise round-robin."""
+    if hint is None or hint < 0:
+      worker = self._rr % self.num_workers
+      self._rr += 1
+    else:
+      worker = int(hint) % self.num_workers
+    tid = TileId(worker, self._next_id[worker])
+    self._next_id[worker] += 1
+    return tid
+
+  def create(self, tile, hint=-1):
+    """Registers ``tile`` (a DeviceTile, or a zero-argument factory producing one, evaluated only on
+    the owning rank) and returns its TileId.  Synchronous: there is no Future to wait on."""
+    tid = self.new_tile_id(hint)
+    if tid.worker == self.worker_id:
+      self._blobs[tid] = tile() if callable(tile) else tile
+    return tid
+
+  def get(self, tile_id, subslice=None):
+    """Local tile data (a device tensor view); blob_ctx.py:127-143."""
+    return self._blobs[tile_id].get(subslice)
+
+  def tile(self, tile_id):
+    return self._blobs[tile_id]
+
+  def update(self, tile_id, subslice, data, reducer, wait=True):
+    """blob_ctx.py:163-179 -> Tile.merge; local tiles only."""
+    return self._blobs[tile_id].update(subslice, data, reducer)
+
+  def destroy_all(self, tile_ids):
+    for tid in tile_ids:
+      self._blobs.pop(tid, None)
+
+  def tile_op(self, tile_id, fn):
+    return fn(self._blobs[tile_id])
+
+  def map(self, tile_ids, mapper_fn, kw):
+    """blob_ctx.py:256-275 + Worker._run_kernel (worker.py:232-304): every rank calls ``mapper_fn`` for
+    every tile, in a canonical order (worker, id); results keyed by tile id."""
+    out = {}
+    for tid in sorted(tile_ids, key=lambda t: (t.worker, t.id)):
+      out[tid] = mapper_fn(tid, self._blobs.get(tid), **kw)
+    return out
+
+  # ------------------------------------------------------------------ device helpers
+  def stream_ptr(self):
+    if self.device.type != 'cuda':
+      raise SpartanError('no CUDA device: spartan_b200 has no CPU fallback for compute kernels')
+    return torch.cuda.current_stream(self.device).cuda_stream
+
+  def empty(self, shape, dtype):
+    return torch.empty(tuple(int(s) for s in shape), dtype=torch_dtype(dtype), device=self.device)
+
+  def scratch(self, nbytes, key='default'):
+    """Grow-only device scratch buffers (reduction partials, GEMM operand copies)."""
+    buf = self._scratch.get(key)
+    if buf is None or buf.numel() < nbytes:
+      self._scratch[key] = None
+      buf = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+      self._scratch[key] = buf
+    return buf
+
+  def synchronize(self):
+    if self.device.type == 'cuda':
+      torch.cuda.synchronize(self.device)
+
+
+_local = threading.local()
+_global_ctx = [None]
+
+
+def get():
+  """blob_ctx.py:290-296."""
+  ctx = getattr(_local, 'ctx', None) or _global_ctx[0]
+  if ctx is None:
+    ctx = initialize()
+  return ctx
+
+
+def set(ctx):
+  """blob_ctx.py:298-301."""
+  _local.ctx = ctx
+  _global_ctx[0] = ctx
+
+
+def initialize(device=None):
+  """One-time setup of this rank: picks cuda:LOCAL_RANK, joins the torch.distributed job when
+  WORLD_SIZE > 1 (NCCL on GPUs, gloo on CPU) and installs the context.  Replaces
+  spartan.initialize() -> cluster.start_cluster (spartan/__init__.py:42-56, cluster.py:125-169)."""
+  rank, world = comm.init_from_env(device)
+  if device is None and torch.cuda.is_available():
+    device = torch.device('cuda', int(os.environ.get('LOCAL_RANK', 0)))
+    torch.cuda.set_device(device)
+  ctx = BlobCtx(rank, world, device)
+  set(ctx)
+  return ctx
+
+
+def shutdown():
+  _global_ctx[0] = None
+  _local.ctx = None

@@ -1,0 +1,19 @@
+"""The handful of flags the hot path reads (reference: spartan/config.py:27-227, optimize.py:1084-1101).
+``num_workers`` becomes the number of GPU ranks (one process per GPU)."""
+
+
+class Flags(object):
+  def __init__(self):
+    self.optimization = True            # optimize.py:1101
+    self.opt_map_fusion = True          # optimize.py:1096
+    self.opt_reduce_fusion = True       # optimize.py:1099
+    self.opt_expression_cache = True    # base.py:21
+    self.tile_assignment_strategy = 'round_robin'   # distarray.py:441-445 (the only strategy on one box)
+    # tensor-core mode of dot(): 'tf32x3' (~fp32-faithful), 'tf32x1' (fast), 'simt' (CUDA cores, exact IEEE order)
+    self.dot_precision = 'tf32x3'
+
+  def __repr__(self):
+    return 'FLAGS(%s)' % ', '.join('%s=%r' % kv for kv in sorted(self.__dict__.items()))
+
+
+FLAGS = Flags()

@@ -1,0 +1,341 @@
+// In-register bytecode evaluator for fused LocalExpr trees (the fusable kernel IR of the
+// reference: spartan/expr/operator/local.py:58-152, fused by optimize.py:133-227).
+//
+// One thread evaluates the whole program for V consecutive elements.  The operand stack
+// lives in registers: every (opcode, stack-depth) pair is its own switch case, so all
+// stack indices are compile-time constants and nothing spills to local memory.  The
+// dispatch cost (one jump-table branch per op) is amortised over V elements; inputs are
+// loaded up front (all loads in flight before the first op executes).
+#pragma once
+#include "sp_common.h"
+#include <math_constants.h>
+
+namespace sp {
+
+constexpr int kMaxDepth = 4;
+
+template <typename T>
+struct DevProgram {
+  int32_t n_ops;
+  uint8_t op[SP_MAX_PROGRAM];
+  uint8_t arg[SP_MAX_PROGRAM];
+  T consts[SP_MAX_CONSTS];
+};
+
+// How an operand is addressed along the vectorised axis.
+enum OperandKind : int32_t {
+  kVec = 0,      // same dtype as the compute type, unit stride, 16B-aligned vectors
+  kSplat = 1,    // stride 0 along the vector axis: one load, broadcast
+  kGeneric = 2   // any dtype / stride: element loads with conversion
+};
+
+struct DevOperand {
+  const void* ptr;
+  int32_t dtype;
+  int32_t kind;
+  int64_t stride[3];
+};
+
+template <int NI>
+struct DevOperands {
+  DevOperand in[NI];
+  DevOperand out;
+  int32_t n_in;
+};
+
+// ---------------------------------------------------------------------------- scalar helpers
+template <typename T> struct is_fp { static constexpr bool value = false; };
+template <> struct is_fp<float> { static constexpr bool value = true; };
+template <> struct is_fp<double> { static constexpr bool value = true; };
+
+template <typename T>
+__device__ __forceinline__ T load_as(const void* p, int dtype, int64_t idx) {
+  switch (dtype) {
+    case SP_F32: return static_cast<T>(static_cast<const float*>(p)[idx]);
+    case SP_F64: return static_cast<T>(static_cast<const double*>(p)[idx]);
+    case SP_I32: return static_cast<T>(static_cast<const int32_t*>(p)[idx]);
+    case SP_I64: return static_cast<T>(static_cast<const long long*>(p)[idx]);
+    default:     return static_cast<T>(static_cast<const uint8_t*>(p)[idx]);
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void store_as(void* p, int dtype, int64_t idx, T v) {
+  switch (dtype) {
+    case SP_F32: static_cast<float*>(p)[idx] = static_cast<float>(v); break;
+    case SP_F64: static_cast<double*>(p)[idx] = static_cast<double>(v); break;
+    case SP_I32: static_cast<int32_t*>(p)[idx] = static_cast<int32_t>(v); break;
+    case SP_I64: static_cast<long long*>(p)[idx] = static_cast<long long>(v); break;
+    case SP_BOOL: static_cast<uint8_t*>(p)[idx] = (v != T(0)) ? 1 : 0; break;
+    default:     static_cast<uint8_t*>(p)[idx] = static_cast<uint8_t>(v); break;
+  }
+}
+
+// np.mod: result has the sign of the divisor
+__device__ __forceinline__ float op_mod(float a, float b) { float r = fmodf(a, b); return (r != 0.f && ((r < 0.f) != (b < 0.f))) ? r + b : r; }
+__device__ __forceinline__ double op_mod(double a, double b) { double r = fmod(a, b); return (r != 0.0 && ((r < 0.0) != (b < 0.0))) ? r + b : r; }
+__device__ __forceinline__ long long op_mod(long long a, long long b) {
+  if (b == 0) return 0;  // NumPy: integer x % 0 == 0 (with a warning)
+  long long r = a % b;
+  return (r != 0 && ((r < 0) != (b < 0))) ? r + b : r;
+}
+__device__ __forceinline__ float op_fmod(float a, float b) { return fmodf(a, b); }
+__device__ __forceinline__ double op_fmod(double a, double b) { return fmod(a, b); }
+__device__ __forceinline__ long long op_fmod(long long a, long long b) { return b == 0 ? 0 : a % b; }
+__device__ __forceinline__ float op_floordiv(float a, float b) { return floorf(a / b); }
+__device__ __forceinline__ double op_floordiv(double a, double b) { return floor(a / b); }
+__device__ __forceinline__ long long op_floordiv(long long a, long long b) {
+  if (b == 0) return 0;
+  long long q = a / b;
+  return ((a % b != 0) && ((a < 0) != (b < 0))) ? q - 1 : q;
+}
+__device__ __forceinline__ float op_div(float a, float b) { return a / b; }
+__device__ __forceinline__ double op_div(double a, double b) { return a / b; }
+__device__ __forceinline__ long long op_div(long long a, long long b) { return op_floordiv(a, b); }
+__device__ __forceinline__ float op_pow(float a, float b) { return powf(a, b); }
+__device__ __forceinline__ double op_pow(double a, double b) { return pow(a, b); }
+__device__ __forceinline__ long long op_pow(long long a, long long e) {
+  if (e < 0) return 0;
+  long long r = 1;
+  while (e) { if (e & 1) r *= a; a *= a; e >>= 1; }
+  return r;
+}
+// np.maximum / np.minimum propagate NaN
+__device__ __forceinline__ float op_max(float a, float b) { return (a > b || a != a) ? a : b; }
+__device__ __forceinline__ double op_max(double a, double b) { return (a > b || a != a) ? a : b; }
+__device__ __forceinline__ long long op_max(long long a, long long b) { return a > b ? a : b; }
+__device__ __forceinline__ float op_min(float a, float b) { return (a < b || a != a) ? a : b; }
+__device__ __forceinline__ double op_min(double a, double b) { return (a < b || a != a) ? a : b; }
+__device__ __forceinline__ long long op_min(long long a, long long b) { return a < b ? a : b; }
+
+__device__ __forceinline__ float op_abs(float a) { return fabsf(a); }
+__device__ __forceinline__ double op_abs(double a) { return fabs(a); }
+__device__ __forceinline__ long long op_abs(long long a) { return a < 0 ? -a : a; }
+__device__ __forceinline__ float op_sqrt(float a) { return sqrtf(a); }
+__device__ __forceinline__ double op_sqrt(double a) { return sqrt(a); }
+__device__ __forceinline__ long long op_sqrt(long long a) { return static_cast<long long>(sqrt(static_cast<double>(a))); }
+__device__ __forceinline__ float op_exp(float a) { return expf(a); }
+__device__ __forceinline__ double op_exp(double a) { return exp(a); }
+__device__ __forceinline__ long long op_exp(long long a) { return static_cast<long long>(exp(static_cast<double>(a))); }
+__device__ __forceinline__ float op_log(float a) { return logf(a); }
+__device__ __forceinline__ double op_log(double a) { return log(a); }
+__device__ __forceinline__ long long op_log(long long a) { return static_cast<long long>(log(static_cast<double>(a))); }
+__device__ __forceinline__ float op_recip(float a) { return 1.0f / a; }
+__device__ __forceinline__ double op_recip(double a) { return 1.0 / a; }
+__device__ __forceinline__ long long op_recip(long long a) { return a == 0 ? 0 : 1 / a; }
+
+template <typename T> __device__ __forceinline__ T cast_f32(T a) { return static_cast<T>(static_cast<float>(a)); }
+template <typename T> __device__ __forceinline__ T cast_i64(T a) { return static_cast<T>(static_cast<long long>(a)); }
+template <typename T> __device__ __forceinline__ T cast_i32(T a) { return static_cast<T>(static_cast<int32_t>(static_cast<long long>(a))); }
+template <typename T> __device__ __forceinline__ T cast_u8(T a) { return static_cast<T>(static_cast<uint8_t>(static_cast<long long>(a))); }
+
+// ---------------------------------------------------------------------------- the interpreter
+#define SP_B(x) ((x) ? T(1) : T(0))
+
+#define SP_BIN_CASE(OPC, D, EXPR)                                    \
+  case (OPC) * 8 + (D): {                                            \
+    _Pragma("unroll") for (int v = 0; v < V; ++v) {                  \
+      const T a = s[(D) - 2][v];                                     \
+      const T b = s[(D) - 1][v];                                     \
+      s[(D) - 2][v] = (EXPR);                                        \
+    }                                                                \
+    sp = (D) - 1;                                                    \
+    break;                                                           \
+  }
+#define SP_BIN(OPC, EXPR) SP_BIN_CASE(OPC, 2, EXPR) SP_BIN_CASE(OPC, 3, EXPR) SP_BIN_CASE(OPC, 4, EXPR)
+
+#define SP_UN_CASE(OPC, D, EXPR)                                     \
+  case (OPC) * 8 + (D): {                                            \
+    _Pragma("unroll") for (int v = 0; v < V; ++v) {                  \
+      const T a = s[(D) - 1][v];                                     \
+      s[(D) - 1][v] = (EXPR);                                        \
+    }                                                                \
+    break;                                                           \
+  }
+#define SP_UN(OPC, EXPR) SP_UN_CASE(OPC, 1, EXPR) SP_UN_CASE(OPC, 2, EXPR) SP_UN_CASE(OPC, 3, EXPR) SP_UN_CASE(OPC, 4, EXPR)
+
+#define SP_PUSH_CONST_CASE(D)                                        \
+  case SP_OP_CONST * 8 + (D): {                                      \
+    const T c = prog.consts[arg];                                    \
+    _Pragma("unroll") for (int v = 0; v < V; ++v) s[(D)][v] = c;     \
+    sp = (D) + 1;                                                    \
+    break;                                                           \
+  }
+
+// push operand: the operand index is data, the destination depth is static
+#define SP_PUSH_IN_CASE(D)                                           \
+  case SP_OP_IN * 8 + (D): {                                         \
+    _Pragma("unroll") for (int i = 0; i < NI; ++i) {                 \
+      if (i == arg) {                                                \
+        _Pragma("unroll") for (int v = 0; v < V; ++v) s[(D)][v] = in[i][v]; \
+      }                                                              \
+    }                                                                \
+    sp = (D) + 1;                                                    \
+    break;                                                           \
+  }
+
+// Evaluates `prog` on the V-wide inputs; result left in out[V].
+template <typename T, int V, int NI>
+__device__ __forceinline__ void run_program(const DevProgram<T>& prog, const T (&in)[NI][V], T (&out)[V]) {
+  T s[kMaxDepth][V];
+  int sp = 0;
+  const int n = prog.n_ops;
+  for (int pc = 0; pc < n; ++pc) {
+    const int opc = prog.op[pc];
+    const int arg = prog.arg[pc];
+    switch (opc * 8 + sp) {
+      SP_PUSH_IN_CASE(0) SP_PUSH_IN_CASE(1) SP_PUSH_IN_CASE(2) SP_PUSH_IN_CASE(3)
+      SP_PUSH_CONST_CASE(0) SP_PUSH_CONST_CASE(1) SP_PUSH_CONST_CASE(2) SP_PUSH_CONST_CASE(3)
+      SP_BIN(SP_OP_ADD, a + b)
+      SP_BIN(SP_OP_SUB, a - b)
+      SP_BIN(SP_OP_MUL, a * b)
+      SP_BIN(SP_OP_DIV, op_div(a, b))
+      SP_BIN(SP_OP_MOD, op_mod(a, b))
+      SP_BIN(SP_OP_POW, op_pow(a, b))
+      SP_BIN(SP_OP_MAX, op_max(a, b))
+      SP_BIN(SP_OP_MIN, op_min(a, b))
+      SP_BIN(SP_OP_EQ, SP_B(a == b))
+      SP_BIN(SP_OP_NE, SP_B(a != b))
+      SP_BIN(SP_OP_LT, SP_B(a < b))
+      SP_BIN(SP_OP_LE, SP_B(a <= b))
+      SP_BIN(SP_OP_GT, SP_B(a > b))
+      SP_BIN(SP_OP_GE, SP_B(a >= b))
+      SP_BIN(SP_OP_AND, SP_B((a != T(0)) && (b != T(0))))
+      SP_BIN(SP_OP_OR, SP_B((a != T(0)) || (b != T(0))))
+      SP_BIN(SP_OP_XOR, SP_B((a != T(0)) != (b != T(0))))
+      SP_BIN(SP_OP_FMOD, op_fmod(a, b))
+      SP_BIN(SP_OP_FLOORDIV, op_floordiv(a, b))
+      SP_UN(SP_OP_NEG, -a)
+      SP_UN(SP_OP_ABS, op_abs(a))
+      SP_UN(SP_OP_SQRT, op_sqrt(a))
+      SP_UN(SP_OP_EXP, op_exp(a))
+      SP_UN(SP_OP_LOG, op_log(a))
+      SP_UN(SP_OP_SQUARE, a * a)
+      SP_UN(SP_OP_RECIP, op_recip(a))
+      SP_UN(SP_OP_NOT, SP_B(a == T(0)))
+      SP_UN(SP_OP_NONZERO, SP_B(a != T(0)))
+      SP_UN(SP_OP_ISZERO, SP_B(a == T(0)))
+      SP_UN(SP_OP_CAST_F32, cast_f32(a))
+      SP_UN(SP_OP_CAST_I64, cast_i64(a))
+      SP_UN(SP_OP_CAST_I32, cast_i32(a))
+      SP_UN(SP_OP_CAST_BOOL, SP_B(a != T(0)))
+      SP_UN(SP_OP_CAST_U8, cast_u8(a))
+      default: break;   // validated on the host; unreachable
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < V; ++v) out[v] = s[0][v];
+}
+
+// ---------------------------------------------------------------------------- operand access
+template <typename T, int V> struct VecLoad;
+template <> struct VecLoad<float, 8> {
+  static __device__ __forceinline__ void ld(const float* p, float (&r)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float (&r)[8]) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(r[0], r[1], r[2], r[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(r[4], r[5], r[6], r[7]);
+  }
+};
+template <> struct VecLoad<float, 4> {
+  static __device__ __forceinline__ void ld(const float* p, float (&r)[4]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float (&r)[4]) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(r[0], r[1], r[2], r[3]);
+  }
+};
+template <typename T> struct VecLoad<T, 4> {   // 8-byte types
+  static __device__ __forceinline__ void ld(const T* p, T (&r)[4]) {
+    const longlong2 a = __ldg(reinterpret_cast<const longlong2*>(p));
+    const longlong2 b = __ldg(reinterpret_cast<const longlong2*>(p) + 1);
+    long long t[4] = {a.x, a.y, b.x, b.y};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = *reinterpret_cast<T*>(&t[i]);
+  }
+  static __device__ __forceinline__ void st(T* p, const T (&r)[4]) {
+    long long t[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t[i] = *reinterpret_cast<const long long*>(&r[i]);
+    reinterpret_cast<longlong2*>(p)[0] = make_longlong2(t[0], t[1]);
+    reinterpret_cast<longlong2*>(p)[1] = make_longlong2(t[2], t[3]);
+  }
+};
+template <typename T> struct VecLoad<T, 2> {
+  static __device__ __forceinline__ void ld(const T* p, T (&r)[2]) {
+    const longlong2 a = __ldg(reinterpret_cast<const longlong2*>(p));
+    long long t[2] = {a.x, a.y};
+    r[0] = *reinterpret_cast<T*>(&t[0]);
+    r[1] = *reinterpret_cast<T*>(&t[1]);
+  }
+  static __device__ __forceinline__ void st(T* p, const T (&r)[2]) {
+    reinterpret_cast<longlong2*>(p)[0] =
+        make_longlong2(*reinterpret_cast<const long long*>(&r[0]), *reinterpret_cast<const long long*>(&r[1]));
+  }
+};
+
+// Loads V elements of operand `o` starting at element offset `base` (already includes the d0/d1
+// terms), stepping `vstride` elements along the vector axis; `valid` = number of in-range lanes.
+template <typename T, int V>
+__device__ __forceinline__ void load_operand(const DevOperand& o, int64_t base, int64_t vstride, int valid, T (&r)[V]) {
+  if (o.kind == kVec && valid == V) {
+    VecLoad<T, V>::ld(static_cast<const T*>(o.ptr) + base, r);
+  } else if (o.kind == kSplat) {
+    const T x = load_as<T>(o.ptr, o.dtype, base);
+#pragma unroll
+    for (int v = 0; v < V; ++v) r[v] = x;
+  } else {
+#pragma unroll
+    for (int v = 0; v < V; ++v) r[v] = (v < valid) ? load_as<T>(o.ptr, o.dtype, base + v * vstride) : T(0);
+  }
+}
+
+template <typename T, int V>
+__device__ __forceinline__ void store_operand(const DevOperand& o, int64_t base, int64_t vstride, int valid, const T (&r)[V]) {
+  if (o.kind == kVec && valid == V) {
+    VecLoad<T, V>::st(static_cast<T*>(const_cast<void*>(o.ptr)) + base, r);
+  } else {
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+      if (v < valid) store_as<T>(const_cast<void*>(o.ptr), o.dtype, base + v * vstride, r[v]);
+  }
+}
+
+// ---------------------------------------------------------------------------- reductions
+template <typename T> __device__ __forceinline__ T red_identity(int op);
+template <> __device__ __forceinline__ float red_identity<float>(int op) {
+  return op == SP_RED_SUM ? 0.f : op == SP_RED_PROD ? 1.f : op == SP_RED_MIN ? CUDART_INF_F : -CUDART_INF_F;
+}
+template <> __device__ __forceinline__ double red_identity<double>(int op) {
+  return op == SP_RED_SUM ? 0.0 : op == SP_RED_PROD ? 1.0 : op == SP_RED_MIN ? CUDART_INF : -CUDART_INF;
+}
+template <> __device__ __forceinline__ long long red_identity<long long>(int op) {
+  return op == SP_RED_SUM ? 0ll : op == SP_RED_PROD ? 1ll : op == SP_RED_MIN ? 0x7fffffffffffffffll : (-0x7fffffffffffffffll - 1);
+}
+
+template <typename T>
+__device__ __forceinline__ T red_apply(int op, T a, T b) {
+  switch (op) {
+    case SP_RED_SUM: return a + b;
+    case SP_RED_PROD: return a * b;
+    case SP_RED_MIN: return op_min(a, b);
+    default: return op_max(a, b);
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ T shfl_down_t(T v, int delta) {
+  if constexpr (sizeof(T) == 4) {
+    return __shfl_down_sync(0xffffffffu, v, delta);
+  } else {
+    long long x = *reinterpret_cast<long long*>(&v);
+    x = __shfl_down_sync(0xffffffffu, x, delta);
+    return *reinterpret_cast<T*>(&x);
+  }
+}
+
+}  // namespace sp

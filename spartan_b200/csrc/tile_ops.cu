@@ -1,0 +1,247 @@
+// Tile-level utility kernels: fill / iota / counter-based RNG, the same-device combiner and
+// strided rectangle copies.  All HBM-bound, one pass over the data.
+//
+// Reference call sites:
+//   fill      creation.py:67-68 np.zeros, :92-93 np.ones, :135-141 np.arange per tile,
+//             srandom.py:40-47 np.random.rand / randn per tile
+//   combine   Tile.merge dense path  reducer(old, update)          tile.pyx:263-283
+//   copy_rect DistArrayImpl.fetch stitching / update splitting     distarray.py:294-422
+#include "sp_common.h"
+
+namespace sp {
+
+// ---------------------------------------------------------------------------- Philox4x32-10
+struct Philox {
+  static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  __host__ __device__ static inline void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+    const uint64_t p0 = static_cast<uint64_t>(M0) * c[0];
+    const uint64_t p1 = static_cast<uint64_t>(M1) * c[2];
+    const uint32_t hi0 = static_cast<uint32_t>(p0 >> 32), lo0 = static_cast<uint32_t>(p0);
+    const uint32_t hi1 = static_cast<uint32_t>(p1 >> 32), lo1 = static_cast<uint32_t>(p1);
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+  }
+  // counter = 64-bit block index, key = 64-bit seed -> 4 x 32 random bits
+  __host__ __device__ static inline void block(uint64_t counter, uint64_t seed, uint32_t (&out)[4]) {
+    uint32_t c[4] = {static_cast<uint32_t>(counter), static_cast<uint32_t>(counter >> 32), 0u, 0u};
+    uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      round(c, k0, k1);
+      k0 += W0; k1 += W1;
+    }
+    out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+  }
+};
+
+// element i of the stream: uniform in [0,1) with 24 (f32) / 53 (f64) random bits
+__device__ __forceinline__ float u01_f32(uint32_t x) { return (x >> 8) * (1.0f / 16777216.0f); }
+__device__ __forceinline__ double u01_f64(uint32_t hi, uint32_t lo) {
+  const uint64_t v = ((static_cast<uint64_t>(hi) << 32) | lo) >> 11;
+  return v * (1.0 / 9007199254740992.0);
+}
+
+template <typename T>
+__global__ void fill_const_kernel(T* __restrict__ dst, int64_t n, T value) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dst[i] = value;
+}
+
+template <typename T>
+__global__ void fill_iota_kernel(T* __restrict__ dst, int64_t n, double a, double b, int64_t offset, int integral) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    if (integral) {
+      dst[i] = static_cast<T>(static_cast<long long>(a) + static_cast<long long>(b) * (offset + i));
+    } else {
+      dst[i] = static_cast<T>(a + b * static_cast<double>(offset + i));
+    }
+  }
+}
+
+// Each Philox block yields 4 f32 (or 2 f64) values; element e uses block e/4 (e/2), lane e%4 (e%2),
+// so any sub-range of the stream can be regenerated independently (tiles of one array share a seed
+// and use their global element offset as `offset`).
+template <typename T>
+__global__ void fill_rand_kernel(T* __restrict__ dst, int64_t n, uint64_t seed, int64_t offset, int normal) {
+  constexpr int PER = (sizeof(T) == 4) ? 4 : 2;
+  const int64_t first_blk = offset / PER;
+  const int64_t last_blk = (offset + n - 1) / PER;
+  const int64_t nblk = last_blk - first_blk + 1;
+  for (int64_t bi = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; bi < nblk;
+       bi += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t blk = first_blk + bi;
+    uint32_t r[4];
+    Philox::block(static_cast<uint64_t>(blk), seed, r);
+    T vals[PER];
+    if constexpr (sizeof(T) == 4) {
+      if (normal) {   // Box-Muller on pairs
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          const float u1 = 1.0f - u01_f32(r[2 * p]);           // (0,1]
+          const float u2 = u01_f32(r[2 * p + 1]);
+          const float rad = sqrtf(-2.0f * logf(u1));
+          float s, c;
+          sincospif(2.0f * u2, &s, &c);
+          vals[2 * p] = rad * c;
+          vals[2 * p + 1] = rad * s;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) vals[j] = u01_f32(r[j]);
+      }
+    } else {
+      const double a = u01_f64(r[0], r[1]), b = u01_f64(r[2], r[3]);
+      if (normal) {
+        const double rad = sqrt(-2.0 * log(1.0 - a));
+        double s, c;
+        sincospi(2.0 * b, &s, &c);
+        vals[0] = rad * c; vals[1] = rad * s;
+      } else {
+        vals[0] = a; vals[1] = b;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int64_t e = blk * PER + j - offset;
+      if (e >= 0 && e < n) dst[e] = vals[j];
+    }
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ T combine_op(int op, T a, T b) {
+  switch (op) {
+    case SP_RED_SUM: return a + b;
+    case SP_RED_PROD: return a * b;
+    case SP_RED_MIN: return (a < b || a != a) ? a : b;
+    case SP_RED_MAX: return (a > b || a != a) ? a : b;
+    case SP_RED_ALL: return static_cast<T>((a != T(0)) && (b != T(0)));
+    default: return static_cast<T>((a != T(0)) || (b != T(0)));
+  }
+}
+
+template <typename T>
+__global__ void combine_kernel(T* __restrict__ dst, const T* __restrict__ src, int64_t n, int op) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dst[i] = combine_op<T>(op, dst[i], src[i]);
+}
+
+template <typename T>
+__global__ void copy_rect_kernel(T* __restrict__ dst, int64_t ds0, int64_t ds1, int64_t ds2, const T* __restrict__ src,
+                                 int64_t ss0, int64_t ss1, int64_t ss2, int64_t d0, int64_t d1, int64_t d2) {
+  const int64_t total = d0 * d1 * d2;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t i2 = i % d2;
+    const int64_t t = i / d2;
+    const int64_t i1 = t % d1;
+    const int64_t i0 = t / d1;
+    dst[i0 * ds0 + i1 * ds1 + i2 * ds2] = src[i0 * ss0 + i1 * ss1 + i2 * ss2];
+  }
+}
+
+static inline int grid_for(int64_t n) {
+  const int64_t want = (n + 255) / 256;
+  return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(num_sms()) * 16)));
+}
+
+template <typename T>
+static int fill_t(void* dst, int64_t n, int kind, double a, double b, uint64_t seed, int64_t offset, int integral,
+                  cudaStream_t stream) {
+  T* p = static_cast<T*>(dst);
+  switch (kind) {
+    case SP_FILL_CONST: fill_const_kernel<T><<<grid_for(n), 256, 0, stream>>>(p, n, static_cast<T>(a)); break;
+    case SP_FILL_IOTA: fill_iota_kernel<T><<<grid_for(n), 256, 0, stream>>>(p, n, a, b, offset, integral); break;
+    default:
+      set_error("sp_fill: kind %d not valid for this dtype", kind);
+      return SP_ERR_UNSUPPORTED;
+  }
+  SP_CUDA_CHECK(cudaGetLastError());
+  return SP_OK;
+}
+
+}  // namespace sp
+
+using namespace sp;
+
+extern "C" int sp_fill(void* dst, int dtype, int64_t n, int kind, double a, double b, uint64_t seed, int64_t offset,
+                       void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SP_REQUIRE(n >= 0, SP_ERR_INVALID, "sp_fill: negative length");
+  if (n == 0) return SP_OK;
+  SP_REQUIRE(dst != nullptr, SP_ERR_INVALID, "sp_fill: null destination");
+  if (kind == SP_FILL_RAND || kind == SP_FILL_RANDN) {
+    SP_REQUIRE(offset >= 0, SP_ERR_INVALID, "sp_fill: negative stream offset");
+    const int normal = (kind == SP_FILL_RANDN);
+    if (dtype == SP_F32) {
+      fill_rand_kernel<float><<<grid_for((n + 3) / 4 + 1), 256, 0, stream>>>(static_cast<float*>(dst), n, seed, offset, normal);
+    } else if (dtype == SP_F64) {
+      fill_rand_kernel<double><<<grid_for((n + 1) / 2 + 1), 256, 0, stream>>>(static_cast<double*>(dst), n, seed, offset, normal);
+    } else {
+      set_error("sp_fill: random fill needs a float dtype, got %d", dtype);
+      return SP_ERR_UNSUPPORTED;
+    }
+    SP_CUDA_CHECK(cudaGetLastError());
+    return SP_OK;
+  }
+  switch (dtype) {
+    case SP_F32: return fill_t<float>(dst, n, kind, a, b, seed, offset, 0, stream);
+    case SP_F64: return fill_t<double>(dst, n, kind, a, b, seed, offset, 0, stream);
+    case SP_I32: return fill_t<int32_t>(dst, n, kind, a, b, seed, offset, 1, stream);
+    case SP_I64: return fill_t<long long>(dst, n, kind, a, b, seed, offset, 1, stream);
+    case SP_U8:
+    case SP_BOOL: return fill_t<uint8_t>(dst, n, kind, a, b, seed, offset, 1, stream);
+    default:
+      set_error("sp_fill: bad dtype %d", dtype);
+      return SP_ERR_INVALID;
+  }
+}
+
+extern "C" int sp_combine(void* dst, const void* src, int dtype, int64_t n, int reduce_op, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SP_REQUIRE(n >= 0 && reduce_op >= SP_RED_SUM && reduce_op <= SP_RED_ANY, SP_ERR_INVALID, "sp_combine: bad arguments");
+  if (n == 0) return SP_OK;
+  SP_REQUIRE(dst != nullptr && src != nullptr, SP_ERR_INVALID, "sp_combine: null pointer");
+  const int g = grid_for(n);
+  switch (dtype) {
+    case SP_F32: combine_kernel<float><<<g, 256, 0, stream>>>(static_cast<float*>(dst), static_cast<const float*>(src), n, reduce_op); break;
+    case SP_F64: combine_kernel<double><<<g, 256, 0, stream>>>(static_cast<double*>(dst), static_cast<const double*>(src), n, reduce_op); break;
+    case SP_I32: combine_kernel<int32_t><<<g, 256, 0, stream>>>(static_cast<int32_t*>(dst), static_cast<const int32_t*>(src), n, reduce_op); break;
+    case SP_I64: combine_kernel<long long><<<g, 256, 0, stream>>>(static_cast<long long*>(dst), static_cast<const long long*>(src), n, reduce_op); break;
+    case SP_U8:
+    case SP_BOOL: combine_kernel<uint8_t><<<g, 256, 0, stream>>>(static_cast<uint8_t*>(dst), static_cast<const uint8_t*>(src), n, reduce_op); break;
+    default:
+      set_error("sp_combine: bad dtype %d", dtype);
+      return SP_ERR_INVALID;
+  }
+  SP_CUDA_CHECK(cudaGetLastError());
+  return SP_OK;
+}
+
+extern "C" int sp_copy_rect(void* dst, const int64_t dst_stride[3], const void* src, const int64_t src_stride[3],
+                            const int64_t dims[3], int dtype, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SP_REQUIRE(dims[0] >= 0 && dims[1] >= 0 && dims[2] >= 0, SP_ERR_INVALID, "sp_copy_rect: negative dims");
+  const int64_t total = dims[0] * dims[1] * dims[2];
+  if (total == 0) return SP_OK;
+  SP_REQUIRE(dst != nullptr && src != nullptr, SP_ERR_INVALID, "sp_copy_rect: null pointer");
+  const int g = grid_for(total);
+#define SP_COPY(T)                                                                                                  \
+  copy_rect_kernel<T><<<g, 256, 0, stream>>>(static_cast<T*>(dst), dst_stride[0], dst_stride[1], dst_stride[2],     \
+                                             static_cast<const T*>(src), src_stride[0], src_stride[1], src_stride[2], \
+                                             dims[0], dims[1], dims[2])
+  switch (dtype_size(dtype)) {
+    case 1: SP_COPY(uint8_t); break;
+    case 4: SP_COPY(uint32_t); break;
+    case 8: SP_COPY(uint64_t); break;
+    default:
+      set_error("sp_copy_rect: bad dtype %d", dtype);
+      return SP_ERR_INVALID;
+  }
+#undef SP_COPY
+  SP_CUDA_CHECK(cudaGetLastError());
+  return SP_OK;
+}

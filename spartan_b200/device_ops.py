@@ -1,0 +1,315 @@
+"""Thin Python wrappers that marshal torch device tensors into C-ABI calls (include/spartan_b200.h).
+
+Nothing here computes: every function validates shapes, collapses the iteration space to the three
+dimensions the kernels take, and launches through libspartan_b200.so on the current CUDA stream.
+"""
+import ctypes
+import itertools
+
+import numpy as np
+import torch
+
+from . import blob_ctx
+from ._lib import (lib, check, sp_program, sp_operand, sp_gemm_segment, i64arr, SpartanError, OP,
+                   SP_F32, SP_F64, SP_I32, SP_I64, SP_U8, SP_BOOL, SP_RED_SUM, SP_RED_MIN, SP_RED_MAX, SP_RED_PROD,
+                   SP_RED_ALL, SP_RED_ANY, SP_FILL_CONST, SP_FILL_IOTA, SP_FILL_RAND, SP_FILL_RANDN,
+                   SP_GEMM_TF32X1, SP_GEMM_TF32X3, SP_GEMM_SIMT, SP_GEMM_MAX_TERMS)
+
+_SP_DTYPE = {torch.float32: SP_F32, torch.float64: SP_F64, torch.int32: SP_I32, torch.int64: SP_I64,
+             torch.uint8: SP_U8, torch.bool: SP_BOOL}
+_NP_TO_SP = {np.dtype(np.float32): SP_F32, np.dtype(np.float64): SP_F64, np.dtype(np.int32): SP_I32,
+             np.dtype(np.int64): SP_I64, np.dtype(np.uint8): SP_U8, np.dtype(np.bool_): SP_BOOL}
+
+
+def sp_dtype_of(t):
+  try:
+    return _SP_DTYPE[t.dtype]
+  except KeyError:
+    raise SpartanError('tensor dtype %s is not supported on the device path' % t.dtype)
+
+
+def sp_dtype_of_np(dtype):
+  try:
+    return _NP_TO_SP[np.dtype(dtype)]
+  except KeyError:
+    raise SpartanError('dtype %s is not supported on the device path' % np.dtype(dtype))
+
+
+def _require_cuda(*tensors):
+  for t in tensors:
+    if t is not None and t.device.type != 'cuda':
+      raise SpartanError('compute kernels need CUDA tensors (got %s); spartan_b200 has no CPU fallback' % t.device)
+
+
+def _stream():
+  return blob_ctx.get().stream_ptr()
+
+
+def _count_launch(n=1):
+  blob_ctx.get().kernel_launches += n
+
+
+# ------------------------------------------------------------------------------------ iteration space
+def collapse(shape, strides_list):
+  """Drops size-1 dims and merges adjacent dims that are contiguous for every operand.
+  ``strides_list``: one stride tuple (elements; 0 = broadcast) per operand, output included.
+  Returns (shape, strides_list) with as few dims as possible."""
+  dims = [i for i, s in enumerate(shape) if s != 1]
+  shape = [int(shape[i]) for i in dims]
+  strides = [[int(st[i]) for i in dims] for st in strides_list]
+  i = 0
+  while i + 1 < len(shape):
+    if all(st[i] == st[i + 1] * shape[i + 1] for st in strides):
+      shape[i] = shape[i] * shape[i + 1]
+      for st in strides:
+        st[i] = st[i + 1]
+        del st[i + 1]
+      del shape[i + 1]
+    else:
+      i += 1
+  return shape, strides
+
+
+def _pad3(shape, strides):
+  k = 3 - len(shape)
+  return [1] * k + list(shape), [[0] * k + list(st) for st in strides]
+
+
+def _operand(t, stride3, offset_elems=0):
+  o = sp_operand()
+  o.ptr = t.data_ptr() + offset_elems * t.element_size()
+  o.dtype = sp_dtype_of(t)
+  for i in range(3):
+    o.stride[i] = int(stride3[i])
+  return o
+
+
+def broadcast_strides(t, out_shape):
+  """Element strides of ``t`` viewed against ``out_shape`` (NumPy right-aligned broadcasting)."""
+  nd = len(out_shape)
+  shp = (1,) * (nd - t.dim()) + tuple(t.shape)
+  st = (0,) * (nd - t.dim()) + tuple(t.stride())
+  out = []
+  for i in range(nd):
+    if shp[i] == out_shape[i] and shp[i] != 1:
+      out.append(st[i])
+    elif shp[i] == 1:
+      out.append(0)
+    else:
+      raise SpartanError('operand of shape %s does not broadcast to %s' % (tuple(t.shape), tuple(out_shape)))
+  return out
+
+
+def _leading_loops(shape, strides, keep):
+  """Yields (per-operand element offsets) for the leading dims beyond ``keep`` trailing ones."""
+  lead = len(shape) - keep
+  if lead <= 0:
+    yield [0] * len(strides)
+    return
+  for idx in itertools.product(*[range(s) for s in shape[:lead]]):
+    yield [sum(i * st[d] for d, i in enumerate(idx)) for st in strides]
+
+
+# ------------------------------------------------------------------------------------ map / reduce
+def run_map(prog, inputs, out):
+  """out[...] = prog(inputs...) element-wise with broadcasting; ``out`` may be a strided view."""
+  _require_cuda(out, *inputs)
+  out_shape = tuple(out.shape)
+  if out.numel() == 0:
+    return
+  strides = [broadcast_strides(t, out_shape) for t in inputs] + [list(out.stride())]
+  shape, strides = collapse(out_shape, strides)
+  n_in = len(inputs)
+  tensors = list(inputs) + [out]
+  for offs in _leading_loops(shape, strides, 3):
+    s3, st3 = _pad3(shape[-3:], [st[-3:] for st in strides])
+    ops = (sp_operand * max(1, n_in))()
+    for i in range(n_in):
+      ops[i] = _operand(tensors[i], st3[i], offs[i])
+    o = _operand(out, st3[n_in], offs[n_in])
+    check(lib.sp_map(ctypes.byref(prog), n_in, ops, ctypes.byref(o), i64arr(s3), _stream()), 'sp_map')
+    _count_launch()
+
+
+def run_map_reduce(prog, inputs, in_shape, axis, red_op, out, accumulate):
+  """out = red_{axis} prog(inputs...) where inputs broadcast to ``in_shape``.  axis=None reduces
+  everything (out is 0-d).  ``out`` holds the reduced shape (axis dropped)."""
+  _require_cuda(out, *inputs)
+  in_shape = tuple(int(s) for s in in_shape)
+  nd = len(in_shape)
+  ctx = blob_ctx.get()
+  in_strides = [broadcast_strides(t, in_shape) for t in inputs]
+  if axis is None:
+    # flatten: every operand must collapse to one (or zero) strides
+    shape, strides = collapse(in_shape, in_strides)
+    if len(shape) == 0:
+      shape, strides = [1], [[0] for _ in in_strides]
+    if len(shape) != 1:
+      raise SpartanError('axis=None reduction over non-collapsible operand strides is not supported')
+    dims = [1, shape[0], 1]
+    st3 = [[0, st[0], 0] for st in strides]
+    out_stride = [0, 0, 0]
+    _launch_reduce(ctx, prog, inputs, st3, [0] * len(inputs), out, out_stride, 0, dims, red_op, accumulate)
+    return
+  axis = axis + nd if axis < 0 else axis
+  outer_shape, inner_shape = in_shape[:axis], in_shape[axis + 1:]
+  # collapse outer and inner groups independently (the reduced axis stays its own dim)
+  o_shape, o_str = collapse(outer_shape, [st[:axis] for st in in_strides] + [list(out.stride())[:axis]])
+  i_shape, i_str = collapse(inner_shape, [st[axis + 1:] for st in in_strides] + [list(out.stride())[axis:]])
+  if len(i_shape) > 1:
+    raise SpartanError('reduction with a non-collapsible inner block is not supported')
+  n_in = len(inputs)
+  d2 = i_shape[0] if i_shape else 1
+  for offs in _leading_loops(o_shape, o_str, 1):
+    d0 = o_shape[-1] if o_shape else 1
+    st3 = []
+    for i in range(n_in):
+      st3.append([o_str[i][-1] if o_shape else 0, in_strides[i][axis], i_str[i][0] if i_shape else 0])
+    out_stride = [o_str[n_in][-1] if o_shape else 0, 0, i_str[n_in][0] if i_shape else 0]
+    _launch_reduce(ctx, prog, inputs, st3, offs[:n_in], out, out_stride, offs[n_in], [d0, in_shape[axis], d2], red_op,
+                   accumulate)
+
+
+def _launch_reduce(ctx, prog, inputs, st3, in_offs, out, out_stride, out_off, dims, red_op, accumulate):
+  n_in = len(inputs)
+  ops = (sp_operand * max(1, n_in))()
+  for i in range(n_in):
+    ops[i] = _operand(inputs[i], st3[i], in_offs[i])
+  o = _operand(out, out_stride, out_off)
+  d = i64arr(dims)
+  need = lib.sp_map_reduce_scratch_bytes(d, prog.compute_dtype)
+  if need < 0:
+    raise SpartanError('bad compute dtype for reduction')
+  scratch = ctx.scratch(need, 'reduce')
+  check(lib.sp_map_reduce(ctypes.byref(prog), n_in, ops, ctypes.byref(o), d, int(red_op), int(bool(accumulate)),
+                          scratch.data_ptr(), scratch.numel(), _stream()), 'sp_map_reduce')
+  _count_launch(2)
+
+
+def make_program(ops, compute_dtype, consts=()):
+  """ops: list of (opcode-name-or-int, arg)."""
+  p = sp_program()
+  if len(ops) > len(p.op):
+    raise SpartanError('expression too long for one kernel (%d ops)' % len(ops))
+  p.n_ops = len(ops)
+  p.compute_dtype = compute_dtype
+  for i, (op, arg) in enumerate(ops):
+    p.op[i] = OP[op] if isinstance(op, str) else int(op)
+    p.arg[i] = int(arg)
+  if len(consts) > len(p.consts):
+    raise SpartanError('too many scalar constants in one expression (%d)' % len(consts))
+  for i, c in enumerate(consts):
+    p.consts[i] = float(c)
+    try:
+      p.iconsts[i] = int(c)
+    except (OverflowError, ValueError):
+      p.iconsts[i] = 0
+  return p
+
+
+_COMPUTE_OF = {torch.float32: SP_F32, torch.float64: SP_F64, torch.int64: SP_I64, torch.int32: SP_I64,
+               torch.uint8: SP_I64, torch.bool: SP_I64}
+
+
+def copy_into(dst, src):
+  """dst[...] = src (with dtype conversion), both possibly strided device views."""
+  prog = make_program([('IN', 0)], _COMPUTE_OF[torch.promote_types(dst.dtype, src.dtype)])
+  run_map(prog, [src], dst)
+
+
+_COMBINE_OPCODE = {SP_RED_SUM: 'ADD', SP_RED_MIN: 'MIN', SP_RED_MAX: 'MAX', SP_RED_PROD: 'MUL', SP_RED_ALL: 'AND',
+                   SP_RED_ANY: 'OR'}
+
+
+def combine_into(dst, src, red_op):
+  """dst = op(dst, src) element-wise -- the combiner (tile.pyx:263-283) on one device."""
+  _require_cuda(dst, src)
+  if dst.is_contiguous() and src.is_contiguous() and dst.dtype == src.dtype and dst.shape == src.shape:
+    check(lib.sp_combine(dst.data_ptr(), src.data_ptr(), sp_dtype_of(dst), dst.numel(), int(red_op), _stream()),
+          'sp_combine')
+    _count_launch()
+    return
+  prog = make_program([('IN', 0), ('IN', 1), (_COMBINE_OPCODE[red_op], 0)],
+                      _COMPUTE_OF[torch.promote_types(dst.dtype, src.dtype)])
+  run_map(prog, [dst, src], dst)
+
+
+# ------------------------------------------------------------------------------------ fill / copy
+def fill(t, kind, a=0.0, b=0.0, seed=0, offset=0):
+  """In-place fill of a *contiguous* device tensor."""
+  _require_cuda(t)
+  assert t.is_contiguous()
+  check(lib.sp_fill(t.data_ptr(), sp_dtype_of(t), t.numel(), int(kind), float(a), float(b), int(seed) & (2 ** 64 - 1),
+                    int(offset), _stream()), 'sp_fill')
+  _count_launch()
+
+
+def fill_view(t, kind, a=0.0, b=0.0):
+  """Constant fill of a possibly strided view (through the map kernel)."""
+  if t.is_contiguous():
+    return fill(t, kind, a, b)
+  prog = make_program([('CONST', 0)], _COMPUTE_OF[t.dtype], [a])
+  run_map(prog, [], t)
+
+
+def copy_rect(dst, src):
+  """Same-dtype strided rectangle copy (distarray.py:294-422 stitching/splitting)."""
+  _require_cuda(dst, src)
+  assert dst.shape == src.shape and dst.dtype == src.dtype, (dst.shape, src.shape, dst.dtype, src.dtype)
+  if dst.numel() == 0:
+    return
+  shape, strides = collapse(tuple(dst.shape), [list(dst.stride()), list(src.stride())])
+  for offs in _leading_loops(shape, strides, 3):
+    s3, st3 = _pad3(shape[-3:], [st[-3:] for st in strides])
+    check(lib.sp_copy_rect(dst.data_ptr() + offs[0] * dst.element_size(), i64arr(st3[0]),
+                           src.data_ptr() + offs[1] * src.element_size(), i64arr(st3[1]), i64arr(s3),
+                           sp_dtype_of(dst), _stream()), 'sp_copy_rect')
+    _count_launch()
+
+
+# ------------------------------------------------------------------------------------ gemm
+_PRECISIONS = {'tf32x1': SP_GEMM_TF32X1, 'tf32x3': SP_GEMM_TF32X3, 'simt': SP_GEMM_SIMT}
+
+
+def gemm(segments, C, accumulate=False, precision='tf32x3'):
+  """C (+)= sum_s A_s @ B_s for row-major 2-D device tensors (inner stride 1).
+
+  float32 operands run on the tcgen05 tensor-core kernel (or CUDA cores when precision='simt');
+  float64 / int64 / int32 always run the exact CUDA-core kernel."""
+  ctx = blob_ctx.get()
+  _require_cuda(C, *[t for seg in segments for t in seg])
+  M, N = C.shape
+  for A, B in segments:
+    assert A.dim() == 2 and B.dim() == 2 and A.shape[0] == M and B.shape[1] == N and A.shape[1] == B.shape[0], \
+      (A.shape, B.shape, C.shape)
+    assert A.stride(1) == 1 and B.stride(1) == 1 and C.stride(1) == 1, 'operands must be row-major'
+    assert A.dtype == C.dtype and B.dtype == C.dtype
+  if M == 0 or N == 0:
+    return
+  prec = _PRECISIONS[precision]
+  if C.dtype != torch.float32 or prec == SP_GEMM_SIMT:
+    acc = accumulate
+    for A, B in segments:
+      check(lib.sp_gemm_simt(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), C.data_ptr(), C.stride(0), M, N,
+                             A.shape[1], sp_dtype_of(C), int(bool(acc)), _stream()), 'sp_gemm_simt')
+      _count_launch()
+      acc = True
+    return
+  per = 3 if prec == SP_GEMM_TF32X3 else 1
+  max_seg = SP_GEMM_MAX_TERMS // per
+  acc = accumulate
+  for lo in range(0, len(segments), max_seg):
+    chunk = segments[lo:lo + max_seg]
+    segs = (sp_gemm_segment * len(chunk))()
+    ks = []
+    for i, (A, B) in enumerate(chunk):
+      segs[i].A = A.data_ptr(); segs[i].lda = A.stride(0)
+      segs[i].B = B.data_ptr(); segs[i].ldb = B.stride(0)
+      segs[i].K = A.shape[1]
+      ks.append(A.shape[1])
+    need = lib.sp_gemm_f32_workspace_bytes(M, N, len(chunk), i64arr(ks), prec)
+    ws = ctx.scratch(need, 'gemm')
+    check(lib.sp_gemm_f32_segments(len(chunk), segs, C.data_ptr(), C.stride(0), M, N, int(bool(acc)), prec,
+                                   ws.data_ptr(), ws.numel(), _stream()), 'sp_gemm_f32_segments')
+    _count_launch(1 + 2 * len(chunk))
+    acc = True

@@ -1,0 +1,172 @@
+"""``dot`` -- dense contraction of tiled arrays (reference: spartan/expr/dot.py:95-299).
+
+The reference routes 2-D x 2-D products through map2 / outer joins: every A tile is re-partitioned
+into a K strip, the matching B strip is fetched, ``tiles[0].dot(tiles[1])`` produces a full-size
+rank-k partial of C and the partials are np.add-merged on the owners of the C tiles
+(dot.py:195-238, map.py:243-286).  That moves #tiles x M x N output bytes and, on grid tilings,
+contracts the wrong K indices.
+
+B200-native plan -- owner computes: each rank produces exactly the C tiles it owns,
+C[R, Cc] = A[R, :] . B[:, Cc], in as few launches as the placement allows (one per contiguous run of
+owned rows x contiguous run of owned columns; ONE launch for a single GPU or for column-block
+placement), with the K loop walking "segments" -- one per (A strip, B strip) pair -- inside a single
+tcgen05 kernel so the accumulator never leaves the SM between strips.  The only data exchange is the
+operand strips a rank does not own: an all-gather of the A slabs over NVLink when the placement is
+regular, point-to-point rectangle fetches otherwise.  No output partial ever crosses a link and the
+summation order is fixed.
+"""
+import numpy as np
+import torch
+
+from .. import blob_ctx, comm, device_ops
+from ..array import distarray, extent
+from ..config import FLAGS
+from .._lib import SpartanError
+from .base import Expr, lazify
+
+
+def _runs(intervals):
+  """Merges sorted disjoint [lo, hi) intervals that touch."""
+  out = []
+  for lo, hi in intervals:
+    if out and out[-1][1] == lo:
+      out[-1] = (out[-1][0], hi)
+    else:
+      out.append((lo, hi))
+  return out
+
+
+def _owned_runs(array, worker):
+  """Per-axis contiguous runs of the tiles of ``array`` owned by ``worker`` (2-D arrays), or None when
+  the owned tiles are not a cartesian product of row and column intervals."""
+  local = [ex for ex, tid in array.tiles.items() if tid.worker == worker]
+  if not local:
+    return [], []
+  axes = distarray._product_layout(local, 2)
+  if axes is None:
+    return None
+  return _runs(axes[0]), _runs(axes[1])
+
+
+class DotExpr(Expr):
+  """dot.py:95-158 (the node the reference defines but no longer constructs -- Q11 -- is the natural
+  home of the GEMM evaluator)."""
+  members = ('matrix_a', 'matrix_b', 'tile_hint')
+
+  def __str__(self):
+    return 'Dot[%s, %s, %s]' % (self.matrix_a, self.matrix_b, self.tile_hint)
+
+  def compute_shape(self):
+    a, b = self.matrix_a.shape, self.matrix_b.shape
+    if len(a) == 1 and len(b) == 1:
+      return (1,)
+    if len(a) > 1 and len(b) == 1:
+      return (a[0],)
+    if len(a) > 1 and len(b) > 1:
+      return (a[0], b[1])
+    raise ValueError('vector x matrix dot is not defined by the reference (tests/test_dot.py:45-53)')
+
+  def _evaluate(self, ctx, deps):
+    av = deps['matrix_a']
+    bv = deps['matrix_b']
+    if isinstance(bv, np.ndarray):
+      bv = distarray.LocalWrapper(bv)      # dot.py:254-262: a NumPy right operand is held by every rank
+    a_nd, b_nd = len(av.shape), len(bv.shape)
+    if a_nd == 1 and b_nd == 1:
+      if av.shape[0] != bv.shape[0]:
+        raise ValueError('objects are not aligned')
+      shape, M, N, K = (1,), 1, 1, av.shape[0]
+    elif a_nd > 1 and b_nd == 1:
+      if av.shape[1] != bv.shape[0]:
+        raise ValueError('objects are not aligned')
+      shape, M, N, K = (av.shape[0],), av.shape[0], 1, av.shape[1]
+    elif a_nd > 1 and b_nd > 1:
+      if av.shape[1] != bv.shape[0]:
+        raise ValueError('objects are not aligned')
+      shape, M, N, K = (av.shape[0], bv.shape[1]), av.shape[0], bv.shape[1], av.shape[1]
+    else:
+      raise ValueError
+    tile_hint = self.tile_hint
+    if tile_hint is None and len(shape) == 2:
+      tile_hint = shape                     # dot.py:281-282
+    dtype = np.result_type(av.dtype, bv.dtype)
+    if dtype.kind == 'b':
+      dtype = np.dtype(np.int64)
+    target = distarray.create(shape, dtype, reducer=np.add, tile_hint=tile_hint)
+
+    precision = FLAGS.dot_precision
+    W = ctx.num_workers
+    me = ctx.worker_id
+    # 2-D views of everything: vectors become [K,1] / [1,K] / [M,1]
+    def a_region(r0, r1):
+      if a_nd == 1:
+        return extent.create((0,), (K,), av.shape)
+      return extent.create((r0, 0), (r1, K), av.shape)
+
+    def b_region(c0, c1):
+      if b_nd == 1:
+        return extent.create((0,), (K,), bv.shape)
+      return extent.create((0, c0), (K, c1), bv.shape)
+
+    def as2d(t, rows, cols):
+      return t.reshape(rows, cols)
+
+    def cast(t):
+      return t if t.dtype == blob_ctx.torch_dtype(dtype) else t.to(blob_ctx.torch_dtype(dtype))
+
+    for w in range(W):
+      if len(shape) == 2:
+        runs = _owned_runs(target, w)
+        if runs is None:     # scattered placement: one block per owned tile
+          blocks = [((ex.ul[0], ex.lr[0]), (ex.ul[1], ex.lr[1])) for ex, tid in target.tiles.items()
+                    if tid.worker == w]
+        else:
+          blocks = [(r, c) for r in runs[0] for c in runs[1]]
+      else:
+        blocks = [((ex.ul[0], ex.lr[0]), (0, 1)) for ex, tid in target.tiles.items() if tid.worker == w]
+        if a_nd == 1:
+          blocks = [((0, 1), (0, 1))] if any(tid.worker == w for tid in target.tiles.values()) else []
+      a_cache, b_cache = {}, {}
+      for (r0, r1), (c0, c1) in blocks:
+        if (r0, r1) not in a_cache:
+          a_cache[(r0, r1)] = av.fetch(a_region(r0, r1), dst=w)
+        if (c0, c1) not in b_cache:
+          b_cache[(c0, c1)] = bv.fetch(b_region(c0, c1), dst=w)
+        if w != me:
+          continue
+        A = cast(as2d(a_cache[(r0, r1)], r1 - r0 if a_nd > 1 else 1, K))
+        B = cast(as2d(b_cache[(c0, c1)], K, c1 - c0 if b_nd > 1 else 1))
+        if A.stride(-1) != 1: A = A.contiguous()
+        if B.stride(-1) != 1: B = B.contiguous()
+        if len(shape) == 2:
+          creg = extent.create((r0, c0), (r1, c1), shape)
+        else:
+          creg = extent.create((r0,), (r1,), shape) if a_nd > 1 else extent.create((0,), (1,), shape)
+        Cv = target.fetch(creg)            # zero-copy view of this rank's slab / tile
+        C2 = Cv.reshape(A.shape[0], B.shape[1])
+        if C2.data_ptr() != Cv.data_ptr() or C2.stride(-1) != 1:
+          raise SpartanError('dot target block is not addressable as a row-major view')
+        device_ops.gemm([(A, B)], C2, accumulate=False, precision=precision)
+    for tid in target.tiles.values():
+      if ctx.is_local(tid):
+        ctx.tile(tid).valid = True
+    return target
+
+
+def dot(a, b, tile_hint=None):
+  """Compute the dot product (matrix multiplication) of 2 arrays (dot.py:243-299).
+
+  :param a: `Expr`
+  :param b: `Expr` or `numpy.ndarray`
+  :param tile_hint: tiling of the result (default: one tile, like the reference)
+  :rtype: `DotExpr`
+  """
+  a = lazify(a)
+  if not isinstance(b, np.ndarray):
+    b = lazify(b)
+  e = DotExpr(matrix_a=a, matrix_b=b, tile_hint=tile_hint)
+  e.compute_shape()       # raises ValueError early for undefined shapes, like dot.py:264-299
+  a_shape, b_shape = a.shape, b.shape
+  if (len(a_shape) == 1 and a_shape[0] != b_shape[0]) or (len(a_shape) > 1 and a_shape[1] != b_shape[0]):
+    raise ValueError('objects are not aligned')
+  return e

@@ -1,0 +1,148 @@
+"""The ``map`` operation (reference: spartan/expr/operator/map.py:33-205 and
+map_with_location.py:22-60).
+
+``a + b`` is ``map((a, b), np.add)``.  Inputs are broadcast to a common shape; the kernel runs once
+per tile of the largest input.  Where the reference's ``tile_mapper`` evaluates the LocalExpr tree
+with one NumPy call (and one temporary) per node, the tree is compiled once per MapExpr to bytecode
+(program.py) and each tile is ONE launch of the fused CUDA map kernel writing straight into the
+output tile in HBM.
+"""
+import collections
+
+import numpy as np
+
+from .. import blob_ctx, device_ops, util
+from ..array import distarray, extent
+from ..array.distarray import Broadcast, broadcast, LocalWrapper
+from ..core import LocalKernelResult
+from ..util import Assert
+from . import program
+from .base import ListExpr, Expr, as_array
+from .local import LocalInput, LocalMapExpr, LocalMapLocationExpr, make_var
+
+
+def bind_operands(children, child_to_var):
+  """LocalInput name -> program.Operand for the evaluated children of a map / reduce."""
+  operands = {}
+  for child, var in zip(children, child_to_var):
+    base = child.base if isinstance(child, Broadcast) else child
+    if isinstance(base, LocalWrapper) and base.shape == ():
+      operands[var] = program.Operand('scalar', base.dtype, value=base.host_data()[()])
+    else:
+      operands[var] = program.Operand('array', child.dtype)
+  return operands
+
+
+def get_local_values(ex, children, child_to_var, used_vars, owner):
+  """Device tensors of every *used* operand for output extent ``ex`` (map.py:33-45).  Broadcast
+  children hand over their un-expanded base region; the kernel broadcasts through zero strides."""
+  values = {}
+  for child, var in zip(children, child_to_var):
+    if var not in used_vars:
+      continue
+    if isinstance(child, Broadcast):
+      values[var] = child.fetch_base_tile(ex, dst=owner)
+    else:
+      values[var] = child.fetch(ex, dst=owner)
+  return values
+
+
+def tile_mapper(ex, children, child_to_var, op, compiled, output):
+  """Runs for each tile of a map (map.py:48-88): one fused kernel launch on the owning GPU."""
+  ctx = blob_ctx.get()
+  tile_id = output.tiles[ex]
+  owner = tile_id.worker
+  values = get_local_values(ex, children, child_to_var, compiled.used_vars, owner)
+  if owner == ctx.worker_id:
+    out_tile = ctx.tile(tile_id)
+    inputs = [values[v] for v in compiled.used_vars]
+    device_ops.run_map(compiled.program, inputs, out_tile.get(None))
+    out_tile.valid = True
+  return LocalKernelResult(result=[(ex, tile_id)])
+
+
+class MapExpr(Expr):
+  """Mapping an operator over one or more inputs (map.py:91-169)."""
+  members = ('children', 'child_to_var', 'op')
+
+  def pretty_str(self):
+    return 'Map[%d](%s, %s)' % (self.expr_id, self.op.pretty_str(), self.children)
+
+  def compute_shape(self):
+    # map.py:104-128
+    orig_shapes = [list(x.shape) for x in self.children]
+    max_dim = max(len(s) for s in orig_shapes)
+    new_shapes = [[1] * (max_dim - len(s)) + s for s in orig_shapes]
+    output_shape = collections.defaultdict(int)
+    for s in new_shapes:
+      for i, v in enumerate(s):
+        output_shape[i] = max(output_shape[i], v)
+    return tuple(output_shape[i] for i in range(len(output_shape)))
+
+  def _evaluate(self, ctx, deps):
+    # map.py:149-169
+    children = list(deps['children'])
+    child_to_var = list(deps['child_to_var'])
+    children = broadcast(children)
+    largest = distarray.largest_value(children)
+    i = children.index(largest)
+    children[0], children[i] = children[i], children[0]
+    child_to_var[0], child_to_var[i] = child_to_var[i], child_to_var[0]
+    if not isinstance(largest, distarray.DistArrayImpl):
+      raise program.NotDeviceMappable('a map needs at least one distributed (non-broadcast) input')
+
+    loc_kernel = getattr(self.op.fn, 'device_location_kernel', None) \
+      if isinstance(self.op, LocalMapLocationExpr) else None
+    if loc_kernel is not None:
+      # map_with_location over a freshly created array (arange, eye...): an extent-aware fill kernel
+      out_dtype = self.op.fn.result_dtype(largest.dtype, self.op.kw)
+      output = distarray.create_like(largest, out_dtype)
+      for ex, tid in sorted(output.tiles.items(), key=lambda kv: (kv[1].worker, kv[1].id)):
+        if ctx.is_local(tid):
+          t = ctx.tile(tid)
+          loc_kernel(t.get(None), ex, **(self.op.kw or {}))
+          t.valid = True
+      return output
+
+    compiled = program.compile_tree(self.op, bind_operands(children, child_to_var))
+    output = distarray.create_like(largest, compiled.out_dtype)
+    largest.foreach_tile(tile_mapper, kw={'children': children, 'child_to_var': child_to_var, 'op': self.op,
+                                          'compiled': compiled, 'output': output})
+    return output
+
+
+def map(inputs, fn, numpy_expr=None, fn_kw=None):
+  """Evaluate ``fn`` over each tile of the input (map.py:172-205)."""
+  assert fn is not None
+  if not util.is_iterable(inputs):
+    inputs = [inputs]
+  op_deps, children, child_to_var = [], [], []
+  for v in inputs:
+    v = as_array(v)
+    varname = make_var()
+    children.append(v)
+    child_to_var.append(varname)
+    op_deps.append(LocalInput(idx=varname))
+  op = LocalMapExpr(fn=fn, kw=fn_kw, pretty_fn=numpy_expr, deps=op_deps)
+  return MapExpr(children=ListExpr(vals=children), child_to_var=child_to_var, op=op)
+
+
+map_tiles = map   # the name BASELINE.json's north_star uses
+
+
+def map_with_location(inputs, fn, numpy_expr=None, fn_kw=None):
+  """map_with_location.py:22-60.  On the device only location kernels built into the library
+  (arange, ...) are supported: ``fn`` must carry a ``device_location_kernel``."""
+  assert fn is not None
+  if not util.is_iterable(inputs):
+    inputs = [inputs]
+  op_deps, children, child_to_var = [], [], []
+  for v in inputs:
+    v = as_array(v)
+    varname = make_var()
+    children.append(v)
+    child_to_var.append(varname)
+    op_deps.append(LocalInput(idx=varname))
+  op_deps += [LocalInput(idx='extent')]
+  op = LocalMapLocationExpr(fn=fn, kw=fn_kw, pretty_fn=numpy_expr, deps=op_deps)
+  return MapExpr(children=ListExpr(vals=children), child_to_var=child_to_var, op=op)

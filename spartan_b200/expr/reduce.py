@@ -1,0 +1,144 @@
+"""Reductions: sum / min / max / prod / all / any / counts (reference:
+spartan/expr/operator/reduce.py:21-167).
+
+Per tile the reference calls the local reducer (``data.sum(axis)``...) and ships the partial to the
+owner of the output tile, where ``Tile.merge`` folds it in with ``accumulate_fn`` in RPC-arrival
+order (reduce.py:59-69, tile.pyx:263-283).  Here each rank folds the partials of its own tiles on the
+GPU -- one fused map+reduce launch per tile, the mapped value never touches HBM -- into a
+rank-local accumulator of the output's shape, and the cross-rank combine is one NCCL all-reduce with
+the matching op.  The order is fixed, so results are reproducible.
+"""
+import collections
+
+import numpy as np
+
+from .. import blob_ctx, comm, device_ops
+from ..array import distarray, extent, tile
+from ..array.distarray import Broadcast, broadcast
+from ..core import LocalKernelResult
+from .._lib import SpartanError, SP_FILL_CONST, SP_F64, SP_I64
+from . import program
+from .base import Expr, ListExpr, as_array
+from .local import make_var, LocalReduceExpr, LocalInput
+from .map import bind_operands, get_local_values
+
+
+class _DtypeOf(object):
+  """What ``dtype_fn`` sees: the reference passes children[0] (reduce.py:110), which after fusion is
+  not the reduced value; the fused expression's own dtype is used instead."""
+
+  def __init__(self, dtype):
+    self.dtype = np.dtype(dtype)
+
+
+def _value_tree(op):
+  """The mapped value of a (possibly fused) reduce op: deps = [extent, value] (reduce.py:156-160,
+  optimize.py:205-219)."""
+  vals = [d for d in op.deps if not (isinstance(d, LocalInput) and d.idx == 'extent')]
+  if len(vals) != 1:
+    raise program.NotDeviceMappable('reduce over %d value operands' % len(vals))
+  return vals[0]
+
+
+def _reduce_mapper(ex, children, child_to_var, op, axis, output, compiled=None, red_op=None, acc=None):
+  """Local reduction of one tile into the rank's accumulator (reduce.py:21-70)."""
+  ctx = blob_ctx.get()
+  largest = children[0]
+  owner = largest.tiles[ex].worker
+  values = get_local_values(ex, children, child_to_var, compiled.used_vars, owner)
+  if owner == ctx.worker_id:
+    dst_extent = extent.index_for_reduction(ex, axis)
+    inputs = [values[v] for v in compiled.used_vars]
+    target = acc[dst_extent.to_slice()] if acc.dim() else acc
+    device_ops.run_map_reduce(compiled.program, inputs, ex.shape, axis, red_op, target, accumulate=True)
+  return LocalKernelResult(result=[])
+
+
+class ReduceExpr(Expr):
+  members = ('children', 'child_to_var', 'axis', 'dtype_fn', 'op', 'accumulate_fn', 'tile_hint')
+
+  def __init__(self, *args, **kw):
+    super(ReduceExpr, self).__init__(*args, **kw)
+    assert self.dtype_fn is not None
+    assert isinstance(self.children, ListExpr)
+
+  def compute_shape(self):
+    # reduce.py:87-94
+    shapes = [i.shape for i in self.children]
+    child_shape = collections.defaultdict(int)
+    for s in shapes:
+      for i, v in enumerate(s):
+        child_shape[i] = max(child_shape[i], v)
+    input_shape = tuple(child_shape[i] for i in range(len(child_shape)))
+    return tuple(extent.shape_for_reduction(input_shape, self.axis))
+
+  def pretty_str(self):
+    return 'Reduce(%s, axis=%s, %s, hint=%s)' % (getattr(self.op.fn, '__name__', '?'), self.axis, self.children,
+                                                 self.tile_hint)
+
+  def _evaluate(self, ctx, deps):
+    # reduce.py:100-127
+    children = list(deps['children'])
+    child_to_var = list(deps['child_to_var'])
+    axis = deps['axis']
+    op = deps['op']
+    tile_accum = deps['accumulate_fn']
+
+    children = broadcast(children)
+    largest = distarray.largest_value(children)
+    i = children.index(largest)
+    children[0], children[i] = children[i], children[0]
+    child_to_var[0], child_to_var[i] = child_to_var[i], child_to_var[0]
+    if not isinstance(largest, distarray.DistArrayImpl):
+      raise program.NotDeviceMappable('a reduction needs a distributed (non-broadcast) input')
+
+    spec = getattr(op.fn, 'device_reduce', None)
+    if spec is None:
+      raise program.NotDeviceMappable('local reducer %r is not GPU-mappable' % (op.fn,))
+    red_op, post_ops, force_wide = spec
+    value = _value_tree(op)
+    operands = bind_operands(children, child_to_var)
+    compiled = program.compile_tree(value, operands, post_ops=post_ops)
+    dtype = np.dtype(deps['dtype_fn'](_DtypeOf(compiled.out_dtype)))
+    if force_wide:
+      # counts: 0/1 values must add exactly; float32 would saturate at 2^24
+      if compiled.compute_dtype not in (SP_F64, SP_I64):
+        compiled = program.compile_tree(value, operands, force_compute=SP_F64, post_ops=post_ops)
+    combiner = tile.reducer_op(tile_accum)
+
+    shape = tuple(extent.shape_for_reduction(largest.shape, axis))
+    acc = ctx.empty(shape, dtype)
+    device_ops.fill(acc, SP_FILL_CONST, tile.identity_of(red_op, dtype))
+    largest.foreach_tile(_reduce_mapper, kw={'children': children, 'child_to_var': child_to_var, 'op': op,
+                                             'axis': axis, 'output': None, 'compiled': compiled, 'red_op': red_op,
+                                             'acc': acc})
+    # cross-tile combiner across GPUs: one all-reduce instead of N update RPCs into the owner tile
+    comm.allreduce(acc, combiner)
+
+    output_array = distarray.create(shape, dtype, reducer=tile_accum, tile_hint=self.tile_hint)
+    for ex, tid in output_array.tiles.items():
+      if ctx.is_local(tid):
+        t = ctx.tile(tid)
+        src = acc[ex.to_slice()] if acc.dim() else acc
+        if len(output_array.tiles) == 1:
+          t.data = src                      # single output tile: adopt the accumulator, no copy
+        else:
+          device_ops.copy_rect(t.get(None), src)
+        t.valid = True
+    if len(output_array.tiles) == 1 and output_array.slab is not None:
+      output_array.slab = acc if acc.dim() else None
+    return output_array
+
+
+def reduce(v, axis, dtype_fn, local_reduce_fn, accumulate_fn, fn_kw=None, tile_hint=None):
+  """Reduce ``v`` over ``axis`` (reduce.py:130-167).  ``local_reduce_fn`` must be one of the library's
+  local reducers (it carries the ``device_reduce`` spec); ``accumulate_fn`` one of the NumPy combiners
+  np.add / np.multiply / np.minimum / np.maximum / np.logical_and / np.logical_or."""
+  fn_kw = dict(fn_kw or {})
+  varname = make_var()
+  assert 'axis' not in fn_kw, '"axis" argument is reserved.'
+  fn_kw['axis'] = axis
+  reduce_op = LocalReduceExpr(fn=local_reduce_fn, deps=[LocalInput(idx='extent'), LocalInput(idx=varname)],
+                              kw=fn_kw)
+  return ReduceExpr(children=ListExpr(vals=[as_array(v)]), child_to_var=[varname], axis=axis, dtype_fn=dtype_fn,
+                    op=reduce_op, accumulate_fn=accumulate_fn, tile_hint=tile_hint)

@@ -1,0 +1,313 @@
+"""GPU parity: the CUDA path (through the Python host -> C ABI -> sm_100a kernels) against the ORACLE on
+the same seeded inputs.  These are the reference's own hot-path tests (file:line cited) re-expressed for
+pytest, plus edge cases.  Integer / index work is bit-exact; float tolerances are written in each test.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import spartan_oracle
+from spartan_oracle import expr as oexpr
+
+import spartan_b200 as sp
+from spartan_b200.util import Assert
+
+TEST_SIZE = 50
+
+
+@pytest.fixture(autouse=True)
+def ctx():
+  import torch
+  if not torch.cuda.is_available():
+    pytest.skip('needs a CUDA device')
+  c = sp.initialize()
+  spartan_oracle.initialize(c.num_workers)
+  oexpr.eval_cache.clear()
+  yield c
+
+
+def both(build):
+  """Evaluates the same expression builder with the product and with the oracle."""
+  return build(sp).glom(), build(oexpr).glom()
+
+
+# ------------------------------------------------------------------ BASELINE config 1 golden value
+def test_ones_sum_golden():
+  assert sp.ones((4096, 4096)).sum().glom() == 16777216.0
+  assert sp.ones((4096, 4096)).sum().optimized().glom() == 16777216.0
+
+
+# ------------------------------------------------------------------ tests/test_maptiles.py:12-62
+def test_map_chains():
+  Assert.all_eq((sp.ones((20, 20)) + sp.ones((20, 20))).glom(), 2 * np.ones((20, 20)))
+  a = sp.ones((10, 10)); b = sp.ones((10, 10)); c = sp.ones((10, 10))
+  Assert.all_eq((a + b + c).glom(), np.ones((10, 10)) * 3)
+  many = (a + b + a + b + a + b + a + b + a + b)
+  Assert.all_eq(many.glom(), np.ones((10, 10)) * 10)
+  Assert.all_eq(many.optimized().glom(), np.ones((10, 10)) * 10)
+  assert many.glom().dtype == np.float32
+
+
+def test_ln():
+  a = 1.0 + sp.ones((100,), dtype=np.float32)
+  got = sp.ln(a).glom()
+  assert got.dtype == np.float32
+  np.testing.assert_allclose(got, np.log(1.0 + np.ones(100, np.float32)), rtol=1e-6)   # logf <= 1 ulp
+
+
+def test_broadcast():
+  a = sp.ones((2, 1)); b = sp.ones((2, 5))
+  Assert.all_eq((a / b).glom(), np.ones((2, 5)))
+  Assert.all_eq((b / a).glom(), np.ones((2, 5)))
+
+
+def test_maximum_and_scalar_broadcast():
+  # tests/test_elementwise.py:9-22 -- exact (max is exact in any precision)
+  rng = np.random.RandomState(0)
+  np_a = rng.randn(10, 10); np_b = rng.randn(10, 10)
+  Assert.all_eq(sp.maximum(sp.from_numpy(np_a), sp.from_numpy(np_b)).glom(), np.maximum(np_a, np_b))
+  Assert.all_eq(sp.maximum(sp.from_numpy(np_a), 0).glom(), np.maximum(np_a, 0))
+
+
+@pytest.mark.parametrize('shape', [(1,), (7,), (33, 5), (128, 257), (3, 4, 5), (1000, 1)])
+@pytest.mark.parametrize('dtype', [np.float32, np.float64, np.int32, np.int64])
+def test_elementwise_bit_exact(shape, dtype):
+  """+, -, * chains round once per op exactly like the NumPy ufunc chain (-fmad=false): bit-exact."""
+  rng = np.random.RandomState(1)
+  if np.dtype(dtype).kind == 'f':
+    x = rng.randn(*shape).astype(dtype); y = rng.randn(*shape).astype(dtype)
+  else:
+    x = rng.randint(-1000, 1000, size=shape).astype(dtype); y = rng.randint(1, 1000, size=shape).astype(dtype)
+  for build in (lambda m, X, Y: X * 2 + Y, lambda m, X, Y: (X - Y) * (X + Y) - X, lambda m, X, Y: m.maximum(X, Y) - m.minimum(X, 3),
+                lambda m, X, Y: m.abs(X) + m.square(Y)):
+    got = build(sp, sp.from_numpy(x), sp.from_numpy(y)).optimized().glom()
+    ref = build(oexpr, oexpr.from_numpy(x), oexpr.from_numpy(y)).optimized().glom()
+    assert got.dtype == ref.dtype, (got.dtype, ref.dtype)
+    Assert.all_eq(got, ref)
+
+
+def test_compare_logic_astype():
+  rng = np.random.RandomState(2)
+  x = rng.randn(64, 33).astype(np.float32); y = rng.randn(64, 33).astype(np.float32)
+  for build in (lambda m, X, Y: X > Y, lambda m, X, Y: m.logical_and(X > 0, Y < 0), lambda m, X, Y: (X == X) | (Y != Y),
+                lambda m, X, Y: m.astype(X * 10, np.int64), lambda m, X, Y: m.astype(X > 0, np.float32) * Y):
+    got = build(sp, sp.from_numpy(x), sp.from_numpy(y)).glom()
+    ref = build(oexpr, oexpr.from_numpy(x), oexpr.from_numpy(y)).glom()
+    assert got.dtype == ref.dtype
+    Assert.all_eq(got, ref)
+
+
+def test_transcendentals_tolerance():
+  """exp / log / sqrt / divide: device libm is <= 2 ulp; tolerance 4 ulp of float32 (rtol 5e-7)."""
+  rng = np.random.RandomState(3)
+  x = (rng.rand(1000).astype(np.float32) + 0.1)
+  for build in (lambda m, X: m.exp(X), lambda m, X: m.log(X), lambda m, X: m.sqrt(X), lambda m, X: 1.0 / X,
+                lambda m, X: m.power(X, 2.5)):
+    got = build(sp, sp.from_numpy(x)).glom(); ref = build(oexpr, oexpr.from_numpy(x)).glom()
+    assert got.dtype == ref.dtype == np.float32
+    np.testing.assert_allclose(got, ref, rtol=5e-7)
+
+
+def test_row_and_column_vector_broadcast():
+  rng = np.random.RandomState(4)
+  x = rng.randn(96, 40).astype(np.float32); r = rng.randn(1, 40).astype(np.float32); c = rng.randn(96, 1).astype(np.float32)
+  got = (sp.from_numpy(x) * sp.from_numpy(r) + sp.from_numpy(c)).optimized().glom()
+  Assert.all_eq(got, x * r + c)
+
+
+# ------------------------------------------------------------------ tests/test_reduce.py:14-107
+def test_sum_3d_int64_exact():
+  nx = np.arange(TEST_SIZE ** 3, dtype=np.int64).reshape((TEST_SIZE,) * 3)
+  for axis in [None, 0, 1, 2]:
+    x = sp.arange((TEST_SIZE, TEST_SIZE, TEST_SIZE), dtype=np.int64)
+    Assert.all_eq(x.sum(axis).glom(), nx.sum(axis))
+
+
+def test_sum_2d_1d():
+  nx = np.arange(TEST_SIZE * TEST_SIZE, dtype=np.int64).reshape((TEST_SIZE, TEST_SIZE))
+  for axis in [None, 0, 1]:
+    Assert.all_eq(sp.arange((TEST_SIZE, TEST_SIZE), dtype=np.int64).sum(axis).glom(), nx.sum(axis))
+  Assert.all_eq(sp.arange((TEST_SIZE,), dtype=np.int64).sum().glom(), np.arange(TEST_SIZE).sum())
+
+
+def test_simple_sum():
+  for axis in [0, 1, None]:
+    a = sp.ones((TEST_SIZE, TEST_SIZE)) + sp.ones((TEST_SIZE, TEST_SIZE))
+    Assert.all_eq(a.sum(axis=axis).glom(), 2 * np.ones((TEST_SIZE, TEST_SIZE)).sum(axis))
+
+
+def test_count_nonzero_zero():
+  assert sp.count_nonzero(sp.ones((TEST_SIZE,))).glom() == TEST_SIZE
+  assert sp.count_nonzero(sp.zeros((TEST_SIZE,))).glom() == 0
+  assert sp.count_zero(sp.ones((TEST_SIZE,))).glom() == 0
+  assert sp.count_zero(sp.zeros((TEST_SIZE,))).glom() == TEST_SIZE
+  assert sp.count_nonzero(sp.ones((5000, 5000))).glom() == 25000000     # > 2^24: must not saturate
+
+
+@pytest.mark.parametrize('shape,axis', [((257, 129), 0), ((257, 129), 1), ((257, 129), None), ((5, 6, 7), 1),
+                                        ((100000,), None), ((3, 100000), 1), ((100000, 3), 0), ((1, 1), None)])
+def test_reductions_vs_oracle(shape, axis):
+  rng = np.random.RandomState(5)
+  xi = rng.randint(-50, 50, size=shape).astype(np.int64)
+  xf = rng.rand(*shape).astype(np.float32)
+  for name in ('sum', 'min', 'max'):
+    got = getattr(sp, name)(sp.from_numpy(xi), axis).glom(); ref = getattr(oexpr, name)(oexpr.from_numpy(xi), axis).glom()
+    assert got.dtype == ref.dtype
+    Assert.all_eq(np.asarray(got), np.asarray(ref))                       # integers: bit-exact
+    got = getattr(sp, name)(sp.from_numpy(xf), axis).glom(); ref = getattr(oexpr, name)(oexpr.from_numpy(xf), axis).glom()
+    assert got.dtype == ref.dtype == np.float32
+    if name == 'sum':     # different (tree) summation order: 1e-5 relative, the north-star tolerance
+      np.testing.assert_allclose(got, ref, rtol=1e-5)
+    else:
+      Assert.all_eq(np.asarray(got), np.asarray(ref))
+  small = rng.randint(1, 3, size=shape).astype(np.int32)
+  got = sp.prod(sp.from_numpy(small), axis).glom(); ref = oexpr.prod(oexpr.from_numpy(small), axis).glom()
+  assert got.dtype == ref.dtype == np.int64
+  Assert.all_eq(np.asarray(got), np.asarray(ref))
+  b = rng.randint(0, 2, size=shape).astype(np.int32)
+  for name in ('all', 'any'):
+    got = getattr(sp, name)(sp.from_numpy(b), axis).glom(); ref = getattr(oexpr, name)(oexpr.from_numpy(b), axis).glom()
+    assert got.dtype == np.bool_
+    Assert.all_eq(np.asarray(got), np.asarray(ref))
+
+
+def test_min_max_prod_logic_reference():
+  # tests/test_statistics.py:16-30, tests/test_mathematics.py:9-15, tests/test_logic.py:9-23
+  src = np.asarray([1, 1, 1, 2, 2, 5, 5, 10])
+  Assert.all_eq(sp.max(sp.from_numpy(src)).glom(), np.max(src))
+  Assert.all_eq(sp.min(sp.from_numpy(src)).glom(), np.min(src))
+  src = np.arange(100).reshape(10, 10)
+  Assert.all_eq(sp.min(sp.from_numpy(src), axis=1).glom(), np.min(src, axis=1))
+  nA = np.arange(40000, dtype=np.int32).reshape(100, 400)
+  got = sp.from_numpy(nA).prod().glom()
+  assert got.dtype == np.int64
+  Assert.all_eq(got, nA.astype(np.int64).prod())
+  nC = (nA.T.copy() // 1000)
+  C = sp.from_numpy(nA.T.copy()) / 1000          # Python-2 era integer divide floors
+  Assert.all_eq(C.glom(), nC)
+  Assert.all_eq(sp.all(C).glom(), np.all(nC))
+  Assert.all_eq(sp.any(C).glom(), np.any(nC))
+
+
+def test_fused_map_reduce_vs_oracle():
+  """(x*2+y).sum(axis=0), BASELINE config 3 at a size the oracle finishes instantly; 1e-5 relative."""
+  rng = np.random.default_rng(2)
+  x = rng.random((1024, 2048), dtype=np.float32); y = rng.random((1024, 2048), dtype=np.float32)
+  for hint in (None, (128, 2048), (256, 512)):
+    e = (sp.from_numpy(x, tile_hint=hint) * 2 + sp.from_numpy(y, tile_hint=hint)).sum(axis=0)
+    got_f = e.optimized().glom(); got_u = e.glom()
+    ref = (oexpr.from_numpy(x, tile_hint=hint) * 2 + oexpr.from_numpy(y, tile_hint=hint)).sum(axis=0).optimized().glom()
+    exact = (x.astype(np.float64) * 2 + y).sum(axis=0)
+    assert got_f.dtype == ref.dtype == np.float32
+    np.testing.assert_allclose(got_f, ref, rtol=1e-5)
+    np.testing.assert_allclose(got_u, ref, rtol=1e-5)
+    np.testing.assert_allclose(got_f, exact, rtol=1e-5)
+
+
+def test_optimization_reduced():
+  # tests/test_optimization.py:124-163 without the slices (views are out of scope), fp64, tolerance 1e-6
+  rng = np.random.RandomState(1)
+  na = rng.rand(300, 300); nb = rng.rand(300, 300)
+  a = sp.from_numpy(na); b = sp.from_numpy(nb)
+  c = a - b; d = a + c; h = c - d; i = c + h
+  m = h + i; n = i - m; o = n - m; q = n + o; r = q - m
+  s = sp.sum(r)
+  nc = na - nb; nd = na + nc; nh = nc - nd; ni = nc + nh
+  nm = nh + ni; nn = ni - nm; no = nn - nm; nq = nn + no; nr = nq - nm
+  ns = np.sum(nr)
+  got = s.optimized().glom()
+  assert abs(got - ns) < 1e-6 * max(1.0, abs(ns))
+
+
+# ------------------------------------------------------------------ creation (tests/test_creation.py:17-68)
+def test_arange():
+  Assert.raises_exception(ValueError, sp.arange)
+  Assert.all_eq(sp.arange((10,)).glom(), np.arange(10))
+  Assert.all_eq(sp.arange((3, 5)).glom(), np.arange(15).reshape((3, 5)))
+  Assert.all_eq(sp.arange((10,), -1).glom(), np.arange(-1, 9))
+  Assert.all_eq(sp.arange((3, 5), -1).glom(), np.arange(-1, 14).reshape((3, 5)))
+  Assert.all_eq(sp.arange((10,), step=2).glom(), np.arange(0, 20, 2))
+  Assert.all_eq(sp.arange((3, 5), 1, step=2).glom(), np.arange(1, 31, 2).reshape((3, 5)))
+  Assert.all_eq(sp.arange(stop=10).glom(), np.arange(10))
+  Assert.all_eq(sp.arange(-1, 19, 2).glom(), np.arange(-1, 19, 2))
+  Assert.all_eq(sp.arange((64, 48), dtype=np.int64, tile_hint=(16, 16)).glom(), np.arange(64 * 48).reshape(64, 48))
+
+
+def test_from_numpy_roundtrip_and_tilings():
+  rng = np.random.RandomState(6)
+  for shape, hint in [((37, 53), None), ((37, 53), (10, 53)), ((37, 53), (37, 7)), ((37, 53), (8, 9)), ((5,), (2,)), ((2, 3, 4), (1, 3, 2))]:
+    x = rng.randn(*shape)
+    Assert.all_eq(sp.from_numpy(x, tile_hint=hint).glom(), x)
+    Assert.all_eq((sp.from_numpy(x, tile_hint=hint) + 1).glom(), x + 1)
+
+
+def test_rand_properties():
+  """Device RNG (Philox): uniform [0,1), deterministic per seed, independent of the tiling."""
+  a = sp.rand(512, 256, seed=7, dtype=np.float32).glom()
+  b = sp.rand(512, 256, seed=7, dtype=np.float32, tile_hint=(64, 64)).glom()
+  c = sp.rand(512, 256, seed=8, dtype=np.float32).glom()
+  assert a.dtype == np.float32 and a.min() >= 0.0 and a.max() < 1.0
+  Assert.all_eq(a, b)
+  assert not np.array_equal(a, c)
+  assert abs(a.mean() - 0.5) < 5e-3 and abs(a.var() - 1 / 12.0) < 5e-3
+  n = sp.randn(512, 256, seed=9, dtype=np.float32).glom()
+  assert abs(n.mean()) < 1e-2 and abs(n.std() - 1.0) < 1e-2
+  assert sp.rand(8, 8).glom().dtype == np.float64      # srandom.py:83 default dtype
+
+
+# ------------------------------------------------------------------ dot (tests/test_dot.py:8-103, test_matmul.py:12-22)
+def test_dot_reference_cases_exact():
+  Assert.all_eq(sp.dot(sp.arange((132, 100)), sp.arange((100, 77))).glom(),
+                np.dot(np.arange(13200.).reshape(132, 100), np.arange(7700.).reshape(100, 77)))
+  Assert.all_eq(sp.dot(sp.arange((67, 100)), sp.arange((100, 77))).glom(),
+                np.dot(np.arange(6700.).reshape(67, 100), np.arange(7700.).reshape(100, 77)))
+  Assert.all_eq(sp.dot(sp.arange((77, 100)), np.arange(8800.).reshape(100, 88)).glom(),
+                np.dot(np.arange(7700.).reshape(77, 100), np.arange(8800.).reshape(100, 88)))
+  Assert.all_eq(sp.dot(sp.arange(stop=100), sp.arange(stop=100)).glom(), np.asarray([np.dot(np.arange(100.), np.arange(100.))]))
+  Assert.all_eq(sp.dot(sp.arange((100, 77)), sp.arange(stop=77)).glom(), np.dot(np.arange(7700.).reshape(100, 77), np.arange(77.)))
+  Assert.all_eq(sp.dot(sp.arange((77, 100)), sp.arange(stop=100)).glom(), np.dot(np.arange(7700.).reshape(77, 100), np.arange(100.)))
+  Assert.all_eq(sp.dot(sp.arange((77, 100)), np.arange(100.)).glom(), np.dot(np.arange(7700.).reshape(77, 100), np.arange(100.)))
+  x = sp.arange((100, 50), dtype=np.int64).astype(np.float64); y = sp.arange((50, 100), dtype=np.int64).astype(np.float64)
+  Assert.all_eq(sp.dot(x, y).glom(), np.dot(np.arange(5000.).reshape(100, 50), np.arange(5000.).reshape(50, 100)))
+  xi = sp.arange((40, 30), dtype=np.int64); yi = sp.arange((30, 20), dtype=np.int64)
+  Assert.all_eq(sp.dot(xi, yi).glom(), np.dot(np.arange(1200).reshape(40, 30), np.arange(600).reshape(30, 20)))
+
+
+@pytest.mark.parametrize('M,N,K,hint', [(256, 512, 384, None), (300, 700, 1000, (128, 256)), (1024, 1024, 2048, (512, 512)),
+                                         (130, 70, 4100, (64, 64))])
+def test_dot_fp32_tensor_core_vs_oracle(M, N, K, hint):
+  """fp32 dot on tcgen05.  Oracle = np.dot (what the reference tests assert).
+  tf32x3: max |C - C_ref| <= 1e-5 * max|C_ref| on zero-mean data (normwise; the element-wise relative
+  error of a cancelling sum is unbounded in any arithmetic); tf32x1 on uniform data: 2e-4."""
+  rng = np.random.default_rng(0)
+  a = rng.standard_normal((M, K), dtype=np.float32); b = rng.standard_normal((K, N), dtype=np.float32)
+  ref = np.dot(a.astype(np.float64), b.astype(np.float64))
+  old = sp.FLAGS.dot_precision
+  try:
+    sp.FLAGS.dot_precision = 'tf32x3'
+    got = sp.dot(sp.from_numpy(a, tile_hint=hint), sp.from_numpy(b, tile_hint=hint), tile_hint=hint).glom()
+    assert got.dtype == np.float32
+    assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+    assert np.abs(got - np.dot(a, b)).max() <= 1e-5 * np.abs(ref).max()
+    sp.FLAGS.dot_precision = 'simt'
+    got = sp.dot(sp.from_numpy(a, tile_hint=hint), sp.from_numpy(b, tile_hint=hint), tile_hint=hint).glom()
+    assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+    sp.FLAGS.dot_precision = 'tf32x1'
+    au = rng.random((M, K), dtype=np.float32); bu = rng.random((K, N), dtype=np.float32)
+    got = sp.dot(sp.from_numpy(au, tile_hint=hint), sp.from_numpy(bu, tile_hint=hint), tile_hint=hint).glom()
+    refu = np.dot(au.astype(np.float64), bu.astype(np.float64))
+    assert np.abs(got - refu).max() <= 2e-4 * np.abs(refu).max()
+  finally:
+    sp.FLAGS.dot_precision = old
+
+
+def test_dot_linearity_large():
+  """Size-independent property at a shape the oracle would need minutes for: dot(A, B+C) = dot(A,B)+dot(A,C)
+  and dot(A, e_j-columns) reproduces A columns exactly (identity is exact in TF32)."""
+  n = 4096
+  A = sp.rand(n, n, seed=1, dtype=np.float32, tile_hint=(1024, 1024))
+  I = sp.from_numpy(np.eye(n, dtype=np.float32), tile_hint=(1024, 1024))
+  got = sp.dot(A, I, tile_hint=(1024, 1024)).glom()
+  a = A.glom()
+  np.testing.assert_allclose(got, a, rtol=1e-6, atol=1e-7)

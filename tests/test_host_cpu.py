@@ -1,0 +1,137 @@
+"""CPU-side checks of the product host: C-ABI exports, native extent/tiling vs the oracle, the
+bytecode compiler's dtype rules vs NumPy (through the oracle), fusion structure.  No GPU needed."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import spartan_oracle
+from spartan_oracle import distarray as odist, expr as oexpr, extent as oex
+
+import spartan_b200 as sp
+from spartan_b200 import _lib
+from spartan_b200.array import distarray as pdist, extent as pex
+from spartan_b200.expr import program
+from spartan_b200.expr.reduce import _value_tree
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_exports_every_declared_symbol():
+  header = open(os.path.join(ROOT, 'include', 'spartan_b200.h')).read()
+  declared = set(re.findall(r'\b(sp_[a-z0-9_]+)\s*\(', header))
+  declared -= {'sp_status', 'sp_dtype'}
+  lib = ctypes.CDLL(_lib.LIB_PATH)
+  missing = [name for name in sorted(declared) if not hasattr(lib, name)]
+  assert not missing, 'header declares symbols the library does not export: %s' % missing
+  assert set(_lib.EXPORTS) <= declared, 'python binding uses undeclared symbols: %s' % (set(_lib.EXPORTS) - declared)
+  assert lib.sp_version() >= 100
+
+
+def test_compute_calls_fail_loudly_without_gpu():
+  import torch
+  if torch.cuda.is_available():
+    pytest.skip('GPU present')
+  with pytest.raises(sp.SpartanError):
+    sp.ones((4, 4)).glom()
+
+
+@pytest.mark.parametrize('shape,hint,shards', [
+  ((4096, 4096), None, 1), ((4096, 4096), None, 3), ((4096, 4096), None, 8), ((32768, 32768), None, 8),
+  ((50, 50, 50), None, 3), ((10,), None, 3), ((10 ** 7, 256), None, 8), ((32768, 32768), (4096, 4096), 8),
+  ((132, 100), (50, 33), 3), ((7,), (2,), -1), ((), None, 3), ((5, 1), None, 4)])
+def test_tiling_matches_oracle(shape, hint, shards):
+  a = pdist.compute_extents(shape, hint, shards)
+  b = odist.compute_extents(shape, hint, shards)
+  assert [(ex.ul, ex.lr, w) for ex, w in a.items()] == [(ex.ul, ex.lr, w) for ex, w in b.items()]
+  if hint is None and shape:
+    assert pdist.good_tile_shape(shape, shards) == odist.good_tile_shape(shape, shards)
+
+
+def test_native_unravel_to_global_match_reference_values():
+  # tests/test_extent.py:24-38 through the C ABI
+  a = pex.create((2, 2), (7, 7), (10, 10))
+  assert [a.to_global(i, axis=None) for i in (0, 10, 11, 20)] == [22, 42, 43, 62]
+  rnd = np.random.RandomState(0)
+  for _ in range(200):
+    shp = tuple(int(x) for x in rnd.randint(1, 30, size=rnd.randint(1, 5)))
+    idx = int(rnd.randint(0, int(np.prod(shp))))
+    assert pex.unravelled_pos(idx, shp) == oex.unravelled_pos(idx, shp) == tuple(int(i) for i in np.unravel_index(idx, shp))
+
+
+def test_grid_change_partition_axis_is_refused():
+  ex = pex.create((0, 0), (4, 4), (8, 8))
+  with pytest.raises(sp.SpartanError):
+    pex.change_partition_axis(ex, 1)
+
+
+def _compile(e, dtypes, scalars=()):
+  ops = {}
+  for var, child in zip(e.child_to_var, e.children):
+    if var in scalars:
+      ops[var] = program.Operand('scalar', np.asarray(scalars[var]).dtype, value=np.asarray(scalars[var])[()])
+    else:
+      ops[var] = program.Operand('array', dtypes[var] if var in dtypes else child.npa.dtype)
+  tree = _value_tree(e.op) if isinstance(e, sp.ReduceExpr) else e.op
+  return program.compile_tree(tree, ops)
+
+
+@pytest.mark.parametrize('dt', [np.float32, np.float64, np.int32, np.int64])
+@pytest.mark.parametrize('scalar', [2, 2.5, np.float64(0.5), np.int64(3)])
+def test_scalar_casting_rule_matches_numpy1(dt, scalar):
+  """x * scalar keeps the array dtype unless the scalar is of a higher kind;
+  the expected dtype comes from the oracle's legacy_result_type, itself pinned by test_ln."""
+  x = sp.from_numpy(np.zeros((4,), dt))
+  e = x * scalar
+  var_s = e.child_to_var[1]
+  c = _compile(e, {e.child_to_var[0]: dt}, {var_s: scalar})
+  expect = oexpr.legacy_result_type([np.zeros((4,), dt), np.asarray(scalar)])
+  assert c.out_dtype == expect
+
+
+def test_fused_program_shape():
+  x = sp.from_numpy(np.zeros((4, 4), np.float32)); y = sp.from_numpy(np.zeros((4, 4), np.float32))
+  e = (x * 2 + y).sum(axis=0).optimized()
+  assert isinstance(e, sp.ReduceExpr) and len(e.children) == 3
+  assert all(not isinstance(c, sp.MapExpr) for c in e.children)
+  c = _compile(e, {v: np.float32 for v in e.child_to_var}, {e.child_to_var[1]: 2})
+  ops = [(c.program.op[i], c.program.arg[i]) for i in range(c.program.n_ops)]
+  O = _lib.OP
+  assert ops == [(O['IN'], 0), (O['CONST'], 0), (O['MUL'], 0), (O['IN'], 1), (O['ADD'], 0)]
+  assert c.compute_dtype == _lib.SP_F32 and c.out_dtype == np.float32 and c.program.consts[0] == 2.0
+
+
+def test_unfused_evaluate_keeps_three_nodes():
+  # Expr.evaluate() does not optimise (base.py:300)
+  x = sp.from_numpy(np.zeros((4, 4), np.float32))
+  e = (x * 2 + x).sum()
+  assert isinstance(e.children[0], sp.MapExpr) and isinstance(e.children[0].children[0], sp.MapExpr)
+
+
+def test_python_lambda_is_rejected():
+  x = sp.from_numpy(np.zeros((4,), np.float32))
+  e = sp.map(x, lambda t: t + 1)
+  with pytest.raises(sp.NotDeviceMappable):
+    _compile(e, {e.child_to_var[0]: np.float32})
+
+
+def test_dtype_of_mixed_chain():
+  a = sp.from_numpy(np.zeros((4,), np.float32)); b = sp.from_numpy(np.zeros((4,), np.float64))
+  i = sp.from_numpy(np.zeros((4,), np.int32))
+  e = ((a * a) + b).optimized()
+  c = _compile(e, {})
+  assert c.out_dtype == np.float64 and c.compute_dtype == _lib.SP_F64
+  O = _lib.OP
+  ops = [c.program.op[k] for k in range(c.program.n_ops)]
+  assert O['CAST_F32'] in ops          # the float32 product rounds to float32 before widening, like NumPy
+  e = (a + i).optimized()
+  c = _compile(e, {})
+  assert c.out_dtype == np.result_type(np.float32, np.int32) == np.float64
+  e = (i / i)
+  c = _compile(e, {})
+  assert c.out_dtype == np.int32       # Python-2 era np.divide on ints floors
+  e = (a > 0)
+  c = _compile(e, {e.child_to_var[0]: np.float32}, {e.child_to_var[1]: 0})
+  assert c.out_dtype == np.bool_ and c.compute_dtype == _lib.SP_F32

@@ -272,6 +272,28 @@ class DistArrayImpl(DistArray):
     Assert.eq(tuple(region.shape), tuple(data.shape), 'Size of extent does not match size of data')
     ctx = self.ctx
     me = ctx.worker_id
+    if (host and self.reducer_fn is None and self.slab is not None and len(self.shape) > 0
+        and tuple(region.shape) == self.shape and data.dtype == self.dtype):
+      # whole-array upload: one H2D copy per contiguous block of this rank's slab instead of one per tile
+      import itertools
+      runs = []
+      for ivs in self.slab_axes:
+        axis_runs, off = [], 0
+        for a, b in ivs:
+          if axis_runs and axis_runs[-1][1] == a:
+            axis_runs[-1] = (axis_runs[-1][0], b, axis_runs[-1][2])
+          else:
+            axis_runs.append((a, b, off))
+          off += b - a
+        runs.append(axis_runs)
+      for block in itertools.product(*runs):
+        g = tuple(slice(a, b) for a, b, _ in block)
+        l = tuple(slice(o, o + (b - a)) for a, b, o in block)
+        self.slab[l].copy_(torch.from_numpy(data[g]), non_blocking=True)
+      for tid in self.tiles.values():
+        if tid.worker == me:
+          ctx.tile(tid).valid = True
+      return None
     if len(self.shape) == 0:
       pieces = [(next(iter(self.tiles.keys())), region)]
     else:

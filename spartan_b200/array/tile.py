@@ -92,7 +92,7 @@ def merge(old_tile, subslice, update, reducer):
   region = data if full else data[subslice]
   if not old_tile.valid:
     if not full:
-      device_ops.fill_view(data, SP_FILL_CONST, identity_of(red, old_tile.dtype) if red is not None else 0)
+      data.fill_(identity_of(red, old_tile.dtype) if red is not None else 0)
     device_ops.copy_into(region, update)          # first write replaces (and casts to the tile dtype, :267)
     old_tile.valid = True
   elif red is None:

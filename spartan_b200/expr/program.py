@@ -121,6 +121,26 @@ def tree_is_mappable(op):
   return False
 
 
+def tree_cost(op):
+  """(evaluation-stack depth with left-to-right operand order, set of input names) of a LocalExpr tree."""
+  if isinstance(op, local.LocalInput):
+    return 1, {op.idx}
+  depth, names = 1, set()
+  for i, d in enumerate(op.deps):
+    dd, nn = tree_cost(d)
+    depth = max(depth, i + dd)
+    names |= nn
+  return depth, names
+
+
+def fits_one_kernel(op):
+  """True when the tree can run as ONE fused kernel: stack depth and operand count within the
+  evaluator's register budget.  Fusion passes stop fusing at this boundary; the un-fused child is then
+  evaluated (once, cached by expression id) into a temporary array."""
+  depth, names = tree_cost(op)
+  return depth <= SP_MAX_STACK and len(names) <= SP_MAX_OPERANDS
+
+
 def _analyse(node, operands):
   if isinstance(node, local.LocalInput):
     if node.idx not in operands:

@@ -108,7 +108,7 @@ class ReduceExpr(Expr):
 
     shape = tuple(extent.shape_for_reduction(largest.shape, axis))
     acc = ctx.empty(shape, dtype)
-    device_ops.fill(acc, SP_FILL_CONST, tile.identity_of(red_op, dtype))
+    acc.fill_(tile.identity_of(red_op, dtype))     # exact for int64 extremes (a double immediate is not)
     largest.foreach_tile(_reduce_mapper, kw={'children': children, 'child_to_var': child_to_var, 'op': op,
                                              'axis': axis, 'output': None, 'compiled': compiled, 'red_op': red_op,
                                              'acc': acc})

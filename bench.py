@@ -37,7 +37,7 @@ def parse_args():
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--n', type=int, default=32768, help='matrix order of the dot workload')
   ap.add_argument('--tile', type=int, default=4096)
-  ap.add_argument('--precision', default=os.environ.get('SPARTAN_DOT_PRECISION', 'tf32x1'))
+  ap.add_argument('--precision', default=os.environ.get('SPARTAN_DOT_PRECISION', 'bf16x3'))
   ap.add_argument('--mr-log2', type=int, default=30, help='log2(#elements) of the map+reduce workload')
   ap.add_argument('--skip-e2e', action='store_true')
   ap.add_argument('--skip-mapreduce', action='store_true')

@@ -155,7 +155,7 @@ typedef enum {
 #define SP_MAX_PROGRAM 64
 #define SP_MAX_OPERANDS 8
 #define SP_MAX_CONSTS 16
-#define SP_MAX_STACK 8
+#define SP_MAX_STACK 4 /* evaluation-stack depth of one fused kernel (register resident) */
 
 typedef struct {
   int32_t n_ops;
@@ -214,10 +214,12 @@ int sp_copy_rect(void* dst, const int64_t dst_stride[3], const void* src, const 
 typedef enum {
   SP_GEMM_TF32X1 = 0, /* one tcgen05 kind::tf32 pass over RN-rounded operands */
   SP_GEMM_TF32X3 = 1, /* hi/lo split, 3 passes: ~fp32-faithful (error ~2^-21 per product) */
-  SP_GEMM_SIMT = 2    /* CUDA-core reference path, exact per-dtype arithmetic (also f64 / i64 / i32) */
+  SP_GEMM_SIMT = 2,   /* CUDA-core reference path, exact per-dtype arithmetic (also f64 / i64 / i32) */
+  SP_GEMM_BF16X3 = 3  /* bf16 hi/lo split, 3 kind::f16 passes at twice the tf32 rate (error ~2^-16 per product) */
 } sp_gemm_precision;
 
 #define SP_GEMM_MAX_TERMS 24
+#define SP_GEMM_MAX_SEGMENTS 8 /* (A strip, B strip) pairs per launch */
 
 typedef struct {
   const float* A; /* [M, K] row-major, leading dimension lda */
@@ -228,7 +230,11 @@ typedef struct {
 } sp_gemm_segment;
 
 /* C[M,N] (+)= sum_s A_s[M,K_s] * B_s[K_s,N]: one launch for a whole strip-joined dot
- * (join_mapper, map.py:243-286).  accumulate != 0 adds into C (np.add combiner). */
+ * (join_mapper, map.py:243-286).  accumulate != 0 adds into C (np.add combiner).
+ * The tensor-core accumulator truncates, so partial sums are promoted to fp32 registers
+ * (round-to-nearest) every few k-blocks; sp_gemm_set_chunk_kblocks overrides that interval
+ * (0 = per-mode default) -- a tuning / test hook. */
+int sp_gemm_set_chunk_kblocks(int k_blocks);
 int64_t sp_gemm_f32_workspace_bytes(int64_t M, int64_t N, int n_seg, const int64_t* seg_k, int precision);
 int sp_gemm_f32_segments(int n_seg, const sp_gemm_segment* segs, float* C, int64_t ldc, int64_t M, int64_t N,
                          int accumulate, int precision, void* workspace, int64_t workspace_bytes, void* stream);

@@ -20,7 +20,8 @@ SP_F32, SP_F64, SP_I32, SP_I64, SP_U8, SP_BOOL = range(6)
 SP_AXIS_NONE = -1000
 SP_FILL_CONST, SP_FILL_IOTA, SP_FILL_RAND, SP_FILL_RANDN = range(4)
 SP_RED_SUM, SP_RED_MIN, SP_RED_MAX, SP_RED_PROD, SP_RED_ALL, SP_RED_ANY = range(6)
-SP_GEMM_TF32X1, SP_GEMM_TF32X3, SP_GEMM_SIMT = range(3)
+SP_GEMM_TF32X1, SP_GEMM_TF32X3, SP_GEMM_SIMT, SP_GEMM_BF16X3 = range(4)
+SP_GEMM_MAX_SEGMENTS = 8
 SP_MAX_PROGRAM, SP_MAX_OPERANDS, SP_MAX_CONSTS, SP_MAX_STACK = 64, 8, 16, 4
 SP_GEMM_MAX_TERMS = 24
 
@@ -72,6 +73,7 @@ _SIGS = {
                            _i64p, _int, _int, _vp, _i64, _vp]),
   'sp_combine': (_int, [_vp, _vp, _int, _i64, _int, _vp]),
   'sp_copy_rect': (_int, [_vp, _i64p, _vp, _i64p, _i64p, _int, _vp]),
+  'sp_gemm_set_chunk_kblocks': (_int, [_int]),
   'sp_gemm_f32_workspace_bytes': (_i64, [_i64, _i64, _int, _i64p, _int]),
   'sp_gemm_f32_segments': (_int, [_int, ctypes.POINTER(sp_gemm_segment), _vp, _i64, _i64, _i64, _int, _int, _vp, _i64, _vp]),
   'sp_gemm_f32': (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp, _i64, _vp]),

@@ -9,8 +9,9 @@ class Flags(object):
     self.opt_reduce_fusion = True       # optimize.py:1099
     self.opt_expression_cache = True    # base.py:21
     self.tile_assignment_strategy = 'round_robin'   # distarray.py:441-445 (the only strategy on one box)
-    # tensor-core mode of dot(): 'tf32x3' (~fp32-faithful), 'tf32x1' (fast), 'simt' (CUDA cores, exact IEEE order)
-    self.dot_precision = 'tf32x3'
+    # tensor-core mode of dot(): 'bf16x3' (default: 16-bit-mantissa split, 3 bf16 passes), 'tf32x3' (22-bit),
+    # 'tf32x1' (fastest, 11-bit operands), 'simt' (CUDA cores, plain IEEE fp32)
+    self.dot_precision = 'bf16x3'
 
   def __repr__(self):
     return 'FLAGS(%s)' % ', '.join('%s=%r' % kv for kv in sorted(self.__dict__.items()))

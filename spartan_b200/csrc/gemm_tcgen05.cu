@@ -6,55 +6,66 @@
 // (spartan/array/tile.pyx:263-268) with one persistent, warp-specialised
 // tcgen05 kernel:
 //
-//   C[m, n] (+)= sum over terms t, k :  A_t[m, k] * Bt_t[n, k]
+//   C[m, n] (+)= sum over segments s, terms t, k :  A_{s,t}[m, k] * Bt_{s,t}[n, k]
 //
-// * operands are *prepared* copies (prep_a / prep_bt below): fp32 values
-//   rounded to TF32 with round-to-nearest (the tensor core would otherwise
-//   truncate, a systematic -2^-11 bias), B transposed so both operands are
-//   K-major, K zero-padded to a multiple of 32 so TMA strides are 16B aligned;
-// * "terms" express both precision splitting (tf32x3: lo*hi + hi*lo + hi*hi)
-//   and K-segments (one term per (A strip, B strip) pair of a tiled dot), so a
-//   whole tiled contraction is ONE launch and the accumulator never leaves
-//   TMEM between strips;
+// * operands are *prepared* copies (prep kernels below): fp32 values rounded
+//   (round-to-nearest; the tensor core would otherwise truncate) to TF32 or
+//   split into bf16 pieces, B transposed so both operands are K-major, K
+//   zero-padded to the k-block so TMA strides are 16B aligned;
+// * "segments" are the (A strip, B strip) pairs of a tiled dot, "terms" the
+//   precision split (x3: lo*hi + hi*lo + hi*hi), so a whole tiled contraction
+//   is ONE launch;
 // * TMA (cp.async.bulk.tensor, 128B swizzle) -> 4-stage smem ring -> one
-//   elected thread issues tcgen05.mma.kind::tf32 (M=128, N=256, K=8) into a
-//   double-buffered 2x256-column TMEM accumulator -> 4 epilogue warps drain
-//   TMEM with tcgen05.ld and store/accumulate C.
+//   elected thread issues tcgen05.mma (kind::tf32 M=128,N=256,K=8 or kind::f16
+//   bf16 K=16) into a double-buffered 2x256-column TMEM accumulator;
+// * the tensor core's fp32 accumulator TRUNCATES on every accumulate (measured
+//   on B200: relative bias ~ -6e-9 per K element, profiles/r01_gemm_probe_v1.log),
+//   so TMEM only ever holds a short K chunk: every `chunk_kb` k-blocks the 8
+//   epilogue warps drain the chunk with tcgen05.ld and add it to fp32 REGISTER
+//   accumulators with round-to-nearest (128 per thread; registers are moved from
+//   the producer warpgroup to the two epilogue warpgroups with setmaxnreg);
+// * precision modes: tf32x1 (1 pass), tf32x3 / bf16x3 (hi/lo split, 3 passes).
 //
 // Roofline: tensor pipe. Algorithmic work = 2*M*N*K flop per dot.
 #include "sp_common.h"
 #include <cuda.h>
+#include <cuda_bf16.h>
+#include <algorithm>
+#include <string.h>
 
 namespace sp {
 namespace gemm {
 
 constexpr int BM = 128;
 constexpr int BN = 256;
-constexpr int BK = 32;            // fp32 elements = one 128B swizzle row
-constexpr int UMMA_K = 8;         // tf32: 32 bytes of K per MMA
 constexpr int STAGES = 4;
-constexpr int A_STAGE_BYTES = BM * BK * 4;   // 16 KiB
-constexpr int B_STAGE_BYTES = BN * BK * 4;   // 32 KiB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int A_STAGE_BYTES = BM * 128;      // 128 rows x 128 B (one swizzle row of K)
+constexpr int B_STAGE_BYTES = BN * 128;
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;   // 48 KiB
 constexpr int NUM_ACC = 2;
 constexpr int TMEM_COLS = NUM_ACC * BN;      // 512
-constexpr int NUM_THREADS = 256;             // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 epilogue
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 128 + 32 * NUM_EPI_WARPS;   // WG0: TMA / MMA / TMEM-alloc / idle, WG1-2: epilogue
 constexpr int EPI_WARP0 = 4;
 constexpr int GROUP_M = 16;                  // tile rasterisation group (L2 reuse)
-constexpr int MAX_TERMS = SP_GEMM_MAX_TERMS;
+constexpr int MAX_SEGMENTS = SP_GEMM_MAX_TERMS;
+constexpr int MAX_MAPS = 4 * 8;              // per launch: <= 8 segments x (A_hi, A_lo, B_hi, B_lo)
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int REGS_PRODUCER = 40;
+constexpr int REGS_EPILOGUE = 232;
 
-struct Term {
-  int a_map;
-  int b_map;
+struct Segment {
   int k_blocks;
-  int pad;
+  int n_terms;
+  int a_map[3];
+  int b_map[3];
 };
 
 struct Params {
-  CUtensorMap maps[2 * MAX_TERMS];
-  Term terms[MAX_TERMS];
-  int n_terms;
+  CUtensorMap maps[MAX_MAPS];
+  Segment segs[8];
+  int n_segs;
+  int chunk_kb;          // k-blocks accumulated in TMEM before promotion to registers
   int M, N;
   int m_blocks, n_blocks;
   int accumulate;
@@ -68,19 +79,15 @@ struct Params {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
-
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
@@ -92,46 +99,50 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "WAIT_DONE:\n\t"
       "}" ::"r"(bar), "r"(parity) : "memory");
 }
-
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
-
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
-
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
-
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
 
-// D[tmem] (+)= A[smem desc] * B[smem desc], tf32 inputs, fp32 accumulate.
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
-      : "memory");
+// D[tmem] (+)= A[smem desc] * B[smem desc]; fp32 accumulate.  KIND 0: tf32, 1: bf16 (kind::f16).
+template <int KIND>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  if constexpr (KIND == 0) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+        : "memory");
+  }
 }
-
 // Arrives on `bar` once every previously issued tcgen05.mma of this thread retired.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -144,8 +155,10 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
       : "r"(taddr)
       : "memory");
 }
-
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
 // Field layout follows the sm_100 shared-memory matrix descriptor
@@ -160,13 +173,10 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
-  return (1u << 4)                      // D format: F32
-         | (2u << 7)                    // A format: TF32
-         | (2u << 10)                   // B format: TF32
-         | (0u << 15) | (0u << 16)      // A, B K-major
-         | (static_cast<uint32_t>(n >> 3) << 17)
-         | (static_cast<uint32_t>(m >> 4) << 24);
+// instruction descriptor: D fp32, A/B format fmt (0 f16, 1 bf16, 2 tf32), both K-major
+__host__ __device__ constexpr uint32_t make_idesc(int fmt, int m, int n) {
+  return (1u << 4) | (static_cast<uint32_t>(fmt) << 7) | (static_cast<uint32_t>(fmt) << 10) |
+         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 __device__ __forceinline__ void tile_coords(int tile, int m_blocks, int n_blocks, int& m_blk, int& n_blk) {
@@ -180,14 +190,19 @@ __device__ __forceinline__ void tile_coords(int tile, int m_blocks, int n_blocks
 }
 
 // ----------------------------------------------------------------------------
-// The kernel
+// The kernel.  KIND 0: tf32 operands (BK = 32 elements), KIND 1: bf16 (BK = 64).
 // ----------------------------------------------------------------------------
+template <int KIND>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tf32_kernel(const __grid_constant__ Params p) {
+gemm_kernel(const __grid_constant__ Params p) {
+  constexpr int ELEM = (KIND == 0) ? 4 : 2;
+  constexpr int BK = 128 / ELEM;               // elements per 128B swizzle row
+  constexpr int UMMA_K = 32 / ELEM;            // 32 bytes of K per MMA
+  constexpr uint32_t IDESC = make_idesc(KIND == 0 ? 2 : 1, BM, BN);
+
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
-  // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[NUM_ACC], tmem_empty[NUM_ACC], tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
@@ -199,10 +214,11 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
   const int num_tiles = p.m_blocks * p.n_blocks;
 
   if (warp == 0 && lane == 0) {
-    for (int t = 0; t < p.n_terms; ++t) {
-      tma_prefetch_desc(&p.maps[p.terms[t].a_map]);
-      tma_prefetch_desc(&p.maps[p.terms[t].b_map]);
-    }
+    for (int s = 0; s < p.n_segs; ++s)
+      for (int t = 0; t < p.segs[s].n_terms; ++t) {
+        tma_prefetch_desc(&p.maps[p.segs[s].a_map[t]]);
+        tma_prefetch_desc(&p.maps[p.segs[s].b_map[t]]);
+      }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -211,13 +227,11 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
     }
     for (int a = 0; a < NUM_ACC; ++a) {
       mbar_init(tmem_full_bar(a), 1);
-      mbar_init(tmem_empty_bar(a), 4);   // one arrive per epilogue warp
+      mbar_init(tmem_empty_bar(a), NUM_EPI_WARPS);   // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
-    tmem_alloc(tmem_ptr_smem, TMEM_COLS);
-  }
+  if (warp == 2) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -225,117 +239,146 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        int m_blk, n_blk;
-        tile_coords(tile, p.m_blocks, p.n_blocks, m_blk, n_blk);
-        for (int t = 0; t < p.n_terms; ++t) {
-          const Term term = p.terms[t];
-          const CUtensorMap* map_a = &p.maps[term.a_map];
-          const CUtensorMap* map_b = &p.maps[term.b_map];
-          for (int kb = 0; kb < term.k_blocks; ++kb) {
-            mbar_wait(empty_bar(stage), phase ^ 1);
-            const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
-            const uint32_t b_dst = a_dst + A_STAGE_BYTES;
-            mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-            tma_load_2d(a_dst, map_a, full_bar(stage), kb * BK, m_blk * BM);
-            tma_load_2d(b_dst, map_b, full_bar(stage), kb * BK, n_blk * BN);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          }
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
-        uint32_t accum = 0;
-        for (int t = 0; t < p.n_terms; ++t) {
-          const int k_blocks = p.terms[t].k_blocks;
-          for (int kb = 0; kb < k_blocks; ++kb) {
-            mbar_wait(full_bar(stage), phase);
-            tc_fence_after();
-            const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
-            const uint32_t b_addr = a_addr + A_STAGE_BYTES;
-#pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              const uint64_t da = make_kmajor_sw128_desc(a_addr + k * UMMA_K * 4);
-              const uint64_t db = make_kmajor_sw128_desc(b_addr + k * UMMA_K * 4);
-              umma_tf32(tmem_d, da, db, idesc, accum);
-              accum = 1;
+  if (warp < EPI_WARP0) {
+    reg_dec<REGS_PRODUCER>();
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          int m_blk, n_blk;
+          tile_coords(tile, p.m_blocks, p.n_blocks, m_blk, n_blk);
+          for (int s = 0; s < p.n_segs; ++s) {
+            const Segment seg = p.segs[s];
+            for (int kb = 0; kb < seg.k_blocks; ++kb) {
+              for (int t = 0; t < seg.n_terms; ++t) {
+                mbar_wait(empty_bar(stage), phase ^ 1);
+                const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
+                const uint32_t b_dst = a_dst + A_STAGE_BYTES;
+                mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+                tma_load_2d(a_dst, &p.maps[seg.a_map[t]], full_bar(stage), kb * BK, m_blk * BM);
+                tma_load_2d(b_dst, &p.maps[seg.b_map[t]], full_bar(stage), kb * BK, n_blk * BN);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+              }
             }
-            umma_commit(empty_bar(stage));      // frees the smem slot when these MMAs retire
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
-        umma_commit(tmem_full_bar(acc));        // accumulator complete -> epilogue
-        if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
       }
+      __syncwarp();
+    } else if (warp == 1) {
+      // ===================== MMA issuer =====================
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          int in_chunk = 0;          // k-blocks issued into the current TMEM chunk
+          uint32_t accum = 0;
+          bool chunk_open = false;
+          for (int s = 0; s < p.n_segs; ++s) {
+            const int k_blocks = p.segs[s].k_blocks;
+            const int n_terms = p.segs[s].n_terms;
+            for (int kb = 0; kb < k_blocks; ++kb) {
+              if (!chunk_open) {
+                mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);   // epilogue drained this buffer
+                tc_fence_after();
+                chunk_open = true;
+                accum = 0;
+                in_chunk = 0;
+              }
+              const uint32_t tmem_d = tmem_base + acc * BN;
+              for (int t = 0; t < n_terms; ++t) {
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
+                const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                  const uint64_t da = make_kmajor_sw128_desc(a_addr + k * 32);
+                  const uint64_t db = make_kmajor_sw128_desc(b_addr + k * 32);
+                  umma<KIND>(tmem_d, da, db, IDESC, accum);
+                  accum = 1;
+                }
+                umma_commit(empty_bar(stage));      // frees the smem slot when these MMAs retire
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+              }
+              if (++in_chunk == p.chunk_kb) {
+                umma_commit(tmem_full_bar(acc));    // chunk complete -> epilogue promotes it
+                chunk_open = false;
+                if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
+              }
+            }
+          }
+          if (chunk_open) {
+            umma_commit(tmem_full_bar(acc));
+            if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
+          }
+        }
+      }
+      __syncwarp();
     }
-    __syncwarp();
-  } else if (warp >= EPI_WARP0) {
-    // ===================== Epilogue: TMEM -> registers -> C =====================
-    const int q = warp - EPI_WARP0;              // TMEM lane quarter owned by this warp (warp % 4)
+  } else {
+    // ===================== Epilogue: TMEM chunk -> fp32 register accumulators -> C =====================
+    reg_inc<REGS_EPILOGUE>();
+    const int q = warp & 3;                        // TMEM lane quarter this warp may read (warp % 4)
+    const int half = (warp - EPI_WARP0) >> 2;      // which 128-column half of the tile
+    int total_kb = 0;
+    for (int s = 0; s < p.n_segs; ++s) total_kb += p.segs[s].k_blocks;
+    const int n_chunks = (total_kb + p.chunk_kb - 1) / p.chunk_kb;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m_blk, n_blk;
       tile_coords(tile, p.m_blocks, p.n_blocks, m_blk, n_blk);
-      mbar_wait(tmem_full_bar(acc), acc_phase);
-      tc_fence_after();
+      float sum[128];
+#pragma unroll
+      for (int j = 0; j < 128; ++j) sum[j] = 0.0f;
+      for (int c = 0; c < n_chunks; ++c) {
+        mbar_wait(tmem_full_bar(acc), acc_phase);
+        tc_fence_after();
+        const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * 128;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tbase + g * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[g * 32 + j] += __uint_as_float(r[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+        if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
+      }
       const int row = m_blk * BM + q * 32 + lane;
-      const bool row_ok = row < p.M;
-      float* c_row = p.C + static_cast<int64_t>(row) * p.ldc;
-      const bool vec_ok = ((reinterpret_cast<uint64_t>(p.C) & 15) == 0) && ((p.ldc & 3) == 0);
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c;
-        tmem_ld_32x32b_x32(taddr, r);
-        tmem_ld_wait();
-        const int col0 = n_blk * BN + c;
-        if (row_ok) {
-          if (vec_ok && col0 + 32 <= p.N) {
-            float4* dst = reinterpret_cast<float4*>(c_row + col0);
+      const int col0 = n_blk * BN + half * 128;
+      if (row < p.M) {
+        float* c_row = p.C + static_cast<int64_t>(row) * p.ldc;
+        const bool vec_ok = ((reinterpret_cast<uint64_t>(p.C) & 15) == 0) && ((p.ldc & 3) == 0) && (col0 + 128 <= p.N);
+        if (vec_ok) {
+          float4* dst = reinterpret_cast<float4*>(c_row + col0);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                     __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-              if (p.accumulate) {
-                const float4 o = dst[j];
-                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-              }
-              dst[j] = v;
+          for (int j = 0; j < 32; ++j) {
+            float4 v = make_float4(sum[4 * j], sum[4 * j + 1], sum[4 * j + 2], sum[4 * j + 3]);
+            if (p.accumulate) {
+              const float4 o = dst[j];
+              v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
             }
-          } else {
+            dst[j] = v;
+          }
+        } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (col0 + j < p.N) {
-                float v = __uint_as_float(r[j]);
-                if (p.accumulate) v += c_row[col0 + j];
-                c_row[col0 + j] = v;
-              }
+          for (int j = 0; j < 128; ++j) {
+            if (col0 + j < p.N) {
+              float v = sum[j];
+              if (p.accumulate) v += c_row[col0 + j];
+              c_row[col0 + j] = v;
             }
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
-      if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -348,8 +391,10 @@ gemm_tf32_kernel(const __grid_constant__ Params p) {
 }
 
 // ----------------------------------------------------------------------------
-// Operand preparation: RN-round to TF32, optional hi/lo split, pad K to 32,
-// transpose B.  HBM-bound: reads the operand once, writes 1 (or 2) copies.
+// Operand preparation (HBM-bound: reads the fp32 operand once, writes 1 or 2 rounded copies).
+//   SPLIT 0: tf32 hi            SPLIT 1: tf32 hi + lo
+//   SPLIT 2: bf16 hi + lo
+// Output rows have Kp elements (zero tail); B is written transposed ([N, Kp]).
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ float rn_tf32(float x) {
   uint32_t r;
@@ -357,43 +402,56 @@ __device__ __forceinline__ float rn_tf32(float x) {
   return __uint_as_float(r);
 }
 
-// A: [M, K] with leading dim lda  ->  hi/lo: [M, Kp] (Kp multiple of 32, zero tail)
-__global__ void prep_a_kernel(const float* __restrict__ A, int64_t lda, int M, int K, int Kp,
-                              float* __restrict__ hi, float* __restrict__ lo) {
-  const int64_t total = static_cast<int64_t>(M) * Kp;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t m = i / Kp;
-    const int k = static_cast<int>(i - m * Kp);
-    const float a = (k < K) ? A[m * lda + k] : 0.0f;
+template <int SPLIT>
+__device__ __forceinline__ void split_store(float a, void* hi, void* lo, int64_t idx) {
+  if constexpr (SPLIT == 2) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(a);
+    static_cast<__nv_bfloat16*>(hi)[idx] = h;
+    static_cast<__nv_bfloat16*>(lo)[idx] = __float2bfloat16_rn(a - __bfloat162float(h));
+  } else {
     const float h = rn_tf32(a);
-    hi[i] = h;
-    if (lo != nullptr) lo[i] = rn_tf32(a - h);
+    static_cast<float*>(hi)[idx] = h;
+    if constexpr (SPLIT == 1) static_cast<float*>(lo)[idx] = rn_tf32(a - h);
   }
 }
 
-// B: [K, N] with leading dim ldb  ->  hiT/loT: [N, Kp]
-__global__ void prep_bt_kernel(const float* __restrict__ B, int64_t ldb, int K, int N, int Kp,
-                               float* __restrict__ hiT, float* __restrict__ loT) {
+// A: [M, K] (lda) -> hi/lo [M, Kp].  One thread per 4 consecutive k (float4 load when aligned).
+template <int SPLIT>
+__global__ void prep_a_kernel(const float* __restrict__ A, int64_t lda, int M, int K, int Kp, void* hi, void* lo) {
+  const int kq = Kp / 4;
+  const int64_t total = static_cast<int64_t>(M) * kq;
+  const bool vec = ((reinterpret_cast<uint64_t>(A) & 15) == 0) && ((lda & 3) == 0);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t m = i / kq;
+    const int k = static_cast<int>(i - m * kq) * 4;
+    float v[4];
+    if (vec && k + 4 <= K) {
+      const float4 x = *reinterpret_cast<const float4*>(A + m * lda + k);
+      v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = (k + j < K) ? A[m * lda + k + j] : 0.0f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_store<SPLIT>(v[j], hi, lo, m * Kp + k + j);
+  }
+}
+
+// B: [K, N] (ldb) -> hiT/loT [N, Kp] through a 32x33 shared tile (coalesced both ways).
+template <int SPLIT>
+__global__ void prep_bt_kernel(const float* __restrict__ B, int64_t ldb, int K, int N, int Kp, void* hiT, void* loT) {
   __shared__ float tile[32][33];
   const int n0 = blockIdx.x * 32;
   const int k0 = blockIdx.y * 32;
-  // read B[k0+ty.., n0+tx] coalesced along n
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int k = k0 + r, n = n0 + threadIdx.x;
     tile[r][threadIdx.x] = (k < K && n < N) ? B[static_cast<int64_t>(k) * ldb + n] : 0.0f;
   }
   __syncthreads();
-  // write out[n0+r, k0+tx] coalesced along k
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int n = n0 + r, k = k0 + threadIdx.x;
-    if (n < N && k < Kp) {
-      const float b = tile[threadIdx.x][r];
-      const float h = rn_tf32(b);
-      const int64_t o = static_cast<int64_t>(n) * Kp + k;
-      hiT[o] = h;
-      if (loT != nullptr) loT[o] = rn_tf32(b - h);
-    }
+    if (n < N && k < Kp) split_store<SPLIT>(tile[threadIdx.x][r], hiT, loT, static_cast<int64_t>(n) * Kp + k);
   }
 }
 
@@ -417,22 +475,43 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D K-major fp32 tensor [rows, Kp], box = [box_rows, BK], 128B swizzle.
-static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t Kp, int box_rows) {
+// 2-D K-major tensor [rows, Kp] of `elem`-byte elements, box = [box_rows, 128 B of K], 128B swizzle.
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t Kp, int box_rows, int elem) {
   EncodeTiledFn enc = get_encode_fn();
   SP_REQUIRE(enc != nullptr, SP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(Kp), static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(Kp) * 4};
-  cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(box_rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(Kp) * elem};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / elem), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(map, elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SP_REQUIRE(r == CUDA_SUCCESS, SP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
   return SP_OK;
 }
 
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+struct Mode {
+  int kind;      // kernel KIND
+  int elem;      // operand element bytes
+  int bk;        // elements per k-block
+  int copies;    // prepared copies per operand
+  int terms;
+  int split;     // prep SPLIT
+  int chunk_kb;  // default promotion interval
+};
+
+static bool mode_of(int precision, Mode* m) {
+  switch (precision) {
+    case SP_GEMM_TF32X1: *m = Mode{0, 4, 32, 1, 1, 0, 8}; return true;
+    case SP_GEMM_TF32X3: *m = Mode{0, 4, 32, 2, 3, 1, 8}; return true;
+    case SP_GEMM_BF16X3: *m = Mode{1, 2, 64, 2, 3, 2, 8}; return true;
+    default: return false;
+  }
+}
+
+static int g_chunk_override = 0;
 
 }  // namespace gemm
 }  // namespace sp
@@ -440,12 +519,20 @@ static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * 
 using namespace sp;
 using namespace sp::gemm;
 
+// Test / tuning hook: k-blocks accumulated inside TMEM before promotion (0 = per-mode default).
+extern "C" int sp_gemm_set_chunk_kblocks(int kb) {
+  SP_REQUIRE(kb >= 0 && kb <= (1 << 20), SP_ERR_INVALID, "bad chunk size %d", kb);
+  g_chunk_override = kb;
+  return SP_OK;
+}
+
 extern "C" int64_t sp_gemm_f32_workspace_bytes(int64_t M, int64_t N, int n_seg, const int64_t* seg_k, int precision) {
-  const int copies = (precision == SP_GEMM_TF32X3) ? 2 : 1;
+  Mode md;
+  if (!mode_of(precision, &md)) return -1;
   int64_t total = 0;
   for (int s = 0; s < n_seg; ++s) {
-    const int64_t Kp = round_up(seg_k[s], BK);
-    total += round_up((M + N) * Kp * 4 * copies, 1024);
+    const int64_t Kp = round_up(seg_k[s], md.bk);
+    total += round_up((M + N) * Kp * md.elem * md.copies, 1024);
   }
   return total + 1024;
 }
@@ -454,16 +541,13 @@ extern "C" int sp_gemm_f32_segments(int n_seg, const sp_gemm_segment* segs, floa
                                      int64_t N, int accumulate, int precision, void* workspace,
                                      int64_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  SP_REQUIRE(precision == SP_GEMM_TF32X1 || precision == SP_GEMM_TF32X3, SP_ERR_INVALID,
-             "sp_gemm_f32_segments: unknown precision %d", precision);
-  const int copies = (precision == SP_GEMM_TF32X3) ? 2 : 1;
-  const int terms_per_seg = (precision == SP_GEMM_TF32X3) ? 3 : 1;
-  SP_REQUIRE(n_seg >= 1 && n_seg * terms_per_seg <= MAX_TERMS, SP_ERR_INVALID,
-             "sp_gemm_f32_segments: %d segments x %d terms exceeds %d", n_seg, terms_per_seg, MAX_TERMS);
+  Mode md;
+  SP_REQUIRE(mode_of(precision, &md), SP_ERR_INVALID, "sp_gemm_f32_segments: unknown precision %d", precision);
+  SP_REQUIRE(n_seg >= 1 && n_seg <= 8, SP_ERR_INVALID, "sp_gemm_f32_segments: %d segments (limit 8 per launch)", n_seg);
   SP_REQUIRE(M > 0 && N > 0 && M < (1ll << 31) && N < (1ll << 31), SP_ERR_INVALID, "bad M/N %lld %lld",
              (long long)M, (long long)N);
   {
-    int64_t ks[MAX_TERMS];
+    int64_t ks[8];
     for (int s = 0; s < n_seg; ++s) ks[s] = segs[s].K;
     const int64_t need = sp_gemm_f32_workspace_bytes(M, N, n_seg, ks, precision);
     SP_REQUIRE(workspace != nullptr && workspace_bytes >= need, SP_ERR_INVALID,
@@ -473,59 +557,72 @@ extern "C" int sp_gemm_f32_segments(int n_seg, const sp_gemm_segment* segs, floa
 
   static bool attr_set = false;
   if (!attr_set) {
-    SP_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SP_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SP_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
 
   Params p;
   memset(&p, 0, sizeof(p));
   uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uint64_t>(workspace) + 1023) & ~1023ull);
-  int n_maps = 0, n_terms = 0;
+  int n_maps = 0;
   for (int s = 0; s < n_seg; ++s) {
     const sp_gemm_segment& g = segs[s];
     SP_REQUIRE(g.K > 0, SP_ERR_INVALID, "segment %d has K=%lld", s, (long long)g.K);
-    const int64_t Kp = round_up(g.K, BK);
-    float* a_hi = reinterpret_cast<float*>(ws);
-    float* b_hi = a_hi + M * Kp;
-    float* a_lo = nullptr;
-    float* b_lo = nullptr;
-    if (copies == 2) {
-      a_lo = b_hi + N * Kp;
-      b_lo = a_lo + M * Kp;
+    const int64_t Kp = round_up(g.K, md.bk);
+    uint8_t* a_hi = ws;
+    uint8_t* b_hi = a_hi + M * Kp * md.elem;
+    uint8_t* a_lo = nullptr;
+    uint8_t* b_lo = nullptr;
+    if (md.copies == 2) {
+      a_lo = b_hi + N * Kp * md.elem;
+      b_lo = a_lo + M * Kp * md.elem;
     }
-    ws += round_up((M + N) * Kp * 4 * copies, 1024);
+    ws += round_up((M + N) * Kp * md.elem * md.copies, 1024);
 
     {
-      const int64_t total = M * Kp;
+      const int64_t total = M * (Kp / 4);
       const int threads = 256;
-      const int blocks = static_cast<int>(std::min<int64_t>((total + threads - 1) / threads, 148 * 16));
-      prep_a_kernel<<<blocks, threads, 0, stream>>>(g.A, g.lda, static_cast<int>(M), static_cast<int>(g.K),
-                                                    static_cast<int>(Kp), a_hi, a_lo);
-      dim3 grid(static_cast<unsigned>((N + 31) / 32), static_cast<unsigned>(Kp / 32));
+      const int blocks = static_cast<int>(std::min<int64_t>((total + threads - 1) / threads, num_sms() * 32));
+      dim3 grid(static_cast<unsigned>((N + 31) / 32), static_cast<unsigned>((Kp + 31) / 32));
       dim3 block(32, 8);
-      prep_bt_kernel<<<grid, block, 0, stream>>>(g.B, g.ldb, static_cast<int>(g.K), static_cast<int>(N),
-                                                 static_cast<int>(Kp), b_hi, b_lo);
+      const int Mi = static_cast<int>(M), Ni = static_cast<int>(N), Ki = static_cast<int>(g.K), Kpi = static_cast<int>(Kp);
+      if (md.split == 0) {
+        prep_a_kernel<0><<<blocks, threads, 0, stream>>>(g.A, g.lda, Mi, Ki, Kpi, a_hi, a_lo);
+        prep_bt_kernel<0><<<grid, block, 0, stream>>>(g.B, g.ldb, Ki, Ni, Kpi, b_hi, b_lo);
+      } else if (md.split == 1) {
+        prep_a_kernel<1><<<blocks, threads, 0, stream>>>(g.A, g.lda, Mi, Ki, Kpi, a_hi, a_lo);
+        prep_bt_kernel<1><<<grid, block, 0, stream>>>(g.B, g.ldb, Ki, Ni, Kpi, b_hi, b_lo);
+      } else {
+        prep_a_kernel<2><<<blocks, threads, 0, stream>>>(g.A, g.lda, Mi, Ki, Kpi, a_hi, a_lo);
+        prep_bt_kernel<2><<<grid, block, 0, stream>>>(g.B, g.ldb, Ki, Ni, Kpi, b_hi, b_lo);
+      }
     }
 
+    Segment& sg = p.segs[s];
+    sg.k_blocks = static_cast<int>(Kp / md.bk);
+    sg.n_terms = md.terms;
     const int ia_hi = n_maps++, ib_hi = n_maps++;
-    int rc = make_map(&p.maps[ia_hi], a_hi, M, Kp, BM);
+    int rc = make_map(&p.maps[ia_hi], a_hi, M, Kp, BM, md.elem);
     if (rc) return rc;
-    rc = make_map(&p.maps[ib_hi], b_hi, N, Kp, BN);
+    rc = make_map(&p.maps[ib_hi], b_hi, N, Kp, BN, md.elem);
     if (rc) return rc;
-    const int kb = static_cast<int>(Kp / BK);
-    if (copies == 2) {
+    if (md.copies == 2) {
       const int ia_lo = n_maps++, ib_lo = n_maps++;
-      rc = make_map(&p.maps[ia_lo], a_lo, M, Kp, BM);
+      rc = make_map(&p.maps[ia_lo], a_lo, M, Kp, BM, md.elem);
       if (rc) return rc;
-      rc = make_map(&p.maps[ib_lo], b_lo, N, Kp, BN);
+      rc = make_map(&p.maps[ib_lo], b_lo, N, Kp, BN, md.elem);
       if (rc) return rc;
       // small cross terms first, dominant term last
-      p.terms[n_terms++] = Term{ia_lo, ib_hi, kb, 0};
-      p.terms[n_terms++] = Term{ia_hi, ib_lo, kb, 0};
+      sg.a_map[0] = ia_lo; sg.b_map[0] = ib_hi;
+      sg.a_map[1] = ia_hi; sg.b_map[1] = ib_lo;
+      sg.a_map[2] = ia_hi; sg.b_map[2] = ib_hi;
+    } else {
+      sg.a_map[0] = ia_hi; sg.b_map[0] = ib_hi;
     }
-    p.terms[n_terms++] = Term{ia_hi, ib_hi, kb, 0};
   }
-  p.n_terms = n_terms;
+  p.n_segs = n_seg;
+  p.chunk_kb = g_chunk_override > 0 ? g_chunk_override : md.chunk_kb;
   p.M = static_cast<int>(M);
   p.N = static_cast<int>(N);
   p.m_blocks = static_cast<int>((M + BM - 1) / BM);
@@ -536,7 +633,8 @@ extern "C" int sp_gemm_f32_segments(int n_seg, const sp_gemm_segment* segs, floa
 
   const int tiles = p.m_blocks * p.n_blocks;
   const int grid = std::min(tiles, num_sms());
-  gemm_tf32_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);
+  if (md.kind == 0) gemm_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);
+  else gemm_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);
   SP_CUDA_CHECK(cudaGetLastError());
   return SP_OK;
 }

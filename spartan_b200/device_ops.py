@@ -13,7 +13,7 @@ from . import blob_ctx
 from ._lib import (lib, check, sp_program, sp_operand, sp_gemm_segment, i64arr, SpartanError, OP,
                    SP_F32, SP_F64, SP_I32, SP_I64, SP_U8, SP_BOOL, SP_RED_SUM, SP_RED_MIN, SP_RED_MAX, SP_RED_PROD,
                    SP_RED_ALL, SP_RED_ANY, SP_FILL_CONST, SP_FILL_IOTA, SP_FILL_RAND, SP_FILL_RANDN,
-                   SP_GEMM_TF32X1, SP_GEMM_TF32X3, SP_GEMM_SIMT, SP_GEMM_MAX_TERMS)
+                   SP_GEMM_TF32X1, SP_GEMM_TF32X3, SP_GEMM_SIMT, SP_GEMM_BF16X3, SP_GEMM_MAX_SEGMENTS)
 
 _SP_DTYPE = {torch.float32: SP_F32, torch.float64: SP_F64, torch.int32: SP_I32, torch.int64: SP_I64,
              torch.uint8: SP_U8, torch.bool: SP_BOOL}
@@ -268,7 +268,7 @@ def copy_rect(dst, src):
 
 
 # ------------------------------------------------------------------------------------ gemm
-_PRECISIONS = {'tf32x1': SP_GEMM_TF32X1, 'tf32x3': SP_GEMM_TF32X3, 'simt': SP_GEMM_SIMT}
+_PRECISIONS = {'tf32x1': SP_GEMM_TF32X1, 'tf32x3': SP_GEMM_TF32X3, 'bf16x3': SP_GEMM_BF16X3, 'simt': SP_GEMM_SIMT}
 
 
 def gemm(segments, C, accumulate=False, precision='tf32x3'):
@@ -295,8 +295,7 @@ def gemm(segments, C, accumulate=False, precision='tf32x3'):
       _count_launch()
       acc = True
     return
-  per = 3 if prec == SP_GEMM_TF32X3 else 1
-  max_seg = SP_GEMM_MAX_TERMS // per
+  max_seg = SP_GEMM_MAX_SEGMENTS
   acc = accumulate
   for lo in range(0, len(segments), max_seg):
     chunk = segments[lo:lo + max_seg]

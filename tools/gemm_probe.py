@@ -21,6 +21,7 @@ lib.sp_gemm_f32_workspace_bytes.argtypes = [ctypes.c_int64, ctypes.c_int64, ctyp
 lib.sp_gemm_f32.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
                             ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
                             ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+lib.sp_gemm_set_chunk_kblocks.argtypes = [ctypes.c_int]
 lib.sp_gemm_simt.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
                              ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
                              ctypes.c_int, ctypes.c_void_p]
@@ -53,6 +54,9 @@ def errs(C, ref):
             "mean_signed_rel": ((C.double() - ref) / ref.abs().clamp_min(1e-30)).mean().item()}
 
 
+MODES = [(0, "tf32x1"), (1, "tf32x3"), (3, "bf16x3")]
+
+
 def check_shapes():
     torch.manual_seed(0)
     for (M, N, K) in [(128, 256, 32), (128, 256, 64), (256, 512, 128), (100, 77, 50), (132, 77, 100),
@@ -60,7 +64,7 @@ def check_shapes():
         A = torch.rand(M, K, device="cuda")
         B = torch.rand(K, N, device="cuda")
         ref = A.double() @ B.double()
-        for prec, name in [(0, "tf32x1"), (1, "tf32x3")]:
+        for prec, name in MODES:
             C = torch.full((M, N), float("nan"), device="cuda")
             gemm(A, B, C, prec)
             torch.cuda.synchronize()
@@ -83,80 +87,65 @@ def check_shapes():
 
 
 def accum_precision():
-    # operands exactly representable in tf32 -> products exact in fp32; any error is accumulation.
+    # operands exactly representable in tf32 AND bf16-split -> products exact; any error is accumulation.
     torch.manual_seed(1)
     M, N = 256, 512
-    for K in [1024, 4096, 32768]:
-        A = (torch.randint(0, 1024, (M, K), device="cuda").float() / 1024.0)
-        B = (torch.randint(0, 1024, (K, N), device="cuda").float() / 1024.0)
-        ref = A.double() @ B.double()
-        C = torch.empty(M, N, device="cuda")
-        gemm(A, B, C, 0)
-        torch.cuda.synchronize()
-        e = errs(C, ref)
-        # same thing in 8 K-chunks accumulated through C (fp32 RN adds in the epilogue)
-        C2 = torch.zeros(M, N, device="cuda")
-        ch = K // 8
-        for i in range(8):
-            gemm(A[:, i * ch:(i + 1) * ch], B[i * ch:(i + 1) * ch, :], C2, 0, accumulate=1)
-        torch.cuda.synchronize()
-        e2 = errs(C2, ref)
-        t = errs((A @ B), ref)  # torch fp32 (cuBLAS) for comparison
-        print(json.dumps({"exp": "accum", "K": K, "single": e, "chunk8": e2, "torch_fp32": t}), flush=True)
-    # zero-mean data, all modes
     for K in [4096, 32768]:
-        A = torch.randn(M, K, device="cuda")
-        B = torch.randn(K, N, device="cuda")
+        A = (torch.randint(0, 256, (M, K), device="cuda").float() / 256.0)
+        B = (torch.randint(0, 256, (K, N), device="cuda").float() / 256.0)
         ref = A.double() @ B.double()
-        out = {"exp": "randn", "K": K}
-        for prec, name in [(0, "tf32x1"), (1, "tf32x3")]:
-            C = torch.empty(M, N, device="cuda")
-            gemm(A, B, C, prec)
-            torch.cuda.synchronize()
-            out[name] = errs(C, ref)
-        out["torch_fp32"] = errs(A @ B, ref)
+        out = {"exp": "accum", "K": K}
+        for prec, name in MODES:
+            for chunk in [0, 1, 2, 4, 8, 16, 1 << 20]:
+                lib.sp_gemm_set_chunk_kblocks(chunk)
+                C = torch.empty(M, N, device="cuda")
+                gemm(A, B, C, prec)
+                torch.cuda.synchronize()
+                e = errs(C, ref)
+                out["%s_chunk%d" % (name, chunk)] = [e["max_rel_to_max"], e["mean_signed_rel"]]
+        lib.sp_gemm_set_chunk_kblocks(0)
+        out["torch_fp32"] = errs(A @ B, ref)["max_rel_to_max"]
         print(json.dumps(out), flush=True)
+    for K in [4096, 32768]:
+        for gen, gname in [(torch.randn, "randn"), (torch.rand, "rand")]:
+            A = gen(M, K, device="cuda")
+            B = gen(K, N, device="cuda")
+            ref = A.double() @ B.double()
+            out = {"exp": gname, "K": K}
+            for prec, name in MODES:
+                C = torch.empty(M, N, device="cuda")
+                gemm(A, B, C, prec)
+                torch.cuda.synchronize()
+                e = errs(C, ref)
+                out[name] = [e["max_rel_to_max"], e["max_elem_rel"], e["mean_signed_rel"]]
+            e = errs(A @ B, ref)
+            out["torch_fp32"] = [e["max_rel_to_max"], e["max_elem_rel"], e["mean_signed_rel"]]
+            print(json.dumps(out), flush=True)
 
 
 def timing():
-    for n in [4096, 8192, 16384, 32768]:
+    for n in [8192, 16384, 32768]:
         A = torch.rand(n, n, device="cuda")
         B = torch.rand(n, n, device="cuda")
         C = torch.empty(n, n, device="cuda")
-        for prec, name in [(0, "tf32x1"), (1, "tf32x3")]:
-            if n == 32768 and prec == 1:
-                reps = 1
-            else:
-                reps = 3
-            gemm(A, B, C, prec)
-            torch.cuda.synchronize()
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record()
-            for _ in range(reps):
+        for prec, name in MODES:
+            for chunk in ([0, 8, 1 << 20] if n == 16384 else [0]):
+                lib.sp_gemm_set_chunk_kblocks(chunk)
+                reps = 1 if n == 32768 else 3
                 gemm(A, B, C, prec)
-            ev1.record()
-            torch.cuda.synchronize()
-            ms = ev0.elapsed_time(ev1) / reps
-            print(json.dumps({"exp": "time", "n": n, "prec": name, "ms": ms,
-                              "tflops": 2.0 * n ** 3 / ms / 1e9}), flush=True)
-        # spot-check a block against fp64
-        ref = A[:256].double() @ B[:, :256].double()
-        gemm(A, B, C, 0)
-        torch.cuda.synchronize()
-        print(json.dumps({"exp": "time_check", "n": n, **errs(C[:256, :256], ref)}), flush=True)
-        if n <= 16384:
-            torch.backends.cuda.matmul.allow_tf32 = True
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.matmul(A, B, out=C)
-            torch.cuda.synchronize()
-            ev0.record()
-            for _ in range(3):
-                torch.matmul(A, B, out=C)
-            ev1.record()
-            torch.cuda.synchronize()
-            ms = ev0.elapsed_time(ev1) / 3
-            print(json.dumps({"exp": "cublas_tf32", "n": n, "ms": ms, "tflops": 2.0 * n ** 3 / ms / 1e9}), flush=True)
-            torch.backends.cuda.matmul.allow_tf32 = False
+                torch.cuda.synchronize()
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+                for _ in range(reps):
+                    gemm(A, B, C, prec)
+                ev1.record()
+                torch.cuda.synchronize()
+                ms = ev0.elapsed_time(ev1) / reps
+                ref = A[:128].double() @ B[:, :256].double()
+                err = errs(C[:128, :256], ref)["max_rel_to_max"]
+                print(json.dumps({"exp": "time", "n": n, "prec": name, "chunk": chunk, "ms": ms,
+                                  "tflops": 2.0 * n ** 3 / ms / 1e9, "max_rel_to_max": err}), flush=True)
+        lib.sp_gemm_set_chunk_kblocks(0)
         del A, B, C
         torch.cuda.empty_cache()
 

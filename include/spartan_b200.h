@@ -97,6 +97,10 @@ typedef enum {
 } sp_fill_kind;
 int sp_fill(void* dst, int dtype, int64_t n, int kind, double a, double b, uint64_t seed, int64_t offset,
             void* stream);
+/* Strided 2-D form: element (r, c) of a tile takes stream index offset + r * index_row_pitch + c, so a tile that is a
+ * sub-rectangle of its array regenerates exactly its share of the array-wide sequence (dst_row_stride in elements). */
+int sp_fill2d(void* dst, int dtype, int64_t rows, int64_t cols, int64_t dst_row_stride, int kind, double a, double b,
+              uint64_t seed, int64_t offset, int64_t index_row_pitch, void* stream);
 
 /* ------------------------------------------------------------------------
  * Fused element-wise map (local.py:115-127 FnCallExpr.evaluate over the tree

@@ -67,6 +67,7 @@ _SIGS = {
   'sp_good_tile_shape': (_int, [_int, _i64p, _i64, _i64p]),
   'sp_compute_extents': (_i64, [_int, _i64p, _i64p, _i64, _i64p, _i64p, _i64p]),
   'sp_fill': (_int, [_vp, _int, _i64, _int, _dbl, _dbl, _u64, _i64, _vp]),
+  'sp_fill2d': (_int, [_vp, _int, _i64, _i64, _i64, _int, _dbl, _dbl, _u64, _i64, _i64, _vp]),
   'sp_map': (_int, [ctypes.POINTER(sp_program), _int, ctypes.POINTER(sp_operand), ctypes.POINTER(sp_operand), _i64p, _vp]),
   'sp_map_reduce_scratch_bytes': (_i64, [_i64p, _int]),
   'sp_map_reduce': (_int, [ctypes.POINTER(sp_program), _int, ctypes.POINTER(sp_operand), ctypes.POINTER(sp_operand),

@@ -11,6 +11,7 @@
 // All three are HBM-bound: algorithmic bytes = sum of operand bytes read once + output written once.
 #pragma once
 #include "interp.cuh"
+#include "stream_kernels.cuh"
 #include <algorithm>
 #include <string.h>
 
@@ -214,6 +215,69 @@ static DevOperand make_operand(const sp_operand& o, int vec_axis, const int64_t 
   return d;
 }
 
+
+// ------------------------------------------------------------------------------------ streaming fast path
+constexpr int kStreamReduceRows = 128;   // rows per reduction work unit (one partial row per unit)
+
+template <typename T>
+static int64_t stream_reduce_chunks(const int64_t dims[3]) {
+  return (dims[1] + kStreamReduceRows - 1) / kStreamReduceRows;
+}
+
+// Fills `plan` and returns true when the launch can use stream_kernel.
+template <typename T, int NI>
+static bool plan_stream(const DevOperands<NI>& ops, const int64_t dims[3], bool has_out, int rc_rows, stream::Plan* plan) {
+  const int64_t row_bytes = dims[2] * static_cast<int64_t>(sizeof(T));
+  if (row_bytes < stream::kSegBytes || (row_bytes % 16) != 0) return false;
+  if (has_out && ops.out.kind != kVec) return false;
+  int n_stream = 0;
+  for (int i = 0; i < NI; ++i) plan->stream_slot[i] = -1;
+  for (int i = 0; i < ops.n_in; ++i) {
+    if (ops.in[i].kind == kVec) plan->stream_slot[i] = n_stream++;
+  }
+  if (n_stream == 0 || n_stream > 8) return false;
+  int rb = 16;
+  while (rb * n_stream > 32) rb >>= 1;
+  plan->d0 = dims[0]; plan->d1 = dims[1]; plan->d2 = dims[2];
+  plan->n_panels = static_cast<int>((row_bytes + stream::kSegBytes - 1) / stream::kSegBytes);
+  plan->rb = rb;
+  plan->rc = rc_rows > 0 ? rc_rows : rb * 4;
+  plan->n_chunks = (dims[1] + plan->rc - 1) / plan->rc;
+  plan->n_units = dims[0] * plan->n_chunks * plan->n_panels;
+  plan->n_stream = n_stream;
+  return plan->n_units > 0;
+}
+
+template <typename T, int NI, int MODE>
+static int launch_stream(const DevProgram<T>& dp, const DevOperands<NI>& ops, const stream::Plan& plan, int red_op,
+                         T* scratch, cudaStream_t stream_) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SP_CUDA_CHECK(cudaFuncSetAttribute(stream::stream_kernel<T, NI, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       stream::kSmemBytes));
+    attr_set = true;
+  }
+  const int grid = static_cast<int>(std::min<int64_t>(plan.n_units, num_sms()));
+  stream::stream_kernel<T, NI, MODE><<<grid, stream::kThreads, stream::kSmemBytes, stream_>>>(dp, ops, plan, red_op, scratch);
+  SP_CUDA_CHECK(cudaGetLastError());
+  return SP_OK;
+}
+
+// A flat contiguous map (d0 = d1 = 1) is re-viewed as rows of `kFlatRow` elements so the ring carries full stages.
+template <typename T, int NI>
+static bool reshape_flat(DevOperands<NI>& ops, int64_t dims[3]) {
+  constexpr int64_t kFlatRow = 16384 / sizeof(T);
+  if (dims[0] * dims[1] != 1 || dims[2] < kFlatRow * 8 || dims[2] % kFlatRow != 0) return false;
+  for (int i = 0; i < ops.n_in; ++i)
+    if (ops.in[i].stride[2] != 0 && ops.in[i].stride[2] != 1) return false;
+  if (ops.out.stride[2] != 1) return false;
+  dims[1] = dims[2] / kFlatRow;
+  dims[2] = kFlatRow;
+  for (int i = 0; i < ops.n_in; ++i) ops.in[i].stride[1] = ops.in[i].stride[2] * kFlatRow;
+  ops.out.stride[1] = kFlatRow;
+  return true;
+}
+
 template <typename T, int V, int NI>
 static int launch_map_v(const sp_program* prog, int n_in, const sp_operand* in, const sp_operand* out,
                         const int64_t dims[3], cudaStream_t stream) {
@@ -225,10 +289,18 @@ static int launch_map_v(const sp_program* prog, int n_in, const sp_operand* in, 
   for (int i = 0; i < n_in; ++i) ops.in[i] = make_operand<T, V>(in[i], 2, dims);
   ops.out = make_operand<T, V>(*out, 2, dims);
   if (ops.out.kind == kSplat) ops.out.kind = kGeneric;
+  if (dims[0] * dims[1] * dims[2] == 0) return SP_OK;
+  if (V == 32 / sizeof(T)) {     // the streaming kernel uses the 32-byte-per-lane vector width
+    int64_t sd[3] = {dims[0], dims[1], dims[2]};
+    DevOperands<NI> sops = ops;
+    reshape_flat<T, NI>(sops, sd);
+    stream::Plan plan;
+    if (plan_stream<T, NI>(sops, sd, true, 0, &plan))
+      return launch_stream<T, NI, 0>(dp, sops, plan, 0, nullptr, stream);
+  }
   Dims3 d{dims[0], dims[1], dims[2]};
   const int64_t d2v = (dims[2] + V - 1) / V;
   const int64_t total = dims[0] * dims[1] * d2v;
-  if (total == 0) return SP_OK;
   const int64_t want = (total + 255) / 256;
   const int blocks = static_cast<int>(std::min<int64_t>(want, static_cast<int64_t>(num_sms()) * 16));
   map_kernel<T, V, NI><<<blocks, 256, 0, stream>>>(dp, ops, d, d2v, total);
@@ -282,7 +354,9 @@ static ReducePlan plan_reduce(const int64_t dims[3]) {
 template <typename T, int V>
 static int64_t reduce_scratch_elems(const int64_t dims[3]) {
   const ReducePlan p = plan_reduce<V>(dims);
-  return static_cast<int64_t>(p.splits) * dims[0] * dims[2];
+  const int64_t simple = static_cast<int64_t>(p.splits) * dims[0] * dims[2];
+  const int64_t streamed = stream_reduce_chunks<T>(dims) * dims[0] * dims[2];
+  return std::max(simple, streamed);
 }
 
 template <typename T, int V, int NI>
@@ -307,6 +381,21 @@ static int launch_reduce_v(const sp_program* prog, int n_in, const sp_operand* i
   const int64_t n_out = dims[0] * dims[2];
   if (n_out == 0) return SP_OK;
   T* sc = static_cast<T*>(scratch);
+  if (!p.row && V == 32 / sizeof(T)) {
+    stream::Plan plan;
+    if (plan_stream<T, NI>(ops, dims, false, kStreamReduceRows, &plan)) {
+      const int64_t sneed = plan.n_chunks * dims[0] * dims[2] * static_cast<int64_t>(sizeof(T));
+      SP_REQUIRE(scratch_bytes >= sneed, SP_ERR_INVALID, "sp_map_reduce: scratch %lld B < required %lld B",
+                 (long long)scratch_bytes, (long long)sneed);
+      int rc = launch_stream<T, NI, 1>(dp, ops, plan, red_op, sc, stream);
+      if (rc) return rc;
+      const int fb = static_cast<int>(std::min<int64_t>((n_out + 255) / 256, 4096));
+      finalize_kernel<T><<<fb, 256, 0, stream>>>(sc, n_out, static_cast<int>(plan.n_chunks), n_out, 1, o, dims[2], red_op,
+                                                 accumulate);
+      SP_CUDA_CHECK(cudaGetLastError());
+      return SP_OK;
+    }
+  }
   if (p.row) {
     SP_REQUIRE(p.blocks_x < (1ll << 31), SP_ERR_INVALID, "sp_map_reduce: too many rows (%lld)", (long long)dims[0]);
     const int64_t nvec = (dims[1] + V - 1) / V;

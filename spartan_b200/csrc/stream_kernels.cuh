@@ -1,0 +1,245 @@
+// Streaming fast path of the fused map and map+reduce(axis = leading) kernels.
+//
+// The simple kernels in map_reduce_impl.cuh keep only ~32 KB of loads in flight per SM (the
+// interpreter's register footprint caps occupancy), which is less than half of what HBM3e needs.
+// Here the loads are decoupled from the interpreter: one producer warp issues 1 KiB
+// cp.async.bulk copies (TMA engine, SASS UBLKCP) into a 4 x 32 KiB shared-memory ring guarded by
+// mbarriers, eight consumer warps read the ring with conflict-free 16-byte LDS, run the bytecode
+// and either store the result (map) or fold it into per-thread accumulators (reduce).  Up to
+// 128 KiB per SM is in flight regardless of register pressure.  One CTA per SM, persistent over
+// work units.
+//
+// Work unit = RC consecutive rows x one 1 KiB-wide column panel.  A row segment of the panel is
+// 1024 B = 32 lanes x 2 x 16 B: lane L owns bytes [16L, 16L+16) and [512+16L, 512+16L+16), i.e.
+// V = 32 / sizeof(T) elements in two contiguous halves (both LDS.128 and STG.128 stay conflict-free
+// and coalesced).  Reduction partials are written per unit and combined in fixed order by
+// finalize_kernel (deterministic).
+//
+// Eligibility (checked on the host): every array operand is either streamable (compute dtype, unit
+// stride, 16-byte aligned rows) or constant along the vector axis; row length >= 1 KiB.
+#pragma once
+#include "interp.cuh"
+
+namespace sp {
+namespace stream {
+
+constexpr int kStages = 4;
+constexpr int kStageBytes = 32 * 1024;
+constexpr int kSegBytes = 1024;               // one row segment of a panel
+constexpr int kConsumerWarps = 8;
+constexpr int kThreads = 32 * (1 + kConsumerWarps);
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 8 * 1024 /*reduce scratch*/ + 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "SWAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni SWAIT_DONE;\n\t"
+      "bra.uni SWAIT_LOOP;\n\t"
+      "SWAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kConsumerWarps) : "memory"); }
+
+struct Plan {
+  int64_t d0, d1, d2;        // iteration space; vectors run along d2; reduce folds d1
+  int n_panels;              // ceil(d2 * sizeof(T) / 1024)
+  int rc;                    // rows per unit
+  int64_t n_chunks;          // ceil(d1 / rc)      (reduce: per d0)    map: rows = d0*d1 flattened is NOT assumed
+  int64_t n_units;           // d0 * n_chunks * n_panels
+  int n_stream;              // streamed operands
+  int rb;                    // rows per stage  (n_stream * rb <= 32)
+  int stream_slot[SP_MAX_OPERANDS];   // operand -> slot in the stage, or -1 (loaded directly)
+};
+
+// Loads the two halves of a non-streamed operand (constant or generic along the vector axis).
+template <typename T, int V>
+__device__ __forceinline__ void load_direct_split(const DevOperand& o, int64_t base, int64_t col_a, int64_t col_b,
+                                                  int valid_a, int valid_b, T (&r)[V]) {
+  constexpr int H = V / 2;
+  if (o.stride[2] == 0) {
+    const T x = load_as<T>(o.ptr, o.dtype, base);
+#pragma unroll
+    for (int v = 0; v < V; ++v) r[v] = x;
+    return;
+  }
+#pragma unroll
+  for (int v = 0; v < H; ++v) {
+    r[v] = (v < valid_a) ? load_as<T>(o.ptr, o.dtype, base + (col_a + v) * o.stride[2]) : T(0);
+    r[H + v] = (v < valid_b) ? load_as<T>(o.ptr, o.dtype, base + (col_b + v) * o.stride[2]) : T(0);
+  }
+}
+
+// MODE 0: map (store), MODE 1: reduce over d1 (partials to scratch[chunk][d0][d2])
+template <typename T, int NI, int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+stream_kernel(const DevProgram<T> prog, const DevOperands<NI> ops, const Plan plan, const int red_op,
+              T* __restrict__ scratch) {
+  constexpr int V = 32 / sizeof(T);
+  constexpr int H = V / 2;
+  constexpr int EPS = kSegBytes / sizeof(T);      // elements per row segment (panel width)
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + kStages * kStageBytes + 8 * 1024;
+  T* red_smem = reinterpret_cast<T*>(smem_gen + kStages * kStageBytes);   // [8 warps][32 lanes][V] <= 8 KiB
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), kConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int rb = plan.rb;
+  const int stages_per_unit = (plan.rc + rb - 1) / rb;
+
+  if (warp == 0) {
+    // ===================== producer: one bulk copy per (operand, row) per lane =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    const int slot = lane / rb;            // which streamed operand this lane copies
+    const int r_in = lane - slot * rb;     // which row of the stage
+    int my_op = -1;
+    for (int i = 0; i < NI; ++i)
+      if (i < ops.n_in && plan.stream_slot[i] == slot) my_op = i;
+    for (int64_t u = blockIdx.x; u < plan.n_units; u += gridDim.x) {
+      const int panel = static_cast<int>(u % plan.n_panels);
+      const int64_t t = u / plan.n_panels;
+      const int64_t chunk = t % plan.n_chunks;
+      const int64_t i0 = t / plan.n_chunks;
+      const int64_t col0 = static_cast<int64_t>(panel) * EPS;
+      const int64_t cols = min(static_cast<int64_t>(EPS), plan.d2 - col0);
+      const uint32_t seg_bytes = static_cast<uint32_t>(cols * sizeof(T));
+      const int64_t row_end = min(plan.d1, (chunk + 1) * plan.rc);
+      for (int st = 0; st < stages_per_unit; ++st) {
+        const int64_t row0 = chunk * plan.rc + static_cast<int64_t>(st) * rb;
+        if (row0 >= row_end) break;
+        const int rows = static_cast<int>(min(static_cast<int64_t>(rb), row_end - row0));
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        if (lane == 0) mbar_expect_tx(full_bar(stage), seg_bytes * rows * plan.n_stream);
+        __syncwarp();
+        if (my_op >= 0 && slot < plan.n_stream && r_in < rows) {
+          const DevOperand& o = ops.in[my_op];
+          const T* src = static_cast<const T*>(o.ptr) + i0 * o.stride[0] + (row0 + r_in) * o.stride[1] + col0;
+          const uint32_t dst = smem_base + stage * kStageBytes + (slot * rb + r_in) * kSegBytes;
+          bulk_g2s(dst, src, seg_bytes, full_bar(stage));
+        }
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== consumers =====================
+    const int cw = warp - 1;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t u = blockIdx.x; u < plan.n_units; u += gridDim.x) {
+      const int panel = static_cast<int>(u % plan.n_panels);
+      const int64_t t = u / plan.n_panels;
+      const int64_t chunk = t % plan.n_chunks;
+      const int64_t i0 = t / plan.n_chunks;
+      const int64_t col0 = static_cast<int64_t>(panel) * EPS;
+      const int64_t cols = min(static_cast<int64_t>(EPS), plan.d2 - col0);
+      const int64_t col_a = col0 + lane * H;                 // first half of this lane's vector
+      const int64_t col_b = col0 + EPS / 2 + lane * H;       // second half
+      const int valid_a = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(H), col0 + cols - col_a)));
+      const int valid_b = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(H), col0 + cols - col_b)));
+      const int64_t row_end = min(plan.d1, (chunk + 1) * plan.rc);
+      T acc[V];
+      if (MODE == 1) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[v] = red_identity<T>(red_op);
+      }
+      for (int st = 0; st < stages_per_unit; ++st) {
+        const int64_t row0 = chunk * plan.rc + static_cast<int64_t>(st) * rb;
+        if (row0 >= row_end) break;
+        const int rows = static_cast<int>(min(static_cast<int64_t>(rb), row_end - row0));
+        mbar_wait(full_bar(stage), phase);
+        const uint8_t* sbase = smem_gen + stage * kStageBytes;
+        for (int r = cw; r < rows; r += kConsumerWarps) {
+          T in[NI][V];
+#pragma unroll
+          for (int i = 0; i < NI; ++i) {
+            if (i < ops.n_in) {
+              const int sl = plan.stream_slot[i];
+              if (sl >= 0) {
+                const uint8_t* seg = sbase + (sl * rb + r) * kSegBytes;
+                const int4 a = *reinterpret_cast<const int4*>(seg + 16 * lane);
+                const int4 b = *reinterpret_cast<const int4*>(seg + 512 + 16 * lane);
+                T tmp[V];
+                *reinterpret_cast<int4*>(&tmp[0]) = a;
+                *reinterpret_cast<int4*>(&tmp[H]) = b;
+#pragma unroll
+                for (int v = 0; v < V; ++v) in[i][v] = tmp[v];
+              } else {
+                const DevOperand& o = ops.in[i];
+                load_direct_split<T, V>(o, i0 * o.stride[0] + (row0 + r) * o.stride[1], col_a, col_b, valid_a, valid_b,
+                                        in[i]);
+              }
+            }
+          }
+          T res[V];
+          run_program<T, V, NI>(prog, in, res);
+          if (MODE == 0) {
+            const DevOperand& o = ops.out;
+            T* dst = static_cast<T*>(const_cast<void*>(o.ptr)) + i0 * o.stride[0] + (row0 + r) * o.stride[1];
+            if (valid_a == H) *reinterpret_cast<int4*>(dst + col_a) = *reinterpret_cast<const int4*>(&res[0]);
+            else
+              for (int v = 0; v < valid_a; ++v) dst[col_a + v] = res[v];
+            if (valid_b == H) *reinterpret_cast<int4*>(dst + col_b) = *reinterpret_cast<const int4*>(&res[H]);
+            else
+              for (int v = 0; v < valid_b; ++v) dst[col_b + v] = res[H + v];
+          } else {
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[v] = red_apply<T>(red_op, acc[v], res[v]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar(stage));
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      if (MODE == 1) {
+        // fold the 8 consumer warps (fixed order), warp 0 of the consumers writes the unit's partial
+#pragma unroll
+        for (int v = 0; v < V; ++v) red_smem[(cw * 32 + lane) * V + v] = acc[v];
+        consumer_bar();
+        if (cw == 0) {
+#pragma unroll
+          for (int w = 1; w < kConsumerWarps; ++w)
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[v] = red_apply<T>(red_op, acc[v], red_smem[(w * 32 + lane) * V + v]);
+          T* dst = scratch + (chunk * plan.d0 + i0) * plan.d2;
+          for (int v = 0; v < valid_a; ++v) dst[col_a + v] = acc[v];
+          for (int v = 0; v < valid_b; ++v) dst[col_b + v] = acc[H + v];
+        }
+        consumer_bar();
+      }
+    }
+  }
+}
+
+}  // namespace stream
+}  // namespace sp

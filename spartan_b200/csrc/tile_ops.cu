@@ -110,6 +110,55 @@ __global__ void fill_rand_kernel(T* __restrict__ dst, int64_t n, uint64_t seed, 
   }
 }
 
+// 2-D (strided) fill: element (r, c) takes stream index offset + r * pitch + c, so a tile that is a
+// sub-rectangle of its array reproduces exactly the values of the array-wide stream.
+template <typename T>
+__global__ void fill2d_kernel(T* __restrict__ dst, int64_t rows, int64_t cols, int64_t dst_stride, int kind, double a,
+                              double b, uint64_t seed, int64_t offset, int64_t pitch, int integral) {
+  constexpr int PER = (sizeof(T) == 4) ? 4 : 2;
+  const int64_t total = rows * cols;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cols, c = i - r * cols;
+    const int64_t idx = offset + r * pitch + c;
+    T v;
+    if (kind == SP_FILL_CONST) {
+      v = static_cast<T>(a);
+    } else if (kind == SP_FILL_IOTA) {
+      v = integral ? static_cast<T>(static_cast<long long>(a) + static_cast<long long>(b) * idx)
+                   : static_cast<T>(a + b * static_cast<double>(idx));
+    } else {
+      uint32_t rr[4];
+      Philox::block(static_cast<uint64_t>(idx / PER), seed, rr);
+      const int lane = static_cast<int>(idx % PER);
+      if constexpr (sizeof(T) == 4) {
+        if (kind == SP_FILL_RANDN) {
+          const int p = lane >> 1;
+          const float u1 = 1.0f - u01_f32(rr[2 * p]);
+          const float u2 = u01_f32(rr[2 * p + 1]);
+          const float rad = sqrtf(-2.0f * logf(u1));
+          float sn, cs;
+          sincospif(2.0f * u2, &sn, &cs);
+          v = static_cast<T>((lane & 1) ? rad * sn : rad * cs);
+        } else {
+          v = static_cast<T>(u01_f32(rr[lane]));
+        }
+      } else {
+        const double x = u01_f64(rr[0], rr[1]), y = u01_f64(rr[2], rr[3]);
+        if (kind == SP_FILL_RANDN) {
+          const double rad = sqrt(-2.0 * log(1.0 - x));
+          double sn, cs;
+          sincospi(2.0 * y, &sn, &cs);
+          v = static_cast<T>(lane ? rad * sn : rad * cs);
+        } else {
+          v = static_cast<T>(lane ? y : x);
+        }
+      }
+    }
+    dst[r * dst_stride + c] = v;
+  }
+}
+
 template <typename T>
 __device__ __forceinline__ T combine_op(int op, T a, T b) {
   switch (op) {
@@ -198,6 +247,32 @@ extern "C" int sp_fill(void* dst, int dtype, int64_t n, int kind, double a, doub
       set_error("sp_fill: bad dtype %d", dtype);
       return SP_ERR_INVALID;
   }
+}
+
+extern "C" int sp_fill2d(void* dst, int dtype, int64_t rows, int64_t cols, int64_t dst_row_stride, int kind, double a,
+                         double b, uint64_t seed, int64_t offset, int64_t index_row_pitch, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SP_REQUIRE(rows >= 0 && cols >= 0 && offset >= 0, SP_ERR_INVALID, "sp_fill2d: bad shape / offset");
+  if (rows * cols == 0) return SP_OK;
+  SP_REQUIRE(dst != nullptr, SP_ERR_INVALID, "sp_fill2d: null destination");
+  const bool rnd = (kind == SP_FILL_RAND || kind == SP_FILL_RANDN);
+  SP_REQUIRE(kind >= SP_FILL_CONST && kind <= SP_FILL_RANDN, SP_ERR_INVALID, "sp_fill2d: bad kind %d", kind);
+  const int g = grid_for(rows * cols);
+#define SP_FILL2D(T, INTEGRAL)                                                                                      \
+  fill2d_kernel<T><<<g, 256, 0, stream>>>(static_cast<T*>(dst), rows, cols, dst_row_stride, kind, a, b, seed, offset, \
+                                          index_row_pitch, INTEGRAL)
+  switch (dtype) {
+    case SP_F32: SP_FILL2D(float, 0); break;
+    case SP_F64: SP_FILL2D(double, 0); break;
+    case SP_I32: SP_REQUIRE(!rnd, SP_ERR_UNSUPPORTED, "random fill needs a float dtype"); SP_FILL2D(int32_t, 1); break;
+    case SP_I64: SP_REQUIRE(!rnd, SP_ERR_UNSUPPORTED, "random fill needs a float dtype"); SP_FILL2D(long long, 1); break;
+    default:
+      set_error("sp_fill2d: unsupported dtype %d", dtype);
+      return SP_ERR_UNSUPPORTED;
+  }
+#undef SP_FILL2D
+  SP_CUDA_CHECK(cudaGetLastError());
+  return SP_OK;
 }
 
 extern "C" int sp_combine(void* dst, const void* src, int dtype, int64_t n, int reduce_op, void* stream_) {

@@ -244,6 +244,15 @@ def fill(t, kind, a=0.0, b=0.0, seed=0, offset=0):
   _count_launch()
 
 
+def fill2d(t, kind, a=0.0, b=0.0, seed=0, offset=0, pitch=0):
+  """Fill of a 2-D (possibly row-strided) device view; element (r, c) uses stream index offset + r*pitch + c."""
+  _require_cuda(t)
+  assert t.dim() == 2 and (t.stride(1) == 1 or t.shape[1] == 1)
+  check(lib.sp_fill2d(t.data_ptr(), sp_dtype_of(t), t.shape[0], t.shape[1], t.stride(0), int(kind), float(a), float(b),
+                      int(seed) & (2 ** 64 - 1), int(offset), int(pitch), _stream()), 'sp_fill2d')
+  _count_launch()
+
+
 def fill_view(t, kind, a=0.0, b=0.0):
   """Constant fill of a possibly strided view (through the map kernel)."""
   if t.is_contiguous():

@@ -90,17 +90,24 @@ def _arange_mapper(tile, ex, start, stop, step, dtype=None):
   raise SpartanError('host evaluation is not available')
 
 
-def _arange_kernel(out, ex, start, stop, step, dtype=None):
-  """Extent-aware iota: element = start + step * (global C-order index).  A tile that spans the full
-  trailing dimensions is one contiguous run; otherwise one run per row of the tile."""
+def _fill_by_global_index(out, ex, kind, a=0.0, b=0.0, seed=0):
+  """Fills tile ``out`` (extent ``ex``) so that element = f(global C-order index): one launch when the tile
+  spans the full trailing dimensions, one 2-D launch per leading index otherwise."""
   shape = ex.array_shape
-  if out.is_contiguous() and (out.dim() <= 1 or all(ex.shape[d] == shape[d] for d in range(1, len(shape)))):
-    device_ops.fill(out.reshape(-1), SP_FILL_IOTA, start, step, offset=extent.ravelled_pos(ex.ul, shape))
+  nd = len(shape)
+  if out.is_contiguous() and (nd <= 1 or all(ex.shape[d] == shape[d] for d in range(1, nd))):
+    device_ops.fill(out.reshape(-1), kind, a, b, seed=seed, offset=extent.ravelled_pos(ex.ul, shape))
     return
-  lead = out.shape[:-1]
-  for idx in np.ndindex(*lead):
-    pos = tuple(u + i for u, i in zip(ex.ul[:-1], idx)) + (ex.ul[-1],)
-    device_ops.fill(out[idx], SP_FILL_IOTA, start, step, offset=extent.ravelled_pos(pos, shape))
+  pitch = int(np.prod(shape[nd - 1:]))          # elements per step of the second-to-last index
+  for idx in np.ndindex(*out.shape[:-2]):
+    pos = tuple(u + i for u, i in zip(ex.ul[:-2], idx)) + tuple(ex.ul[-2:])
+    view = out[idx] if idx else out
+    device_ops.fill2d(view, kind, a, b, seed=seed, offset=extent.ravelled_pos(pos, shape), pitch=pitch)
+
+
+def _arange_kernel(out, ex, start, stop, step, dtype=None):
+  """Extent-aware iota: element = start + step * (global C-order index)."""
+  _fill_by_global_index(out, ex, SP_FILL_IOTA, start, step)
 
 
 _arange_mapper.device_location_kernel = _arange_kernel
@@ -138,13 +145,7 @@ def arange(start=None, stop=None, step=1, dtype=np.float64, tile_hint=None):
 def _rand_kernel_for(kind):
   def kernel(out, ex, seed=0, dtype=None):
     # one Philox stream per array; a tile regenerates exactly its elements (global C-order offsets)
-    shape = ex.array_shape
-    if out.is_contiguous() and (out.dim() <= 1 or all(ex.shape[d] == shape[d] for d in range(1, len(shape)))):
-      device_ops.fill(out.reshape(-1), kind, seed=seed, offset=extent.ravelled_pos(ex.ul, shape))
-      return
-    for idx in np.ndindex(*out.shape[:-1]):
-      pos = tuple(u + i for u, i in zip(ex.ul[:-1], idx)) + (ex.ul[-1],)
-      device_ops.fill(out[idx], kind, seed=seed, offset=extent.ravelled_pos(pos, shape))
+    _fill_by_global_index(out, ex, kind, seed=seed)
   return kernel
 
 

@@ -311,3 +311,46 @@ def test_dot_linearity_large():
   got = sp.dot(A, I, tile_hint=(1024, 1024)).glom()
   a = A.glom()
   np.testing.assert_allclose(got, a, rtol=1e-6, atol=1e-7)
+
+
+# ------------------------------------------------------------------ streaming (smem-ring) fast path
+@pytest.mark.parametrize('shape', [(300, 512), (64, 4100), (1, 1 << 20), (1000, 1024), (7, 3, 2048)])
+@pytest.mark.parametrize('dtype', [np.float32, np.float64, np.int64])
+def test_streaming_map_bit_exact(shape, dtype):
+  """Rows >= 1 KiB take the TMA-bulk/shared-memory-ring kernels; results must stay bit-exact."""
+  rng = np.random.RandomState(11)
+  if np.dtype(dtype).kind == 'f':
+    x = rng.randn(*shape).astype(dtype); y = rng.randn(*shape).astype(dtype); z = rng.randn(*shape).astype(dtype)
+  else:
+    x = rng.randint(-99, 99, size=shape).astype(dtype); y = rng.randint(1, 99, size=shape).astype(dtype)
+    z = rng.randint(-9, 9, size=shape).astype(dtype)
+  row = x[..., :1, :] * 0 + np.arange(shape[-1]).astype(dtype)            # broadcast along rows
+  col = (x[..., :, :1] * 0 + 3).astype(dtype)                            # broadcast along columns
+  builds = (lambda m, X, Y, Z, R, C: X * 2 + Y,
+            lambda m, X, Y, Z, R, C: (X - Y) * Z + X,                    # three streamed operands
+            lambda m, X, Y, Z, R, C: X * R + C,
+            lambda m, X, Y, Z, R, C: m.maximum(X, Y) - m.abs(Z))
+  for build in builds:
+    got = build(sp, *[sp.from_numpy(a) for a in (x, y, z, row, col)]).optimized().glom()
+    ref = build(oexpr, *[oexpr.from_numpy(a) for a in (x, y, z, row, col)]).optimized().glom()
+    assert got.dtype == ref.dtype
+    Assert.all_eq(got, ref)
+
+
+@pytest.mark.parametrize('shape', [(1000, 1024), (129, 4100), (4096, 512), (5, 300, 256)])
+def test_streaming_reduce_axis0(shape):
+  rng = np.random.RandomState(12)
+  xi = rng.randint(-50, 50, size=shape).astype(np.int64); yi = rng.randint(-50, 50, size=shape).astype(np.int64)
+  xf = rng.rand(*shape).astype(np.float32); yf = rng.rand(*shape).astype(np.float32)
+  xd = rng.rand(*shape)
+  axis = len(shape) - 2
+  for name in ('sum', 'min', 'max'):
+    got = getattr(sp, name)(sp.from_numpy(xi) * 3 - sp.from_numpy(yi), axis).optimized().glom()
+    ref = getattr(oexpr, name)(oexpr.from_numpy(xi) * 3 - oexpr.from_numpy(yi), axis).optimized().glom()
+    Assert.all_eq(got, ref)
+  got = (sp.from_numpy(xf) * 2 + sp.from_numpy(yf)).sum(axis=axis).optimized().glom()
+  ref = (xf.astype(np.float64) * 2 + yf).sum(axis=axis)
+  np.testing.assert_allclose(got, ref, rtol=1e-5)
+  got = sp.from_numpy(xd).sum(axis=axis).glom()
+  np.testing.assert_allclose(got, xd.sum(axis=axis), rtol=1e-12)
+  Assert.all_eq(sp.max(sp.from_numpy(xf), axis).glom(), xf.max(axis=axis))

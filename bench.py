@@ -40,6 +40,7 @@ def parse_args():
   ap.add_argument('--precision', default=os.environ.get('SPARTAN_DOT_PRECISION', 'bf16x3'))
   ap.add_argument('--mr-log2', type=int, default=30, help='log2(#elements) of the map+reduce workload')
   ap.add_argument('--skip-e2e', action='store_true')
+  ap.add_argument('--skip-dot', action='store_true', help='tuning aid: only the map+reduce workload')
   ap.add_argument('--skip-mapreduce', action='store_true')
   ap.add_argument('--skip-cpu', action='store_true')
   return ap.parse_args()
@@ -185,6 +186,9 @@ def run_b200(args):
     return float(t.item())
 
   # ---------------- inputs, generated on the device (Philox) and kept resident in HBM
+  if args.skip_dot:
+    n = args.n = 2048
+    args.skip_e2e = True
   A = sp.rand(n, n, seed=0, dtype=np.float32, tile_hint=(tile, tile)).evaluate()
   B = sp.rand(n, n, seed=1, dtype=np.float32, tile_hint=(tile, tile)).evaluate()
   holder = {}

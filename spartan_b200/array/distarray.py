@@ -209,6 +209,36 @@ class DistArrayImpl(DistArray):
       slices.append(slice(lo, hi))
     return self.slab[tuple(slices)]
 
+  def local_blocks(self):
+    """This rank's share as few rectangular regions as possible: the product of the contiguous runs of
+    its slab intervals (each block is addressable as ONE zero-copy slab view), or its tiles one by one
+    when there is no slab.  One kernel launch per block instead of one per tile."""
+    me = self.ctx.worker_id
+    if self.slab is None or not self.shape:
+      return [ex for ex, tid in self.tiles.items() if tid.worker == me]
+    import itertools
+    runs = []
+    for ivs in self.slab_axes:
+      axis_runs = []
+      for a, b in ivs:
+        if axis_runs and axis_runs[-1][1] == a:
+          axis_runs[-1] = (axis_runs[-1][0], b)
+        else:
+          axis_runs.append((a, b))
+      runs.append(axis_runs)
+    return [extent.create([a for a, _ in blk], [b for _, b in blk], self.shape) for blk in itertools.product(*runs)]
+
+  def same_layout(self, other):
+    """True when ``other`` has exactly this array's tiles on the same owners (then every block of one is a
+    zero-copy block of the other)."""
+    if not isinstance(other, DistArrayImpl) or other.shape != self.shape or len(other.tiles) != len(self.tiles):
+      return False
+    for ex, tid in self.tiles.items():
+      o = other.tiles.get(ex)
+      if o is None or o.worker != tid.worker:
+        return False
+    return other.slab is not None and self.slab is not None
+
   # ------------------------------------------------------------------ fetch / update / glom
   def fetch(self, region, dst=None):
     """Device tensor holding ``region`` (distarray.py:294-367).

@@ -4,7 +4,7 @@
 // interpreter's register footprint caps occupancy), which is less than half of what HBM3e needs.
 // Here the loads are decoupled from the interpreter: one producer warp issues 1 KiB
 // cp.async.bulk copies (TMA engine, SASS UBLKCP) into a 4 x 32 KiB shared-memory ring guarded by
-// mbarriers, eight consumer warps read the ring with conflict-free 16-byte LDS, run the bytecode
+// mbarriers, sixteen consumer warps read the ring with conflict-free 16-byte LDS, run the bytecode
 // and either store the result (map) or fold it into per-thread accumulators (reduce).  Up to
 // 128 KiB per SM is in flight regardless of register pressure.  One CTA per SM, persistent over
 // work units.
@@ -26,9 +26,10 @@ namespace stream {
 constexpr int kStages = 4;
 constexpr int kStageBytes = 32 * 1024;
 constexpr int kSegBytes = 1024;               // one row segment of a panel
-constexpr int kConsumerWarps = 8;
+constexpr int kConsumerWarps = 16;
 constexpr int kThreads = 32 * (1 + kConsumerWarps);
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 8 * 1024 /*reduce scratch*/ + 128;
+constexpr int kRedBytes = kConsumerWarps * 32 * 32;   // [warps][32 lanes][V * sizeof(T) = 32 B]
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + kRedBytes + 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -98,8 +99,8 @@ stream_kernel(const DevProgram<T> prog, const DevOperands<NI> ops, const Plan pl
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + kStages * kStageBytes + 8 * 1024;
-  T* red_smem = reinterpret_cast<T*>(smem_gen + kStages * kStageBytes);   // [8 warps][32 lanes][V] <= 8 KiB
+  const uint32_t bar_base = smem_base + kStages * kStageBytes + kRedBytes;
+  T* red_smem = reinterpret_cast<T*>(smem_gen + kStages * kStageBytes);   // [warps][32 lanes][V]
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
 

@@ -47,6 +47,21 @@ def get_local_values(ex, children, child_to_var, used_vars, owner):
   return values
 
 
+def blockwise_ok(largest, children):
+  """A map / reduce can run one launch per contiguous block of the rank's slab (instead of one per tile)
+  when every operand is either tiled and placed exactly like the largest one or is a value every rank
+  holds: no operand region then needs stitching or communication."""
+  if largest.slab is None:
+    return False
+  for child in children:
+    base = child.base if isinstance(child, Broadcast) else child
+    if base is largest or isinstance(base, LocalWrapper):
+      continue
+    if isinstance(child, Broadcast) or not largest.same_layout(base):
+      return False
+  return True
+
+
 def tile_mapper(ex, children, child_to_var, op, compiled, output):
   """Runs for each tile of a map (map.py:48-88): one fused kernel launch on the owning GPU."""
   ctx = blob_ctx.get()
@@ -106,6 +121,16 @@ class MapExpr(Expr):
 
     compiled = program.compile_tree(self.op, bind_operands(children, child_to_var))
     output = distarray.create_like(largest, compiled.out_dtype)
+    if blockwise_ok(largest, children) and output.slab is not None:
+      # one fused launch per contiguous block of this rank's share (the tiling is the reference's unit of
+      # RPC dispatch, not a unit of work the GPU needs)
+      for block in largest.local_blocks():
+        values = get_local_values(block, children, child_to_var, compiled.used_vars, ctx.worker_id)
+        device_ops.run_map(compiled.program, [values[v] for v in compiled.used_vars], output.slab_view(block))
+      for tid in output.tiles.values():
+        if ctx.is_local(tid):
+          ctx.tile(tid).valid = True
+      return output
     largest.foreach_tile(tile_mapper, kw={'children': children, 'child_to_var': child_to_var, 'op': self.op,
                                           'compiled': compiled, 'output': output})
     return output

@@ -20,7 +20,7 @@ from .._lib import SpartanError, SP_FILL_CONST, SP_F64, SP_I64
 from . import program
 from .base import Expr, ListExpr, as_array
 from .local import make_var, LocalReduceExpr, LocalInput
-from .map import bind_operands, get_local_values
+from .map import bind_operands, get_local_values, blockwise_ok
 
 
 class _DtypeOf(object):
@@ -40,11 +40,13 @@ def _value_tree(op):
   return vals[0]
 
 
-def _reduce_mapper(ex, children, child_to_var, op, axis, output, compiled=None, red_op=None, acc=None):
-  """Local reduction of one tile into the rank's accumulator (reduce.py:21-70)."""
+def _reduce_mapper(ex, children, child_to_var, op, axis, output, compiled=None, red_op=None, acc=None, owner=None):
+  """Local reduction of one tile (or one contiguous block of tiles) into the rank's accumulator
+  (reduce.py:21-70)."""
   ctx = blob_ctx.get()
   largest = children[0]
-  owner = largest.tiles[ex].worker
+  if owner is None:
+    owner = largest.tiles[ex].worker
   values = get_local_values(ex, children, child_to_var, compiled.used_vars, owner)
   if owner == ctx.worker_id:
     dst_extent = extent.index_for_reduction(ex, axis)
@@ -109,9 +111,14 @@ class ReduceExpr(Expr):
     shape = tuple(extent.shape_for_reduction(largest.shape, axis))
     acc = ctx.empty(shape, dtype)
     acc.fill_(tile.identity_of(red_op, dtype))     # exact for int64 extremes (a double immediate is not)
-    largest.foreach_tile(_reduce_mapper, kw={'children': children, 'child_to_var': child_to_var, 'op': op,
-                                             'axis': axis, 'output': None, 'compiled': compiled, 'red_op': red_op,
-                                             'acc': acc})
+    if blockwise_ok(largest, children):
+      for block in largest.local_blocks():       # one fused launch per contiguous block of this rank's slab
+        _reduce_mapper(block, children, child_to_var, op, axis, None, compiled=compiled, red_op=red_op, acc=acc,
+                       owner=ctx.worker_id)
+    else:
+      largest.foreach_tile(_reduce_mapper, kw={'children': children, 'child_to_var': child_to_var, 'op': op,
+                                               'axis': axis, 'output': None, 'compiled': compiled, 'red_op': red_op,
+                                               'acc': acc})
     # cross-tile combiner across GPUs: one all-reduce instead of N update RPCs into the owner tile
     comm.allreduce(acc, combiner)
 

@@ -310,7 +310,8 @@ def test_dot_linearity_large():
   I = sp.from_numpy(np.eye(n, dtype=np.float32), tile_hint=(1024, 1024))
   got = sp.dot(A, I, tile_hint=(1024, 1024)).glom()
   a = A.glom()
-  np.testing.assert_allclose(got, a, rtol=1e-6, atol=1e-7)
+  # default mode bf16x3 represents each operand with 16 mantissa bits: |err| <= 2^-17 per element here
+  np.testing.assert_allclose(got, a, rtol=1e-5, atol=1e-7)
 
 
 # ------------------------------------------------------------------ streaming (smem-ring) fast path

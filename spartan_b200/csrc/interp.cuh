@@ -130,102 +130,206 @@ template <typename T> __device__ __forceinline__ T cast_i32(T a) { return static
 template <typename T> __device__ __forceinline__ T cast_u8(T a) { return static_cast<T>(static_cast<uint8_t>(static_cast<long long>(a))); }
 
 // ---------------------------------------------------------------------------- the interpreter
+// The host lowers the postfix program once more before launch (lower_program below): because the
+// stack depth at every instruction is known statically, each instruction becomes ONE dense code
+//   code = dense_op * 4 + slot        (slot = index of the stack register the op writes)
+// so the kernel dispatches with a single jump table (BRX) and keeps no stack pointer at all.
+enum DenseOp : int {
+  D_IN = 0, D_CONST,
+  D_ADD, D_SUB, D_MUL, D_DIV, D_MOD, D_POW, D_MAX, D_MIN, D_EQ, D_NE, D_LT, D_LE, D_GT, D_GE, D_AND, D_OR, D_XOR,
+  D_FMOD, D_FLOORDIV,
+  D_NEG, D_ABS, D_SQRT, D_EXP, D_LOG, D_SQUARE, D_RECIP, D_NOT, D_NONZERO, D_ISZERO, D_CAST_F32, D_CAST_I64,
+  D_CAST_I32, D_CAST_BOOL, D_CAST_U8,
+  D_COUNT
+};
+
+inline int dense_of(int sp_op) {
+  switch (sp_op) {
+    case SP_OP_IN: return D_IN;          case SP_OP_CONST: return D_CONST;
+    case SP_OP_ADD: return D_ADD;        case SP_OP_SUB: return D_SUB;       case SP_OP_MUL: return D_MUL;
+    case SP_OP_DIV: return D_DIV;        case SP_OP_MOD: return D_MOD;       case SP_OP_POW: return D_POW;
+    case SP_OP_MAX: return D_MAX;        case SP_OP_MIN: return D_MIN;       case SP_OP_EQ: return D_EQ;
+    case SP_OP_NE: return D_NE;          case SP_OP_LT: return D_LT;         case SP_OP_LE: return D_LE;
+    case SP_OP_GT: return D_GT;          case SP_OP_GE: return D_GE;         case SP_OP_AND: return D_AND;
+    case SP_OP_OR: return D_OR;          case SP_OP_XOR: return D_XOR;       case SP_OP_FMOD: return D_FMOD;
+    case SP_OP_FLOORDIV: return D_FLOORDIV;
+    case SP_OP_NEG: return D_NEG;        case SP_OP_ABS: return D_ABS;       case SP_OP_SQRT: return D_SQRT;
+    case SP_OP_EXP: return D_EXP;        case SP_OP_LOG: return D_LOG;       case SP_OP_SQUARE: return D_SQUARE;
+    case SP_OP_RECIP: return D_RECIP;    case SP_OP_NOT: return D_NOT;       case SP_OP_NONZERO: return D_NONZERO;
+    case SP_OP_ISZERO: return D_ISZERO;  case SP_OP_CAST_F32: return D_CAST_F32;
+    case SP_OP_CAST_I64: return D_CAST_I64; case SP_OP_CAST_I32: return D_CAST_I32;
+    case SP_OP_CAST_BOOL: return D_CAST_BOOL; case SP_OP_CAST_U8: return D_CAST_U8;
+    default: return -1;
+  }
+}
+
+// Host: validated postfix program -> dense codes.  Returns false if the program is malformed.
+template <typename T>
+inline bool lower_program(const sp_program* prog, DevProgram<T>* out) {
+  out->n_ops = prog->n_ops;
+  int sp = 0;
+  for (int i = 0; i < prog->n_ops; ++i) {
+    const int d = dense_of(prog->op[i]);
+    if (d < 0) return false;
+    int slot;
+    if (d <= D_CONST) { slot = sp; sp += 1; }
+    else if (d <= D_FLOORDIV) { slot = sp - 2; sp -= 1; }
+    else { slot = sp - 1; }
+    if (slot < 0 || slot >= kMaxDepth) return false;
+    out->op[i] = static_cast<uint8_t>(d * 4 + slot);
+    out->arg[i] = prog->arg[i];
+  }
+  return sp == 1;
+}
+
 #define SP_B(x) ((x) ? T(1) : T(0))
 
-#define SP_BIN_CASE(OPC, D, EXPR)                                    \
-  case (OPC) * 8 + (D): {                                            \
+#define SP_BIN_CASE(DOP, S, EXPR)                                    \
+  case (DOP) * 4 + (S): {                                            \
     _Pragma("unroll") for (int v = 0; v < V; ++v) {                  \
-      const T a = s[(D) - 2][v];                                     \
-      const T b = s[(D) - 1][v];                                     \
-      s[(D) - 2][v] = (EXPR);                                        \
-    }                                                                \
-    sp = (D) - 1;                                                    \
-    break;                                                           \
-  }
-#define SP_BIN(OPC, EXPR) SP_BIN_CASE(OPC, 2, EXPR) SP_BIN_CASE(OPC, 3, EXPR) SP_BIN_CASE(OPC, 4, EXPR)
-
-#define SP_UN_CASE(OPC, D, EXPR)                                     \
-  case (OPC) * 8 + (D): {                                            \
-    _Pragma("unroll") for (int v = 0; v < V; ++v) {                  \
-      const T a = s[(D) - 1][v];                                     \
-      s[(D) - 1][v] = (EXPR);                                        \
+      const T a = s[(S)][v];                                         \
+      const T b = s[(S) + 1][v];                                     \
+      s[(S)][v] = (EXPR);                                            \
     }                                                                \
     break;                                                           \
   }
-#define SP_UN(OPC, EXPR) SP_UN_CASE(OPC, 1, EXPR) SP_UN_CASE(OPC, 2, EXPR) SP_UN_CASE(OPC, 3, EXPR) SP_UN_CASE(OPC, 4, EXPR)
+#define SP_BIN(DOP, EXPR) SP_BIN_CASE(DOP, 0, EXPR) SP_BIN_CASE(DOP, 1, EXPR) SP_BIN_CASE(DOP, 2, EXPR)
 
-#define SP_PUSH_CONST_CASE(D)                                        \
-  case SP_OP_CONST * 8 + (D): {                                      \
+#define SP_UN_CASE(DOP, S, EXPR)                                     \
+  case (DOP) * 4 + (S): {                                            \
+    _Pragma("unroll") for (int v = 0; v < V; ++v) {                  \
+      const T a = s[(S)][v];                                         \
+      s[(S)][v] = (EXPR);                                            \
+    }                                                                \
+    break;                                                           \
+  }
+#define SP_UN(DOP, EXPR) SP_UN_CASE(DOP, 0, EXPR) SP_UN_CASE(DOP, 1, EXPR) SP_UN_CASE(DOP, 2, EXPR) SP_UN_CASE(DOP, 3, EXPR)
+
+#define SP_PUSH_CONST_CASE(S)                                        \
+  case D_CONST * 4 + (S): {                                          \
     const T c = prog.consts[arg];                                    \
-    _Pragma("unroll") for (int v = 0; v < V; ++v) s[(D)][v] = c;     \
-    sp = (D) + 1;                                                    \
+    _Pragma("unroll") for (int v = 0; v < V; ++v) s[(S)][v] = c;     \
     break;                                                           \
   }
 
-// push operand: the operand index is data, the destination depth is static
-#define SP_PUSH_IN_CASE(D)                                           \
-  case SP_OP_IN * 8 + (D): {                                         \
+// push operand: the operand index is data, the destination register is static
+#define SP_PUSH_IN_CASE(S)                                           \
+  case D_IN * 4 + (S): {                                             \
     _Pragma("unroll") for (int i = 0; i < NI; ++i) {                 \
       if (i == arg) {                                                \
-        _Pragma("unroll") for (int v = 0; v < V; ++v) s[(D)][v] = in[i][v]; \
+        _Pragma("unroll") for (int v = 0; v < V; ++v) s[(S)][v] = in[i][v]; \
       }                                                              \
     }                                                                \
-    sp = (D) + 1;                                                    \
     break;                                                           \
   }
 
-// Evaluates `prog` on the V-wide inputs; result left in out[V].
+// One instruction.  With compile-time-constant `code` / `arg` (static programs below) the switch folds
+// away and only the selected case's V arithmetic instructions remain.
+template <typename T, int V, int NI>
+__device__ __forceinline__ void exec_op(const int code, const int arg, const DevProgram<T>& prog, const T (&in)[NI][V],
+                                        T (&s)[kMaxDepth][V]) {
+  switch (code) {
+      SP_PUSH_IN_CASE(0) SP_PUSH_IN_CASE(1) SP_PUSH_IN_CASE(2) SP_PUSH_IN_CASE(3)
+      SP_PUSH_CONST_CASE(0) SP_PUSH_CONST_CASE(1) SP_PUSH_CONST_CASE(2) SP_PUSH_CONST_CASE(3)
+      SP_BIN(D_ADD, a + b)
+      SP_BIN(D_SUB, a - b)
+      SP_BIN(D_MUL, a * b)
+      SP_BIN(D_DIV, op_div(a, b))
+      SP_BIN(D_MOD, op_mod(a, b))
+      SP_BIN(D_POW, op_pow(a, b))
+      SP_BIN(D_MAX, op_max(a, b))
+      SP_BIN(D_MIN, op_min(a, b))
+      SP_BIN(D_EQ, SP_B(a == b))
+      SP_BIN(D_NE, SP_B(a != b))
+      SP_BIN(D_LT, SP_B(a < b))
+      SP_BIN(D_LE, SP_B(a <= b))
+      SP_BIN(D_GT, SP_B(a > b))
+      SP_BIN(D_GE, SP_B(a >= b))
+      SP_BIN(D_AND, SP_B((a != T(0)) && (b != T(0))))
+      SP_BIN(D_OR, SP_B((a != T(0)) || (b != T(0))))
+      SP_BIN(D_XOR, SP_B((a != T(0)) != (b != T(0))))
+      SP_BIN(D_FMOD, op_fmod(a, b))
+      SP_BIN(D_FLOORDIV, op_floordiv(a, b))
+      SP_UN(D_NEG, -a)
+      SP_UN(D_ABS, op_abs(a))
+      SP_UN(D_SQRT, op_sqrt(a))
+      SP_UN(D_EXP, op_exp(a))
+      SP_UN(D_LOG, op_log(a))
+      SP_UN(D_SQUARE, a * a)
+      SP_UN(D_RECIP, op_recip(a))
+      SP_UN(D_NOT, SP_B(a == T(0)))
+      SP_UN(D_NONZERO, SP_B(a != T(0)))
+      SP_UN(D_ISZERO, SP_B(a == T(0)))
+      SP_UN(D_CAST_F32, cast_f32(a))
+      SP_UN(D_CAST_I64, cast_i64(a))
+      SP_UN(D_CAST_I32, cast_i32(a))
+      SP_UN(D_CAST_BOOL, SP_B(a != T(0)))
+      SP_UN(D_CAST_U8, cast_u8(a))
+    default: break;   // slot 3 of a binary op: unreachable for validated programs
+  }
+}
+
+// Evaluates `prog` on the V-wide inputs; result left in out[V].  General path: one jump-table dispatch per op.
 template <typename T, int V, int NI>
 __device__ __forceinline__ void run_program(const DevProgram<T>& prog, const T (&in)[NI][V], T (&out)[V]) {
   T s[kMaxDepth][V];
-  int sp = 0;
   const int n = prog.n_ops;
-  for (int pc = 0; pc < n; ++pc) {
-    const int opc = prog.op[pc];
-    const int arg = prog.arg[pc];
-    switch (opc * 8 + sp) {
-      SP_PUSH_IN_CASE(0) SP_PUSH_IN_CASE(1) SP_PUSH_IN_CASE(2) SP_PUSH_IN_CASE(3)
-      SP_PUSH_CONST_CASE(0) SP_PUSH_CONST_CASE(1) SP_PUSH_CONST_CASE(2) SP_PUSH_CONST_CASE(3)
-      SP_BIN(SP_OP_ADD, a + b)
-      SP_BIN(SP_OP_SUB, a - b)
-      SP_BIN(SP_OP_MUL, a * b)
-      SP_BIN(SP_OP_DIV, op_div(a, b))
-      SP_BIN(SP_OP_MOD, op_mod(a, b))
-      SP_BIN(SP_OP_POW, op_pow(a, b))
-      SP_BIN(SP_OP_MAX, op_max(a, b))
-      SP_BIN(SP_OP_MIN, op_min(a, b))
-      SP_BIN(SP_OP_EQ, SP_B(a == b))
-      SP_BIN(SP_OP_NE, SP_B(a != b))
-      SP_BIN(SP_OP_LT, SP_B(a < b))
-      SP_BIN(SP_OP_LE, SP_B(a <= b))
-      SP_BIN(SP_OP_GT, SP_B(a > b))
-      SP_BIN(SP_OP_GE, SP_B(a >= b))
-      SP_BIN(SP_OP_AND, SP_B((a != T(0)) && (b != T(0))))
-      SP_BIN(SP_OP_OR, SP_B((a != T(0)) || (b != T(0))))
-      SP_BIN(SP_OP_XOR, SP_B((a != T(0)) != (b != T(0))))
-      SP_BIN(SP_OP_FMOD, op_fmod(a, b))
-      SP_BIN(SP_OP_FLOORDIV, op_floordiv(a, b))
-      SP_UN(SP_OP_NEG, -a)
-      SP_UN(SP_OP_ABS, op_abs(a))
-      SP_UN(SP_OP_SQRT, op_sqrt(a))
-      SP_UN(SP_OP_EXP, op_exp(a))
-      SP_UN(SP_OP_LOG, op_log(a))
-      SP_UN(SP_OP_SQUARE, a * a)
-      SP_UN(SP_OP_RECIP, op_recip(a))
-      SP_UN(SP_OP_NOT, SP_B(a == T(0)))
-      SP_UN(SP_OP_NONZERO, SP_B(a != T(0)))
-      SP_UN(SP_OP_ISZERO, SP_B(a == T(0)))
-      SP_UN(SP_OP_CAST_F32, cast_f32(a))
-      SP_UN(SP_OP_CAST_I64, cast_i64(a))
-      SP_UN(SP_OP_CAST_I32, cast_i32(a))
-      SP_UN(SP_OP_CAST_BOOL, SP_B(a != T(0)))
-      SP_UN(SP_OP_CAST_U8, cast_u8(a))
-      default: break;   // validated on the host; unreachable
-    }
-  }
+  for (int pc = 0; pc < n; ++pc) exec_op<T, V, NI>(prog.op[pc], prog.arg[pc], prog, in, s);
 #pragma unroll
   for (int v = 0; v < V; ++v) out[v] = s[0][v];
 }
+
+// ---------------------------------------------------------------------------- static programs
+// The hottest fused shapes are also instantiated at compile time: the instruction list is a template
+// parameter pack, exec_op is inlined with constant operands, and the kernel body is straight-line code
+// (no dispatch at all).  The host matches the lowered program against this catalogue and otherwise uses
+// the interpreter above.  PK packs (dense op, stack slot, argument).
+#define SP_PK(DOP, SLOT, ARG) ((((DOP) * 4 + (SLOT)) << 8) | (ARG))
+
+struct DynamicProgram {
+  template <typename T, int V, int NI>
+  static __device__ __forceinline__ void run(const DevProgram<T>& prog, const T (&in)[NI][V], T (&out)[V]) {
+    run_program<T, V, NI>(prog, in, out);
+  }
+};
+
+template <int... PKS>
+struct StaticProgram {
+  static constexpr int kLen = sizeof...(PKS);
+  template <typename T, int V, int NI>
+  static __device__ __forceinline__ void run(const DevProgram<T>& prog, const T (&in)[NI][V], T (&out)[V]) {
+    T s[kMaxDepth][V];
+    (exec_op<T, V, NI>(PKS >> 8, PKS & 0xff, prog, in, s), ...);
+#pragma unroll
+    for (int v = 0; v < V; ++v) out[v] = s[0][v];
+  }
+  static bool matches(const uint8_t* op, const uint8_t* arg, int n) {
+    const int pk[] = {PKS...};
+    if (n != kLen) return false;
+    for (int i = 0; i < n; ++i)
+      if (((static_cast<int>(op[i]) << 8) | arg[i]) != pk[i]) return false;
+    return true;
+  }
+};
+
+template <int DOP> using BinaryOf = StaticProgram<SP_PK(D_IN, 0, 0), SP_PK(D_IN, 1, 1), SP_PK(DOP, 0, 0)>;
+template <int DOP> using ScalarOf = StaticProgram<SP_PK(D_IN, 0, 0), SP_PK(D_CONST, 1, 0), SP_PK(DOP, 0, 0)>;
+
+// catalogue of statically compiled programs (operands: in0, in1, scalar c0)
+using SProg0 = StaticProgram<SP_PK(D_IN, 0, 0)>;          // x   (copy, cast, plain reduce)
+using SProg1 = BinaryOf<D_ADD>;  using SProg2 = BinaryOf<D_SUB>;  using SProg3 = BinaryOf<D_MUL>;
+using SProg4 = BinaryOf<D_DIV>;  using SProg5 = BinaryOf<D_MAX>;  using SProg6 = BinaryOf<D_MIN>;
+using SProg7 = ScalarOf<D_ADD>;  using SProg8 = ScalarOf<D_SUB>;  using SProg9 = ScalarOf<D_MUL>;
+using SProg10 = ScalarOf<D_DIV>; using SProg11 = ScalarOf<D_MAX>; using SProg12 = ScalarOf<D_MIN>;
+// x * c + y -- the fused chain of BASELINE config 3  (x * y + z has three operands: interpreter, 8-operand variant)
+using SProg13 = StaticProgram<SP_PK(D_IN, 0, 0), SP_PK(D_CONST, 1, 0), SP_PK(D_MUL, 0, 0), SP_PK(D_IN, 1, 1),
+                              SP_PK(D_ADD, 0, 0)>;
+
+#define SP_STATIC_PROGRAMS(X)                                                                              \
+  X(0, SProg0) X(1, SProg1) X(2, SProg2) X(3, SProg3) X(4, SProg4) X(5, SProg5) X(6, SProg6) X(7, SProg7)   \
+  X(8, SProg8) X(9, SProg9) X(10, SProg10) X(11, SProg11) X(12, SProg12) X(13, SProg13)
+
+constexpr int kNumStaticPrograms = 14;
 
 // ---------------------------------------------------------------------------- operand access
 template <typename T, int V> struct VecLoad;

@@ -14,6 +14,7 @@
 #include "stream_kernels.cuh"
 #include <algorithm>
 #include <string.h>
+#include <type_traits>
 
 namespace sp {
 
@@ -185,11 +186,8 @@ template <> struct TypeTag<long long> { static constexpr int dtype = SP_I64; sta
 
 template <typename T>
 static void convert_program(const sp_program* prog, DevProgram<T>* out) {
-  out->n_ops = prog->n_ops;
-  for (int i = 0; i < SP_MAX_PROGRAM; ++i) {
-    out->op[i] = prog->op[i];
-    out->arg[i] = prog->arg[i];
-  }
+  memset(out, 0, sizeof(*out));
+  lower_program<T>(prog, out);      // the program was validated by the C-ABI entry point
   for (int i = 0; i < SP_MAX_CONSTS; ++i) {
     if (TypeTag<T>::dtype == SP_I64) out->consts[i] = static_cast<T>(prog->iconsts[i]);
     else out->consts[i] = static_cast<T>(prog->consts[i]);
@@ -248,19 +246,44 @@ static bool plan_stream(const DevOperands<NI>& ops, const int64_t dims[3], bool 
   return plan->n_units > 0;
 }
 
-template <typename T, int NI, int MODE>
-static int launch_stream(const DevProgram<T>& dp, const DevOperands<NI>& ops, const stream::Plan& plan, int red_op,
-                         T* scratch, cudaStream_t stream_) {
+template <typename T, int NI, int MODE, typename PROG>
+static int launch_stream_as(const DevProgram<T>& dp, const DevOperands<NI>& ops, const stream::Plan& plan, int red_op,
+                            T* scratch, cudaStream_t stream_) {
   static bool attr_set = false;
   if (!attr_set) {
-    SP_CUDA_CHECK(cudaFuncSetAttribute(stream::stream_kernel<T, NI, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       stream::kSmemBytes));
+    SP_CUDA_CHECK(cudaFuncSetAttribute(stream::stream_kernel<T, NI, MODE, PROG>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, stream::kSmemBytes));
     attr_set = true;
   }
   const int grid = static_cast<int>(std::min<int64_t>(plan.n_units, num_sms()));
-  stream::stream_kernel<T, NI, MODE><<<grid, stream::kThreads, stream::kSmemBytes, stream_>>>(dp, ops, plan, red_op, scratch);
+  stream::stream_kernel<T, NI, MODE, PROG><<<grid, stream::kThreads, stream::kSmemBytes, stream_>>>(dp, ops, plan, red_op,
+                                                                                                  scratch);
   SP_CUDA_CHECK(cudaGetLastError());
   return SP_OK;
+}
+
+// Index of the statically compiled program equal to `dp`, or -1.
+template <typename T>
+static int match_static(const DevProgram<T>& dp) {
+#define SP_MATCH(IDX, TYPE) if (TYPE::matches(dp.op, dp.arg, dp.n_ops)) return IDX;
+  SP_STATIC_PROGRAMS(SP_MATCH)
+#undef SP_MATCH
+  return -1;
+}
+
+template <typename T, int NI, int MODE>
+static int launch_stream(const DevProgram<T>& dp, const DevOperands<NI>& ops, const stream::Plan& plan, int red_op,
+                         T* scratch, cudaStream_t stream_) {
+  // statically compiled programs exist for the float / double two-operand kernels
+  if constexpr (NI == 2 && !std::is_same<T, long long>::value) {
+    switch (match_static<T>(dp)) {
+#define SP_LAUNCH(IDX, TYPE) case IDX: return launch_stream_as<T, NI, MODE, TYPE>(dp, ops, plan, red_op, scratch, stream_);
+      SP_STATIC_PROGRAMS(SP_LAUNCH)
+#undef SP_LAUNCH
+      default: break;
+    }
+  }
+  return launch_stream_as<T, NI, MODE, DynamicProgram>(dp, ops, plan, red_op, scratch, stream_);
 }
 
 // A flat contiguous map (d0 = d1 = 1) is re-viewed as rows of `kFlatRow` elements so the ring carries full stages.

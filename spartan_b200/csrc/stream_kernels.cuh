@@ -89,7 +89,7 @@ __device__ __forceinline__ void load_direct_split(const DevOperand& o, int64_t b
 }
 
 // MODE 0: map (store), MODE 1: reduce over d1 (partials to scratch[chunk][d0][d2])
-template <typename T, int NI, int MODE>
+template <typename T, int NI, int MODE, typename PROG>
 __global__ void __launch_bounds__(kThreads, 1)
 stream_kernel(const DevProgram<T> prog, const DevOperands<NI> ops, const Plan plan, const int red_op,
               T* __restrict__ scratch) {
@@ -203,7 +203,7 @@ stream_kernel(const DevProgram<T> prog, const DevOperands<NI> ops, const Plan pl
             }
           }
           T res[V];
-          run_program<T, V, NI>(prog, in, res);
+          PROG::template run<T, V, NI>(prog, in, res);
           if (MODE == 0) {
             const DevOperand& o = ops.out;
             T* dst = static_cast<T*>(const_cast<void*>(o.ptr)) + i0 * o.stride[0] + (row0 + r) * o.stride[1];

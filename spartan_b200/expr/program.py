@@ -230,6 +230,9 @@ def _cast_opcode(dtype):
   raise NotDeviceMappable('cannot cast to %s on the device' % dtype)
 
 
+_COMMUTATIVE = ('ADD', 'MUL', 'MAX', 'MIN', 'EQ', 'NE', 'AND', 'OR', 'XOR')
+
+
 class _Emitter(object):
   def __init__(self, compute):
     self.compute = compute
@@ -276,9 +279,11 @@ class _Emitter(object):
       return
     # evaluate deeper operands first (Sethi-Ullman order is not needed: commutativity is not assumed,
     # operands are simply evaluated left to right)
-    for a in t.args:
+    args = t.args
+    if len(args) == 2 and t.op in _COMMUTATIVE and args[0].op == 'const' and args[1].op != 'const':
+      args = [args[1], args[0]]       # canonical operand order (array first): IEEE add/mul/min/max commute exactly
+    for a in args:
       self.emit(a)
-      # weak scalar operands are cast to the op's input dtype by NumPy; constants were emitted as such
     self.ops.append((t.op, 0))
     self.depth -= (len(t.args) - 1)
     if t.dtype.kind != 'b' and _needs_cast(t.dtype, self.compute):

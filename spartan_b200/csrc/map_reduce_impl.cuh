@@ -234,10 +234,10 @@ static bool plan_stream(const DevOperands<NI>& ops, const int64_t dims[3], bool 
     if (ops.in[i].kind == kVec) plan->stream_slot[i] = n_stream++;
   }
   if (n_stream == 0 || n_stream > 8) return false;
-  int rb = 16;
-  while (rb * n_stream > 32) rb >>= 1;
+  int rb = stream::kStageBytes / stream::kPanelBytes;       // 8 rows of one operand fill a stage
+  while (rb * n_stream > stream::kStageBytes / stream::kPanelBytes) rb >>= 1;
   plan->d0 = dims[0]; plan->d1 = dims[1]; plan->d2 = dims[2];
-  plan->n_panels = static_cast<int>((row_bytes + stream::kSegBytes - 1) / stream::kSegBytes);
+  plan->n_panels = static_cast<int>((row_bytes + stream::kPanelBytes - 1) / stream::kPanelBytes);
   plan->rb = rb;
   plan->rc = rc_rows > 0 ? rc_rows : rb * 4;
   plan->n_chunks = (dims[1] + plan->rc - 1) / plan->rc;

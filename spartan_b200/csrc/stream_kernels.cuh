@@ -9,7 +9,9 @@
 // 128 KiB per SM is in flight regardless of register pressure.  One CTA per SM, persistent over
 // work units.
 //
-// Work unit = RC consecutive rows x one 1 KiB-wide column panel.  A row segment of the panel is
+// Work unit = RC consecutive rows x one 4 KiB-wide column panel; one bulk copy moves one row of a panel
+// (measured: with 1 KiB copies the ring stayed empty 58% of the time at 3.9 TB/s, profiles/).  A consumer
+// warp handles one 1 KiB segment of a panel row at a time; a segment is
 // 1024 B = 32 lanes x 2 x 16 B: lane L owns bytes [16L, 16L+16) and [512+16L, 512+16L+16), i.e.
 // V = 32 / sizeof(T) elements in two contiguous halves (both LDS.128 and STG.128 stay conflict-free
 // and coalesced).  Reduction partials are written per unit and combined in fixed order by
@@ -25,7 +27,9 @@ namespace stream {
 
 constexpr int kStages = 4;
 constexpr int kStageBytes = 32 * 1024;
-constexpr int kSegBytes = 1024;               // one row segment of a panel
+constexpr int kSegBytes = 1024;               // what one consumer warp handles per pass (32 lanes x 32 B)
+constexpr int kPanelBytes = 4096;             // one bulk copy = one row x one panel (1 KiB copies starve the TMA unit)
+constexpr int kSegsPerPanel = kPanelBytes / kSegBytes;
 constexpr int kConsumerWarps = 16;
 constexpr int kThreads = 32 * (1 + kConsumerWarps);
 constexpr int kRedBytes = kConsumerWarps * 32 * 32;   // [warps][32 lanes][V * sizeof(T) = 32 B]
@@ -61,12 +65,12 @@ __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" 
 
 struct Plan {
   int64_t d0, d1, d2;        // iteration space; vectors run along d2; reduce folds d1
-  int n_panels;              // ceil(d2 * sizeof(T) / 1024)
+  int n_panels;              // ceil(d2 * sizeof(T) / kPanelBytes)
   int rc;                    // rows per unit
   int64_t n_chunks;          // ceil(d1 / rc)      (reduce: per d0)    map: rows = d0*d1 flattened is NOT assumed
   int64_t n_units;           // d0 * n_chunks * n_panels
   int n_stream;              // streamed operands
-  int rb;                    // rows per stage  (n_stream * rb <= 32)
+  int rb;                    // rows per stage  (n_stream * rb * kPanelBytes <= kStageBytes)
   int stream_slot[SP_MAX_OPERANDS];   // operand -> slot in the stage, or -1 (loaded directly)
 };
 
@@ -95,7 +99,8 @@ stream_kernel(const DevProgram<T> prog, const DevOperands<NI> ops, const Plan pl
               T* __restrict__ scratch) {
   constexpr int V = 32 / sizeof(T);
   constexpr int H = V / 2;
-  constexpr int EPS = kSegBytes / sizeof(T);      // elements per row segment (panel width)
+  constexpr int EPS = kSegBytes / sizeof(T);      // elements per 1 KiB segment
+  constexpr int EPP = kPanelBytes / sizeof(T);    // elements per panel row
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -132,8 +137,8 @@ stream_kernel(const DevProgram<T> prog, const DevOperands<NI> ops, const Plan pl
       const int64_t t = u / plan.n_panels;
       const int64_t chunk = t % plan.n_chunks;
       const int64_t i0 = t / plan.n_chunks;
-      const int64_t col0 = static_cast<int64_t>(panel) * EPS;
-      const int64_t cols = min(static_cast<int64_t>(EPS), plan.d2 - col0);
+      const int64_t col0 = static_cast<int64_t>(panel) * EPP;
+      const int64_t cols = min(static_cast<int64_t>(EPP), plan.d2 - col0);
       const uint32_t seg_bytes = static_cast<uint32_t>(cols * sizeof(T));
       const int64_t row_end = min(plan.d1, (chunk + 1) * plan.rc);
       for (int st = 0; st < stages_per_unit; ++st) {
@@ -146,7 +151,7 @@ stream_kernel(const DevProgram<T> prog, const DevOperands<NI> ops, const Plan pl
         if (my_op >= 0 && slot < plan.n_stream && r_in < rows) {
           const DevOperand& o = ops.in[my_op];
           const T* src = static_cast<const T*>(o.ptr) + i0 * o.stride[0] + (row0 + r_in) * o.stride[1] + col0;
-          const uint32_t dst = smem_base + stage * kStageBytes + (slot * rb + r_in) * kSegBytes;
+          const uint32_t dst = smem_base + stage * kStageBytes + (slot * rb + r_in) * kPanelBytes;
           bulk_g2s(dst, src, seg_bytes, full_bar(stage));
         }
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -162,10 +167,11 @@ stream_kernel(const DevProgram<T> prog, const DevOperands<NI> ops, const Plan pl
       const int64_t t = u / plan.n_panels;
       const int64_t chunk = t % plan.n_chunks;
       const int64_t i0 = t / plan.n_chunks;
-      const int64_t col0 = static_cast<int64_t>(panel) * EPS;
-      const int64_t cols = min(static_cast<int64_t>(EPS), plan.d2 - col0);
-      const int64_t col_a = col0 + lane * H;                 // first half of this lane's vector
-      const int64_t col_b = col0 + EPS / 2 + lane * H;       // second half
+      const int64_t col0 = static_cast<int64_t>(panel) * EPP;
+      const int64_t cols = min(static_cast<int64_t>(EPP), plan.d2 - col0);
+      const int q = cw % kSegsPerPanel;                      // the 1 KiB segment of the panel this warp owns
+      const int64_t col_a = col0 + q * EPS + lane * H;       // first half of this lane's vector
+      const int64_t col_b = col_a + EPS / 2;                 // second half
       const int valid_a = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(H), col0 + cols - col_a)));
       const int valid_b = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(H), col0 + cols - col_b)));
       const int64_t row_end = min(plan.d1, (chunk + 1) * plan.rc);
@@ -180,14 +186,15 @@ stream_kernel(const DevProgram<T> prog, const DevOperands<NI> ops, const Plan pl
         const int rows = static_cast<int>(min(static_cast<int64_t>(rb), row_end - row0));
         mbar_wait(full_bar(stage), phase);
         const uint8_t* sbase = smem_gen + stage * kStageBytes;
-        for (int r = cw; r < rows; r += kConsumerWarps) {
+        for (int item = cw; item < rows * kSegsPerPanel; item += kConsumerWarps) {
+          const int r = item / kSegsPerPanel;                // item % kSegsPerPanel == q for every item of this warp
           T in[NI][V];
 #pragma unroll
           for (int i = 0; i < NI; ++i) {
             if (i < ops.n_in) {
               const int sl = plan.stream_slot[i];
               if (sl >= 0) {
-                const uint8_t* seg = sbase + (sl * rb + r) * kSegBytes;
+                const uint8_t* seg = sbase + (sl * rb + r) * kPanelBytes + q * kSegBytes;
                 const int4 a = *reinterpret_cast<const int4*>(seg + 16 * lane);
                 const int4 b = *reinterpret_cast<const int4*>(seg + 512 + 16 * lane);
                 T tmp[V];
@@ -227,9 +234,9 @@ stream_kernel(const DevProgram<T> prog, const DevOperands<NI> ops, const Plan pl
 #pragma unroll
         for (int v = 0; v < V; ++v) red_smem[(cw * 32 + lane) * V + v] = acc[v];
         consumer_bar();
-        if (cw == 0) {
+        if (cw < kSegsPerPanel) {       // warp q folds the warps that worked on segment q, in fixed order
 #pragma unroll
-          for (int w = 1; w < kConsumerWarps; ++w)
+          for (int w = cw + kSegsPerPanel; w < kConsumerWarps; w += kSegsPerPanel)
 #pragma unroll
             for (int v = 0; v < V; ++v) acc[v] = red_apply<T>(red_op, acc[v], red_smem[(w * 32 + lane) * V + v]);
           T* dst = scratch + (chunk * plan.d0 + i0) * plan.d2;

@@ -66,6 +66,72 @@ class DotExpr(Expr):
       return (a[0], b[1])
     raise ValueError('vector x matrix dot is not defined by the reference (tests/test_dot.py:45-53)')
 
+  def _allgather_path(self, ctx, av, bv, target, shape, M, N, K, dtype, precision):
+    """Multi-GPU fast path for the regular placement (every rank owns whole column blocks of A, B and C, e.g.
+    round-robin over an evenly divisible tile grid): ONE NCCL all-gather moves the A slabs, then every rank
+    contracts C[:, mine] = sum over source ranks p, column intervals (a,b) of p:
+        A_p[:, a:b] (view into the gathered buffer, no copy)  .  B[a:b, mine] (view into this rank's B slab)
+    as K-segments of a single tcgen05 launch per block.  The local segment runs while the gather is in
+    flight.  Returns False when the placement is not of this form (the general rectangle-fetch path follows)."""
+    import torch.distributed as dist
+    W, me = ctx.num_workers, ctx.worker_id
+    if W == 1 or len(shape) != 2 or dtype != np.float32:
+      return False
+    if not (isinstance(av, distarray.DistArrayImpl) and isinstance(bv, distarray.DistArrayImpl)):
+      return False
+    if av.dtype != np.float32 or bv.dtype != np.float32:
+      return False
+    a_axes, c_runs, b_axes = [], [], []
+    for w in range(W):
+      la = [ex for ex, tid in av.tiles.items() if tid.worker == w]
+      lb = [ex for ex, tid in bv.tiles.items() if tid.worker == w]
+      pa = distarray._product_layout(la, 2)
+      pb = distarray._product_layout(lb, 2)
+      rc = _owned_runs(target, w)
+      if pa is None or pb is None or rc is None or not rc[0]:
+        return False
+      if _runs(pa[0]) != [(0, M)] or _runs(pb[0]) != [(0, K)] or rc[0] != [(0, M)]:
+        return False                      # every rank must hold full columns of A and B and full-height C blocks
+      if a_axes and sum(b - a for a, b in pa[1]) != sum(b - a for a, b in a_axes[0][1]):
+        return False                      # equal slab widths (all-gather needs equal contributions)
+      # the B columns this rank needs (= its C columns) must be local to it
+      bcols = pb[1]
+      for c0, c1 in rc[1]:
+        if not any(a <= c0 and c1 <= b for a, b in _runs(bcols)):
+          return False
+      a_axes.append(pa); b_axes.append(pb); c_runs.append(rc)
+    if av.slab is None or bv.slab is None or target.slab is None:
+      return False
+
+    width = av.slab.shape[1]
+    gathered = ctx.scratch(W * M * width * 4, 'dot_allgather').view(torch.float32)[:W * M * width].view(W, M, width)
+    work = dist.all_gather_into_tensor(gathered.view(-1), av.slab.contiguous().view(-1), async_op=True)
+
+    def segments_from(p, c0, c1):
+      segs, off = [], 0
+      src = av.slab if p == me else gathered[p]
+      for a, b in a_axes[p][1]:
+        A = src[:, off:off + (b - a)]
+        B = bv.fetch(extent.create((a, c0), (b, c1), bv.shape))       # zero-copy view of this rank's B slab
+        segs.append((A, B))
+        off += b - a
+      return segs
+
+    blocks = [(r, c) for r in c_runs[me][0] for c in c_runs[me][1]]
+    views = {}
+    for (r0, r1), (c0, c1) in blocks:       # local contribution first: overlaps the all-gather
+      Cv = target.fetch(extent.create((r0, c0), (r1, c1), shape))
+      views[(c0, c1)] = Cv
+      device_ops.gemm(segments_from(me, c0, c1), Cv, accumulate=False, precision=precision)
+    work.wait()
+    for (r0, r1), (c0, c1) in blocks:
+      segs = []
+      for p in range(W):
+        if p != me:
+          segs.extend(segments_from(p, c0, c1))
+      device_ops.gemm(segs, views[(c0, c1)], accumulate=True, precision=precision)
+    return True
+
   def _evaluate(self, ctx, deps):
     av = deps['matrix_a']
     bv = deps['matrix_b']
@@ -113,6 +179,12 @@ class DotExpr(Expr):
 
     def cast(t):
       return t if t.dtype == blob_ctx.torch_dtype(dtype) else t.to(blob_ctx.torch_dtype(dtype))
+
+    if self._allgather_path(ctx, av, bv, target, shape, M, N, K, dtype, precision):
+      for tid in target.tiles.values():
+        if ctx.is_local(tid):
+          ctx.tile(tid).valid = True
+      return target
 
     for w in range(W):
       if len(shape) == 2:

@@ -242,6 +242,23 @@ int sp_gemm_set_chunk_kblocks(int k_blocks);
 int64_t sp_gemm_f32_workspace_bytes(int64_t M, int64_t N, int n_seg, const int64_t* seg_k, int precision);
 int sp_gemm_f32_segments(int n_seg, const sp_gemm_segment* segs, float* C, int64_t ldc, int64_t M, int64_t N,
                          int accumulate, int precision, void* workspace, int64_t workspace_bytes, void* stream);
+/* Split form for multi-GPU dots: a rank prepares (rounds / splits / transposes) only the strips it owns, the
+ * prepared strips are plain byte buffers that can be exchanged (ncclAllGather), and the contraction runs over
+ * prepared operands.  Layout of a prepared operand: [copies][rows][Kp] elements (rows = M for A, N for B;
+ * Kp = sp_gemm_kpad(K): depth padded to the k-block; 128-byte aligned). */
+typedef struct {
+  const void* A; /* prepared A strip */
+  const void* B; /* prepared B strip (transposed) */
+  int64_t Kp;
+} sp_gemm_prepared_segment;
+int64_t sp_gemm_kpad(int64_t K, int precision);
+int64_t sp_gemm_prepared_bytes(int64_t rows, int64_t Kp, int precision);
+int sp_gemm_prepare_a(const float* A, int64_t lda, int64_t M, int64_t K, int precision, void* out, int64_t Kp,
+                      int64_t k_offset, int64_t out_bytes, void* stream);
+int sp_gemm_prepare_b(const float* B, int64_t ldb, int64_t K, int64_t N, int precision, void* out, int64_t Kp,
+                      int64_t k_offset, int64_t out_bytes, void* stream);
+int sp_gemm_prepared(int n_seg, const sp_gemm_prepared_segment* segs, float* C, int64_t ldc, int64_t M, int64_t N,
+                     int accumulate, int precision, void* stream);
 int sp_gemm_f32(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
                 int64_t N, int64_t K, int accumulate, int precision, void* workspace, int64_t workspace_bytes,
                 void* stream);

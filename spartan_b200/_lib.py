@@ -46,6 +46,10 @@ class sp_operand(ctypes.Structure):
               ('stride', ctypes.c_int64 * 3)]
 
 
+class sp_gemm_prepared_segment(ctypes.Structure):
+  _fields_ = [('A', ctypes.c_void_p), ('B', ctypes.c_void_p), ('Kp', ctypes.c_int64)]
+
+
 class sp_gemm_segment(ctypes.Structure):
   _fields_ = [('A', ctypes.c_void_p), ('lda', ctypes.c_int64), ('B', ctypes.c_void_p), ('ldb', ctypes.c_int64),
               ('K', ctypes.c_int64)]
@@ -75,6 +79,11 @@ _SIGS = {
   'sp_combine': (_int, [_vp, _vp, _int, _i64, _int, _vp]),
   'sp_copy_rect': (_int, [_vp, _i64p, _vp, _i64p, _i64p, _int, _vp]),
   'sp_gemm_set_chunk_kblocks': (_int, [_int]),
+  'sp_gemm_kpad': (_i64, [_i64, _int]),
+  'sp_gemm_prepared_bytes': (_i64, [_i64, _i64, _int]),
+  'sp_gemm_prepare_a': (_int, [_vp, _i64, _i64, _i64, _int, _vp, _i64, _i64, _i64, _vp]),
+  'sp_gemm_prepare_b': (_int, [_vp, _i64, _i64, _i64, _int, _vp, _i64, _i64, _i64, _vp]),
+  'sp_gemm_prepared': (_int, [_int, ctypes.POINTER(sp_gemm_prepared_segment), _vp, _i64, _i64, _i64, _int, _int, _vp]),
   'sp_gemm_f32_workspace_bytes': (_i64, [_i64, _i64, _int, _i64p, _int]),
   'sp_gemm_f32_segments': (_int, [_int, ctypes.POINTER(sp_gemm_segment), _vp, _i64, _i64, _i64, _int, _int, _vp, _i64, _vp]),
   'sp_gemm_f32': (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp, _i64, _vp]),

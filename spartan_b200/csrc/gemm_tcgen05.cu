@@ -394,7 +394,7 @@ gemm_kernel(const __grid_constant__ Params p) {
 // Operand preparation (HBM-bound: reads the fp32 operand once, writes 1 or 2 rounded copies).
 //   SPLIT 0: tf32 hi            SPLIT 1: tf32 hi + lo
 //   SPLIT 2: bf16 hi + lo
-// Output rows have Kp elements (zero tail); B is written transposed ([N, Kp]).
+// Output rows have pitch Kp (the caller zero-fills what no strip covers); B is written transposed ([N, Kp]).
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ float rn_tf32(float x) {
   uint32_t r;
@@ -415,10 +415,11 @@ __device__ __forceinline__ void split_store(float a, void* hi, void* lo, int64_t
   }
 }
 
-// A: [M, K] (lda) -> hi/lo [M, Kp].  One thread per 4 consecutive k (float4 load when aligned).
+// A: [M, K] (lda) -> hi/lo rows of pitch Kp.  One thread per 4 consecutive k (float4 load when aligned).
 template <int SPLIT>
-__global__ void prep_a_kernel(const float* __restrict__ A, int64_t lda, int M, int K, int Kp, void* hi, void* lo) {
-  const int kq = Kp / 4;
+__global__ void prep_a_kernel(const float* __restrict__ A, int64_t lda, int M, int K, int Kw, int64_t Kp, void* hi,
+                              void* lo) {
+  const int kq = Kw / 4;       // Kw: width written per row (K rounded up to 4, zero tail); Kp: destination row pitch
   const int64_t total = static_cast<int64_t>(M) * kq;
   const bool vec = ((reinterpret_cast<uint64_t>(A) & 15) == 0) && ((lda & 3) == 0);
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -440,7 +441,7 @@ __global__ void prep_a_kernel(const float* __restrict__ A, int64_t lda, int M, i
 
 // B: [K, N] (ldb) -> hiT/loT [N, Kp] through a 32x33 shared tile (coalesced both ways).
 template <int SPLIT>
-__global__ void prep_bt_kernel(const float* __restrict__ B, int64_t ldb, int K, int N, int Kp, void* hiT, void* loT) {
+__global__ void prep_bt_kernel(const float* __restrict__ B, int64_t ldb, int K, int N, int64_t Kp, void* hiT, void* loT) {
   __shared__ float tile[32][33];
   const int n0 = blockIdx.x * 32;
   const int k0 = blockIdx.y * 32;
@@ -451,7 +452,7 @@ __global__ void prep_bt_kernel(const float* __restrict__ B, int64_t ldb, int K, 
   __syncthreads();
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int n = n0 + r, k = k0 + threadIdx.x;
-    if (n < N && k < Kp) split_store<SPLIT>(tile[threadIdx.x][r], hiT, loT, static_cast<int64_t>(n) * Kp + k);
+    if (n < N && k < K) split_store<SPLIT>(tile[threadIdx.x][r], hiT, loT, static_cast<int64_t>(n) * Kp + k);
   }
 }
 
@@ -526,92 +527,108 @@ extern "C" int sp_gemm_set_chunk_kblocks(int kb) {
   return SP_OK;
 }
 
-extern "C" int64_t sp_gemm_f32_workspace_bytes(int64_t M, int64_t N, int n_seg, const int64_t* seg_k, int precision) {
+extern "C" int64_t sp_gemm_kpad(int64_t K, int precision) {
   Mode md;
   if (!mode_of(precision, &md)) return -1;
-  int64_t total = 0;
-  for (int s = 0; s < n_seg; ++s) {
-    const int64_t Kp = round_up(seg_k[s], md.bk);
-    total += round_up((M + N) * Kp * md.elem * md.copies, 1024);
-  }
-  return total + 1024;
+  return round_up(K, md.bk);
 }
 
-extern "C" int sp_gemm_f32_segments(int n_seg, const sp_gemm_segment* segs, float* C, int64_t ldc, int64_t M,
-                                     int64_t N, int accumulate, int precision, void* workspace,
-                                     int64_t workspace_bytes, void* stream_) {
+// Bytes of one prepared operand with `rows` rows (M for A, N for B) and padded depth Kp: [copies][rows][Kp].
+extern "C" int64_t sp_gemm_prepared_bytes(int64_t rows, int64_t Kp, int precision) {
+  Mode md;
+  if (!mode_of(precision, &md)) return -1;
+  return rows * Kp * md.elem * md.copies;
+}
+
+static int check_prep(const void* out, int64_t out_bytes, int64_t rows, int64_t Kp, int precision, Mode* md) {
+  SP_REQUIRE(mode_of(precision, md), SP_ERR_INVALID, "unknown precision %d", precision);
+  SP_REQUIRE(Kp > 0 && Kp % md->bk == 0, SP_ERR_INVALID, "Kp=%lld is not a multiple of the k-block %d", (long long)Kp, md->bk);
+  SP_REQUIRE(out != nullptr && (reinterpret_cast<uint64_t>(out) % 128) == 0, SP_ERR_INVALID,
+             "prepared operand buffer must be 128-byte aligned");
+  SP_REQUIRE(out_bytes >= rows * Kp * md->elem * md->copies, SP_ERR_INVALID, "prepared operand buffer too small");
+  return SP_OK;
+}
+
+// A strip [M, K] (leading dim lda) -> out[copies][M][Kp] at depth offset k_offset (columns k_offset .. k_offset+K).
+// The caller zero-fills the buffer when the strips it writes do not cover [0, Kp).
+extern "C" int sp_gemm_prepare_a(const float* A, int64_t lda, int64_t M, int64_t K, int precision, void* out,
+                                 int64_t Kp, int64_t k_offset, int64_t out_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   Mode md;
-  SP_REQUIRE(mode_of(precision, &md), SP_ERR_INVALID, "sp_gemm_f32_segments: unknown precision %d", precision);
-  SP_REQUIRE(n_seg >= 1 && n_seg <= 8, SP_ERR_INVALID, "sp_gemm_f32_segments: %d segments (limit 8 per launch)", n_seg);
+  int rc = check_prep(out, out_bytes, M, Kp, precision, &md);
+  if (rc) return rc;
+  SP_REQUIRE(k_offset >= 0 && k_offset % 4 == 0 && k_offset + K <= Kp, SP_ERR_INVALID, "bad k_offset %lld", (long long)k_offset);
+  uint8_t* hi = static_cast<uint8_t*>(out) + k_offset * md.elem;
+  uint8_t* lo = md.copies == 2 ? hi + M * Kp * md.elem : nullptr;
+  // rows of the destination are Kp apart; the kernel pads K up to a multiple of 4 within its strip
+  const int64_t Kq = std::min<int64_t>(round_up(K, 4), Kp - k_offset);
+  const int64_t total = M * (Kq / 4);
+  const int threads = 256;
+  const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((total + threads - 1) / threads, num_sms() * 32)));
+  const int Mi = static_cast<int>(M), Ki = static_cast<int>(K), Kqi = static_cast<int>(Kq);
+  if (md.split == 0) prep_a_kernel<0><<<blocks, threads, 0, stream>>>(A, lda, Mi, Ki, Kqi, Kp, hi, lo);
+  else if (md.split == 1) prep_a_kernel<1><<<blocks, threads, 0, stream>>>(A, lda, Mi, Ki, Kqi, Kp, hi, lo);
+  else prep_a_kernel<2><<<blocks, threads, 0, stream>>>(A, lda, Mi, Ki, Kqi, Kp, hi, lo);
+  SP_CUDA_CHECK(cudaGetLastError());
+  return SP_OK;
+}
+
+// B strip [K, N] (leading dim ldb) -> transposed out[copies][N][Kp] at depth offset k_offset.
+extern "C" int sp_gemm_prepare_b(const float* B, int64_t ldb, int64_t K, int64_t N, int precision, void* out,
+                                 int64_t Kp, int64_t k_offset, int64_t out_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  Mode md;
+  int rc = check_prep(out, out_bytes, N, Kp, precision, &md);
+  if (rc) return rc;
+  SP_REQUIRE(k_offset >= 0 && k_offset + K <= Kp, SP_ERR_INVALID, "bad k_offset %lld", (long long)k_offset);
+  uint8_t* hi = static_cast<uint8_t*>(out) + k_offset * md.elem;
+  uint8_t* lo = md.copies == 2 ? hi + N * Kp * md.elem : nullptr;
+  dim3 grid(static_cast<unsigned>((N + 31) / 32), static_cast<unsigned>((K + 31) / 32));
+  dim3 block(32, 8);
+  const int Ni = static_cast<int>(N), Ki = static_cast<int>(K);
+  if (md.split == 0) prep_bt_kernel<0><<<grid, block, 0, stream>>>(B, ldb, Ki, Ni, Kp, hi, lo);
+  else if (md.split == 1) prep_bt_kernel<1><<<grid, block, 0, stream>>>(B, ldb, Ki, Ni, Kp, hi, lo);
+  else prep_bt_kernel<2><<<grid, block, 0, stream>>>(B, ldb, Ki, Ni, Kp, hi, lo);
+  SP_CUDA_CHECK(cudaGetLastError());
+  return SP_OK;
+}
+
+// C[M,N] (+)= sum_s A_s . B_s over PREPARED operands (sp_gemm_prepare_a / _b), one launch.
+extern "C" int sp_gemm_prepared(int n_seg, const sp_gemm_prepared_segment* segs, float* C, int64_t ldc, int64_t M,
+                                int64_t N, int accumulate, int precision, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  Mode md;
+  SP_REQUIRE(mode_of(precision, &md), SP_ERR_INVALID, "sp_gemm_prepared: unknown precision %d", precision);
+  SP_REQUIRE(n_seg >= 1 && n_seg <= 8, SP_ERR_INVALID, "sp_gemm_prepared: %d segments (limit 8 per launch)", n_seg);
   SP_REQUIRE(M > 0 && N > 0 && M < (1ll << 31) && N < (1ll << 31), SP_ERR_INVALID, "bad M/N %lld %lld",
              (long long)M, (long long)N);
-  {
-    int64_t ks[8];
-    for (int s = 0; s < n_seg; ++s) ks[s] = segs[s].K;
-    const int64_t need = sp_gemm_f32_workspace_bytes(M, N, n_seg, ks, precision);
-    SP_REQUIRE(workspace != nullptr && workspace_bytes >= need, SP_ERR_INVALID,
-               "sp_gemm_f32_segments: workspace %lld B < required %lld B", (long long)workspace_bytes,
-               (long long)need);
-  }
-
   static bool attr_set = false;
   if (!attr_set) {
     SP_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     SP_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
-
   Params p;
   memset(&p, 0, sizeof(p));
-  uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uint64_t>(workspace) + 1023) & ~1023ull);
   int n_maps = 0;
   for (int s = 0; s < n_seg; ++s) {
-    const sp_gemm_segment& g = segs[s];
-    SP_REQUIRE(g.K > 0, SP_ERR_INVALID, "segment %d has K=%lld", s, (long long)g.K);
-    const int64_t Kp = round_up(g.K, md.bk);
-    uint8_t* a_hi = ws;
-    uint8_t* b_hi = a_hi + M * Kp * md.elem;
-    uint8_t* a_lo = nullptr;
-    uint8_t* b_lo = nullptr;
-    if (md.copies == 2) {
-      a_lo = b_hi + N * Kp * md.elem;
-      b_lo = a_lo + M * Kp * md.elem;
-    }
-    ws += round_up((M + N) * Kp * md.elem * md.copies, 1024);
-
-    {
-      const int64_t total = M * (Kp / 4);
-      const int threads = 256;
-      const int blocks = static_cast<int>(std::min<int64_t>((total + threads - 1) / threads, num_sms() * 32));
-      dim3 grid(static_cast<unsigned>((N + 31) / 32), static_cast<unsigned>((Kp + 31) / 32));
-      dim3 block(32, 8);
-      const int Mi = static_cast<int>(M), Ni = static_cast<int>(N), Ki = static_cast<int>(g.K), Kpi = static_cast<int>(Kp);
-      if (md.split == 0) {
-        prep_a_kernel<0><<<blocks, threads, 0, stream>>>(g.A, g.lda, Mi, Ki, Kpi, a_hi, a_lo);
-        prep_bt_kernel<0><<<grid, block, 0, stream>>>(g.B, g.ldb, Ki, Ni, Kpi, b_hi, b_lo);
-      } else if (md.split == 1) {
-        prep_a_kernel<1><<<blocks, threads, 0, stream>>>(g.A, g.lda, Mi, Ki, Kpi, a_hi, a_lo);
-        prep_bt_kernel<1><<<grid, block, 0, stream>>>(g.B, g.ldb, Ki, Ni, Kpi, b_hi, b_lo);
-      } else {
-        prep_a_kernel<2><<<blocks, threads, 0, stream>>>(g.A, g.lda, Mi, Ki, Kpi, a_hi, a_lo);
-        prep_bt_kernel<2><<<grid, block, 0, stream>>>(g.B, g.ldb, Ki, Ni, Kpi, b_hi, b_lo);
-      }
-    }
-
+    const sp_gemm_prepared_segment& g = segs[s];
+    SP_REQUIRE(g.Kp > 0 && g.Kp % md.bk == 0 && g.A != nullptr && g.B != nullptr, SP_ERR_INVALID, "bad prepared segment %d", s);
+    const uint8_t* a_hi = static_cast<const uint8_t*>(g.A);
+    const uint8_t* b_hi = static_cast<const uint8_t*>(g.B);
     Segment& sg = p.segs[s];
-    sg.k_blocks = static_cast<int>(Kp / md.bk);
+    sg.k_blocks = static_cast<int>(g.Kp / md.bk);
     sg.n_terms = md.terms;
     const int ia_hi = n_maps++, ib_hi = n_maps++;
-    int rc = make_map(&p.maps[ia_hi], a_hi, M, Kp, BM, md.elem);
+    int rc = make_map(&p.maps[ia_hi], a_hi, M, g.Kp, BM, md.elem);
     if (rc) return rc;
-    rc = make_map(&p.maps[ib_hi], b_hi, N, Kp, BN, md.elem);
+    rc = make_map(&p.maps[ib_hi], b_hi, N, g.Kp, BN, md.elem);
     if (rc) return rc;
     if (md.copies == 2) {
       const int ia_lo = n_maps++, ib_lo = n_maps++;
-      rc = make_map(&p.maps[ia_lo], a_lo, M, Kp, BM, md.elem);
+      rc = make_map(&p.maps[ia_lo], a_hi + M * g.Kp * md.elem, M, g.Kp, BM, md.elem);
       if (rc) return rc;
-      rc = make_map(&p.maps[ib_lo], b_lo, N, Kp, BN, md.elem);
+      rc = make_map(&p.maps[ib_lo], b_hi + N * g.Kp * md.elem, N, g.Kp, BN, md.elem);
       if (rc) return rc;
       // small cross terms first, dominant term last
       sg.a_map[0] = ia_lo; sg.b_map[0] = ib_hi;
@@ -630,13 +647,60 @@ extern "C" int sp_gemm_f32_segments(int n_seg, const sp_gemm_segment* segs, floa
   p.accumulate = accumulate;
   p.C = C;
   p.ldc = ldc;
-
   const int tiles = p.m_blocks * p.n_blocks;
   const int grid = std::min(tiles, num_sms());
   if (md.kind == 0) gemm_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);
   else gemm_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);
   SP_CUDA_CHECK(cudaGetLastError());
   return SP_OK;
+}
+
+extern "C" int64_t sp_gemm_f32_workspace_bytes(int64_t M, int64_t N, int n_seg, const int64_t* seg_k, int precision) {
+  Mode md;
+  if (!mode_of(precision, &md)) return -1;
+  int64_t total = 0;
+  for (int s = 0; s < n_seg; ++s) {
+    const int64_t Kp = round_up(seg_k[s], md.bk);
+    total += round_up(M * Kp * md.elem * md.copies, 1024) + round_up(N * Kp * md.elem * md.copies, 1024);
+  }
+  return total + 1024;
+}
+
+// Convenience: prepare + contract in one call (workspace holds the prepared operands).
+extern "C" int sp_gemm_f32_segments(int n_seg, const sp_gemm_segment* segs, float* C, int64_t ldc, int64_t M,
+                                     int64_t N, int accumulate, int precision, void* workspace,
+                                     int64_t workspace_bytes, void* stream_) {
+  Mode md;
+  SP_REQUIRE(mode_of(precision, &md), SP_ERR_INVALID, "sp_gemm_f32_segments: unknown precision %d", precision);
+  SP_REQUIRE(n_seg >= 1 && n_seg <= 8, SP_ERR_INVALID, "sp_gemm_f32_segments: %d segments (limit 8 per launch)", n_seg);
+  SP_REQUIRE(M > 0 && N > 0, SP_ERR_INVALID, "bad M/N");
+  {
+    int64_t ks[8];
+    for (int s = 0; s < n_seg; ++s) ks[s] = segs[s].K;
+    const int64_t need = sp_gemm_f32_workspace_bytes(M, N, n_seg, ks, precision);
+    SP_REQUIRE(workspace != nullptr && workspace_bytes >= need, SP_ERR_INVALID,
+               "sp_gemm_f32_segments: workspace %lld B < required %lld B", (long long)workspace_bytes, (long long)need);
+  }
+  uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uint64_t>(workspace) + 1023) & ~1023ull);
+  sp_gemm_prepared_segment ps[8];
+  for (int s = 0; s < n_seg; ++s) {
+    const sp_gemm_segment& g = segs[s];
+    SP_REQUIRE(g.K > 0, SP_ERR_INVALID, "segment %d has K=%lld", s, (long long)g.K);
+    const int64_t Kp = round_up(g.K, md.bk);
+    const int64_t a_bytes = round_up(M * Kp * md.elem * md.copies, 1024);
+    const int64_t b_bytes = round_up(N * Kp * md.elem * md.copies, 1024);
+    uint8_t* a_buf = ws;
+    uint8_t* b_buf = ws + a_bytes;
+    ws += a_bytes + b_bytes;
+    if (Kp != round_up(g.K, 4)) SP_CUDA_CHECK(cudaMemsetAsync(a_buf, 0, a_bytes, static_cast<cudaStream_t>(stream_)));
+    if (Kp != g.K) SP_CUDA_CHECK(cudaMemsetAsync(b_buf, 0, b_bytes, static_cast<cudaStream_t>(stream_)));
+    int rc = sp_gemm_prepare_a(g.A, g.lda, M, g.K, precision, a_buf, Kp, 0, a_bytes, stream_);
+    if (rc) return rc;
+    rc = sp_gemm_prepare_b(g.B, g.ldb, g.K, N, precision, b_buf, Kp, 0, b_bytes, stream_);
+    if (rc) return rc;
+    ps[s].A = a_buf; ps[s].B = b_buf; ps[s].Kp = Kp;
+  }
+  return sp_gemm_prepared(n_seg, ps, C, ldc, M, N, accumulate, precision, stream_);
 }
 
 extern "C" int sp_gemm_f32(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from . import blob_ctx
-from ._lib import (lib, check, sp_program, sp_operand, sp_gemm_segment, i64arr, SpartanError, OP,
+from ._lib import (lib, check, sp_program, sp_operand, sp_gemm_segment, sp_gemm_prepared_segment, i64arr, SpartanError, OP,
                    SP_F32, SP_F64, SP_I32, SP_I64, SP_U8, SP_BOOL, SP_RED_SUM, SP_RED_MIN, SP_RED_MAX, SP_RED_PROD,
                    SP_RED_ALL, SP_RED_ANY, SP_FILL_CONST, SP_FILL_IOTA, SP_FILL_RAND, SP_FILL_RANDN,
                    SP_GEMM_TF32X1, SP_GEMM_TF32X3, SP_GEMM_SIMT, SP_GEMM_BF16X3, SP_GEMM_MAX_SEGMENTS)
@@ -320,4 +320,48 @@ def gemm(segments, C, accumulate=False, precision='tf32x3'):
     check(lib.sp_gemm_f32_segments(len(chunk), segs, C.data_ptr(), C.stride(0), M, N, int(bool(acc)), prec,
                                    ws.data_ptr(), ws.numel(), _stream()), 'sp_gemm_f32_segments')
     _count_launch(1 + 2 * len(chunk))
+    acc = True
+
+
+# ------------------------------------------------------------------------------------ split-form gemm (multi-GPU)
+def gemm_kpad(K, precision):
+  return int(lib.sp_gemm_kpad(int(K), _PRECISIONS[precision]))
+
+
+def gemm_prepared_bytes(rows, Kp, precision):
+  n = int(lib.sp_gemm_prepared_bytes(int(rows), int(Kp), _PRECISIONS[precision]))
+  return (n + 1023) // 1024 * 1024
+
+
+def gemm_prepare_a(A, out, Kp, k_offset, precision):
+  """Rounds / splits the fp32 strip ``A`` [M, K] into the prepared buffer ``out`` (uint8, 1 KiB aligned)."""
+  _require_cuda(A, out)
+  assert A.dim() == 2 and A.stride(1) == 1 and A.dtype == torch.float32
+  check(lib.sp_gemm_prepare_a(A.data_ptr(), A.stride(0), A.shape[0], A.shape[1], _PRECISIONS[precision], out.data_ptr(),
+                              int(Kp), int(k_offset), out.numel(), _stream()), 'sp_gemm_prepare_a')
+  _count_launch()
+
+
+def gemm_prepare_b(B, out, Kp, k_offset, precision):
+  """Rounds / splits / transposes the fp32 strip ``B`` [K, N] into the prepared buffer ``out``."""
+  _require_cuda(B, out)
+  assert B.dim() == 2 and B.stride(1) == 1 and B.dtype == torch.float32
+  check(lib.sp_gemm_prepare_b(B.data_ptr(), B.stride(0), B.shape[0], B.shape[1], _PRECISIONS[precision], out.data_ptr(),
+                              int(Kp), int(k_offset), out.numel(), _stream()), 'sp_gemm_prepare_b')
+  _count_launch()
+
+
+def gemm_prepared(segments, C, accumulate, precision):
+  """segments: [(A_prepared, B_prepared, Kp)]; C (+)= sum A.B over at most 8 segments per launch."""
+  _require_cuda(C)
+  M, N = C.shape
+  acc = accumulate
+  for lo in range(0, len(segments), SP_GEMM_MAX_SEGMENTS):
+    chunk = segments[lo:lo + SP_GEMM_MAX_SEGMENTS]
+    segs = (sp_gemm_prepared_segment * len(chunk))()
+    for i, (A, B, Kp) in enumerate(chunk):
+      segs[i].A = A.data_ptr(); segs[i].B = B.data_ptr(); segs[i].Kp = int(Kp)
+    check(lib.sp_gemm_prepared(len(chunk), segs, C.data_ptr(), C.stride(0), M, N, int(bool(acc)), _PRECISIONS[precision],
+                               _stream()), 'sp_gemm_prepared')
+    _count_launch()
     acc = True

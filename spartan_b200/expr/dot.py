@@ -103,33 +103,44 @@ class DotExpr(Expr):
     if av.slab is None or bv.slab is None or target.slab is None:
       return False
 
+    # Each rank prepares (rounds / splits) ONLY its own A slab; the prepared slabs are what travels.
+    if precision == 'simt':
+      return False
     width = av.slab.shape[1]
-    gathered = ctx.scratch(W * M * width * 4, 'dot_allgather').view(torch.float32)[:W * M * width].view(W, M, width)
-    work = dist.all_gather_into_tensor(gathered.view(-1), av.slab.contiguous().view(-1), async_op=True)
-
-    def segments_from(p, c0, c1):
-      segs, off = [], 0
-      src = av.slab if p == me else gathered[p]
-      for a, b in a_axes[p][1]:
-        A = src[:, off:off + (b - a)]
-        B = bv.fetch(extent.create((a, c0), (b, c1), bv.shape))       # zero-copy view of this rank's B slab
-        segs.append((A, B))
-        off += b - a
-      return segs
+    Kp = device_ops.gemm_kpad(width, precision)
+    a_bytes = device_ops.gemm_prepared_bytes(M, Kp, precision)
+    mine = ctx.scratch(a_bytes, 'dot_a_prepared')[:a_bytes]
+    if Kp != (width + 3) // 4 * 4:
+      mine.zero_()
+    device_ops.gemm_prepare_a(av.slab, mine, Kp, 0, precision)
+    gathered = ctx.scratch(W * a_bytes, 'dot_allgather')[:W * a_bytes]
+    work = dist.all_gather_into_tensor(gathered, mine, async_op=True)
 
     blocks = [(r, c) for r in c_runs[me][0] for c in c_runs[me][1]]
+    # B strips for every source rank p: rows = p's k-intervals (in slab order), columns = this block
+    b_prepared = {}
+    for (r0, r1), (c0, c1) in blocks:
+      b_bytes = device_ops.gemm_prepared_bytes(c1 - c0, Kp, precision)
+      buf = ctx.scratch(W * b_bytes, 'dot_b_prepared_%d_%d' % (c0, c1))[:W * b_bytes]
+      if Kp != width:
+        buf.zero_()
+      for p in range(W):
+        out = buf[p * b_bytes:(p + 1) * b_bytes]
+        off = 0
+        for a, b in a_axes[p][1]:
+          Bv = bv.fetch(extent.create((a, c0), (b, c1), bv.shape))     # zero-copy view of this rank's B slab
+          device_ops.gemm_prepare_b(Bv, out, Kp, off, precision)
+          off += b - a
+        b_prepared[(c0, c1, p)] = out
     views = {}
     for (r0, r1), (c0, c1) in blocks:       # local contribution first: overlaps the all-gather
       Cv = target.fetch(extent.create((r0, c0), (r1, c1), shape))
       views[(c0, c1)] = Cv
-      device_ops.gemm(segments_from(me, c0, c1), Cv, accumulate=False, precision=precision)
+      device_ops.gemm_prepared([(mine, b_prepared[(c0, c1, me)], Kp)], Cv, accumulate=False, precision=precision)
     work.wait()
     for (r0, r1), (c0, c1) in blocks:
-      segs = []
-      for p in range(W):
-        if p != me:
-          segs.extend(segments_from(p, c0, c1))
-      device_ops.gemm(segs, views[(c0, c1)], accumulate=True, precision=precision)
+      segs = [(gathered[p * a_bytes:(p + 1) * a_bytes], b_prepared[(c0, c1, p)], Kp) for p in range(W) if p != me]
+      device_ops.gemm_prepared(segs, views[(c0, c1)], accumulate=True, precision=precision)
     return True
 
   def _evaluate(self, ctx, deps):

@@ -1,0 +1,72 @@
+"""Two-rank NCCL tests (run when the box has >= 2 GPUs): the SPMD paths that need an exchange -- the dot
+all-gather fast path, the general rectangle-fetch path, and the all-reduce combiner of reductions -- against
+NumPy on the same seeded inputs."""
+import os
+import socket
+import sys
+import traceback
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+  s = socket.socket(); s.bind(('127.0.0.1', 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, q):
+  try:
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR='127.0.0.1',
+                      MASTER_PORT=str(port))
+    if ROOT not in sys.path:
+      sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    import spartan_b200 as sp
+    ctx = sp.initialize()
+    rng = np.random.default_rng(0)
+    # dot, regular placement (all-gather of prepared A slabs) and an irregular one (rectangle fetches)
+    for (M, K, N, hint) in [(1024, 1024, 1024, (256, 256)), (512, 768, 640, (128, 128)), (300, 500, 260, (100, 130))]:
+      a = rng.standard_normal((M, K), dtype=np.float32); b = rng.standard_normal((K, N), dtype=np.float32)
+      ref = np.dot(a.astype(np.float64), b.astype(np.float64))
+      for prec, tol in [('bf16x3', 1e-5), ('tf32x3', 1e-5), ('simt', 1e-5)]:
+        sp.FLAGS.dot_precision = prec
+        got = sp.dot(sp.from_numpy(a, tile_hint=hint), sp.from_numpy(b, tile_hint=hint), tile_hint=hint).glom()
+        err = np.abs(got - ref).max() / np.abs(ref).max()
+        assert err <= tol, (M, K, N, hint, prec, err)
+    # fused map + reduce: partials combined by ncclAllReduce
+    x = rng.random((1024, 2048), dtype=np.float32); y = rng.random((1024, 2048), dtype=np.float32)
+    for hint in [(128, 2048), (256, 512), None]:
+      got = (sp.from_numpy(x, tile_hint=hint) * 2 + sp.from_numpy(y, tile_hint=hint)).sum(axis=0).optimized().glom()
+      np.testing.assert_allclose(got, (x.astype(np.float64) * 2 + y).sum(axis=0), rtol=1e-5)
+      got = sp.from_numpy(x, tile_hint=hint).max(axis=1).glom()
+      assert np.array_equal(got, x.max(axis=1))
+    xi = rng.integers(-50, 50, size=(333, 77)).astype(np.int64)
+    assert sp.from_numpy(xi).sum().glom() == xi.sum()
+    # operands with different tilings: pieces travel point-to-point to the owner of each output tile
+    got = (sp.from_numpy(x, tile_hint=(128, 2048)) + sp.from_numpy(y, tile_hint=(1024, 256))).glom()
+    assert np.array_equal(got, x + y)
+    assert sp.ones((4096, 4096)).sum().glom() == 16777216.0
+    dist.barrier()
+    q.put((rank, 'ok'))
+  except Exception:
+    q.put((rank, traceback.format_exc()))
+
+
+def test_two_ranks_nccl():
+  if torch.cuda.device_count() < 2:
+    pytest.skip('needs 2 GPUs')
+  world = 2
+  ctx = mp.get_context('spawn')
+  q = ctx.Queue()
+  port = _free_port()
+  procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+  for p in procs: p.start()
+  results = [q.get(timeout=600) for _ in range(world)]
+  for p in procs: p.join(timeout=60)
+  for rank, msg in results:
+    assert msg == 'ok', 'rank %d failed:\n%s' % (rank, msg)

@@ -355,3 +355,24 @@ def test_streaming_reduce_axis0(shape):
   got = sp.from_numpy(xd).sum(axis=axis).glom()
   np.testing.assert_allclose(got, xd.sum(axis=axis), rtol=1e-12)
   Assert.all_eq(sp.max(sp.from_numpy(xf), axis).glom(), xf.max(axis=axis))
+
+
+def test_gemm_split_form_matches_one_call():
+  """sp_gemm_prepare_a/_b + sp_gemm_prepared (the multi-GPU form) == sp_gemm_f32 (bit-identical)."""
+  import torch
+  from spartan_b200 import device_ops, blob_ctx
+  ctx = blob_ctx.get()
+  torch.manual_seed(0)
+  M, K, N = 384, 1000, 520
+  A = torch.randn(M, K, device=ctx.device); B = torch.randn(K, N, device=ctx.device)
+  for prec in ('tf32x1', 'tf32x3', 'bf16x3'):
+    C1 = torch.empty(M, N, device=ctx.device); C2 = torch.empty(M, N, device=ctx.device)
+    device_ops.gemm([(A, B)], C1, precision=prec)
+    Kp = device_ops.gemm_kpad(K, prec)
+    pa = torch.zeros(device_ops.gemm_prepared_bytes(M, Kp, prec), dtype=torch.uint8, device=ctx.device)
+    pb = torch.zeros(device_ops.gemm_prepared_bytes(N, Kp, prec), dtype=torch.uint8, device=ctx.device)
+    # two K strips written at their depth offsets, like the strips of two source ranks
+    device_ops.gemm_prepare_a(A[:, :600].contiguous(), pa, Kp, 0, prec); device_ops.gemm_prepare_a(A[:, 600:].contiguous(), pa, Kp, 600, prec)
+    device_ops.gemm_prepare_b(B[:600], pb, Kp, 0, prec); device_ops.gemm_prepare_b(B[600:], pb, Kp, 600, prec)
+    device_ops.gemm_prepared([(pa, pb, Kp)], C2, accumulate=False, precision=prec)
+    assert torch.equal(C1, C2), prec

@@ -331,6 +331,9 @@ def run_b200(args):
            'clocks': clocks, 'gpu_launches': launches, 'parity': parity, 'e2e': e2e, 'map_reduce': mr,
            'cpu_baseline': cpu}
     print(json.dumps(out), flush=True)
+  if world > 1:
+    comm.barrier()
+    dist.destroy_process_group()
 
 
 if __name__ == '__main__':

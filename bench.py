@@ -70,7 +70,7 @@ class ClockSampler(object):
   def start(self):
     try:
       self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                    '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                    '--format=csv,noheader,nounits', '-lms', '20'], stdout=subprocess.PIPE,
                                    stderr=subprocess.DEVNULL, text=True)
       self.t = threading.Thread(target=self._read, daemon=True)
       self.t.start()
@@ -79,7 +79,13 @@ class ClockSampler(object):
 
   def _read(self):
     for line in self.proc.stdout:
-      self.lines.append(line.strip())
+      self.lines.append((time.perf_counter(), line.strip()))
+
+  def mark_begin(self):
+    self.t0 = time.perf_counter()
+
+  def mark_end(self):
+    self.t1 = time.perf_counter()
 
   def stop(self):
     if self.proc is None:
@@ -92,7 +98,11 @@ class ClockSampler(object):
       self.proc.kill()
     sm, mx, reasons = [], [], set()
     names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-    for ln in self.lines:
+    t0, t1 = getattr(self, 't0', 0.0), getattr(self, 't1', float('inf'))
+    inside = [ln for ts, ln in self.lines if t0 <= ts <= t1 + 0.03]
+    if not inside:                       # very short timed region: fall back to the samples nearest to it
+      inside = [ln for ts, ln in self.lines if ts >= t0 - 0.05][:3]
+    for ln in inside:
       f = [x.strip() for x in ln.split(',')]
       if len(f) < 9:
         continue
@@ -198,18 +208,20 @@ def run_b200(args):
     holder['C'] = e.evaluate()
 
   sampler = ClockSampler(int(os.environ.get('LOCAL_RANK', 0)))
+  sampler.start()                        # nvidia-smi needs ~100 ms to start: launch it before the warm-up
   launches0 = ctx.kernel_launches
   for _ in range(args.warmup):
     dot_step()
   sync()
   launches_w = ctx.kernel_launches
-  sampler.start()
+  sampler.mark_begin()
   ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   ev0.record()
   for _ in range(args.steps):
     dot_step()
   ev1.record()
   sync()
+  sampler.mark_end()
   clocks = sampler.stop()
   ms = maxreduce(ev0.elapsed_time(ev1)) / args.steps
   launches = (ctx.kernel_launches - launches_w)

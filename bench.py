@@ -46,6 +46,15 @@ def parse_args():
   return ap.parse_args()
 
 
+def measured_traffic(key):
+  path = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+  try:
+    with open(path) as f:
+      return json.load(f).get(key)
+  except Exception:
+    return None
+
+
 def measured_peaks():
   path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
   if os.path.exists(path):
@@ -314,7 +323,9 @@ def run_b200(args):
     mr = {'metric': 'fused (x*2+y).sum(axis=0) GB/s', 'value': gbs, 'unit': 'GB/s', 'ms_per_step': ms_mr,
           'elements': total, 'algorithmic_bytes': bytes_alg,
           'roofline': {'bound': 'hbm', 'achieved': gbs / world, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                       'frac': gbs / world / peaks['hbm_gbs'], 'traffic': None, 'peak_source': peaks['source']},
+                       'frac': gbs / world / peaks['hbm_gbs'],
+                       'traffic': measured_traffic('stream_kernel_mapreduce_2p30') if (world == 1 and args.mr_log2 == 30) else None,
+                       'peak_source': peaks['source']},
           'max_rel_err_vs_fp64': mr_par}
 
   # ---------------- CPU baseline (rank 0, N=1): the oracle's np.dot on a bounded sample
@@ -337,7 +348,9 @@ def run_b200(args):
            'config': {'workload': 'spartan.dot %dx%d fp32, tile_hint=(%d,%d)' % (n, n, tile, tile),
                       'precision': args.precision, 'l2': 'inputs (%.1f GiB) larger than L2' % (2 * n * n * 4 / 2 ** 30)},
            'roofline': {'bound': 'tensor', 'achieved': tf, 'peak': peaks['bf16_tflops_sustained'] / 1e0,
-                        'unit': 'TFLOP/s', 'frac': tf / peaks['bf16_tflops_sustained'], 'traffic': None,
+                        'unit': 'TFLOP/s', 'frac': tf / peaks['bf16_tflops_sustained'],
+                        'traffic': measured_traffic('gemm_kernel_bf16x3_dot32768') if (world == 1 and n == 32768 and args.precision == 'bf16x3') else None,
+                        'executed_mma_frac': tf * (3 if 'x3' in args.precision else 1) / (peaks['bf16_tflops_sustained'] / (2 if args.precision.startswith('tf32') else 1)),
                         'peak_source': peaks['source'] + ' bf16 sustained (tf32 runs at half the bf16 rate)',
                         'per_gpu': True},
            'clocks': clocks, 'gpu_launches': launches, 'parity': parity, 'e2e': e2e, 'map_reduce': mr,

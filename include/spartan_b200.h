@@ -116,6 +116,8 @@ typedef enum {
   /* leaves */
   SP_OP_IN = 0,    /* push operand #arg */
   SP_OP_CONST = 1, /* push immediate #arg (sp_program.consts[arg]) */
+  SP_OP_INDEX = 2, /* push index_base + i0*index_stride[0] + i1*index_stride[1] + i2*index_stride[2]: the position of the
+                      element (map_with_location.py:22-60; argmin/argmax, sorting.py:67-124) */
   /* binary: pop b, pop a, push f(a, b)      (base.py:331-388, mathematics.py, logic.py) */
   SP_OP_ADD = 8,
   SP_OP_SUB = 9,
@@ -168,6 +170,8 @@ typedef struct {
   uint8_t arg[SP_MAX_PROGRAM];
   double consts[SP_MAX_CONSTS];   /* used when compute_dtype is SP_F32 / SP_F64 */
   int64_t iconsts[SP_MAX_CONSTS]; /* used when compute_dtype is SP_I64 */
+  int64_t index_stride[3];        /* SP_OP_INDEX: coefficients of the iteration coordinates (d0, d1, d2) */
+  int64_t index_base;
 } sp_program;
 
 typedef struct {

@@ -25,7 +25,7 @@ SP_GEMM_MAX_SEGMENTS = 8
 SP_MAX_PROGRAM, SP_MAX_OPERANDS, SP_MAX_CONSTS, SP_MAX_STACK = 64, 8, 16, 4
 SP_GEMM_MAX_TERMS = 24
 
-OP = dict(IN=0, CONST=1, ADD=8, SUB=9, MUL=10, DIV=11, MOD=12, POW=13, MAX=14, MIN=15, EQ=16, NE=17, LT=18, LE=19,
+OP = dict(IN=0, CONST=1, INDEX=2, ADD=8, SUB=9, MUL=10, DIV=11, MOD=12, POW=13, MAX=14, MIN=15, EQ=16, NE=17, LT=18, LE=19,
           GT=20, GE=21, AND=22, OR=23, XOR=24, FMOD=25, FLOORDIV=26, NEG=40, ABS=41, SQRT=42, EXP=43, LOG=44,
           SQUARE=45, RECIP=46, NOT=47, NONZERO=48, ISZERO=49, CAST_F32=56, CAST_I64=57, CAST_I32=58, CAST_BOOL=59,
           CAST_U8=60)
@@ -38,7 +38,8 @@ class SpartanError(RuntimeError):
 class sp_program(ctypes.Structure):
   _fields_ = [('n_ops', ctypes.c_int32), ('compute_dtype', ctypes.c_int32),
               ('op', ctypes.c_uint8 * SP_MAX_PROGRAM), ('arg', ctypes.c_uint8 * SP_MAX_PROGRAM),
-              ('consts', ctypes.c_double * SP_MAX_CONSTS), ('iconsts', ctypes.c_int64 * SP_MAX_CONSTS)]
+              ('consts', ctypes.c_double * SP_MAX_CONSTS), ('iconsts', ctypes.c_int64 * SP_MAX_CONSTS),
+              ('index_stride', ctypes.c_int64 * 3), ('index_base', ctypes.c_int64)]
 
 
 class sp_operand(ctypes.Structure):

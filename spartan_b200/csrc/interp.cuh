@@ -20,6 +20,9 @@ struct DevProgram {
   uint8_t op[SP_MAX_PROGRAM];
   uint8_t arg[SP_MAX_PROGRAM];
   T consts[SP_MAX_CONSTS];
+  long long index_stride[3];
+  long long index_base;
+  int32_t uses_index;
 };
 
 // How an operand is addressed along the vectorised axis.
@@ -135,7 +138,7 @@ template <typename T> __device__ __forceinline__ T cast_u8(T a) { return static_
 //   code = dense_op * 4 + slot        (slot = index of the stack register the op writes)
 // so the kernel dispatches with a single jump table (BRX) and keeps no stack pointer at all.
 enum DenseOp : int {
-  D_IN = 0, D_CONST,
+  D_IN = 0, D_CONST, D_INDEX,
   D_ADD, D_SUB, D_MUL, D_DIV, D_MOD, D_POW, D_MAX, D_MIN, D_EQ, D_NE, D_LT, D_LE, D_GT, D_GE, D_AND, D_OR, D_XOR,
   D_FMOD, D_FLOORDIV,
   D_NEG, D_ABS, D_SQRT, D_EXP, D_LOG, D_SQUARE, D_RECIP, D_NOT, D_NONZERO, D_ISZERO, D_CAST_F32, D_CAST_I64,
@@ -145,7 +148,7 @@ enum DenseOp : int {
 
 inline int dense_of(int sp_op) {
   switch (sp_op) {
-    case SP_OP_IN: return D_IN;          case SP_OP_CONST: return D_CONST;
+    case SP_OP_IN: return D_IN;          case SP_OP_CONST: return D_CONST;   case SP_OP_INDEX: return D_INDEX;
     case SP_OP_ADD: return D_ADD;        case SP_OP_SUB: return D_SUB;       case SP_OP_MUL: return D_MUL;
     case SP_OP_DIV: return D_DIV;        case SP_OP_MOD: return D_MOD;       case SP_OP_POW: return D_POW;
     case SP_OP_MAX: return D_MAX;        case SP_OP_MIN: return D_MIN;       case SP_OP_EQ: return D_EQ;
@@ -172,7 +175,7 @@ inline bool lower_program(const sp_program* prog, DevProgram<T>* out) {
     const int d = dense_of(prog->op[i]);
     if (d < 0) return false;
     int slot;
-    if (d <= D_CONST) { slot = sp; sp += 1; }
+    if (d <= D_INDEX) { slot = sp; sp += 1; if (d == D_INDEX) out->uses_index = 1; }
     else if (d <= D_FLOORDIV) { slot = sp - 2; sp -= 1; }
     else { slot = sp - 1; }
     if (slot < 0 || slot >= kMaxDepth) return false;
@@ -212,6 +215,12 @@ inline bool lower_program(const sp_program* prog, DevProgram<T>* out) {
     break;                                                           \
   }
 
+#define SP_PUSH_INDEX_CASE(S)                                        \
+  case D_INDEX * 4 + (S): {                                          \
+    _Pragma("unroll") for (int v = 0; v < V; ++v) s[(S)][v] = idx[v]; \
+    break;                                                           \
+  }
+
 // push operand: the operand index is data, the destination register is static
 #define SP_PUSH_IN_CASE(S)                                           \
   case D_IN * 4 + (S): {                                             \
@@ -227,8 +236,9 @@ inline bool lower_program(const sp_program* prog, DevProgram<T>* out) {
 // away and only the selected case's V arithmetic instructions remain.
 template <typename T, int V, int NI>
 __device__ __forceinline__ void exec_op(const int code, const int arg, const DevProgram<T>& prog, const T (&in)[NI][V],
-                                        T (&s)[kMaxDepth][V]) {
+                                        const T (&idx)[V], T (&s)[kMaxDepth][V]) {
   switch (code) {
+      SP_PUSH_INDEX_CASE(0) SP_PUSH_INDEX_CASE(1) SP_PUSH_INDEX_CASE(2) SP_PUSH_INDEX_CASE(3)
       SP_PUSH_IN_CASE(0) SP_PUSH_IN_CASE(1) SP_PUSH_IN_CASE(2) SP_PUSH_IN_CASE(3)
       SP_PUSH_CONST_CASE(0) SP_PUSH_CONST_CASE(1) SP_PUSH_CONST_CASE(2) SP_PUSH_CONST_CASE(3)
       SP_BIN(D_ADD, a + b)
@@ -271,10 +281,11 @@ __device__ __forceinline__ void exec_op(const int code, const int arg, const Dev
 
 // Evaluates `prog` on the V-wide inputs; result left in out[V].  General path: one jump-table dispatch per op.
 template <typename T, int V, int NI>
-__device__ __forceinline__ void run_program(const DevProgram<T>& prog, const T (&in)[NI][V], T (&out)[V]) {
+__device__ __forceinline__ void run_program(const DevProgram<T>& prog, const T (&in)[NI][V], const T (&idx)[V],
+                                            T (&out)[V]) {
   T s[kMaxDepth][V];
   const int n = prog.n_ops;
-  for (int pc = 0; pc < n; ++pc) exec_op<T, V, NI>(prog.op[pc], prog.arg[pc], prog, in, s);
+  for (int pc = 0; pc < n; ++pc) exec_op<T, V, NI>(prog.op[pc], prog.arg[pc], prog, in, idx, s);
 #pragma unroll
   for (int v = 0; v < V; ++v) out[v] = s[0][v];
 }
@@ -288,8 +299,9 @@ __device__ __forceinline__ void run_program(const DevProgram<T>& prog, const T (
 
 struct DynamicProgram {
   template <typename T, int V, int NI>
-  static __device__ __forceinline__ void run(const DevProgram<T>& prog, const T (&in)[NI][V], T (&out)[V]) {
-    run_program<T, V, NI>(prog, in, out);
+  static __device__ __forceinline__ void run(const DevProgram<T>& prog, const T (&in)[NI][V], const T (&idx)[V],
+                                             T (&out)[V]) {
+    run_program<T, V, NI>(prog, in, idx, out);
   }
 };
 
@@ -297,9 +309,10 @@ template <int... PKS>
 struct StaticProgram {
   static constexpr int kLen = sizeof...(PKS);
   template <typename T, int V, int NI>
-  static __device__ __forceinline__ void run(const DevProgram<T>& prog, const T (&in)[NI][V], T (&out)[V]) {
+  static __device__ __forceinline__ void run(const DevProgram<T>& prog, const T (&in)[NI][V], const T (&idx)[V],
+                                             T (&out)[V]) {
     T s[kMaxDepth][V];
-    (exec_op<T, V, NI>(PKS >> 8, PKS & 0xff, prog, in, s), ...);
+    (exec_op<T, V, NI>(PKS >> 8, PKS & 0xff, prog, in, idx, s), ...);
 #pragma unroll
     for (int v = 0; v < V; ++v) out[v] = s[0][v];
   }
@@ -330,6 +343,16 @@ using SProg13 = StaticProgram<SP_PK(D_IN, 0, 0), SP_PK(D_CONST, 1, 0), SP_PK(D_M
   X(8, SProg8) X(9, SProg9) X(10, SProg10) X(11, SProg11) X(12, SProg12) X(13, SProg13)
 
 constexpr int kNumStaticPrograms = 14;
+
+// Position operand of SP_OP_INDEX for V lanes: lane v sits at coordinate c_vec + v*step along `vec_axis`.
+template <typename T, int V>
+__device__ __forceinline__ void make_index(const DevProgram<T>& prog, long long i0, long long i1, long long i2,
+                                           int vec_axis, T (&idx)[V]) {
+  const long long base = prog.index_base + i0 * prog.index_stride[0] + i1 * prog.index_stride[1] + i2 * prog.index_stride[2];
+  const long long step = prog.index_stride[vec_axis];
+#pragma unroll
+  for (int v = 0; v < V; ++v) idx[v] = static_cast<T>(base + v * step);
+}
 
 // ---------------------------------------------------------------------------- operand access
 template <typename T, int V> struct VecLoad;

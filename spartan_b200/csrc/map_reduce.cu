@@ -35,6 +35,8 @@ static int validate_program(const sp_program* p, int n_in) {
     if (op == SP_OP_IN) {
       SP_REQUIRE(p->arg[i] < n_in, SP_ERR_INVALID, "op %d reads operand %d of %d", i, p->arg[i], n_in);
       ++sp_;
+    } else if (op == SP_OP_INDEX) {
+      ++sp_;
     } else if (op == SP_OP_CONST) {
       SP_REQUIRE(p->arg[i] < SP_MAX_CONSTS, SP_ERR_INVALID, "op %d reads constant %d", i, p->arg[i]);
       ++sp_;

@@ -58,8 +58,9 @@ map_kernel(const DevProgram<T> prog, const DevOperands<NI> ops, const Dims3 dims
         load_operand<T, V>(o, i0 * o.stride[0] + i1 * o.stride[1] + i2 * o.stride[2], o.stride[2], valid, in[i]);
       }
     }
-    T res[V];
-    run_program<T, V, NI>(prog, in, res);
+    T res[V], idx[V];
+    if (prog.uses_index) make_index<T, V>(prog, i0, i1, i2, 2, idx);
+    run_program<T, V, NI>(prog, in, idx, res);
     const DevOperand& o = ops.out;
     store_operand<T, V>(o, i0 * o.stride[0] + i1 * o.stride[1] + i2 * o.stride[2], o.stride[2], valid, res);
   }
@@ -94,10 +95,12 @@ reduce_col_kernel(const DevProgram<T> prog, const DevOperands<NI> ops, const Dim
           load_operand<T, V>(o, i0 * o.stride[0] + r * o.stride[1] + i2 * o.stride[2], o.stride[2], valid, in[i]);
         }
       }
-      T res[V];
-      run_program<T, V, NI>(prog, in, res);
+      T res[V], idx[V];
+      if (prog.uses_index) make_index<T, V>(prog, i0, r, i2, 2, idx);
+      run_program<T, V, NI>(prog, in, idx, res);
 #pragma unroll
-      for (int v = 0; v < V; ++v) acc[v] = red_apply<T>(red_op, acc[v], res[v]);
+      for (int v = 0; v < V; ++v)
+        if (v < valid) acc[v] = red_apply<T>(red_op, acc[v], res[v]);
     }
   }
 #pragma unroll
@@ -141,8 +144,9 @@ reduce_row_kernel(const DevProgram<T> prog, const DevOperands<NI> ops, const Dim
         load_operand<T, V>(o, i0 * o.stride[0] + r * o.stride[1], o.stride[1], valid, in[i]);
       }
     }
-    T res[V];
-    run_program<T, V, NI>(prog, in, res);
+    T res[V], idx[V];
+    if (prog.uses_index) make_index<T, V>(prog, i0, r, 0, 1, idx);
+    run_program<T, V, NI>(prog, in, idx, res);
 #pragma unroll
     for (int v = 0; v < V; ++v)
       if (v < valid) acc[v] = red_apply<T>(red_op, acc[v], res[v]);
@@ -188,6 +192,8 @@ template <typename T>
 static void convert_program(const sp_program* prog, DevProgram<T>* out) {
   memset(out, 0, sizeof(*out));
   lower_program<T>(prog, out);      // the program was validated by the C-ABI entry point
+  for (int i = 0; i < 3; ++i) out->index_stride[i] = prog->index_stride[i];
+  out->index_base = prog->index_base;
   for (int i = 0; i < SP_MAX_CONSTS; ++i) {
     if (TypeTag<T>::dtype == SP_I64) out->consts[i] = static_cast<T>(prog->iconsts[i]);
     else out->consts[i] = static_cast<T>(prog->consts[i]);
@@ -316,10 +322,11 @@ static int launch_map_v(const sp_program* prog, int n_in, const sp_operand* in, 
   if (V == 32 / sizeof(T)) {     // the streaming kernel uses the 32-byte-per-lane vector width
     int64_t sd[3] = {dims[0], dims[1], dims[2]};
     DevOperands<NI> sops = ops;
-    reshape_flat<T, NI>(sops, sd);
+    DevProgram<T> sdp = dp;
+    if (reshape_flat<T, NI>(sops, sd)) sdp.index_stride[1] = sd[2] * sdp.index_stride[2];   // i2 = i1' * row + i2'
     stream::Plan plan;
     if (plan_stream<T, NI>(sops, sd, true, 0, &plan))
-      return launch_stream<T, NI, 0>(dp, sops, plan, 0, nullptr, stream);
+      return launch_stream<T, NI, 0>(sdp, sops, plan, 0, nullptr, stream);
   }
   Dims3 d{dims[0], dims[1], dims[2]};
   const int64_t d2v = (dims[2] + V - 1) / V;

@@ -209,8 +209,16 @@ stream_kernel(const DevProgram<T> prog, const DevOperands<NI> ops, const Plan pl
               }
             }
           }
-          T res[V];
-          PROG::template run<T, V, NI>(prog, in, res);
+          T res[V], idx[V];
+          if (prog.uses_index) {       // two halves of the lane's vector sit EPS/2 elements apart
+            const long long base = prog.index_base + i0 * prog.index_stride[0] + (row0 + r) * prog.index_stride[1];
+#pragma unroll
+            for (int v = 0; v < H; ++v) {
+              idx[v] = static_cast<T>(base + (col_a + v) * prog.index_stride[2]);
+              idx[H + v] = static_cast<T>(base + (col_b + v) * prog.index_stride[2]);
+            }
+          }
+          PROG::template run<T, V, NI>(prog, in, idx, res);
           if (MODE == 0) {
             const DevOperand& o = ops.out;
             T* dst = static_cast<T*>(const_cast<void*>(o.ptr)) + i0 * o.stride[0] + (row0 + r) * o.stride[1];

@@ -111,18 +111,30 @@ def _leading_loops(shape, strides, keep):
 
 
 # ------------------------------------------------------------------------------------ map / reduce
-def run_map(prog, inputs, out):
-  """out[...] = prog(inputs...) element-wise with broadcasting; ``out`` may be a strided view."""
+def _set_index(prog, base, stride3):
+  prog.index_base = int(base)
+  for i in range(3):
+    prog.index_stride[i] = int(stride3[i])
+
+
+def run_map(prog, inputs, out, index=None):
+  """out[...] = prog(inputs...) element-wise with broadcasting; ``out`` may be a strided view.
+  ``index`` = (base, per-dimension coefficients): the value SP_OP_INDEX yields for element (i_0, i_1, ...)
+  is base + sum_d i_d * coef_d (e.g. the element's global position in its array)."""
   _require_cuda(out, *inputs)
   out_shape = tuple(out.shape)
   if out.numel() == 0:
     return
   strides = [broadcast_strides(t, out_shape) for t in inputs] + [list(out.stride())]
+  if index is not None:
+    strides.append(list(index[1]))
   shape, strides = collapse(out_shape, strides)
   n_in = len(inputs)
   tensors = list(inputs) + [out]
   for offs in _leading_loops(shape, strides, 3):
     s3, st3 = _pad3(shape[-3:], [st[-3:] for st in strides])
+    if index is not None:
+      _set_index(prog, index[0] + offs[n_in + 1], st3[n_in + 1])
     ops = (sp_operand * max(1, n_in))()
     for i in range(n_in):
       ops[i] = _operand(tensors[i], st3[i], offs[i])
@@ -131,7 +143,7 @@ def run_map(prog, inputs, out):
     _count_launch()
 
 
-def run_map_reduce(prog, inputs, in_shape, axis, red_op, out, accumulate):
+def run_map_reduce(prog, inputs, in_shape, axis, red_op, out, accumulate, index=None):
   """out = red_{axis} prog(inputs...) where inputs broadcast to ``in_shape``.  axis=None reduces
   everything (out is 0-d).  ``out`` holds the reduced shape (axis dropped)."""
   _require_cuda(out, *inputs)
@@ -139,17 +151,23 @@ def run_map_reduce(prog, inputs, in_shape, axis, red_op, out, accumulate):
   nd = len(in_shape)
   ctx = blob_ctx.get()
   in_strides = [broadcast_strides(t, in_shape) for t in inputs]
+  n_in = len(inputs)
+  if index is not None:
+    in_strides = in_strides + [list(index[1])]       # the position operand collapses like any other operand
   if axis is None:
-    # flatten: every operand must collapse to one (or zero) strides
+    # flatten; what does not collapse to one dimension is looped over on the host (leading dims)
     shape, strides = collapse(in_shape, in_strides)
     if len(shape) == 0:
       shape, strides = [1], [[0] for _ in in_strides]
-    if len(shape) != 1:
-      raise SpartanError('axis=None reduction over non-collapsible operand strides is not supported')
-    dims = [1, shape[0], 1]
-    st3 = [[0, st[0], 0] for st in strides]
-    out_stride = [0, 0, 0]
-    _launch_reduce(ctx, prog, inputs, st3, [0] * len(inputs), out, out_stride, 0, dims, red_op, accumulate)
+    first = True
+    for offs in _leading_loops(shape, strides, 1):
+      dims = [1, shape[-1], 1]
+      st3 = [[0, st[-1], 0] for st in strides]
+      if index is not None:
+        _set_index(prog, index[0] + offs[n_in], st3[n_in])
+      _launch_reduce(ctx, prog, inputs, st3[:n_in], offs[:n_in], out, [0, 0, 0], 0, dims, red_op,
+                     accumulate or not first)
+      first = False
     return
   axis = axis + nd if axis < 0 else axis
   outer_shape, inner_shape = in_shape[:axis], in_shape[axis + 1:]
@@ -158,15 +176,18 @@ def run_map_reduce(prog, inputs, in_shape, axis, red_op, out, accumulate):
   i_shape, i_str = collapse(inner_shape, [st[axis + 1:] for st in in_strides] + [list(out.stride())[axis:]])
   if len(i_shape) > 1:
     raise SpartanError('reduction with a non-collapsible inner block is not supported')
-  n_in = len(inputs)
   d2 = i_shape[0] if i_shape else 1
   for offs in _leading_loops(o_shape, o_str, 1):
     d0 = o_shape[-1] if o_shape else 1
     st3 = []
     for i in range(n_in):
       st3.append([o_str[i][-1] if o_shape else 0, in_strides[i][axis], i_str[i][0] if i_shape else 0])
-    out_stride = [o_str[n_in][-1] if o_shape else 0, 0, i_str[n_in][0] if i_shape else 0]
-    _launch_reduce(ctx, prog, inputs, st3, offs[:n_in], out, out_stride, offs[n_in], [d0, in_shape[axis], d2], red_op,
+    no = len(o_str) - 1          # position of the output in the stride lists (after inputs [+ index])
+    out_stride = [o_str[no][-1] if o_shape else 0, 0, i_str[no][0] if i_shape else 0]
+    if index is not None:
+      _set_index(prog, index[0] + offs[n_in], [o_str[n_in][-1] if o_shape else 0, in_strides[n_in][axis],
+                                               i_str[n_in][0] if i_shape else 0])
+    _launch_reduce(ctx, prog, inputs, st3, offs[:n_in], out, out_stride, offs[no], [d0, in_shape[axis], d2], red_op,
                    accumulate)
 
 

@@ -10,7 +10,7 @@ from .builtins import power, ln, log, square, sqrt, exp
 from .builtins import abs, maximum, minimum, sum, prod
 from .builtins import rand, randn
 from .builtins import max, min, mean
-from .builtins import count_nonzero, count_zero
+from .builtins import count_nonzero, count_zero, argmin, argmax
 from .dot import dot, DotExpr
 
 from .base import Expr, evaluate, optimized_dag
@@ -20,7 +20,7 @@ from ..array.distarray import broadcast
 from .map import map, map_tiles, MapExpr, map_with_location, tile_mapper
 from .ndarray import ndarray, NdArrayExpr
 from .optimize import optimize, MapMapFusion, ReduceMapFusion
-from .reduce import reduce, ReduceExpr
+from .reduce import reduce, ReduceExpr, ArgReduceExpr
 from .write_array import from_numpy, WriteArrayExpr
 from .program import NotDeviceMappable
 from . import local
@@ -31,6 +31,8 @@ _reduce_module = _sys.modules[__name__ + '.reduce']
 # method-style access (expr/__init__.py:68-100)
 Expr.all = all
 Expr.any = any
+Expr.argmax = argmax
+Expr.argmin = argmin
 Expr.astype = astype
 Expr.dot = dot
 Expr.fill = full_like

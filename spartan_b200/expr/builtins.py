@@ -17,7 +17,8 @@ from .base import Expr
 from .map import map, map_with_location
 from .ndarray import ndarray
 from .optimize import not_idempotent
-from .reduce import reduce
+from .reduce import reduce, ArgReduceExpr
+from .base import as_array as _as_array
 
 
 # ------------------------------------------------------------------------------------ creation.py
@@ -355,3 +356,13 @@ def count_zero(array, axis=None):
   """sorting.py:160-172."""
   return reduce(array, axis, dtype_fn=lambda input: np.int64, local_reduce_fn=_countzero_local,
                 accumulate_fn=np.add)
+
+
+def argmin(x, axis=None):
+  """Compute argmin over ``axis`` (sorting.py:88-105)."""
+  return ArgReduceExpr(array=_as_array(x), axis=axis, which='min')
+
+
+def argmax(x, axis=None):
+  """Compute argmax over ``axis`` (sorting.py:108-124)."""
+  return ArgReduceExpr(array=_as_array(x), axis=axis, which='max')

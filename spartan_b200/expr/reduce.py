@@ -149,3 +149,76 @@ def reduce(v, axis, dtype_fn, local_reduce_fn, accumulate_fn, fn_kw=None, tile_h
                               kw=fn_kw)
   return ReduceExpr(children=ListExpr(vals=[as_array(v)]), child_to_var=[varname], axis=axis, dtype_fn=dtype_fn,
                     op=reduce_op, accumulate_fn=accumulate_fn, tile_hint=tile_hint)
+
+
+class ArgReduceExpr(Expr):
+  """argmin / argmax (reference: spartan/expr/sorting.py:67-124).
+
+  The reference composes ``min -> map_with_location(_arg_mapper) -> min``: the extreme value, then for
+  every element its global position if it equals the extreme (else a sentinel = array size), then the
+  smallest position.  Same algorithm here in two fused passes per block of the rank's slab -- pass 2 is one
+  map+reduce whose program reads the element position from the bytecode's INDEX leaf -- with the two
+  cross-tile combines done by ncclAllReduce(min/max) and ncclAllReduce(min)."""
+  members = ('array', 'axis', 'which')
+
+  def compute_shape(self):
+    return tuple(extent.shape_for_reduction(self.array.shape, self.axis))
+
+  def _evaluate(self, ctx, deps):
+    from .._lib import SP_RED_MIN, SP_RED_MAX, SP_F64, SP_I64, SP_F32
+    arr, axis, which = deps['array'], deps['axis'], deps['which']
+    if not isinstance(arr, distarray.DistArrayImpl):
+      raise program.NotDeviceMappable('argmin/argmax need a distributed array')
+    nd = len(arr.shape)
+    if axis is not None and axis < 0:
+      axis += nd
+    red = SP_RED_MIN if which == 'min' else SP_RED_MAX
+    out_shape = tuple(extent.shape_for_reduction(arr.shape, axis))
+    is_float = arr.dtype.kind == 'f'
+    blocks = arr.local_blocks()
+
+    # pass 1: the extreme value of every output cell, replicated on every rank
+    compute1 = SP_F64 if arr.dtype == np.float64 else (SP_F32 if is_float else SP_I64)
+    prog1 = device_ops.make_program([('IN', 0)], compute1)
+    m = ctx.empty(out_shape, arr.dtype)
+    m.fill_(tile.identity_of(red, arr.dtype))
+    for block in blocks:
+      x = arr.fetch(block)
+      dst = extent.index_for_reduction(block, axis)
+      device_ops.run_map_reduce(prog1, [x], block.shape, axis, red, m[dst.to_slice()] if m.dim() else m, True)
+    comm.allreduce(m, red)
+
+    # pass 2: smallest global position whose value equals the extreme; sentinel = number of elements
+    big = int(np.prod(arr.shape, dtype=np.int64))
+    compute2 = SP_F64 if is_float else SP_I64
+    prog2 = device_ops.make_program([('IN', 0), ('IN', 1), ('EQ', 0), ('INDEX', 0), ('CONST', 0), ('SUB', 0),
+                                     ('MUL', 0), ('CONST', 0), ('ADD', 0)], compute2, [big])
+    pos = ctx.empty(out_shape, np.int64)
+    pos.fill_(np.iinfo(np.int64).max)
+    for block in blocks:
+      x = arr.fetch(block)
+      dst = extent.index_for_reduction(block, axis)
+      mb = m[dst.to_slice()] if m.dim() else m
+      if axis is not None:
+        mb = mb.unsqueeze(axis)
+        index = (block.ul[axis], [1 if d == axis else 0 for d in range(nd)])
+      else:
+        coefs = [int(np.prod(arr.shape[d + 1:], dtype=np.int64)) for d in range(nd)]
+        index = (extent.ravelled_pos(block.ul, arr.shape), coefs)
+      device_ops.run_map_reduce(prog2, [x, mb], block.shape, axis, SP_RED_MIN, pos[dst.to_slice()] if pos.dim() else pos,
+                                True, index=index)
+    comm.allreduce(pos, SP_RED_MIN)
+
+    output_array = distarray.create(out_shape, np.int64, reducer=np.minimum)
+    for ex, tid in output_array.tiles.items():
+      if ctx.is_local(tid):
+        t = ctx.tile(tid)
+        src = pos[ex.to_slice()] if pos.dim() else pos
+        if len(output_array.tiles) == 1:
+          t.data = src
+        else:
+          device_ops.copy_rect(t.get(None), src)
+        t.valid = True
+    if len(output_array.tiles) == 1 and output_array.slab is not None:
+      output_array.slab = pos if pos.dim() else None
+    return output_array

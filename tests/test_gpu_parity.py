@@ -376,3 +376,29 @@ def test_gemm_split_form_matches_one_call():
     device_ops.gemm_prepare_b(B[:600], pb, Kp, 0, prec); device_ops.gemm_prepare_b(B[600:], pb, Kp, 600, prec)
     device_ops.gemm_prepared([(pa, pb, Kp)], C2, accumulate=False, precision=prec)
     assert torch.equal(C1, C2), prec
+
+
+# ------------------------------------------------------------------ tests/test_reduce.py:38-90 argmin / argmax
+def test_argmin_argmax_reference_cases():
+  nx1 = np.arange(TEST_SIZE, dtype=np.int64)
+  Assert.all_eq(sp.arange((TEST_SIZE,), dtype=np.int64).argmin().glom(), nx1.argmin())
+  Assert.all_eq(sp.arange((TEST_SIZE,), dtype=np.int64).argmax().glom(), nx1.argmax())
+  nx2 = np.arange(TEST_SIZE * TEST_SIZE, dtype=np.int64).reshape((TEST_SIZE, TEST_SIZE))
+  x2 = sp.arange((TEST_SIZE, TEST_SIZE), dtype=np.int64)
+  Assert.all_eq(x2.argmin(axis=1).glom(), nx2.argmin(axis=1))
+  Assert.all_eq(x2.argmax(axis=1).glom(), nx2.argmax(axis=1))
+  nx3 = np.arange(TEST_SIZE ** 3, dtype=np.int64).reshape((TEST_SIZE,) * 3)
+  for axis in [None, 0, 1, 2]:
+    x3 = sp.arange((TEST_SIZE,) * 3, dtype=np.int64)
+    Assert.all_eq(x3.argmin(axis).glom(), nx3.argmin(axis))
+    Assert.all_eq(x3.argmax(axis).glom(), nx3.argmax(axis))
+
+
+@pytest.mark.parametrize('shape,hint', [((257, 129), None), ((64, 4100), (16, 4100)), ((300, 700), (100, 128)), ((5, 6, 7), None)])
+def test_argmin_argmax_random(shape, hint):
+  """Index results are bit-exact, including ties (smallest index wins, like np.argmin)."""
+  rng = np.random.RandomState(13)
+  for x in (rng.randn(*shape).astype(np.float32), rng.randint(-5, 5, size=shape).astype(np.int64)):
+    for axis in [None] + list(range(len(shape))):
+      Assert.all_eq(np.asarray(sp.argmin(sp.from_numpy(x, tile_hint=hint), axis).glom()), np.asarray(x.argmin(axis)))
+      Assert.all_eq(np.asarray(sp.argmax(sp.from_numpy(x, tile_hint=hint), axis).glom()), np.asarray(x.argmax(axis)))

@@ -266,6 +266,25 @@ int sp_gemm_prepared(int n_seg, const sp_gemm_prepared_segment* segs, float* C, 
 int sp_gemm_f32(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
                 int64_t N, int64_t K, int accumulate, int precision, void* workspace, int64_t workspace_bytes,
                 void* stream);
+/* ------------------------------------------------------------------------
+ * Application kernels on the hot path (BASELINE configs 4, 5).
+ * ------------------------------------------------------------------------ */
+/* One k-means pass over a block of points (examples/sklearn/cluster/k_means_.py:61-97):
+ *   labels[i] = argmin_j |X_i - centers_j|^2   (kmeans_map2_dist_mapper; ties -> smallest j, like np.argmin)
+ *   counts[labels[i]] += 1                      (kmeans_count_mapper)
+ *   sums[labels[i], :] += X_i                   (kmeans_center_mapper)
+ * sums [k, d] and counts [k] are ACCUMULATED into (zero them before the first block); the caller divides and
+ * all-reduces across GPUs.  Distances go through the tensor cores (bf16x3 split GEMM of X . centers^T). */
+#define SP_KMEANS_CHUNK_ROWS 262144
+int64_t sp_kmeans_workspace_bytes(int64_t n, int64_t d, int64_t k);
+int sp_kmeans_assign(const float* X, int64_t ldx, int64_t n, int64_t d, const float* centers, int64_t k,
+                     int32_t* labels, float* sums, int64_t* counts, void* workspace, int64_t workspace_bytes,
+                     void* stream);
+/* y (+)= A x with A in CSR (dot.py:213-217 `tocsr().dot(dense)`; sparse.pyx:103-158 dot_coo_dense_unordered_map).
+ * rowptr[n_rows + 1] int64, colidx int32, values fp32; x, y dense fp32. */
+int sp_spmv_csr(const int64_t* rowptr, const int32_t* colidx, const float* values, int64_t n_rows, const float* x,
+                float* y, int accumulate, void* stream);
+
 /* CUDA-core GEMM for dtypes the tensor path does not carry exactly (reference tests use
  * float64 / int64 operands: tests/test_dot.py:8-103, tests/test_matmul.py:12-22). */
 int sp_gemm_simt(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t M, int64_t N,

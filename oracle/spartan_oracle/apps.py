@@ -1,0 +1,75 @@
+"""ORACLE (test infrastructure only) -- k-means iteration and strip SpMV.
+
+PARITY UNPINNED: the reference's tests for these two paths assert nothing (tests/test_kmeans.py:16-21 is a
+smoke test, tests/test_pagerank.py and tests/test_sparse.py contain no numeric assertion).
+What follows restates the mapper math against SciPy/NumPy directly; tolerances are stated in the tests.
+
+k-means: spartan/examples/sklearn/cluster/k_means_.py:61-97 (mappers) and :130-160 (driver, 'map2').
+SpMV:    spartan/expr/dot.py:213-217 (`tocsr().dot(dense)` per column strip) + np.add merge.
+"""
+import numpy as np
+import scipy.sparse
+from scipy.spatial.distance import cdist
+
+
+def kmeans_dist_mapper(points, centers):
+  return np.argmin(cdist(points, centers), axis=1)                 # k_means_.py:61-66
+
+
+def kmeans_count_mapper(labels, centers_count):
+  return np.bincount(labels.astype(np.int64), minlength=centers_count)   # k_means_.py:69-72
+
+
+def kmeans_center_mapper(points, labels, centers_count):
+  new_centers = np.zeros((centers_count, points.shape[1]))         # k_means_.py:75-97
+  for i in range(centers_count):
+    new_centers[i] = points[labels == i].sum(axis=0)
+  return new_centers
+
+
+def kmeans_fit(X, centers, n_iter, tile_rows, seed=0):
+  """k_means_.py:130-160 with the per-tile results SUMMED across row tiles (the evident intent; the
+  reference's reducer-less map2 targets overwrite) and a seeded re-seed of empty
+  clusters."""
+  rng = np.random.RandomState(seed)
+  n, d = X.shape
+  k = centers.shape[0]
+  centers = centers.astype(np.float64)
+  labels = np.zeros(n, dtype=np.int64)
+  for _ in range(n_iter):
+    counts = np.zeros(k)
+    sums = np.zeros((k, d))
+    for r0 in range(0, n, tile_rows):
+      pts = X[r0:r0 + tile_rows]
+      lab = kmeans_dist_mapper(pts, centers)
+      labels[r0:r0 + tile_rows] = lab
+      counts += kmeans_count_mapper(lab, k)
+      sums += kmeans_center_mapper(pts, lab, k)
+    z = counts == 0
+    if np.any(z):
+      counts[z] = 1
+      sums[z, :] = rng.randn(int(np.count_nonzero(z)), d)
+    centers = sums / counts.reshape(k, 1)
+  return centers, labels
+
+
+def spmv_strips(matrix, x, strip_width):
+  """Per column strip `tiles[0].tocsr().dot(tiles[1])`, partials merged with np.add (dot.py:213-217)."""
+  matrix = scipy.sparse.csc_matrix(matrix)
+  n_rows, n_cols = matrix.shape
+  y = np.zeros(n_rows, dtype=np.float32)
+  xv = np.asarray(x).reshape(-1)
+  for c0 in range(0, n_cols, strip_width):
+    c1 = min(n_cols, c0 + strip_width)
+    y = np.add(y, matrix[:, c0:c1].tocsr().dot(xv[c0:c1]).astype(np.float32))
+  return y
+
+
+def make_weights(n, outlinks, seed):
+  """tests/benchmark_pagerank.py:11-24 with a seeded generator: n*outlinks random (dest, source) pairs."""
+  rng = np.random.default_rng(seed)
+  num_out = n * outlinks
+  source = rng.integers(0, n, num_out)
+  dest = rng.integers(0, n, num_out)
+  value = rng.random(num_out, dtype=np.float32)
+  return scipy.sparse.coo_matrix((value, (source, dest)), shape=(n, n))

@@ -13,6 +13,8 @@ from .expr import *                      # noqa: F401,F403  (spartan/__init__.py
 from .expr import map, sum, min, max, abs, all, any   # noqa: F401  names that shadow builtins on purpose
 from . import expr
 from .array import distarray, extent, tile
+from . import sparse
+from .examples.kmeans import KMeans
 
 
 def initialize(argv=None, device=None):

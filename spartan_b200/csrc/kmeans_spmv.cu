@@ -1,0 +1,162 @@
+// k-means assignment/accumulation and CSR SpMV: the two application kernels on the hot path
+// (BASELINE configs 4 and 5).
+//
+// k-means (reference: spartan/examples/sklearn/cluster/k_means_.py:61-97)
+//   kmeans_map2_dist_mapper   labels = argmin(cdist(points, centers), axis=1)      O(n k d) scalar C in SciPy
+//   kmeans_count_mapper       counts = bincount(labels)
+//   kmeans_center_mapper      sums[c] = points[labels == c].sum(0)                 Python loop over k
+// Here: distances through the tensor cores -- argmin_j |x - c_j|^2 = argmin_j (|c_j|^2 - 2 x.c_j), the
+// x.c_j block is one tcgen05 GEMM per chunk of rows (bf16x3, fp32-faithful) -- then one warp per point
+// picks the label (ties: smallest index, like np.argmin) and adds the point into its centroid with
+// vectorised fire-and-forget float atomics.  Roofline: distance GEMM = tensor pipe (2 n d k flop);
+// label + accumulate = HBM (read n*k distances + n*d points).
+//
+// SpMV (reference: spartan/expr/dot.py:213-217 `tocsr().dot(dense)`, spartan/array/sparse.pyx:103-158)
+//   y (+)= A x, A in CSR: one 8-thread group per row, coalesced val/col loads, gather of x through
+//   the read-only path, shuffle reduction.  Roofline: HBM, 8 B per non-zero + 12 B per row.
+#include "sp_common.h"
+#include <algorithm>
+#include <float.h>
+
+namespace sp {
+
+__global__ void row_sqnorm_kernel(const float* __restrict__ C, int64_t ldc, int k, int d, float* __restrict__ out) {
+  const int row = blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
+  const int lane = threadIdx.x & 31;
+  if (row >= k) return;
+  float s = 0.f;
+  for (int j = lane; j < d; j += 32) {
+    const float v = C[static_cast<int64_t>(row) * ldc + j];
+    s += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) out[row] = s;
+}
+
+// one warp per point: label = argmin_j (cnorm[j] - 2 * D[i, j]); then sums[label] += x_i, counts[label] += 1
+__global__ void __launch_bounds__(256)
+kmeans_label_accumulate_kernel(const float* __restrict__ D, int64_t ldd, const float* __restrict__ cnorm,
+                               const float* __restrict__ X, int64_t ldx, int64_t n, int d, int k,
+                               int32_t* __restrict__ labels, float* __restrict__ sums, unsigned long long* __restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = static_cast<int64_t>(gridDim.x) * (blockDim.x / 32);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x / 32) + (threadIdx.x / 32); i < n; i += warps) {
+    const float* drow = D + i * ldd;
+    float best = FLT_MAX;
+    int best_j = 0x7fffffff;
+    for (int j = lane; j < k; j += 32) {
+      const float v = cnorm[j] - 2.0f * drow[j];
+      if (v < best) { best = v; best_j = j; }     // j increases per lane: first minimum kept
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_down_sync(0xffffffffu, best, o);
+      const int oj = __shfl_down_sync(0xffffffffu, best_j, o);
+      if (ob < best || (ob == best && oj < best_j)) { best = ob; best_j = oj; }
+    }
+    best_j = __shfl_sync(0xffffffffu, best_j, 0);
+    if (lane == 0) {
+      labels[i] = best_j;
+      atomicAdd(counts + best_j, 1ull);
+    }
+    const float* x = X + i * ldx;
+    float* dst = sums + static_cast<int64_t>(best_j) * d;
+    if ((d & 3) == 0 && ((reinterpret_cast<uint64_t>(x) | reinterpret_cast<uint64_t>(dst)) & 15) == 0) {
+      for (int j = lane * 4; j < d; j += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(x + j);
+        atomicAdd(reinterpret_cast<float4*>(dst + j), v);       // red.global.add.v4.f32 (sm_90+)
+      }
+    } else {
+      for (int j = lane; j < d; j += 32) atomicAdd(dst + j, x[j]);
+    }
+  }
+}
+
+// CSR SpMV: GROUP threads per row
+template <int GROUP>
+__global__ void __launch_bounds__(256)
+spmv_csr_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
+                int64_t n_rows, const float* __restrict__ x, float* __restrict__ y, int accumulate) {
+  const int g = threadIdx.x % GROUP;
+  const int64_t groups = static_cast<int64_t>(gridDim.x) * (blockDim.x / GROUP);
+  for (int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x / GROUP) + threadIdx.x / GROUP; row < n_rows;
+       row += groups) {
+    const int64_t lo = rowptr[row], hi = rowptr[row + 1];
+    float s = 0.f;
+    for (int64_t p = lo + g; p < hi; p += GROUP) s += val[p] * __ldg(x + col[p]);
+#pragma unroll
+    for (int o = GROUP / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, GROUP);
+    if (g == 0) y[row] = accumulate ? y[row] + s : s;
+  }
+}
+
+}  // namespace sp
+
+using namespace sp;
+
+extern "C" int64_t sp_kmeans_workspace_bytes(int64_t n, int64_t d, int64_t k) {
+  const int64_t rows = std::min<int64_t>(n, SP_KMEANS_CHUNK_ROWS);
+  const int64_t Kp = sp_gemm_kpad(d, SP_GEMM_BF16X3);
+  return sp_gemm_prepared_bytes(rows, Kp, SP_GEMM_BF16X3) + sp_gemm_prepared_bytes(k, Kp, SP_GEMM_BF16X3) +
+         rows * k * 4 + k * 4 + 4096;
+}
+
+extern "C" int sp_kmeans_assign(const float* X, int64_t ldx, int64_t n, int64_t d, const float* centers, int64_t k,
+                                int32_t* labels, float* sums, int64_t* counts, void* workspace,
+                                int64_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SP_REQUIRE(n >= 0 && d > 0 && k > 0 && k < (1ll << 31) && d < (1ll << 31), SP_ERR_INVALID, "sp_kmeans_assign: bad shape");
+  if (n == 0) return SP_OK;
+  SP_REQUIRE(X && centers && labels && sums && counts, SP_ERR_INVALID, "sp_kmeans_assign: null pointer");
+  SP_REQUIRE(workspace != nullptr && workspace_bytes >= sp_kmeans_workspace_bytes(n, d, k), SP_ERR_INVALID,
+             "sp_kmeans_assign: workspace too small");
+  const int prec = SP_GEMM_BF16X3;
+  const int64_t rows = std::min<int64_t>(n, SP_KMEANS_CHUNK_ROWS);
+  const int64_t Kp = sp_gemm_kpad(d, prec);
+  uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uint64_t>(workspace) + 1023) & ~1023ull);
+  const int64_t a_bytes = (sp_gemm_prepared_bytes(rows, Kp, prec) + 1023) / 1024 * 1024;
+  const int64_t b_bytes = (sp_gemm_prepared_bytes(k, Kp, prec) + 1023) / 1024 * 1024;
+  uint8_t* a_prep = ws;
+  uint8_t* b_prep = a_prep + a_bytes;
+  float* D = reinterpret_cast<float*>(b_prep + b_bytes);
+  float* cnorm = D + rows * k;
+  if (Kp != (d + 3) / 4 * 4) {
+    SP_CUDA_CHECK(cudaMemsetAsync(a_prep, 0, a_bytes, stream));
+    SP_CUDA_CHECK(cudaMemsetAsync(b_prep, 0, b_bytes, stream));
+  }
+  // the centres are already "B transposed" ([k, d] = [N, K]): prepare them like an A operand
+  int rc = sp_gemm_prepare_a(centers, d, k, d, prec, b_prep, Kp, 0, b_bytes, stream);
+  if (rc) return rc;
+  row_sqnorm_kernel<<<static_cast<unsigned>((k + 7) / 8), 256, 0, stream>>>(centers, d, static_cast<int>(k),
+                                                                            static_cast<int>(d), cnorm);
+  for (int64_t r0 = 0; r0 < n; r0 += rows) {
+    const int64_t m = std::min<int64_t>(rows, n - r0);
+    rc = sp_gemm_prepare_a(X + r0 * ldx, ldx, m, d, prec, a_prep, Kp, 0, a_bytes, stream);
+    if (rc) return rc;
+    sp_gemm_prepared_segment seg;
+    seg.A = a_prep; seg.B = b_prep; seg.Kp = Kp;
+    rc = sp_gemm_prepared(1, &seg, D, k, m, k, 0, prec, stream);
+    if (rc) return rc;
+    const int blocks = static_cast<int>(std::min<int64_t>((m + 7) / 8, static_cast<int64_t>(num_sms()) * 8));
+    kmeans_label_accumulate_kernel<<<blocks, 256, 0, stream>>>(D, k, cnorm, X + r0 * ldx, ldx, m, static_cast<int>(d),
+                                                               static_cast<int>(k), labels + r0, sums,
+                                                               reinterpret_cast<unsigned long long*>(counts));
+    SP_CUDA_CHECK(cudaGetLastError());
+  }
+  return SP_OK;
+}
+
+extern "C" int sp_spmv_csr(const int64_t* rowptr, const int32_t* colidx, const float* values, int64_t n_rows,
+                           const float* x, float* y, int accumulate, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SP_REQUIRE(n_rows >= 0, SP_ERR_INVALID, "sp_spmv_csr: negative row count");
+  if (n_rows == 0) return SP_OK;
+  SP_REQUIRE(rowptr && x && y, SP_ERR_INVALID, "sp_spmv_csr: null pointer");
+  const int64_t groups_per_block = 256 / 8;
+  const int blocks = static_cast<int>(std::min<int64_t>((n_rows + groups_per_block - 1) / groups_per_block,
+                                                        static_cast<int64_t>(num_sms()) * 16));
+  spmv_csr_kernel<8><<<blocks, 256, 0, stream>>>(rowptr, colidx, values, n_rows, x, y, accumulate);
+  SP_CUDA_CHECK(cudaGetLastError());
+  return SP_OK;
+}

@@ -1,0 +1,68 @@
+"""K-Means on the device (reference: spartan/examples/sklearn/cluster/k_means_.py:61-160, the 'map2'
+implementation: kmeans_map2_dist_mapper -> kmeans_count_mapper -> kmeans_center_mapper per row tile).
+
+One iteration = one `sp_kmeans_assign` per contiguous block of this rank's rows (distance GEMM on the tensor
+cores + label/accumulate kernel) followed by ncclAllReduce of the (k x d) sums and the k counts -- the
+cross-tile combine the reference's map2 targets were meant to do (they have no reducer and overwrite,
+SURVEY.md section 9 Q7).  Empty clusters are re-seeded on the host exactly like the reference does
+(k_means_.py:148-157) but from a seeded generator so every rank agrees."""
+import numpy as np
+import torch
+
+from .. import blob_ctx, comm, device_ops
+from .._lib import lib, check, SP_RED_SUM, SpartanError
+from ..array import distarray, extent
+from ..expr.base import Expr, evaluate
+
+
+class KMeans(object):
+  def __init__(self, n_clusters=8, n_iter=100):
+    self.n_clusters = n_clusters
+    self.n_iter = n_iter
+
+  def fit(self, X, centers=None, implementation='map2', seed=0):
+    """X: (n_samples, n_features) float32 array tiled by rows.  centers: initial (k, d) ndarray or None.
+    Returns (centers ndarray float32, labels DistArray int32)."""
+    ctx = blob_ctx.get()
+    X = evaluate(X) if isinstance(X, Expr) else X
+    if not isinstance(X, distarray.DistArrayImpl) or len(X.shape) != 2 or X.dtype != np.float32:
+      raise SpartanError('KMeans.fit needs a 2-D float32 distributed array')
+    n, d = X.shape
+    k = self.n_clusters
+    for ex in X.tiles:
+      if ex.ul[1] != 0 or ex.lr[1] != d:
+        raise SpartanError('KMeans.fit: X must be tiled by rows (k_means_.py:122)')
+    rng = np.random.RandomState(seed)
+    if centers is None:
+      centers = rng.rand(k, d)                                   # k_means_.py:132
+    centers = np.ascontiguousarray(centers, dtype=np.float32)
+    tile_rows = X.tile_shape()[0]
+    labels = distarray.create((n,), np.int32, tile_hint=(tile_rows,))
+    sums = torch.zeros((k, d), dtype=torch.float32, device=ctx.device)
+    counts = torch.zeros((k,), dtype=torch.int64, device=ctx.device)
+    for it in range(self.n_iter):
+      sums.zero_(); counts.zero_()
+      c_dev = torch.from_numpy(centers).to(ctx.device)
+      for block in X.local_blocks():
+        x = X.fetch(block)
+        lab = labels.fetch(extent.create((block.ul[0],), (block.lr[0],), (n,)))
+        m = x.shape[0]
+        need = lib.sp_kmeans_workspace_bytes(m, d, k)
+        ws = ctx.scratch(need, 'kmeans')
+        check(lib.sp_kmeans_assign(x.data_ptr(), x.stride(0), m, d, c_dev.data_ptr(), k, lab.data_ptr(),
+                                   sums.data_ptr(), counts.data_ptr(), ws.data_ptr(), ws.numel(), ctx.stream_ptr()),
+              'sp_kmeans_assign')
+        ctx.kernel_launches += 6
+      comm.allreduce(sums, SP_RED_SUM)
+      comm.allreduce(counts, SP_RED_SUM)
+      counts_h = counts.cpu().numpy().astype(np.float64)
+      centers_h = sums.cpu().numpy().astype(np.float64)
+      zcount = counts_h == 0                                     # k_means_.py:148-157
+      if np.any(zcount):
+        counts_h[zcount] = 1
+        centers_h[zcount, :] = rng.randn(int(np.count_nonzero(zcount)), d)
+      centers = (centers_h / counts_h.reshape(k, 1)).astype(np.float32)   # k_means_.py:159
+    for tid in labels.tiles.values():
+      if ctx.is_local(tid):
+        ctx.tile(tid).valid = True
+    return centers, labels

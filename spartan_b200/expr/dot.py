@@ -244,6 +244,9 @@ def dot(a, b, tile_hint=None):
   :param tile_hint: tiling of the result (default: one tile, like the reference)
   :rtype: `DotExpr`
   """
+  from ..sparse import SparseStripsExpr, spmv
+  if isinstance(a, SparseStripsExpr):          # dot.py:212-217 sparse branch: sparse strips x dense vector
+    return spmv(a, b, tile_hint)
   a = lazify(a)
   if not isinstance(b, np.ndarray):
     b = lazify(b)

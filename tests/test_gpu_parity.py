@@ -402,3 +402,42 @@ def test_argmin_argmax_random(shape, hint):
     for axis in [None] + list(range(len(shape))):
       Assert.all_eq(np.asarray(sp.argmin(sp.from_numpy(x, tile_hint=hint), axis).glom()), np.asarray(x.argmin(axis)))
       Assert.all_eq(np.asarray(sp.argmax(sp.from_numpy(x, tile_hint=hint), axis).glom()), np.asarray(x.argmax(axis)))
+
+
+# ------------------------------------------------------------------ k-means and SpMV (reference parity unpinned)
+@pytest.mark.parametrize('n,d,k,tile_rows', [(20000, 32, 16, 5000), (3000, 50, 7, 1000), (70000, 256, 64, 70000)])
+def test_kmeans_vs_oracle(n, d, k, tile_rows):
+  """Labels come from fp32 tensor-core distances vs SciPy's float64 cdist: points within ~1e-5 relative distance of
+  a cluster boundary may flip.  Tolerance: >= 99.9 % identical labels after the first pass, centres within 1e-3."""
+  from spartan_oracle import apps
+  rng = np.random.default_rng(4)
+  X = rng.random((n, d), dtype=np.float32)
+  c0 = X[:k].copy()
+  km = sp.KMeans(n_clusters=k, n_iter=1)
+  centers, labels = km.fit(sp.from_numpy(X, tile_hint=(tile_rows, d)), centers=c0)
+  ref_c, ref_l = apps.kmeans_fit(X, c0, 1, tile_rows)
+  got_l = labels.glom()
+  assert got_l.dtype == np.int32 and centers.dtype == np.float32
+  assert (got_l == ref_l).mean() >= 0.999
+  np.testing.assert_allclose(centers, ref_c, rtol=1e-3, atol=1e-4)
+  centers3, _ = sp.KMeans(n_clusters=k, n_iter=3).fit(sp.from_numpy(X, tile_hint=(tile_rows, d)), centers=c0)
+  ref_c3, _ = apps.kmeans_fit(X, c0, 3, tile_rows)
+  np.testing.assert_allclose(centers3, ref_c3, rtol=5e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize('n,outlinks,strip', [(5000, 10, 625), (12345, 3, 5000), (40000, 10, 40000)])
+def test_spmv_vs_oracle(n, outlinks, strip):
+  """PageRank step y = W p (benchmark_pagerank.py shape).  fp32 sums in a different order: 1e-5 relative."""
+  from spartan_oracle import apps
+  W = apps.make_weights(n, outlinks, seed=5)
+  rng = np.random.default_rng(6)
+  p = rng.random((n, 1), dtype=np.float32)
+  wts = sp.sparse.from_scipy(W, strip_width=strip)
+  got = sp.dot(wts, sp.from_numpy(p, tile_hint=(strip, 1))).glom()
+  ref = apps.spmv_strips(W, p, strip)
+  exact = (W.tocsr().astype(np.float64) @ p.astype(np.float64)).reshape(-1)
+  assert got.shape == (n, 1) and got.dtype == np.float32
+  np.testing.assert_allclose(got.reshape(-1), ref, rtol=1e-5, atol=1e-6)
+  np.testing.assert_allclose(got.reshape(-1), exact, rtol=1e-5, atol=1e-6)
+  ones = sp.dot(wts, sp.ones((n, 1), tile_hint=(strip, 1))).glom().reshape(-1)       # p = ones, as in the benchmark
+  np.testing.assert_allclose(ones, np.asarray(W.tocsr().sum(axis=1)).reshape(-1), rtol=1e-5, atol=1e-6)

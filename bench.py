@@ -261,7 +261,7 @@ def run_b200(args):
   if not args.skip_e2e:
     import psutil
     ne = n
-    need = 3 * ne * ne * 4 * (world if world > 1 else 1)       # every rank holds pinned a, b and its read-back buffer
+    need = 3 * ne * ne * 4 * world       # every rank holds pinned a, b and a read-back buffer
     if psutil.virtual_memory().available < 2 * need:
       e2e = {'skipped': 'host memory: need %.0f GiB pinned across ranks' % (need / 2 ** 30)}
     else:
@@ -269,7 +269,8 @@ def run_b200(args):
       b_host = torch.empty((ne, ne), dtype=torch.float32, pin_memory=True)
       a_host.uniform_(0, 1); b_host.uniform_(0, 1)
       a_np, b_np = a_host.numpy(), b_host.numpy()
-      out_host = torch.empty((ne * ne // world + 1,), dtype=torch.float32, pin_memory=True)
+      out_host = torch.empty((ne, ne), dtype=torch.float32, pin_memory=True)
+      out_np = out_host.numpy()
       out_bytes = [0]
 
       def e2e_step():
@@ -277,14 +278,7 @@ def run_b200(args):
         e = sp.dot(sp.from_numpy(a_np, tile_hint=(tile, tile)), sp.from_numpy(b_np, tile_hint=(tile, tile)),
                    tile_hint=(tile, tile))
         c = e.evaluate()
-        # result read-back (D2H into pinned memory): this rank's share of C
-        pieces = [c.slab] if c.slab is not None else [ctx.get(tid, None) for ex, tid in c.tiles.items() if ctx.is_local(tid)]
-        off = 0
-        for t in pieces:
-          k = t.numel()
-          out_host[off:off + k].view(t.shape).copy_(t, non_blocking=True)
-          off += k
-        out_bytes[0] = off * 4
+        out_bytes[0] = c.read_local_into(out_np)          # D2H of this rank's share of C into pinned memory
         torch.cuda.current_stream().synchronize()
 
       steps_e = max(1, min(args.steps, 3))

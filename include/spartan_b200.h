@@ -215,6 +215,13 @@ int sp_combine(void* dst, const void* src, int dtype, int64_t n, int reduce_op, 
 int sp_copy_rect(void* dst, const int64_t dst_stride[3], const void* src, const int64_t src_stride[3],
                  const int64_t dims[3], int dtype, void* stream);
 
+/* Host <-> device rectangle transfers (pitched DMA; asynchronous on `stream` when the host buffer is pinned).
+ * Replaces the pickled-ndarray payloads of BlobCtx.get / update (blob_ctx.py:127-179) at the host boundary. */
+int sp_upload_2d(void* dst_device, int64_t dst_pitch_bytes, const void* src_host, int64_t src_pitch_bytes,
+                 int64_t width_bytes, int64_t rows, void* stream);
+int sp_download_2d(void* dst_host, int64_t dst_pitch_bytes, const void* src_device, int64_t src_pitch_bytes,
+                   int64_t width_bytes, int64_t rows, void* stream);
+
 /* ------------------------------------------------------------------------
  * Dense contraction (dot.py:195-238 dot_map2_mapper / dot_outer_mapper:
  * `tiles[0].dot(tiles[1])`, partials merged with np.add).
@@ -281,9 +288,10 @@ int sp_kmeans_assign(const float* X, int64_t ldx, int64_t n, int64_t d, const fl
                      int32_t* labels, float* sums, int64_t* counts, void* workspace, int64_t workspace_bytes,
                      void* stream);
 /* y (+)= A x with A in CSR (dot.py:213-217 `tocsr().dot(dense)`; sparse.pyx:103-158 dot_coo_dense_unordered_map).
- * rowptr[n_rows + 1] int64, colidx int32, values fp32; x, y dense fp32. */
+ * rowptr[n_rows + 1] int64, colidx int32, values fp32; x, y dense fp32.  avg_nnz_per_row (0 = unknown) picks the
+ * number of threads that share a row. */
 int sp_spmv_csr(const int64_t* rowptr, const int32_t* colidx, const float* values, int64_t n_rows, const float* x,
-                float* y, int accumulate, void* stream);
+                float* y, int accumulate, int avg_nnz_per_row, void* stream);
 
 /* CUDA-core GEMM for dtypes the tensor path does not carry exactly (reference tests use
  * float64 / int64 operands: tests/test_dot.py:8-103, tests/test_matmul.py:12-22). */

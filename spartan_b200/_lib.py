@@ -80,6 +80,8 @@ _SIGS = {
   'sp_combine': (_int, [_vp, _vp, _int, _i64, _int, _vp]),
   'sp_copy_rect': (_int, [_vp, _i64p, _vp, _i64p, _i64p, _int, _vp]),
   'sp_gemm_set_chunk_kblocks': (_int, [_int]),
+  'sp_upload_2d': (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _vp]),
+  'sp_download_2d': (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _vp]),
   'sp_gemm_kpad': (_i64, [_i64, _int]),
   'sp_gemm_prepared_bytes': (_i64, [_i64, _i64, _int]),
   'sp_gemm_prepare_a': (_int, [_vp, _i64, _i64, _i64, _int, _vp, _i64, _i64, _i64, _vp]),
@@ -90,7 +92,7 @@ _SIGS = {
   'sp_gemm_f32': (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp, _i64, _vp]),
   'sp_kmeans_workspace_bytes': (_i64, [_i64, _i64, _i64]),
   'sp_kmeans_assign': (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),
-  'sp_spmv_csr': (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _int, _vp]),
+  'sp_spmv_csr': (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _int, _int, _vp]),
   'sp_gemm_simt': (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp]),
 }
 

@@ -319,7 +319,7 @@ class DistArrayImpl(DistArray):
       for block in itertools.product(*runs):
         g = tuple(slice(a, b) for a, b, _ in block)
         l = tuple(slice(o, o + (b - a)) for a, b, o in block)
-        self.slab[l].copy_(torch.from_numpy(data[g]), non_blocking=True)
+        device_ops.upload_rect(self.slab[l], data[g])      # pitched DMA straight from the (pinned) host array
       for tid in self.tiles.values():
         if tid.worker == me:
           ctx.tile(tid).valid = True
@@ -346,6 +346,24 @@ class DistArrayImpl(DistArray):
       full = tuple(piece.shape) == tuple(dst_extent.shape) or len(self.shape) == 0
       ctx.update(tid, None if full else dst_slice, piece, self.reducer_fn)
     return None
+
+  def read_local_into(self, out):
+    """Copies THIS rank's share into the matching region of the full-size host array ``out`` (pitched D2H per
+    contiguous slab block; asynchronous when ``out`` is pinned: synchronise before reading).  Returns bytes."""
+    ctx = self.ctx
+    total = 0
+    if self.slab is not None and self.shape:
+      for block in self.local_blocks():
+        view = self.slab_view(block)
+        device_ops.download_rect(out[block.to_slice()], view)
+        total += view.numel() * view.element_size()
+      return total
+    for ex, tid in self.tiles.items():
+      if ctx.is_local(tid):
+        t = ctx.get(tid, None)
+        device_ops.download_rect(out[ex.to_slice()] if self.shape else out, t)
+        total += t.numel() * t.element_size()
+    return total
 
   def glom(self):
     """Gathers the whole array to host memory on every rank (distarray.py:198-200)."""

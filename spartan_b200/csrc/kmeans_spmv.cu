@@ -148,15 +148,22 @@ extern "C" int sp_kmeans_assign(const float* X, int64_t ldx, int64_t n, int64_t 
 }
 
 extern "C" int sp_spmv_csr(const int64_t* rowptr, const int32_t* colidx, const float* values, int64_t n_rows,
-                           const float* x, float* y, int accumulate, void* stream_) {
+                           const float* x, float* y, int accumulate, int avg_nnz_per_row, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SP_REQUIRE(n_rows >= 0, SP_ERR_INVALID, "sp_spmv_csr: negative row count");
   if (n_rows == 0) return SP_OK;
   SP_REQUIRE(rowptr && x && y, SP_ERR_INVALID, "sp_spmv_csr: null pointer");
-  const int64_t groups_per_block = 256 / 8;
+  // threads per row follow the average row length (passed by the caller; <= 0 means unknown -> 8)
+  const int group = avg_nnz_per_row <= 0 ? 8 : avg_nnz_per_row <= 2 ? 2 : avg_nnz_per_row <= 4 ? 4 : avg_nnz_per_row <= 16 ? 8 : 32;
+  const int64_t groups_per_block = 256 / group;
   const int blocks = static_cast<int>(std::min<int64_t>((n_rows + groups_per_block - 1) / groups_per_block,
                                                         static_cast<int64_t>(num_sms()) * 16));
-  spmv_csr_kernel<8><<<blocks, 256, 0, stream>>>(rowptr, colidx, values, n_rows, x, y, accumulate);
+  switch (group) {
+    case 2: spmv_csr_kernel<2><<<blocks, 256, 0, stream>>>(rowptr, colidx, values, n_rows, x, y, accumulate); break;
+    case 4: spmv_csr_kernel<4><<<blocks, 256, 0, stream>>>(rowptr, colidx, values, n_rows, x, y, accumulate); break;
+    case 8: spmv_csr_kernel<8><<<blocks, 256, 0, stream>>>(rowptr, colidx, values, n_rows, x, y, accumulate); break;
+    default: spmv_csr_kernel<32><<<blocks, 256, 0, stream>>>(rowptr, colidx, values, n_rows, x, y, accumulate); break;
+  }
   SP_CUDA_CHECK(cudaGetLastError());
   return SP_OK;
 }

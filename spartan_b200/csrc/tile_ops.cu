@@ -320,3 +320,30 @@ extern "C" int sp_copy_rect(void* dst, const int64_t dst_stride[3], const void* 
   SP_CUDA_CHECK(cudaGetLastError());
   return SP_OK;
 }
+
+// Host <-> device rectangle transfers (BlobCtx.get / update across the host boundary, blob_ctx.py:127-179;
+// from_numpy's upload, write_array.py:424-445).  Pitched DMA: a column block of a row-major host array moves
+// in one call at full PCIe rate when the host buffer is pinned.
+extern "C" int sp_upload_2d(void* dst_device, int64_t dst_pitch_bytes, const void* src_host, int64_t src_pitch_bytes,
+                            int64_t width_bytes, int64_t rows, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SP_REQUIRE(width_bytes >= 0 && rows >= 0, SP_ERR_INVALID, "sp_upload_2d: bad extent");
+  if (width_bytes == 0 || rows == 0) return SP_OK;
+  SP_REQUIRE(dst_device && src_host, SP_ERR_INVALID, "sp_upload_2d: null pointer");
+  SP_CUDA_CHECK(cudaMemcpy2DAsync(dst_device, static_cast<size_t>(dst_pitch_bytes), src_host,
+                                  static_cast<size_t>(src_pitch_bytes), static_cast<size_t>(width_bytes),
+                                  static_cast<size_t>(rows), cudaMemcpyHostToDevice, stream));
+  return SP_OK;
+}
+
+extern "C" int sp_download_2d(void* dst_host, int64_t dst_pitch_bytes, const void* src_device, int64_t src_pitch_bytes,
+                              int64_t width_bytes, int64_t rows, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SP_REQUIRE(width_bytes >= 0 && rows >= 0, SP_ERR_INVALID, "sp_download_2d: bad extent");
+  if (width_bytes == 0 || rows == 0) return SP_OK;
+  SP_REQUIRE(dst_host && src_device, SP_ERR_INVALID, "sp_download_2d: null pointer");
+  SP_CUDA_CHECK(cudaMemcpy2DAsync(dst_host, static_cast<size_t>(dst_pitch_bytes), src_device,
+                                  static_cast<size_t>(src_pitch_bytes), static_cast<size_t>(width_bytes),
+                                  static_cast<size_t>(rows), cudaMemcpyDeviceToHost, stream));
+  return SP_OK;
+}

@@ -386,3 +386,40 @@ def gemm_prepared(segments, C, accumulate, precision):
                                _stream()), 'sp_gemm_prepared')
     _count_launch()
     acc = True
+
+
+# ------------------------------------------------------------------------------------ host <-> device rectangles
+def _as_2d_rows(shape, strides, itemsize):
+  """(rows, width_bytes, pitch_bytes) of a <=2-D row-major rectangle, or None."""
+  if len(shape) == 0:
+    return 1, itemsize, itemsize
+  if len(shape) == 1:
+    return (1, shape[0] * itemsize, shape[0] * itemsize) if strides[0] == itemsize or shape[0] == 1 else None
+  if len(shape) == 2 and (strides[1] == itemsize or shape[1] == 1):
+    return shape[0], shape[1] * itemsize, strides[0]
+  return None
+
+
+def upload_rect(dst, src_np):
+  """dst (device view, <=2-D, unit inner stride) <- src_np (host ndarray view of the same shape and dtype)."""
+  if dst.device.type != 'cuda':      # host-logic tests on CPU: plain data movement, no kernel involved
+    dst.copy_(torch.from_numpy(np.ascontiguousarray(src_np)))
+    return
+  d = _as_2d_rows(tuple(dst.shape), tuple(s * dst.element_size() for s in dst.stride()), dst.element_size())
+  h = _as_2d_rows(src_np.shape, src_np.strides, src_np.itemsize)
+  if d is None or h is None or d[:2] != h[:2]:
+    dst.copy_(torch.from_numpy(np.ascontiguousarray(src_np)), non_blocking=True)
+    return
+  check(lib.sp_upload_2d(dst.data_ptr(), d[2], src_np.ctypes.data, h[2], d[1], d[0], _stream()), 'sp_upload_2d')
+
+
+def download_rect(dst_np, src):
+  """dst_np (host ndarray view) <- src (device view); asynchronous when dst_np is pinned -- synchronise the stream
+  before reading it."""
+  _require_cuda(src)
+  d = _as_2d_rows(dst_np.shape, dst_np.strides, dst_np.itemsize)
+  h = _as_2d_rows(tuple(src.shape), tuple(s * src.element_size() for s in src.stride()), src.element_size())
+  if d is None or h is None or d[:2] != h[:2]:
+    dst_np[...] = src.cpu().numpy()
+    return
+  check(lib.sp_download_2d(dst_np.ctypes.data, d[2], src.data_ptr(), h[2], d[1], d[0], _stream()), 'sp_download_2d')

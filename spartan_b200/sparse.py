@@ -31,19 +31,30 @@ class SparseStrips(object):
     n_rows, n_cols = self.shape
     if strip_width is None:
       strip_width = -(-n_cols // ctx.num_workers)
-    self.strips = []          # (c0, c1, owner, (rowptr, col, val) device tensors or None)
+    self.strips = []          # (c0, c1, owner): the reference's column strips and their round-robin owners
     self.nnz = int(matrix.nnz)
     for i, c0 in enumerate(range(0, n_cols, strip_width)):
-      c1 = min(n_cols, c0 + strip_width)
-      owner = i % ctx.num_workers
-      dev = None
+      self.strips.append((c0, min(n_cols, c0 + strip_width), i % ctx.num_workers))
+    # Adjacent strips of one owner are stored as ONE CSR block (one launch per contiguous block of the
+    # rank's share, like the dense slabs): (c0, c1, owner, device CSR or None, nnz)
+    self.blocks = []
+    for c0, c1, owner in self.strips:
+      if self.blocks and self.blocks[-1][2] == owner and self.blocks[-1][1] == c0:
+        self.blocks[-1] = (self.blocks[-1][0], c1, owner)
+      else:
+        self.blocks.append((c0, c1, owner))
+    built = []
+    for c0, c1, owner in self.blocks:
+      dev, nnz = None, 0
       if owner == ctx.worker_id:
         csr = matrix[:, c0:c1].tocsr()
         csr.sum_duplicates()
+        nnz = int(csr.nnz)
         dev = (torch.from_numpy(csr.indptr.astype(np.int64)).to(ctx.device),
                torch.from_numpy(csr.indices.astype(np.int32)).to(ctx.device),
                torch.from_numpy(csr.data.astype(np.float32)).to(ctx.device))
-      self.strips.append((c0, c1, owner, dev))
+      built.append((c0, c1, owner, dev, nnz))
+    self.blocks = built
 
 
 class SparseStripsExpr(Expr):
@@ -84,7 +95,7 @@ class SpMVExpr(Expr):
     if vshape not in ((n_cols,), (n_cols, 1)) or np.dtype(xv.dtype) != np.float32:
       raise SpartanError('SpMV needs a float32 vector of length %d (got %s %s)' % (n_cols, vshape, xv.dtype))
     y = torch.zeros((n_rows,), dtype=torch.float32, device=ctx.device)
-    for c0, c1, owner, dev in A.strips:          # every rank walks every strip: fetches may be collective
+    for c0, c1, owner, dev, nnz in A.blocks:     # every rank walks every block: fetches may be collective
       region = extent.create((c0,), (c1,), vshape) if len(vshape) == 1 else extent.create((c0, 0), (c1, 1), vshape)
       xs = xv.fetch(region, dst=owner)
       if owner != ctx.worker_id:
@@ -94,7 +105,7 @@ class SpMVExpr(Expr):
         xs = xs.contiguous()
       rowptr, col, val = dev
       check(lib.sp_spmv_csr(rowptr.data_ptr(), col.data_ptr(), val.data_ptr(), n_rows, xs.data_ptr(), y.data_ptr(), 1,
-                            ctx.stream_ptr()), 'sp_spmv_csr')
+                            max(1, -(-nnz // max(1, n_rows))), ctx.stream_ptr()), 'sp_spmv_csr')
       ctx.kernel_launches += 1
     comm.allreduce(y, SP_RED_SUM)                # the np.add merge of the strips' partial y (tile.pyx:263-268)
     out_shape = self.compute_shape()

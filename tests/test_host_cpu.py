@@ -135,3 +135,52 @@ def test_dtype_of_mixed_chain():
   e = (a > 0)
   c = _compile(e, {e.child_to_var[0]: np.float32}, {e.child_to_var[1]: 0})
   assert c.out_dtype == np.bool_ and c.compute_dtype == _lib.SP_F32
+
+
+# ------------------------------------------------------------------ C-ABI argument validation (runs before any launch)
+def _prog(ops, compute=None):
+  from spartan_b200 import device_ops
+  return device_ops.make_program(ops, _lib.SP_F32 if compute is None else compute, [1.0])
+
+
+def test_cabi_rejects_malformed_programs():
+  lib = _lib.lib
+  dims = _lib.i64arr([1, 1, 4])
+  buf = (ctypes.c_float * 4)()
+  o = _lib.sp_operand(); o.ptr = ctypes.addressof(buf); o.dtype = _lib.SP_F32; o.stride[2] = 1
+  ins = (_lib.sp_operand * 1)(); ins[0] = o
+  cases = [
+    ([('ADD', 0)], 'stack underflow'),                                   # binary op on an empty stack
+    ([('IN', 0), ('IN', 0)], 'leaves 2 values'),                         # two results
+    ([('IN', 3)], 'reads operand 3'),                                    # operand index out of range
+    ([('IN', 0)] * 5 + [('ADD', 0)] * 4, 'deeper than 4'),               # exceeds the register stack
+    ([(7, 0)], 'unknown opcode'),
+  ]
+  for ops, msg in cases:
+    p = _prog(ops)
+    rc = lib.sp_map(ctypes.byref(p), 1, ins, ctypes.byref(o), dims, None)
+    assert rc in (_lib.lib.sp_map.restype(-1), -1, -3), (ops, rc)
+    assert msg in _lib.last_error(), (ops, _lib.last_error())
+  p = _prog([('IN', 0)], compute=_lib.SP_I32)                            # int32 is not a register type
+  assert lib.sp_map(ctypes.byref(p), 1, ins, ctypes.byref(o), dims, None) == -3
+  p = _prog([('IN', 0)])
+  assert lib.sp_map_reduce(ctypes.byref(p), 1, ins, ctypes.byref(o), _lib.i64arr([1, 0, 4]), 0, 0, None, 0, None) == -1
+  assert 'empty axis' in _lib.last_error()
+  assert lib.sp_map_reduce(ctypes.byref(p), 1, ins, ctypes.byref(o), dims, 99, 0, None, 0, None) == -1
+
+
+def test_cabi_gemm_and_fill_argument_checks():
+  lib = _lib.lib
+  assert lib.sp_gemm_f32_workspace_bytes(128, 128, 1, _lib.i64arr([64]), 99) == -1
+  segs = (_lib.sp_gemm_segment * 1)()
+  assert lib.sp_gemm_f32_segments(0, segs, None, 0, 128, 128, 0, _lib.SP_GEMM_BF16X3, None, 0, None) == -1
+  assert lib.sp_gemm_f32_segments(1, segs, None, 0, 128, 128, 0, _lib.SP_GEMM_BF16X3, None, 0, None) == -1
+  assert 'workspace' in _lib.last_error()
+  assert lib.sp_gemm_kpad(100, _lib.SP_GEMM_BF16X3) == 128 and lib.sp_gemm_kpad(100, _lib.SP_GEMM_TF32X1) == 128
+  assert lib.sp_gemm_kpad(33, _lib.SP_GEMM_TF32X3) == 64
+  assert lib.sp_gemm_prepared_bytes(10, 64, _lib.SP_GEMM_BF16X3) == 10 * 64 * 2 * 2
+  assert lib.sp_fill(None, _lib.SP_F32, -1, 0, 0.0, 0.0, 0, 0, None) == -1
+  assert lib.sp_fill(None, _lib.SP_F32, 0, 0, 0.0, 0.0, 0, 0, None) == 0          # empty fill is a no-op
+  assert lib.sp_fill(None, _lib.SP_F32, 4, 0, 0.0, 0.0, 0, 0, None) == -1
+  assert lib.sp_spmv_csr(None, None, None, 0, None, None, 0, 0, None) == 0
+  assert lib.sp_kmeans_assign(None, 0, 4, 0, None, 1, None, None, None, None, 0, None) == -1

@@ -17,7 +17,7 @@ from .base import Expr, evaluate, optimized_dag
 from .base import eager, lazify, as_array, glom
 from .base import NotShapeable, newaxis, Val, AsArray, ListExpr, TupleExpr
 from ..array.distarray import broadcast
-from .map import map, map_tiles, MapExpr, map_with_location, tile_mapper
+from .map import map, map_tiles, MapExpr, map_with_location, tile_mapper, map2, outer
 from .ndarray import ndarray, NdArrayExpr
 from .optimize import optimize, MapMapFusion, ReduceMapFusion
 from .reduce import reduce, ReduceExpr, ArgReduceExpr

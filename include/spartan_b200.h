@@ -270,6 +270,12 @@ int sp_gemm_prepare_b(const float* B, int64_t ldb, int64_t K, int64_t N, int pre
                       int64_t k_offset, int64_t out_bytes, void* stream);
 int sp_gemm_prepared(int n_seg, const sp_gemm_prepared_segment* segs, float* C, int64_t ldc, int64_t M, int64_t N,
                      int accumulate, int precision, void* stream);
+/* Fused row-argmin epilogue over prepared operands (no C is stored): for every row and every 128-column half tile,
+ * part_val[row][p] = min_j (col_bias[j] - 2 * (A.B)[row, j]) and part_idx[row][p] = arg min (ties: smallest j);
+ * p < sp_gemm_argmin_parts(N).  k-means assignment: col_bias = |c_j|^2 (k_means_.py:61-66). */
+int64_t sp_gemm_argmin_parts(int64_t N);
+int sp_gemm_prepared_argmin(int n_seg, const sp_gemm_prepared_segment* segs, int64_t M, int64_t N, const float* col_bias,
+                            float* part_val, int32_t* part_idx, int precision, void* stream);
 int sp_gemm_f32(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
                 int64_t N, int64_t K, int accumulate, int precision, void* workspace, int64_t workspace_bytes,
                 void* stream);

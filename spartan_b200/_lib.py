@@ -87,6 +87,8 @@ _SIGS = {
   'sp_gemm_prepare_a': (_int, [_vp, _i64, _i64, _i64, _int, _vp, _i64, _i64, _i64, _vp]),
   'sp_gemm_prepare_b': (_int, [_vp, _i64, _i64, _i64, _int, _vp, _i64, _i64, _i64, _vp]),
   'sp_gemm_prepared': (_int, [_int, ctypes.POINTER(sp_gemm_prepared_segment), _vp, _i64, _i64, _i64, _int, _int, _vp]),
+  'sp_gemm_argmin_parts': (_i64, [_i64]),
+  'sp_gemm_prepared_argmin': (_int, [_int, ctypes.POINTER(sp_gemm_prepared_segment), _i64, _i64, _vp, _vp, _vp, _int, _vp]),
   'sp_gemm_f32_workspace_bytes': (_i64, [_i64, _i64, _int, _i64p, _int]),
   'sp_gemm_f32_segments': (_int, [_int, ctypes.POINTER(sp_gemm_segment), _vp, _i64, _i64, _i64, _int, _int, _vp, _i64, _vp]),
   'sp_gemm_f32': (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp, _i64, _vp]),

@@ -71,6 +71,12 @@ struct Params {
   int accumulate;
   float* C;
   int64_t ldc;
+  // epilogue mode 1 (k-means): instead of storing C, each (row, 128-column half tile) emits
+  //   min_j (col_bias[j] - 2 * C[row, j]) and its column index  ->  part_val / part_idx [M][n_blocks * 2]
+  int epi_mode;
+  const float* col_bias;
+  float* part_val;
+  int* part_idx;
 };
 
 // ----------------------------------------------------------------------------
@@ -354,7 +360,23 @@ gemm_kernel(const __grid_constant__ Params p) {
       }
       const int row = m_blk * BM + q * 32 + lane;
       const int col0 = n_blk * BN + half * 128;
-      if (row < p.M) {
+      if (p.epi_mode == 1) {
+        float best = 3.402823466e+38f;
+        int best_j = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < 128; ++j) {       // fully unrolled: sum[] must stay in registers
+          const int col = col0 + j;
+          if (col < p.N) {
+            const float v = __ldg(p.col_bias + col) - 2.0f * sum[j];
+            if (v < best) { best = v; best_j = col; }        // first minimum: ties resolve to the smallest index
+          }
+        }
+        if (row < p.M) {
+          const int64_t o = static_cast<int64_t>(row) * (p.n_blocks * 2) + n_blk * 2 + half;
+          p.part_val[o] = best;
+          p.part_idx[o] = best_j;
+        }
+      } else if (row < p.M) {
         float* c_row = p.C + static_cast<int64_t>(row) * p.ldc;
         const bool vec_ok = ((reinterpret_cast<uint64_t>(p.C) & 15) == 0) && ((p.ldc & 3) == 0) && (col0 + 128 <= p.N);
         if (vec_ok) {
@@ -593,9 +615,9 @@ extern "C" int sp_gemm_prepare_b(const float* B, int64_t ldb, int64_t K, int64_t
   return SP_OK;
 }
 
-// C[M,N] (+)= sum_s A_s . B_s over PREPARED operands (sp_gemm_prepare_a / _b), one launch.
-extern "C" int sp_gemm_prepared(int n_seg, const sp_gemm_prepared_segment* segs, float* C, int64_t ldc, int64_t M,
-                                int64_t N, int accumulate, int precision, void* stream_) {
+static int launch_prepared(int n_seg, const sp_gemm_prepared_segment* segs, float* C, int64_t ldc, int64_t M, int64_t N,
+                           int accumulate, int precision, int epi_mode, const float* col_bias, float* part_val,
+                           int* part_idx, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   Mode md;
   SP_REQUIRE(mode_of(precision, &md), SP_ERR_INVALID, "sp_gemm_prepared: unknown precision %d", precision);
@@ -647,12 +669,34 @@ extern "C" int sp_gemm_prepared(int n_seg, const sp_gemm_prepared_segment* segs,
   p.accumulate = accumulate;
   p.C = C;
   p.ldc = ldc;
+  p.epi_mode = epi_mode;
+  p.col_bias = col_bias;
+  p.part_val = part_val;
+  p.part_idx = part_idx;
   const int tiles = p.m_blocks * p.n_blocks;
   const int grid = std::min(tiles, num_sms());
   if (md.kind == 0) gemm_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);
   else gemm_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);
   SP_CUDA_CHECK(cudaGetLastError());
   return SP_OK;
+}
+
+// C[M,N] (+)= sum_s A_s . B_s over PREPARED operands (sp_gemm_prepare_a / _b), one launch.
+extern "C" int sp_gemm_prepared(int n_seg, const sp_gemm_prepared_segment* segs, float* C, int64_t ldc, int64_t M,
+                                int64_t N, int accumulate, int precision, void* stream_) {
+  SP_REQUIRE(C != nullptr, SP_ERR_INVALID, "sp_gemm_prepared: null C");
+  return launch_prepared(n_seg, segs, C, ldc, M, N, accumulate, precision, 0, nullptr, nullptr, nullptr, stream_);
+}
+
+// Fused row-argmin epilogue (k-means assignment, k_means_.py:61-66): for every row and every 128-column half tile
+// emits  min_j (col_bias[j] - 2 * (A.B)[row, j])  and the arg min; parts = sp_gemm_argmin_parts(N) entries per row.
+extern "C" int64_t sp_gemm_argmin_parts(int64_t N) { return ((N + BN - 1) / BN) * 2; }
+
+extern "C" int sp_gemm_prepared_argmin(int n_seg, const sp_gemm_prepared_segment* segs, int64_t M, int64_t N,
+                                       const float* col_bias, float* part_val, int32_t* part_idx, int precision,
+                                       void* stream_) {
+  SP_REQUIRE(col_bias && part_val && part_idx, SP_ERR_INVALID, "sp_gemm_prepared_argmin: null pointer");
+  return launch_prepared(n_seg, segs, nullptr, 0, M, N, 0, precision, 1, col_bias, part_val, part_idx, stream_);
 }
 
 extern "C" int64_t sp_gemm_f32_workspace_bytes(int64_t M, int64_t N, int n_seg, const int64_t* seg_k, int precision) {

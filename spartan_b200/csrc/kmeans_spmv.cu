@@ -5,11 +5,12 @@
 //   kmeans_map2_dist_mapper   labels = argmin(cdist(points, centers), axis=1)      O(n k d) scalar C in SciPy
 //   kmeans_count_mapper       counts = bincount(labels)
 //   kmeans_center_mapper      sums[c] = points[labels == c].sum(0)                 Python loop over k
-// Here: distances through the tensor cores -- argmin_j |x - c_j|^2 = argmin_j (|c_j|^2 - 2 x.c_j), the
-// x.c_j block is one tcgen05 GEMM per chunk of rows (bf16x3, fp32-faithful) -- then one warp per point
-// picks the label (ties: smallest index, like np.argmin) and adds the point into its centroid with
+// Here: distances through the tensor cores -- argmin_j |x - c_j|^2 = argmin_j (|c_j|^2 - 2 x.c_j): one tcgen05
+// GEMM per chunk of rows (bf16x3, fp32-faithful) whose EPILOGUE reduces every 128-column half tile to its
+// (min, arg min), so the n x k distance matrix never exists in HBM -- then one warp per point picks the label
+// among the candidates (ties: smallest index, like np.argmin) and adds the point into its centroid with
 // vectorised fire-and-forget float atomics.  Roofline: distance GEMM = tensor pipe (2 n d k flop);
-// label + accumulate = HBM (read n*k distances + n*d points).
+// label + accumulate = HBM (n*d point bytes read twice + atomics).
 //
 // SpMV (reference: spartan/expr/dot.py:213-217 `tocsr().dot(dense)`, spartan/array/sparse.pyx:103-158)
 //   y (+)= A x, A in CSR: one 8-thread group per row, coalesced val/col loads, gather of x through
@@ -34,20 +35,21 @@ __global__ void row_sqnorm_kernel(const float* __restrict__ C, int64_t ldc, int 
   if (lane == 0) out[row] = s;
 }
 
-// one warp per point: label = argmin_j (cnorm[j] - 2 * D[i, j]); then sums[label] += x_i, counts[label] += 1
+// one warp per point: label = arg min over the per-half-tile candidates the GEMM epilogue emitted
+// (part_val / part_idx [n][parts]); then sums[label] += x_i, counts[label] += 1
 __global__ void __launch_bounds__(256)
-kmeans_label_accumulate_kernel(const float* __restrict__ D, int64_t ldd, const float* __restrict__ cnorm,
-                               const float* __restrict__ X, int64_t ldx, int64_t n, int d, int k,
+kmeans_label_accumulate_kernel(const float* __restrict__ part_val, const int* __restrict__ part_idx, int parts,
+                               const float* __restrict__ X, int64_t ldx, int64_t n, int d,
                                int32_t* __restrict__ labels, float* __restrict__ sums, unsigned long long* __restrict__ counts) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = static_cast<int64_t>(gridDim.x) * (blockDim.x / 32);
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x / 32) + (threadIdx.x / 32); i < n; i += warps) {
-    const float* drow = D + i * ldd;
     float best = FLT_MAX;
     int best_j = 0x7fffffff;
-    for (int j = lane; j < k; j += 32) {
-      const float v = cnorm[j] - 2.0f * drow[j];
-      if (v < best) { best = v; best_j = j; }     // j increases per lane: first minimum kept
+    for (int j = lane; j < parts; j += 32) {
+      const float v = part_val[i * parts + j];
+      const int c = part_idx[i * parts + j];
+      if (v < best || (v == best && c < best_j)) { best = v; best_j = c; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -99,7 +101,7 @@ extern "C" int64_t sp_kmeans_workspace_bytes(int64_t n, int64_t d, int64_t k) {
   const int64_t rows = std::min<int64_t>(n, SP_KMEANS_CHUNK_ROWS);
   const int64_t Kp = sp_gemm_kpad(d, SP_GEMM_BF16X3);
   return sp_gemm_prepared_bytes(rows, Kp, SP_GEMM_BF16X3) + sp_gemm_prepared_bytes(k, Kp, SP_GEMM_BF16X3) +
-         rows * k * 4 + k * 4 + 4096;
+         rows * sp_gemm_argmin_parts(k) * 8 + k * 4 + 8192;
 }
 
 extern "C" int sp_kmeans_assign(const float* X, int64_t ldx, int64_t n, int64_t d, const float* centers, int64_t k,
@@ -119,8 +121,10 @@ extern "C" int sp_kmeans_assign(const float* X, int64_t ldx, int64_t n, int64_t 
   const int64_t b_bytes = (sp_gemm_prepared_bytes(k, Kp, prec) + 1023) / 1024 * 1024;
   uint8_t* a_prep = ws;
   uint8_t* b_prep = a_prep + a_bytes;
-  float* D = reinterpret_cast<float*>(b_prep + b_bytes);
-  float* cnorm = D + rows * k;
+  const int parts = static_cast<int>(sp_gemm_argmin_parts(k));
+  float* part_val = reinterpret_cast<float*>(b_prep + b_bytes);
+  int32_t* part_idx = reinterpret_cast<int32_t*>(part_val + rows * parts);
+  float* cnorm = reinterpret_cast<float*>(part_idx + rows * parts);
   if (Kp != (d + 3) / 4 * 4) {
     SP_CUDA_CHECK(cudaMemsetAsync(a_prep, 0, a_bytes, stream));
     SP_CUDA_CHECK(cudaMemsetAsync(b_prep, 0, b_bytes, stream));
@@ -136,11 +140,11 @@ extern "C" int sp_kmeans_assign(const float* X, int64_t ldx, int64_t n, int64_t 
     if (rc) return rc;
     sp_gemm_prepared_segment seg;
     seg.A = a_prep; seg.B = b_prep; seg.Kp = Kp;
-    rc = sp_gemm_prepared(1, &seg, D, k, m, k, 0, prec, stream);
+    rc = sp_gemm_prepared_argmin(1, &seg, m, k, cnorm, part_val, part_idx, prec, stream);   // no n x k matrix in HBM
     if (rc) return rc;
     const int blocks = static_cast<int>(std::min<int64_t>((m + 7) / 8, static_cast<int64_t>(num_sms()) * 8));
-    kmeans_label_accumulate_kernel<<<blocks, 256, 0, stream>>>(D, k, cnorm, X + r0 * ldx, ldx, m, static_cast<int>(d),
-                                                               static_cast<int>(k), labels + r0, sums,
+    kmeans_label_accumulate_kernel<<<blocks, 256, 0, stream>>>(part_val, part_idx, parts, X + r0 * ldx, ldx, m,
+                                                               static_cast<int>(d), labels + r0, sums,
                                                                reinterpret_cast<unsigned long long*>(counts));
     SP_CUDA_CHECK(cudaGetLastError());
   }

@@ -300,8 +300,14 @@ def run_b200(args):
     X = sp.rand(rows, cols, seed=2, dtype=np.float32, tile_hint=(trow, cols)).evaluate()
     Y = sp.rand(rows, cols, seed=3, dtype=np.float32, tile_hint=(trow, cols)).evaluate()
 
+    general = os.environ.get('SPARTAN_MR_EXPR') == 'general'    # tuning aid: a chain outside the static catalogue
+
     def mr_step():
-      e = (lazify(X) * 2 + lazify(Y)).sum(axis=0).optimized()
+      if general:
+        x, y = lazify(X), lazify(Y)
+        e = (sp.abs(x - y) * x + sp.maximum(y, 0.5)).sum(axis=0).optimized()
+      else:
+        e = (lazify(X) * 2 + lazify(Y)).sum(axis=0).optimized()
       holder['S'] = e.evaluate()
 
     ms_mr = timed(mr_step, max(args.steps, 5), max(args.warmup, 3), sync, maxreduce)
@@ -312,7 +318,8 @@ def run_b200(args):
     mr_par = None
     if xs is not None:
       ys = Y.fetch(sp.extent.create((0, 0), (rows, 256), (rows, cols)))
-      ref = (xs.cpu().numpy().astype(np.float64) * 2 + ys.cpu().numpy()).sum(axis=0)
+      xh, yh = xs.cpu().numpy().astype(np.float64), ys.cpu().numpy().astype(np.float64)
+      ref = (np.abs(xh - yh) * xh + np.maximum(yh, 0.5)).sum(axis=0) if general else (xh * 2 + yh).sum(axis=0)
       mr_par = float(np.abs(got[:256] - ref).max() / np.abs(ref).max())
     mr = {'metric': 'fused (x*2+y).sum(axis=0) GB/s', 'value': gbs, 'unit': 'GB/s', 'ms_per_step': ms_mr,
           'elements': total, 'algorithmic_bytes': bytes_alg,

@@ -1,11 +1,9 @@
 // In-register bytecode evaluator for fused LocalExpr trees (the fusable kernel IR of the
 // reference: spartan/expr/operator/local.py:58-152, fused by optimize.py:133-227).
 //
-// One thread evaluates the whole program for V consecutive elements.  The operand stack
-// lives in registers: every (opcode, stack-depth) pair is its own switch case, so all
-// stack indices are compile-time constants and nothing spills to local memory.  The
-// dispatch cost (one jump-table branch per op) is amortised over V elements; inputs are
-// loaded up front (all loads in flight before the first op executes).
+// One thread evaluates the whole program for V elements.  Inputs are loaded up front (all
+// loads in flight before the first instruction executes); the program runs on a V-wide
+// accumulator (see "the interpreter" below); dispatch cost is amortised over V elements.
 #pragma once
 #include "sp_common.h"
 #include <math_constants.h>
@@ -17,7 +15,8 @@ constexpr int kMaxDepth = 4;
 template <typename T>
 struct DevProgram {
   int32_t n_ops;
-  uint8_t op[SP_MAX_PROGRAM];
+  uint8_t op[SP_MAX_PROGRAM];    // accumulator-machine code produced by lower_program()
+  uint8_t src[SP_MAX_PROGRAM];
   uint8_t arg[SP_MAX_PROGRAM];
   T consts[SP_MAX_CONSTS];
   long long index_stride[3];
@@ -133,169 +132,257 @@ template <typename T> __device__ __forceinline__ T cast_i32(T a) { return static
 template <typename T> __device__ __forceinline__ T cast_u8(T a) { return static_cast<T>(static_cast<uint8_t>(static_cast<long long>(a))); }
 
 // ---------------------------------------------------------------------------- the interpreter
-// The host lowers the postfix program once more before launch (lower_program below): because the
-// stack depth at every instruction is known statically, each instruction becomes ONE dense code
-//   code = dense_op * 4 + slot        (slot = index of the stack register the op writes)
-// so the kernel dispatches with a single jump table (BRX) and keeps no stack pointer at all.
-enum DenseOp : int {
-  D_IN = 0, D_CONST, D_INDEX,
-  D_ADD, D_SUB, D_MUL, D_DIV, D_MOD, D_POW, D_MAX, D_MIN, D_EQ, D_NE, D_LT, D_LE, D_GT, D_GE, D_AND, D_OR, D_XOR,
-  D_FMOD, D_FLOORDIV,
-  D_NEG, D_ABS, D_SQRT, D_EXP, D_LOG, D_SQUARE, D_RECIP, D_NOT, D_NONZERO, D_ISZERO, D_CAST_F32, D_CAST_I64,
-  D_CAST_I32, D_CAST_BOOL, D_CAST_U8,
-  D_COUNT
+// The C ABI carries a postfix (stack) program.  A register-resident *stack* machine turned out to be
+// slow on B200: every instruction is a switch case that rewrites part of the V-wide stack, so the
+// loop-carried state is the whole stack and ptxas copies ~40 registers per instruction (measured: ~100
+// warp-instructions per op, profiles/).  The library therefore lowers the postfix program once per launch
+// (lower_program, host) to an ACCUMULATOR machine:
+//     acc = x                      A_LOAD        x = in[i] | constant | tmp[k] | element position
+//     acc = f(acc, x) / f(x, acc)  binary ops (R* = reversed operands for the non-commutative ones)
+//     acc = f(acc)                 unary ops / casts
+//     tmp[k] = acc                 A_SAVE        only when both operands of a binary node are sub-trees
+// The only loop-carried registers are acc[V]; operands are selected per instruction; tmp lives in local
+// memory (L1) and is touched only by A_SAVE / src TMP.  Expression `x*c+y` is 3 instructions.
+enum AOp : int {
+  A_LOAD = 0, A_SAVE,
+  A_ADD, A_SUB, A_MUL, A_DIV, A_MOD, A_POW, A_MAX, A_MIN, A_EQ, A_NE, A_LT, A_LE, A_GT, A_GE, A_AND, A_OR, A_XOR,
+  A_FMOD, A_FLOORDIV,
+  A_RSUB, A_RDIV, A_RMOD, A_RPOW, A_RFMOD, A_RFLOORDIV,
+  A_NEG, A_ABS, A_SQRT, A_EXP, A_LOG, A_SQUARE, A_RECIP, A_NOT, A_NONZERO, A_ISZERO, A_CAST_F32, A_CAST_I64,
+  A_CAST_I32, A_CAST_BOOL, A_CAST_U8,
+  A_COUNT
 };
+enum ASrc : int { S_IN0 = 0, S_CONST = 8, S_TMP = 9, S_INDEX = 10, S_NONE = 11 };
+constexpr int kMaxTmp = 4;
 
-inline int dense_of(int sp_op) {
+struct PostfixNode { int op, arg, l, r; };
+
+inline int aop_binary(int sp_op, bool reversed) {
   switch (sp_op) {
-    case SP_OP_IN: return D_IN;          case SP_OP_CONST: return D_CONST;   case SP_OP_INDEX: return D_INDEX;
-    case SP_OP_ADD: return D_ADD;        case SP_OP_SUB: return D_SUB;       case SP_OP_MUL: return D_MUL;
-    case SP_OP_DIV: return D_DIV;        case SP_OP_MOD: return D_MOD;       case SP_OP_POW: return D_POW;
-    case SP_OP_MAX: return D_MAX;        case SP_OP_MIN: return D_MIN;       case SP_OP_EQ: return D_EQ;
-    case SP_OP_NE: return D_NE;          case SP_OP_LT: return D_LT;         case SP_OP_LE: return D_LE;
-    case SP_OP_GT: return D_GT;          case SP_OP_GE: return D_GE;         case SP_OP_AND: return D_AND;
-    case SP_OP_OR: return D_OR;          case SP_OP_XOR: return D_XOR;       case SP_OP_FMOD: return D_FMOD;
-    case SP_OP_FLOORDIV: return D_FLOORDIV;
-    case SP_OP_NEG: return D_NEG;        case SP_OP_ABS: return D_ABS;       case SP_OP_SQRT: return D_SQRT;
-    case SP_OP_EXP: return D_EXP;        case SP_OP_LOG: return D_LOG;       case SP_OP_SQUARE: return D_SQUARE;
-    case SP_OP_RECIP: return D_RECIP;    case SP_OP_NOT: return D_NOT;       case SP_OP_NONZERO: return D_NONZERO;
-    case SP_OP_ISZERO: return D_ISZERO;  case SP_OP_CAST_F32: return D_CAST_F32;
-    case SP_OP_CAST_I64: return D_CAST_I64; case SP_OP_CAST_I32: return D_CAST_I32;
-    case SP_OP_CAST_BOOL: return D_CAST_BOOL; case SP_OP_CAST_U8: return D_CAST_U8;
+    case SP_OP_ADD: return A_ADD;   case SP_OP_MUL: return A_MUL;   case SP_OP_MAX: return A_MAX;
+    case SP_OP_MIN: return A_MIN;   case SP_OP_EQ: return A_EQ;     case SP_OP_NE: return A_NE;
+    case SP_OP_AND: return A_AND;   case SP_OP_OR: return A_OR;     case SP_OP_XOR: return A_XOR;
+    case SP_OP_SUB: return reversed ? A_RSUB : A_SUB;
+    case SP_OP_DIV: return reversed ? A_RDIV : A_DIV;
+    case SP_OP_MOD: return reversed ? A_RMOD : A_MOD;
+    case SP_OP_POW: return reversed ? A_RPOW : A_POW;
+    case SP_OP_FMOD: return reversed ? A_RFMOD : A_FMOD;
+    case SP_OP_FLOORDIV: return reversed ? A_RFLOORDIV : A_FLOORDIV;
+    case SP_OP_LT: return reversed ? A_GT : A_LT;    // x < acc  <=>  acc > x
+    case SP_OP_LE: return reversed ? A_GE : A_LE;
+    case SP_OP_GT: return reversed ? A_LT : A_GT;
+    case SP_OP_GE: return reversed ? A_LE : A_GE;
+    default: return -1;
+  }
+}
+inline int aop_unary(int sp_op) {
+  switch (sp_op) {
+    case SP_OP_NEG: return A_NEG;       case SP_OP_ABS: return A_ABS;         case SP_OP_SQRT: return A_SQRT;
+    case SP_OP_EXP: return A_EXP;       case SP_OP_LOG: return A_LOG;         case SP_OP_SQUARE: return A_SQUARE;
+    case SP_OP_RECIP: return A_RECIP;   case SP_OP_NOT: return A_NOT;         case SP_OP_NONZERO: return A_NONZERO;
+    case SP_OP_ISZERO: return A_ISZERO; case SP_OP_CAST_F32: return A_CAST_F32;
+    case SP_OP_CAST_I64: return A_CAST_I64; case SP_OP_CAST_I32: return A_CAST_I32;
+    case SP_OP_CAST_BOOL: return A_CAST_BOOL; case SP_OP_CAST_U8: return A_CAST_U8;
     default: return -1;
   }
 }
 
-// Host: validated postfix program -> dense codes.  Returns false if the program is malformed.
+template <typename T>
+struct Lowering {
+  DevProgram<T>* out;
+  const PostfixNode* nodes;
+  bool ok = true;
+  int tmp_used = 0;
+  void put(int op, int src, int arg) {
+    if (out->n_ops >= SP_MAX_PROGRAM) { ok = false; return; }
+    out->op[out->n_ops] = static_cast<uint8_t>(op);
+    out->src[out->n_ops] = static_cast<uint8_t>(src);
+    out->arg[out->n_ops] = static_cast<uint8_t>(arg);
+    out->n_ops++;
+  }
+  bool leaf(int n) const { return nodes[n].op == SP_OP_IN || nodes[n].op == SP_OP_CONST || nodes[n].op == SP_OP_INDEX; }
+  void src_of(int n, int* src, int* arg) {
+    const PostfixNode& nd = nodes[n];
+    if (nd.op == SP_OP_IN) { *src = S_IN0 + nd.arg; *arg = 0; }
+    else if (nd.op == SP_OP_CONST) { *src = S_CONST; *arg = nd.arg; }
+    else { *src = S_INDEX; *arg = 0; out->uses_index = 1; }
+  }
+  void emit(int n) {
+    if (!ok) return;
+    const PostfixNode& nd = nodes[n];
+    int src, arg;
+    if (leaf(n)) { src_of(n, &src, &arg); put(A_LOAD, src, arg); return; }
+    if (nd.r < 0) {                       // unary
+      emit(nd.l);
+      const int a = aop_unary(nd.op);
+      if (a < 0) { ok = false; return; }
+      put(a, S_NONE, 0);
+      return;
+    }
+    if (leaf(nd.r)) {                     // acc = f(L, leaf)
+      emit(nd.l);
+      src_of(nd.r, &src, &arg);
+      put(aop_binary(nd.op, false), src, arg);
+    } else if (leaf(nd.l)) {              // acc = f(leaf, R)
+      emit(nd.r);
+      src_of(nd.l, &src, &arg);
+      put(aop_binary(nd.op, true), src, arg);
+    } else {                              // both sub-trees: park R in a temporary
+      emit(nd.r);
+      if (tmp_used >= kMaxTmp) { ok = false; return; }
+      const int k = tmp_used++;
+      put(A_SAVE, S_NONE, k);
+      emit(nd.l);
+      put(aop_binary(nd.op, false), S_TMP, k);
+      tmp_used--;
+    }
+  }
+};
+
+// Host: validated postfix program -> accumulator code.  Returns false if it cannot be lowered.
 template <typename T>
 inline bool lower_program(const sp_program* prog, DevProgram<T>* out) {
-  out->n_ops = prog->n_ops;
+  PostfixNode nodes[SP_MAX_PROGRAM];
+  int stack[SP_MAX_PROGRAM];
   int sp = 0;
   for (int i = 0; i < prog->n_ops; ++i) {
-    const int d = dense_of(prog->op[i]);
-    if (d < 0) return false;
-    int slot;
-    if (d <= D_INDEX) { slot = sp; sp += 1; if (d == D_INDEX) out->uses_index = 1; }
-    else if (d <= D_FLOORDIV) { slot = sp - 2; sp -= 1; }
-    else { slot = sp - 1; }
-    if (slot < 0 || slot >= kMaxDepth) return false;
-    out->op[i] = static_cast<uint8_t>(d * 4 + slot);
-    out->arg[i] = prog->arg[i];
+    const int op = prog->op[i];
+    nodes[i] = PostfixNode{op, prog->arg[i], -1, -1};
+    if (op == SP_OP_IN || op == SP_OP_CONST || op == SP_OP_INDEX) {
+      stack[sp++] = i;
+    } else if (aop_unary(op) >= 0) {
+      if (sp < 1) return false;
+      nodes[i].l = stack[sp - 1];
+      stack[sp - 1] = i;
+    } else if (aop_binary(op, false) >= 0) {
+      if (sp < 2) return false;
+      nodes[i].l = stack[sp - 2];
+      nodes[i].r = stack[sp - 1];
+      sp -= 1;
+      stack[sp - 1] = i;
+    } else {
+      return false;
+    }
   }
-  return sp == 1;
+  if (sp != 1) return false;
+  out->n_ops = 0;
+  Lowering<T> lw{out, nodes};
+  lw.emit(stack[0]);
+  return lw.ok;
 }
 
 #define SP_B(x) ((x) ? T(1) : T(0))
-
-#define SP_BIN_CASE(DOP, S, EXPR)                                    \
-  case (DOP) * 4 + (S): {                                            \
+#define SP_ACC(AOP, EXPR)                                            \
+  case AOP: {                                                        \
     _Pragma("unroll") for (int v = 0; v < V; ++v) {                  \
-      const T a = s[(S)][v];                                         \
-      const T b = s[(S) + 1][v];                                     \
-      s[(S)][v] = (EXPR);                                            \
-    }                                                                \
-    break;                                                           \
-  }
-#define SP_BIN(DOP, EXPR) SP_BIN_CASE(DOP, 0, EXPR) SP_BIN_CASE(DOP, 1, EXPR) SP_BIN_CASE(DOP, 2, EXPR)
-
-#define SP_UN_CASE(DOP, S, EXPR)                                     \
-  case (DOP) * 4 + (S): {                                            \
-    _Pragma("unroll") for (int v = 0; v < V; ++v) {                  \
-      const T a = s[(S)][v];                                         \
-      s[(S)][v] = (EXPR);                                            \
-    }                                                                \
-    break;                                                           \
-  }
-#define SP_UN(DOP, EXPR) SP_UN_CASE(DOP, 0, EXPR) SP_UN_CASE(DOP, 1, EXPR) SP_UN_CASE(DOP, 2, EXPR) SP_UN_CASE(DOP, 3, EXPR)
-
-#define SP_PUSH_CONST_CASE(S)                                        \
-  case D_CONST * 4 + (S): {                                          \
-    const T c = prog.consts[arg];                                    \
-    _Pragma("unroll") for (int v = 0; v < V; ++v) s[(S)][v] = c;     \
-    break;                                                           \
-  }
-
-#define SP_PUSH_INDEX_CASE(S)                                        \
-  case D_INDEX * 4 + (S): {                                          \
-    _Pragma("unroll") for (int v = 0; v < V; ++v) s[(S)][v] = idx[v]; \
-    break;                                                           \
-  }
-
-// push operand: the operand index is data, the destination register is static
-#define SP_PUSH_IN_CASE(S)                                           \
-  case D_IN * 4 + (S): {                                             \
-    _Pragma("unroll") for (int i = 0; i < NI; ++i) {                 \
-      if (i == arg) {                                                \
-        _Pragma("unroll") for (int v = 0; v < V; ++v) s[(S)][v] = in[i][v]; \
-      }                                                              \
+      const T a = acc[v];                                            \
+      const T b = x[v];                                              \
+      acc[v] = (EXPR);                                               \
     }                                                                \
     break;                                                           \
   }
 
-// One instruction.  With compile-time-constant `code` / `arg` (static programs below) the switch folds
-// away and only the selected case's V arithmetic instructions remain.
+// One instruction.  With compile-time-constant arguments (static programs below) both switches fold away.
 template <typename T, int V, int NI>
-__device__ __forceinline__ void exec_op(const int code, const int arg, const DevProgram<T>& prog, const T (&in)[NI][V],
-                                        const T (&idx)[V], T (&s)[kMaxDepth][V]) {
-  switch (code) {
-      SP_PUSH_INDEX_CASE(0) SP_PUSH_INDEX_CASE(1) SP_PUSH_INDEX_CASE(2) SP_PUSH_INDEX_CASE(3)
-      SP_PUSH_IN_CASE(0) SP_PUSH_IN_CASE(1) SP_PUSH_IN_CASE(2) SP_PUSH_IN_CASE(3)
-      SP_PUSH_CONST_CASE(0) SP_PUSH_CONST_CASE(1) SP_PUSH_CONST_CASE(2) SP_PUSH_CONST_CASE(3)
-      SP_BIN(D_ADD, a + b)
-      SP_BIN(D_SUB, a - b)
-      SP_BIN(D_MUL, a * b)
-      SP_BIN(D_DIV, op_div(a, b))
-      SP_BIN(D_MOD, op_mod(a, b))
-      SP_BIN(D_POW, op_pow(a, b))
-      SP_BIN(D_MAX, op_max(a, b))
-      SP_BIN(D_MIN, op_min(a, b))
-      SP_BIN(D_EQ, SP_B(a == b))
-      SP_BIN(D_NE, SP_B(a != b))
-      SP_BIN(D_LT, SP_B(a < b))
-      SP_BIN(D_LE, SP_B(a <= b))
-      SP_BIN(D_GT, SP_B(a > b))
-      SP_BIN(D_GE, SP_B(a >= b))
-      SP_BIN(D_AND, SP_B((a != T(0)) && (b != T(0))))
-      SP_BIN(D_OR, SP_B((a != T(0)) || (b != T(0))))
-      SP_BIN(D_XOR, SP_B((a != T(0)) != (b != T(0))))
-      SP_BIN(D_FMOD, op_fmod(a, b))
-      SP_BIN(D_FLOORDIV, op_floordiv(a, b))
-      SP_UN(D_NEG, -a)
-      SP_UN(D_ABS, op_abs(a))
-      SP_UN(D_SQRT, op_sqrt(a))
-      SP_UN(D_EXP, op_exp(a))
-      SP_UN(D_LOG, op_log(a))
-      SP_UN(D_SQUARE, a * a)
-      SP_UN(D_RECIP, op_recip(a))
-      SP_UN(D_NOT, SP_B(a == T(0)))
-      SP_UN(D_NONZERO, SP_B(a != T(0)))
-      SP_UN(D_ISZERO, SP_B(a == T(0)))
-      SP_UN(D_CAST_F32, cast_f32(a))
-      SP_UN(D_CAST_I64, cast_i64(a))
-      SP_UN(D_CAST_I32, cast_i32(a))
-      SP_UN(D_CAST_BOOL, SP_B(a != T(0)))
-      SP_UN(D_CAST_U8, cast_u8(a))
-    default: break;   // slot 3 of a binary op: unreachable for validated programs
+__device__ __forceinline__ void exec_op(const int op, const int src, const int arg, const DevProgram<T>& prog,
+                                        const T (&in)[NI][V], const T (&idx)[V], T (&acc)[V], T (&tmp)[kMaxTmp][V]) {
+  T x[V];
+  switch (src) {
+    case S_CONST: {
+      const T c = prog.consts[arg];
+#pragma unroll
+      for (int v = 0; v < V; ++v) x[v] = c;
+      break;
+    }
+    case S_TMP:
+#pragma unroll
+      for (int v = 0; v < V; ++v) x[v] = tmp[arg][v];
+      break;
+    case S_INDEX:
+#pragma unroll
+      for (int v = 0; v < V; ++v) x[v] = idx[v];
+      break;
+    case S_NONE:
+#pragma unroll
+      for (int v = 0; v < V; ++v) x[v] = T(0);
+      break;
+    default:
+#pragma unroll
+      for (int i = 0; i < NI; ++i)
+        if (i == src) {
+#pragma unroll
+          for (int v = 0; v < V; ++v) x[v] = in[i][v];
+        }
+      break;
+  }
+  switch (op) {
+    case A_LOAD:
+#pragma unroll
+      for (int v = 0; v < V; ++v) acc[v] = x[v];
+      break;
+    case A_SAVE:
+#pragma unroll
+      for (int v = 0; v < V; ++v) tmp[arg][v] = acc[v];
+      break;
+    SP_ACC(A_ADD, a + b)
+    SP_ACC(A_SUB, a - b)
+    SP_ACC(A_MUL, a * b)
+    SP_ACC(A_DIV, op_div(a, b))
+    SP_ACC(A_MOD, op_mod(a, b))
+    SP_ACC(A_POW, op_pow(a, b))
+    SP_ACC(A_MAX, op_max(a, b))
+    SP_ACC(A_MIN, op_min(a, b))
+    SP_ACC(A_EQ, SP_B(a == b))
+    SP_ACC(A_NE, SP_B(a != b))
+    SP_ACC(A_LT, SP_B(a < b))
+    SP_ACC(A_LE, SP_B(a <= b))
+    SP_ACC(A_GT, SP_B(a > b))
+    SP_ACC(A_GE, SP_B(a >= b))
+    SP_ACC(A_AND, SP_B((a != T(0)) && (b != T(0))))
+    SP_ACC(A_OR, SP_B((a != T(0)) || (b != T(0))))
+    SP_ACC(A_XOR, SP_B((a != T(0)) != (b != T(0))))
+    SP_ACC(A_FMOD, op_fmod(a, b))
+    SP_ACC(A_FLOORDIV, op_floordiv(a, b))
+    SP_ACC(A_RSUB, b - a)
+    SP_ACC(A_RDIV, op_div(b, a))
+    SP_ACC(A_RMOD, op_mod(b, a))
+    SP_ACC(A_RPOW, op_pow(b, a))
+    SP_ACC(A_RFMOD, op_fmod(b, a))
+    SP_ACC(A_RFLOORDIV, op_floordiv(b, a))
+    SP_ACC(A_NEG, -a)
+    SP_ACC(A_ABS, op_abs(a))
+    SP_ACC(A_SQRT, op_sqrt(a))
+    SP_ACC(A_EXP, op_exp(a))
+    SP_ACC(A_LOG, op_log(a))
+    SP_ACC(A_SQUARE, a * a)
+    SP_ACC(A_RECIP, op_recip(a))
+    SP_ACC(A_NOT, SP_B(a == T(0)))
+    SP_ACC(A_NONZERO, SP_B(a != T(0)))
+    SP_ACC(A_ISZERO, SP_B(a == T(0)))
+    SP_ACC(A_CAST_F32, cast_f32(a))
+    SP_ACC(A_CAST_I64, cast_i64(a))
+    SP_ACC(A_CAST_I32, cast_i32(a))
+    SP_ACC(A_CAST_BOOL, SP_B(a != T(0)))
+    SP_ACC(A_CAST_U8, cast_u8(a))
+    default: break;
   }
 }
 
-// Evaluates `prog` on the V-wide inputs; result left in out[V].  General path: one jump-table dispatch per op.
+// Evaluates `prog` on the V-wide inputs; result left in out[V].  General path: two small dispatches per instruction.
 template <typename T, int V, int NI>
 __device__ __forceinline__ void run_program(const DevProgram<T>& prog, const T (&in)[NI][V], const T (&idx)[V],
                                             T (&out)[V]) {
-  T s[kMaxDepth][V];
+  T tmp[kMaxTmp][V];
   const int n = prog.n_ops;
-  for (int pc = 0; pc < n; ++pc) exec_op<T, V, NI>(prog.op[pc], prog.arg[pc], prog, in, idx, s);
-#pragma unroll
-  for (int v = 0; v < V; ++v) out[v] = s[0][v];
+  for (int pc = 0; pc < n; ++pc) exec_op<T, V, NI>(prog.op[pc], prog.src[pc], prog.arg[pc], prog, in, idx, out, tmp);
 }
 
 // ---------------------------------------------------------------------------- static programs
 // The hottest fused shapes are also instantiated at compile time: the instruction list is a template
 // parameter pack, exec_op is inlined with constant operands, and the kernel body is straight-line code
 // (no dispatch at all).  The host matches the lowered program against this catalogue and otherwise uses
-// the interpreter above.  PK packs (dense op, stack slot, argument).
-#define SP_PK(DOP, SLOT, ARG) ((((DOP) * 4 + (SLOT)) << 8) | (ARG))
+// the interpreter above.  PK packs (accumulator op, operand source, argument).
+#define SP_PK(AOP, SRC, ARG) (((AOP) << 16) | ((SRC) << 8) | (ARG))
 
 struct DynamicProgram {
   template <typename T, int V, int NI>
@@ -311,32 +398,29 @@ struct StaticProgram {
   template <typename T, int V, int NI>
   static __device__ __forceinline__ void run(const DevProgram<T>& prog, const T (&in)[NI][V], const T (&idx)[V],
                                              T (&out)[V]) {
-    T s[kMaxDepth][V];
-    (exec_op<T, V, NI>(PKS >> 8, PKS & 0xff, prog, in, idx, s), ...);
-#pragma unroll
-    for (int v = 0; v < V; ++v) out[v] = s[0][v];
+    T tmp[kMaxTmp][V];
+    (exec_op<T, V, NI>(PKS >> 16, (PKS >> 8) & 0xff, PKS & 0xff, prog, in, idx, out, tmp), ...);
   }
-  static bool matches(const uint8_t* op, const uint8_t* arg, int n) {
+  static bool matches(const uint8_t* op, const uint8_t* src, const uint8_t* arg, int n) {
     const int pk[] = {PKS...};
     if (n != kLen) return false;
     for (int i = 0; i < n; ++i)
-      if (((static_cast<int>(op[i]) << 8) | arg[i]) != pk[i]) return false;
+      if (((static_cast<int>(op[i]) << 16) | (static_cast<int>(src[i]) << 8) | arg[i]) != pk[i]) return false;
     return true;
   }
 };
 
-template <int DOP> using BinaryOf = StaticProgram<SP_PK(D_IN, 0, 0), SP_PK(D_IN, 1, 1), SP_PK(DOP, 0, 0)>;
-template <int DOP> using ScalarOf = StaticProgram<SP_PK(D_IN, 0, 0), SP_PK(D_CONST, 1, 0), SP_PK(DOP, 0, 0)>;
+template <int AOP> using BinaryOf = StaticProgram<SP_PK(A_LOAD, S_IN0, 0), SP_PK(AOP, S_IN0 + 1, 0)>;
+template <int AOP> using ScalarOf = StaticProgram<SP_PK(A_LOAD, S_IN0, 0), SP_PK(AOP, S_CONST, 0)>;
 
 // catalogue of statically compiled programs (operands: in0, in1, scalar c0)
-using SProg0 = StaticProgram<SP_PK(D_IN, 0, 0)>;          // x   (copy, cast, plain reduce)
-using SProg1 = BinaryOf<D_ADD>;  using SProg2 = BinaryOf<D_SUB>;  using SProg3 = BinaryOf<D_MUL>;
-using SProg4 = BinaryOf<D_DIV>;  using SProg5 = BinaryOf<D_MAX>;  using SProg6 = BinaryOf<D_MIN>;
-using SProg7 = ScalarOf<D_ADD>;  using SProg8 = ScalarOf<D_SUB>;  using SProg9 = ScalarOf<D_MUL>;
-using SProg10 = ScalarOf<D_DIV>; using SProg11 = ScalarOf<D_MAX>; using SProg12 = ScalarOf<D_MIN>;
-// x * c + y -- the fused chain of BASELINE config 3  (x * y + z has three operands: interpreter, 8-operand variant)
-using SProg13 = StaticProgram<SP_PK(D_IN, 0, 0), SP_PK(D_CONST, 1, 0), SP_PK(D_MUL, 0, 0), SP_PK(D_IN, 1, 1),
-                              SP_PK(D_ADD, 0, 0)>;
+using SProg0 = StaticProgram<SP_PK(A_LOAD, S_IN0, 0)>;          // x   (copy, cast, plain reduce)
+using SProg1 = BinaryOf<A_ADD>;  using SProg2 = BinaryOf<A_SUB>;  using SProg3 = BinaryOf<A_MUL>;
+using SProg4 = BinaryOf<A_DIV>;  using SProg5 = BinaryOf<A_MAX>;  using SProg6 = BinaryOf<A_MIN>;
+using SProg7 = ScalarOf<A_ADD>;  using SProg8 = ScalarOf<A_SUB>;  using SProg9 = ScalarOf<A_MUL>;
+using SProg10 = ScalarOf<A_DIV>; using SProg11 = ScalarOf<A_MAX>; using SProg12 = ScalarOf<A_MIN>;
+// x * c + y -- the fused chain of BASELINE config 3
+using SProg13 = StaticProgram<SP_PK(A_LOAD, S_IN0, 0), SP_PK(A_MUL, S_CONST, 0), SP_PK(A_ADD, S_IN0 + 1, 0)>;
 
 #define SP_STATIC_PROGRAMS(X)                                                                              \
   X(0, SProg0) X(1, SProg1) X(2, SProg2) X(3, SProg3) X(4, SProg4) X(5, SProg5) X(6, SProg6) X(7, SProg7)   \

@@ -189,15 +189,16 @@ template <> struct TypeTag<double> { static constexpr int dtype = SP_F64; static
 template <> struct TypeTag<long long> { static constexpr int dtype = SP_I64; static constexpr int VA = 4, VB = 2; };
 
 template <typename T>
-static void convert_program(const sp_program* prog, DevProgram<T>* out) {
+static bool convert_program(const sp_program* prog, DevProgram<T>* out) {
   memset(out, 0, sizeof(*out));
-  lower_program<T>(prog, out);      // the program was validated by the C-ABI entry point
+  const bool ok = lower_program<T>(prog, out);      // postfix (ABI) -> accumulator code
   for (int i = 0; i < 3; ++i) out->index_stride[i] = prog->index_stride[i];
   out->index_base = prog->index_base;
   for (int i = 0; i < SP_MAX_CONSTS; ++i) {
     if (TypeTag<T>::dtype == SP_I64) out->consts[i] = static_cast<T>(prog->iconsts[i]);
     else out->consts[i] = static_cast<T>(prog->consts[i]);
   }
+  return ok;
 }
 
 // vec_axis: which of stride[] runs along the vector (2 for map / reduce_col, 1 for reduce_row)
@@ -271,7 +272,7 @@ static int launch_stream_as(const DevProgram<T>& dp, const DevOperands<NI>& ops,
 // Index of the statically compiled program equal to `dp`, or -1.
 template <typename T>
 static int match_static(const DevProgram<T>& dp) {
-#define SP_MATCH(IDX, TYPE) if (TYPE::matches(dp.op, dp.arg, dp.n_ops)) return IDX;
+#define SP_MATCH(IDX, TYPE) if (TYPE::matches(dp.op, dp.src, dp.arg, dp.n_ops)) return IDX;
   SP_STATIC_PROGRAMS(SP_MATCH)
 #undef SP_MATCH
   return -1;
@@ -311,7 +312,8 @@ template <typename T, int V, int NI>
 static int launch_map_v(const sp_program* prog, int n_in, const sp_operand* in, const sp_operand* out,
                         const int64_t dims[3], cudaStream_t stream) {
   DevProgram<T> dp;
-  convert_program<T>(prog, &dp);
+  SP_REQUIRE(convert_program<T>(prog, &dp), SP_ERR_UNSUPPORTED,
+             "expression needs more than %d temporaries; split it (the fusion pass does)", kMaxTmp);
   DevOperands<NI> ops;
   memset(&ops, 0, sizeof(ops));
   ops.n_in = n_in;
@@ -398,7 +400,8 @@ static int launch_reduce_v(const sp_program* prog, int n_in, const sp_operand* i
   SP_REQUIRE(scratch != nullptr && scratch_bytes >= need, SP_ERR_INVALID,
              "sp_map_reduce: scratch %lld B < required %lld B", (long long)scratch_bytes, (long long)need);
   DevProgram<T> dp;
-  convert_program<T>(prog, &dp);
+  SP_REQUIRE(convert_program<T>(prog, &dp), SP_ERR_UNSUPPORTED,
+             "expression needs more than %d temporaries; split it (the fusion pass does)", kMaxTmp);
   DevOperands<NI> ops;
   memset(&ops, 0, sizeof(ops));
   ops.n_in = n_in;

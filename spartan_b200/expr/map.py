@@ -24,12 +24,16 @@ from .local import LocalInput, LocalMapExpr, LocalMapLocationExpr, make_var
 def bind_operands(children, child_to_var):
   """LocalInput name -> program.Operand for the evaluated children of a map / reduce."""
   operands = {}
+  seen = {}
   for child, var in zip(children, child_to_var):
     base = child.base if isinstance(child, Broadcast) else child
     if isinstance(base, LocalWrapper) and base.shape == ():
       operands[var] = program.Operand('scalar', base.dtype, value=base.host_data()[()])
     else:
-      operands[var] = program.Operand('array', child.dtype)
+      # the same array used twice (x*x, (x-y)*x ...) is one operand: read once per element
+      key = (id(base), tuple(child.shape))
+      operands[var] = program.Operand('array', child.dtype, alias=seen.get(key))
+      seen.setdefault(key, var)
   return operands
 
 

@@ -71,13 +71,14 @@ def legacy_result_type(items):
 
 class Operand(object):
   """What a LocalInput name is bound to when a tile kernel is launched."""
-  __slots__ = ('kind', 'dtype', 'value', 'index')
+  __slots__ = ('kind', 'dtype', 'value', 'index', 'alias')
 
-  def __init__(self, kind, dtype, value=None, index=None):
+  def __init__(self, kind, dtype, value=None, index=None, alias=None):
     self.kind = kind          # 'array' (device tensor operand) | 'scalar' (host 0-d value)
     self.dtype = np.dtype(dtype)
     self.value = value
     self.index = index
+    self.alias = alias        # name of an earlier input bound to the very same array: loaded once
 
 
 class _Typed(object):
@@ -148,7 +149,7 @@ def _analyse(node, operands):
     o = operands[node.idx]
     if o.kind == 'scalar':
       return _Typed('const', [], o.dtype, weak=True, value=o.value)
-    return _Typed('in', [], o.dtype, leaf=node.idx)
+    return _Typed('in', [], o.dtype, leaf=o.alias or node.idx)
   if not isinstance(node, local.FnCallExpr):
     raise NotDeviceMappable('cannot lower %r' % (node,))
   if node.fn in _SPECIAL:

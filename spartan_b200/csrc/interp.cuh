@@ -10,8 +10,6 @@
 
 namespace sp {
 
-constexpr int kMaxDepth = 4;
-
 template <typename T>
 struct DevProgram {
   int32_t n_ops;

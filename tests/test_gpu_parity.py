@@ -451,3 +451,31 @@ def test_spmv_vs_oracle(n, outlinks, strip):
   np.testing.assert_allclose(got.reshape(-1), exact, rtol=1e-5, atol=1e-6)
   ones = sp.dot(wts, sp.ones((n, 1), tile_hint=(strip, 1))).glom().reshape(-1)       # p = ones, as in the benchmark
   np.testing.assert_allclose(ones, np.asarray(W.tocsr().sum(axis=1)).reshape(-1), rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------ edge cases: 0-d, empty, ragged, tiny
+def test_zero_dim_and_empty_arrays():
+  s = sp.from_numpy(np.array(3.0, dtype=np.float32))
+  assert (s * 2 + 1).glom() == 7.0
+  assert (s * 2 + 1).glom().shape == ()
+  for shape in [(0,), (0, 5), (3, 0)]:
+    z = sp.zeros(shape)
+    assert z.glom().shape == shape
+    assert (z + 1).glom().shape == shape
+    assert sp.sum(z).glom() == 0.0
+  assert sp.sum(sp.zeros((0, 5)), axis=0).glom().shape == (5,)
+  Assert.all_eq(sp.sum(sp.zeros((0, 5)), axis=0).glom(), np.zeros((5,), np.float32))
+
+
+def test_general_expression_outside_the_static_catalogue():
+  """A chain that needs a temporary (both operands of '+' are sub-trees) and reuses an operand: interpreter path,
+  streaming and non-streaming shapes; +,-,*,abs,max are exact so the result is bit-identical to NumPy."""
+  rng = np.random.RandomState(21)
+  for shape in [(40, 33), (600, 2048), (3, 1 << 18)]:
+    x = rng.randn(*shape).astype(np.float32); y = rng.randn(*shape).astype(np.float32)
+    X, Y = sp.from_numpy(x), sp.from_numpy(y)
+    e = (sp.abs(X - Y) * X + sp.maximum(Y, 0.5))
+    Assert.all_eq(e.optimized().glom(), np.abs(x - y) * x + np.maximum(y, np.float32(0.5)))
+    got = e.sum(axis=0).optimized().glom()
+    np.testing.assert_allclose(got, (np.abs(x - y).astype(np.float64) * x + np.maximum(y, 0.5)).sum(axis=0), rtol=2e-5, atol=1e-4)
+    Assert.all_eq(((X - Y) / (sp.abs(Y) + 1) - (X * X - 3)).optimized().glom(), (x - y) / (np.abs(y) + 1) - (x * x - 3))

@@ -593,9 +593,10 @@ def broadcast(args):
     assert len(axis_shape) <= 2, 'Mismatched shapes for broadcast: %s' % orig_shapes
     if len(axis_shape) == 2:
       assert 1 in axis_shape, 'Mismatched shapes for broadcast: %s' % orig_shapes
-    max_size = max(shp[axis] for shp in new_shapes)
+    # NumPy rule: sizes are equal or 1; the result takes the size that is not 1 (which may be 0)
+    size = next((v for v in (shp[axis] for shp in new_shapes) if v != 1), 1)
     for shp in new_shapes:
-      shp[axis] = max_size
+      shp[axis] = size
   results = []
   for i in range(len(args)):
     if new_shapes[i] == orig_shapes[i]:

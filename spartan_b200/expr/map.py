@@ -92,11 +92,11 @@ class MapExpr(Expr):
     orig_shapes = [list(x.shape) for x in self.children]
     max_dim = max(len(s) for s in orig_shapes)
     new_shapes = [[1] * (max_dim - len(s)) + s for s in orig_shapes]
-    output_shape = collections.defaultdict(int)
-    for s in new_shapes:
-      for i, v in enumerate(s):
-        output_shape[i] = max(output_shape[i], v)
-    return tuple(output_shape[i] for i in range(len(output_shape)))
+    out = []
+    for i in range(max_dim):
+      sizes = [s[i] for s in new_shapes]
+      out.append(next((v for v in sizes if v != 1), 1))     # the size that is not 1 (it may be 0)
+    return tuple(out)
 
   def _evaluate(self, ctx, deps):
     # map.py:149-169

@@ -184,3 +184,17 @@ def test_cabi_gemm_and_fill_argument_checks():
   assert lib.sp_fill(None, _lib.SP_F32, 4, 0, 0.0, 0.0, 0, 0, None) == -1
   assert lib.sp_spmv_csr(None, None, None, 0, None, None, 0, 0, None) == 0
   assert lib.sp_kmeans_assign(None, 0, 4, 0, None, 1, None, None, None, None, 0, None) == -1
+
+
+def test_broadcast_shapes_including_empty():
+  z = sp.zeros((0, 5)); o = sp.ones((1, 5)); c = sp.ones((3, 1))
+  assert (z + 1).shape == (0, 5) and (z + o).shape == (0, 5) and (o + c).shape == (3, 5)
+  assert (sp.zeros((0,)) + 1).shape == (0,)
+  assert sp.sum(z, axis=0).shape == (5,) and sp.sum(z).shape == ()
+  from spartan_b200.array import distarray as d
+  class A(d.DistArray):
+    def __init__(self, shape): self.shape = shape; self.dtype = np.dtype(np.float32); self.tiles = {}
+  got = d.broadcast([A((0,)), A(())])
+  assert [g.shape for g in got] == [(0,), (0,)]
+  got = d.broadcast([A((3, 1)), A((1, 5))])
+  assert [g.shape for g in got] == [(3, 5), (3, 5)]

@@ -270,98 +270,110 @@ inline bool lower_program(const sp_program* prog, DevProgram<T>* out) {
 }
 
 #define SP_B(x) ((x) ? T(1) : T(0))
-#define SP_ACC(AOP, EXPR)                                            \
-  case AOP: {                                                        \
+
+// acc[v] = EXPR(a = acc[v], b = operand[v]) with the operand read straight from its home (no staging copy):
+// one case per operand source, so every index is a compile-time constant.
+#define SP_APPLY(BEXPR, EXPR)                                        \
+  {                                                                  \
     _Pragma("unroll") for (int v = 0; v < V; ++v) {                  \
       const T a = acc[v];                                            \
-      const T b = x[v];                                              \
+      const T b = (BEXPR);                                           \
       acc[v] = (EXPR);                                               \
     }                                                                \
     break;                                                           \
   }
+#define SP_IN(I) in[(I) < NI ? (I) : 0][v]
+#define SP_BINARY(AOP, EXPR)                                         \
+  case AOP: {                                                        \
+    switch (src) {                                                   \
+      case 0: SP_APPLY(SP_IN(0), EXPR)                               \
+      case 1: SP_APPLY(SP_IN(1), EXPR)                               \
+      case 2: SP_APPLY(SP_IN(2), EXPR)                               \
+      case 3: SP_APPLY(SP_IN(3), EXPR)                               \
+      case 4: SP_APPLY(SP_IN(4), EXPR)                               \
+      case 5: SP_APPLY(SP_IN(5), EXPR)                               \
+      case 6: SP_APPLY(SP_IN(6), EXPR)                               \
+      case 7: SP_APPLY(SP_IN(7), EXPR)                               \
+      case S_CONST: SP_APPLY(cst, EXPR)                              \
+      case S_TMP: SP_APPLY(tmp[arg][v], EXPR)                        \
+      default: SP_APPLY(idx[v], EXPR) /* S_INDEX */                  \
+    }                                                                \
+    break;                                                           \
+  }
+// Long-bodied operators (pow, mod, integer division ...) stage the operand once so their code exists once per
+// operator instead of once per source.
+#define SP_HEAVY(AOP, EXPR)                                          \
+  case AOP: {                                                        \
+    T x[V];                                                          \
+    switch (src) {                                                   \
+      case 0: _Pragma("unroll") for (int v = 0; v < V; ++v) x[v] = SP_IN(0); break; \
+      case 1: _Pragma("unroll") for (int v = 0; v < V; ++v) x[v] = SP_IN(1); break; \
+      case 2: _Pragma("unroll") for (int v = 0; v < V; ++v) x[v] = SP_IN(2); break; \
+      case 3: _Pragma("unroll") for (int v = 0; v < V; ++v) x[v] = SP_IN(3); break; \
+      case 4: _Pragma("unroll") for (int v = 0; v < V; ++v) x[v] = SP_IN(4); break; \
+      case 5: _Pragma("unroll") for (int v = 0; v < V; ++v) x[v] = SP_IN(5); break; \
+      case 6: _Pragma("unroll") for (int v = 0; v < V; ++v) x[v] = SP_IN(6); break; \
+      case 7: _Pragma("unroll") for (int v = 0; v < V; ++v) x[v] = SP_IN(7); break; \
+      case S_CONST: _Pragma("unroll") for (int v = 0; v < V; ++v) x[v] = cst; break; \
+      case S_TMP: _Pragma("unroll") for (int v = 0; v < V; ++v) x[v] = tmp[arg][v]; break; \
+      default: _Pragma("unroll") for (int v = 0; v < V; ++v) x[v] = idx[v]; break; \
+    }                                                                \
+    SP_APPLY(x[v], EXPR)                                             \
+  }
+#define SP_UNARY(AOP, EXPR)                                          \
+  case AOP: SP_APPLY(T(0), EXPR)
 
 // One instruction.  With compile-time-constant arguments (static programs below) both switches fold away.
 template <typename T, int V, int NI>
 __device__ __forceinline__ void exec_op(const int op, const int src, const int arg, const DevProgram<T>& prog,
                                         const T (&in)[NI][V], const T (&idx)[V], T (&acc)[V], T (&tmp)[kMaxTmp][V]) {
-  T x[V];
-  switch (src) {
-    case S_CONST: {
-      const T c = prog.consts[arg];
-#pragma unroll
-      for (int v = 0; v < V; ++v) x[v] = c;
-      break;
-    }
-    case S_TMP:
-#pragma unroll
-      for (int v = 0; v < V; ++v) x[v] = tmp[arg][v];
-      break;
-    case S_INDEX:
-#pragma unroll
-      for (int v = 0; v < V; ++v) x[v] = idx[v];
-      break;
-    case S_NONE:
-#pragma unroll
-      for (int v = 0; v < V; ++v) x[v] = T(0);
-      break;
-    default:
-#pragma unroll
-      for (int i = 0; i < NI; ++i)
-        if (i == src) {
-#pragma unroll
-          for (int v = 0; v < V; ++v) x[v] = in[i][v];
-        }
-      break;
-  }
+  const T cst = prog.consts[src == S_CONST ? arg : 0];
   switch (op) {
-    case A_LOAD:
-#pragma unroll
-      for (int v = 0; v < V; ++v) acc[v] = x[v];
-      break;
+    SP_BINARY(A_LOAD, b)
     case A_SAVE:
 #pragma unroll
       for (int v = 0; v < V; ++v) tmp[arg][v] = acc[v];
       break;
-    SP_ACC(A_ADD, a + b)
-    SP_ACC(A_SUB, a - b)
-    SP_ACC(A_MUL, a * b)
-    SP_ACC(A_DIV, op_div(a, b))
-    SP_ACC(A_MOD, op_mod(a, b))
-    SP_ACC(A_POW, op_pow(a, b))
-    SP_ACC(A_MAX, op_max(a, b))
-    SP_ACC(A_MIN, op_min(a, b))
-    SP_ACC(A_EQ, SP_B(a == b))
-    SP_ACC(A_NE, SP_B(a != b))
-    SP_ACC(A_LT, SP_B(a < b))
-    SP_ACC(A_LE, SP_B(a <= b))
-    SP_ACC(A_GT, SP_B(a > b))
-    SP_ACC(A_GE, SP_B(a >= b))
-    SP_ACC(A_AND, SP_B((a != T(0)) && (b != T(0))))
-    SP_ACC(A_OR, SP_B((a != T(0)) || (b != T(0))))
-    SP_ACC(A_XOR, SP_B((a != T(0)) != (b != T(0))))
-    SP_ACC(A_FMOD, op_fmod(a, b))
-    SP_ACC(A_FLOORDIV, op_floordiv(a, b))
-    SP_ACC(A_RSUB, b - a)
-    SP_ACC(A_RDIV, op_div(b, a))
-    SP_ACC(A_RMOD, op_mod(b, a))
-    SP_ACC(A_RPOW, op_pow(b, a))
-    SP_ACC(A_RFMOD, op_fmod(b, a))
-    SP_ACC(A_RFLOORDIV, op_floordiv(b, a))
-    SP_ACC(A_NEG, -a)
-    SP_ACC(A_ABS, op_abs(a))
-    SP_ACC(A_SQRT, op_sqrt(a))
-    SP_ACC(A_EXP, op_exp(a))
-    SP_ACC(A_LOG, op_log(a))
-    SP_ACC(A_SQUARE, a * a)
-    SP_ACC(A_RECIP, op_recip(a))
-    SP_ACC(A_NOT, SP_B(a == T(0)))
-    SP_ACC(A_NONZERO, SP_B(a != T(0)))
-    SP_ACC(A_ISZERO, SP_B(a == T(0)))
-    SP_ACC(A_CAST_F32, cast_f32(a))
-    SP_ACC(A_CAST_I64, cast_i64(a))
-    SP_ACC(A_CAST_I32, cast_i32(a))
-    SP_ACC(A_CAST_BOOL, SP_B(a != T(0)))
-    SP_ACC(A_CAST_U8, cast_u8(a))
+    SP_BINARY(A_ADD, a + b)
+    SP_BINARY(A_SUB, a - b)
+    SP_BINARY(A_MUL, a * b)
+    SP_HEAVY(A_DIV, op_div(a, b))
+    SP_HEAVY(A_MOD, op_mod(a, b))
+    SP_HEAVY(A_POW, op_pow(a, b))
+    SP_BINARY(A_MAX, op_max(a, b))
+    SP_BINARY(A_MIN, op_min(a, b))
+    SP_BINARY(A_EQ, SP_B(a == b))
+    SP_BINARY(A_NE, SP_B(a != b))
+    SP_BINARY(A_LT, SP_B(a < b))
+    SP_BINARY(A_LE, SP_B(a <= b))
+    SP_BINARY(A_GT, SP_B(a > b))
+    SP_BINARY(A_GE, SP_B(a >= b))
+    SP_BINARY(A_AND, SP_B((a != T(0)) && (b != T(0))))
+    SP_BINARY(A_OR, SP_B((a != T(0)) || (b != T(0))))
+    SP_BINARY(A_XOR, SP_B((a != T(0)) != (b != T(0))))
+    SP_HEAVY(A_FMOD, op_fmod(a, b))
+    SP_HEAVY(A_FLOORDIV, op_floordiv(a, b))
+    SP_BINARY(A_RSUB, b - a)
+    SP_HEAVY(A_RDIV, op_div(b, a))
+    SP_HEAVY(A_RMOD, op_mod(b, a))
+    SP_HEAVY(A_RPOW, op_pow(b, a))
+    SP_HEAVY(A_RFMOD, op_fmod(b, a))
+    SP_HEAVY(A_RFLOORDIV, op_floordiv(b, a))
+    SP_UNARY(A_NEG, -a)
+    SP_UNARY(A_ABS, op_abs(a))
+    SP_UNARY(A_SQRT, op_sqrt(a))
+    SP_UNARY(A_EXP, op_exp(a))
+    SP_UNARY(A_LOG, op_log(a))
+    SP_UNARY(A_SQUARE, a * a)
+    SP_UNARY(A_RECIP, op_recip(a))
+    SP_UNARY(A_NOT, SP_B(a == T(0)))
+    SP_UNARY(A_NONZERO, SP_B(a != T(0)))
+    SP_UNARY(A_ISZERO, SP_B(a == T(0)))
+    SP_UNARY(A_CAST_F32, cast_f32(a))
+    SP_UNARY(A_CAST_I64, cast_i64(a))
+    SP_UNARY(A_CAST_I32, cast_i32(a))
+    SP_UNARY(A_CAST_BOOL, SP_B(a != T(0)))
+    SP_UNARY(A_CAST_U8, cast_u8(a))
     default: break;
   }
 }

@@ -77,6 +77,7 @@ class Expr(object):
     self.expr_id = next(unique_id) if expr_id is None else expr_id
     self.shape_cache = shape_cache
     self.optimized_expr = None
+    self.is_optimized = False
     eval_cache.register(self.expr_id)
     self.needs_cache = self.needs_cache and FLAGS.opt_expression_cache
 
@@ -180,9 +181,17 @@ class Expr(object):
 
   def optimized(self):
     """base.py:477-492."""
+    if self.is_optimized:
+      return self
     if self.optimized_expr is None:
-      self.optimized_expr = optimized_dag(self)
-      self.optimized_expr.optimized_expr = self.optimized_expr
+      opt = optimized_dag(self)
+      if opt is self:
+        self.is_optimized = True
+        return self
+      self.optimized_expr = opt
+      # a flag, not the reference's self-reference (`opt.optimized_expr = opt`): a cycle would keep the cached
+      # result tiles -- device memory here -- alive until the cycle collector happens to run
+      self.optimized_expr.is_optimized = True
     return self.optimized_expr
 
   def glom(self):

@@ -198,3 +198,21 @@ def test_broadcast_shapes_including_empty():
   assert [g.shape for g in got] == [(0,), (0,)]
   got = d.broadcast([A((3, 1)), A((1, 5))])
   assert [g.shape for g in got] == [(3, 5), (3, 5)]
+
+
+def test_optimized_expressions_leave_no_reference_cycles():
+  """A cached result holds device memory: dropping the last reference to an expression must free it at once,
+  not whenever the cycle collector next runs (the reference's `opt.optimized_expr = opt` is a self-cycle)."""
+  import gc
+  a = sp.from_numpy(np.zeros((4, 4), np.float32))
+  gc.collect()
+  gc.disable()
+  try:
+    for make in (lambda: (a * 2 + a).optimized(), lambda: (a + a).sum(axis=0).optimized(),
+                 lambda: sp.dot(a, a).optimized(), lambda: a.optimized()):
+      e = make()
+      assert e.optimized() is e
+      del e
+      assert gc.collect() == 0
+  finally:
+    gc.enable()

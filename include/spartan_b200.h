@@ -250,6 +250,9 @@ typedef struct {
  * (round-to-nearest) every few k-blocks; sp_gemm_set_chunk_kblocks overrides that interval
  * (0 = per-mode default) -- a tuning / test hook. */
 int sp_gemm_set_chunk_kblocks(int k_blocks);
+/* Test / tuning hook: kernel variant of the tensor-core paths. 0 = choose by shape (default), 1 = one CTA per
+ * 128 x 256 tile, 2 = CTA pairs (tcgen05 cta_group::2) on 256 x 256 tiles. Results are identical bit for bit. */
+int sp_gemm_set_variant(int variant);
 int64_t sp_gemm_f32_workspace_bytes(int64_t M, int64_t N, int n_seg, const int64_t* seg_k, int precision);
 int sp_gemm_f32_segments(int n_seg, const sp_gemm_segment* segs, float* C, int64_t ldc, int64_t M, int64_t N,
                          int accumulate, int precision, void* workspace, int64_t workspace_bytes, void* stream);

@@ -53,6 +53,13 @@ constexpr int MAX_MAPS = 4 * 8;              // per launch: <= 8 segments x (A_h
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int REGS_PRODUCER = 40;
 constexpr int REGS_EPILOGUE = 232;
+// CTA-pair variant (cta_group::2): the two CTAs of a cluster own one 256 x 256 tile of C.  Each CTA loads its own 128 rows
+// of A and 128 of the 256 rows of Bt, every operand tile ONCE per k-block (hi and lo copies side by side in the stage), and
+// the leader issues M=256 MMAs that read both CTAs' shared memory: 64 KiB of L2->smem traffic per CTA per k-block instead
+// of 144 KiB, and half the B bytes per MMA out of each SM's shared memory.
+constexpr int PAIR_TILE_BYTES = 128 * 128;                 // 128 rows x one 128 B swizzle row of K
+constexpr int PAIR_RING_BYTES = 12 * PAIR_TILE_BYTES;      // 192 KiB: 3 stages x 4 tiles (split modes), 6 x 2 (tf32x1)
+constexpr int PAIR_SMEM_BYTES = PAIR_RING_BYTES + 1024 + 256;
 
 struct Segment {
   int k_blocks;
@@ -166,6 +173,77 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
+// ---- CTA-pair (cta_group::2) forms ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t num_clusters_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on a barrier that lives in another CTA of the cluster (address from map_to_cta)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// TMA load whose completion bytes are credited to a barrier in the pair's leader CTA
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(cluster_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+template <int KIND>
+__device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  if constexpr (KIND == 0) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+        : "memory");
+  }
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair once the pair's MMAs retired
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
 // Field layout follows the sm_100 shared-memory matrix descriptor
 // (start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout [61,64)).
@@ -197,49 +275,67 @@ __device__ __forceinline__ void tile_coords(int tile, int m_blocks, int n_blocks
 
 // ----------------------------------------------------------------------------
 // The kernel.  KIND 0: tf32 operands (BK = 32 elements), KIND 1: bf16 (BK = 64).
+// PAIR false: one CTA per 128 x 256 tile, a pipeline stage = the (A, Bt) tiles of one precision term.
+// PAIR true : launched as clusters of 2; the pair owns a 256 x 256 tile (this CTA: rows rank*128 .. +128), a stage =
+//             every distinct operand tile of one k-block ([A copies][Bt-half copies], 16 KiB each); only the leader
+//             (cluster rank 0) issues MMAs (cta_group::2, M = 256) and its commits arrive on both CTAs' barriers.
 // ----------------------------------------------------------------------------
-template <int KIND>
+constexpr int MAX_STAGES = 6;
+
+template <int KIND, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ Params p) {
   constexpr int ELEM = (KIND == 0) ? 4 : 2;
   constexpr int BK = 128 / ELEM;               // elements per 128B swizzle row
   constexpr int UMMA_K = 32 / ELEM;            // 32 bytes of K per MMA
-  constexpr uint32_t IDESC = make_idesc(KIND == 0 ? 2 : 1, BM, BN);
+  constexpr uint32_t IDESC = make_idesc(KIND == 0 ? 2 : 1, PAIR ? 2 * BM : BM, BN);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  const int copies = (p.segs[0].n_terms == 3) ? 2 : 1;
+  const int stage_bytes = PAIR ? 2 * copies * PAIR_TILE_BYTES : STAGE_BYTES;
+  const int n_stages = PAIR ? PAIR_RING_BYTES / stage_bytes : STAGES;
+  const uint32_t bar_base = smem_base + (PAIR ? PAIR_RING_BYTES : STAGES * STAGE_BYTES);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
-  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + NUM_ACC + a); };
-  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * STAGES + 2 * NUM_ACC);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + NUM_ACC + a); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * MAX_STAGES + 2 * NUM_ACC);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.m_blocks * p.n_blocks;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;          // 0 = leader of the pair
+  const int first_tile = PAIR ? static_cast<int>(cluster_id_x()) : static_cast<int>(blockIdx.x);
+  const int tile_step = PAIR ? static_cast<int>(num_clusters_x()) : static_cast<int>(gridDim.x);
+  const int m_tiles = PAIR ? (p.m_blocks + 1) / 2 : p.m_blocks;  // tile rows (256 rows each in pair mode)
+  const int num_tiles = m_tiles * p.n_blocks;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.n_segs; ++s)
-      for (int t = 0; t < p.segs[s].n_terms; ++t) {
+      for (int t = 0; t < (PAIR ? copies : p.segs[s].n_terms); ++t) {
         tma_prefetch_desc(&p.maps[p.segs[s].a_map[t]]);
         tma_prefetch_desc(&p.maps[p.segs[s].b_map[t]]);
       }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < n_stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < NUM_ACC; ++a) {
       mbar_init(tmem_full_bar(a), 1);
-      mbar_init(tmem_empty_bar(a), NUM_EPI_WARPS);   // one arrive per epilogue warp
+      // one arrive per epilogue warp; in pair mode the leader's barrier also collects the peer's warps
+      mbar_init(tmem_empty_bar(a), PAIR ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  if (warp == 2) {
+    if constexpr (PAIR) tmem_alloc_pair(tmem_ptr_smem, TMEM_COLS);
+    else tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();      // the peer's barriers must exist before anything arrives on them
+  else __syncthreads();
   tc_fence_after();
 
   uint32_t tmem_base;
@@ -252,34 +348,49 @@ gemm_kernel(const __grid_constant__ Params p) {
       if (lane == 0) {
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
           int m_blk, n_blk;
-          tile_coords(tile, p.m_blocks, p.n_blocks, m_blk, n_blk);
+          tile_coords(tile, m_tiles, p.n_blocks, m_blk, n_blk);
           for (int s = 0; s < p.n_segs; ++s) {
             const Segment seg = p.segs[s];
             for (int kb = 0; kb < seg.k_blocks; ++kb) {
-              for (int t = 0; t < seg.n_terms; ++t) {
+              if constexpr (PAIR) {
                 mbar_wait(empty_bar(stage), phase ^ 1);
-                const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
-                const uint32_t b_dst = a_dst + A_STAGE_BYTES;
-                mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-                tma_load_2d(a_dst, &p.maps[seg.a_map[t]], full_bar(stage), kb * BK, m_blk * BM);
-                tma_load_2d(b_dst, &p.maps[seg.b_map[t]], full_bar(stage), kb * BK, n_blk * BN);
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                // the leader's barrier counts the bytes of both CTAs' loads of this stage
+                if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * stage_bytes);
+                const uint32_t leader_full = map_to_cta(full_bar(stage), 0);
+                const uint32_t dst = smem_base + stage * stage_bytes;
+                const int a_row = (m_blk * 2 + static_cast<int>(rank)) * BM;
+                const int b_row = n_blk * BN + static_cast<int>(rank) * (BN / 2);
+                for (int c = 0; c < copies; ++c)
+                  tma_load_2d_pair(dst + c * PAIR_TILE_BYTES, &p.maps[seg.a_map[c]], leader_full, kb * BK, a_row);
+                for (int c = 0; c < copies; ++c)
+                  tma_load_2d_pair(dst + (copies + c) * PAIR_TILE_BYTES, &p.maps[seg.b_map[c]], leader_full, kb * BK, b_row);
+                if (++stage == n_stages) { stage = 0; phase ^= 1; }
+              } else {
+                for (int t = 0; t < seg.n_terms; ++t) {
+                  mbar_wait(empty_bar(stage), phase ^ 1);
+                  const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
+                  const uint32_t b_dst = a_dst + A_STAGE_BYTES;
+                  mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+                  tma_load_2d(a_dst, &p.maps[seg.a_map[t]], full_bar(stage), kb * BK, m_blk * BM);
+                  tma_load_2d(b_dst, &p.maps[seg.b_map[t]], full_bar(stage), kb * BK, n_blk * BN);
+                  if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
               }
             }
           }
         }
       }
       __syncwarp();
-    } else if (warp == 1) {
+    } else if (warp == 1 && rank == 0) {
       // ===================== MMA issuer =====================
       if (lane == 0) {
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
           int in_chunk = 0;          // k-blocks issued into the current TMEM chunk
           uint32_t accum = 0;
           bool chunk_open = false;
@@ -288,37 +399,59 @@ gemm_kernel(const __grid_constant__ Params p) {
             const int n_terms = p.segs[s].n_terms;
             for (int kb = 0; kb < k_blocks; ++kb) {
               if (!chunk_open) {
-                mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);   // epilogue drained this buffer
+                mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);   // epilogue(s) drained this buffer
                 tc_fence_after();
                 chunk_open = true;
                 accum = 0;
                 in_chunk = 0;
               }
               const uint32_t tmem_d = tmem_base + acc * BN;
-              for (int t = 0; t < n_terms; ++t) {
+              if constexpr (PAIR) {
                 mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
-                const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
-                const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+                const uint32_t base = smem_base + stage * stage_bytes;
+                for (int t = 0; t < n_terms; ++t) {
+                  // small cross terms first, dominant term last: (lo,hi) (hi,lo) (hi,hi); single copy: (hi,hi)
+                  const int ai = (n_terms == 3 && t == 0) ? 1 : 0;
+                  const int bi = (n_terms == 3 && t == 1) ? 1 : 0;
+                  const uint32_t a_addr = base + ai * PAIR_TILE_BYTES;
+                  const uint32_t b_addr = base + (copies + bi) * PAIR_TILE_BYTES;
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
-                  const uint64_t da = make_kmajor_sw128_desc(a_addr + k * 32);
-                  const uint64_t db = make_kmajor_sw128_desc(b_addr + k * 32);
-                  umma<KIND>(tmem_d, da, db, IDESC, accum);
-                  accum = 1;
+                  for (int k = 0; k < BK / UMMA_K; ++k) {
+                    umma_pair<KIND>(tmem_d, make_kmajor_sw128_desc(a_addr + k * 32), make_kmajor_sw128_desc(b_addr + k * 32),
+                                    IDESC, accum);
+                    accum = 1;
+                  }
                 }
-                umma_commit(empty_bar(stage));      // frees the smem slot when these MMAs retire
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                umma_commit_pair(empty_bar(stage));   // frees this stage in both CTAs when these MMAs retire
+                if (++stage == n_stages) { stage = 0; phase ^= 1; }
+              } else {
+                for (int t = 0; t < n_terms; ++t) {
+                  mbar_wait(full_bar(stage), phase);
+                  tc_fence_after();
+                  const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
+                  const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+                  for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint64_t da = make_kmajor_sw128_desc(a_addr + k * 32);
+                    const uint64_t db = make_kmajor_sw128_desc(b_addr + k * 32);
+                    umma<KIND>(tmem_d, da, db, IDESC, accum);
+                    accum = 1;
+                  }
+                  umma_commit(empty_bar(stage));      // frees the smem slot when these MMAs retire
+                  if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
               }
               if (++in_chunk == p.chunk_kb) {
-                umma_commit(tmem_full_bar(acc));    // chunk complete -> epilogue promotes it
+                // chunk complete -> epilogue promotes it
+                if constexpr (PAIR) umma_commit_pair(tmem_full_bar(acc)); else umma_commit(tmem_full_bar(acc));
                 chunk_open = false;
                 if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
               }
             }
           }
           if (chunk_open) {
-            umma_commit(tmem_full_bar(acc));
+            if constexpr (PAIR) umma_commit_pair(tmem_full_bar(acc)); else umma_commit(tmem_full_bar(acc));
             if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
           }
         }
@@ -335,9 +468,10 @@ gemm_kernel(const __grid_constant__ Params p) {
     const int n_chunks = (total_kb + p.chunk_kb - 1) / p.chunk_kb;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
       int m_blk, n_blk;
-      tile_coords(tile, p.m_blocks, p.n_blocks, m_blk, n_blk);
+      tile_coords(tile, m_tiles, p.n_blocks, m_blk, n_blk);
+      if constexpr (PAIR) m_blk = m_blk * 2 + static_cast<int>(rank);     // this CTA's 128-row block
       float sum[128];
 #pragma unroll
       for (int j = 0; j < 128; ++j) sum[j] = 0.0f;
@@ -355,7 +489,10 @@ gemm_kernel(const __grid_constant__ Params p) {
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+        if (lane == 0) {
+          if constexpr (PAIR) mbar_arrive_cluster(map_to_cta(tmem_empty_bar(acc), 0));   // the issuer lives in the leader
+          else mbar_arrive(tmem_empty_bar(acc));
+        }
         if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
       }
       const int row = m_blk * BM + q * 32 + lane;
@@ -405,10 +542,12 @@ gemm_kernel(const __grid_constant__ Params p) {
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();      // nobody leaves while the pair may still touch its shared memory / TMEM
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -535,6 +674,7 @@ static bool mode_of(int precision, Mode* m) {
 }
 
 static int g_chunk_override = 0;
+static int g_variant = 0;      // 0: choose, 1: one CTA per tile, 2: CTA pairs
 
 }  // namespace gemm
 }  // namespace sp
@@ -546,6 +686,13 @@ using namespace sp::gemm;
 extern "C" int sp_gemm_set_chunk_kblocks(int kb) {
   SP_REQUIRE(kb >= 0 && kb <= (1 << 20), SP_ERR_INVALID, "bad chunk size %d", kb);
   g_chunk_override = kb;
+  return SP_OK;
+}
+
+// Test / tuning hook: 0 = choose by shape (default), 1 = one CTA per 128x256 tile, 2 = CTA pairs on 256x256 tiles.
+extern "C" int sp_gemm_set_variant(int variant) {
+  SP_REQUIRE(variant >= 0 && variant <= 2, SP_ERR_INVALID, "bad gemm variant %d", variant);
+  g_variant = variant;
   return SP_OK;
 }
 
@@ -624,15 +771,35 @@ static int launch_prepared(int n_seg, const sp_gemm_prepared_segment* segs, floa
   SP_REQUIRE(n_seg >= 1 && n_seg <= 8, SP_ERR_INVALID, "sp_gemm_prepared: %d segments (limit 8 per launch)", n_seg);
   SP_REQUIRE(M > 0 && N > 0 && M < (1ll << 31) && N < (1ll << 31), SP_ERR_INVALID, "bad M/N %lld %lld",
              (long long)M, (long long)N);
+  // CTA pairs pay off as soon as there are two 128-row blocks to pair up
+  const bool pair = g_variant == 2 || (g_variant == 0 && M > BM);
   static bool attr_set = false;
+  static int max_clusters = 0;
   if (!attr_set) {
-    SP_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    SP_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SP_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SP_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SP_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES));
+    SP_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES));
+    cudaLaunchConfig_t qc = {};
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+    qc.gridDim = dim3(static_cast<unsigned>(num_sms() / 2 * 2));
+    qc.blockDim = dim3(NUM_THREADS);
+    qc.dynamicSmemBytes = PAIR_SMEM_BYTES;
+    qc.attrs = qa; qc.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_kernel<1, true>, &qc) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = num_sms() / 2;
+    }
+    max_clusters = n;
     attr_set = true;
   }
   Params p;
   memset(&p, 0, sizeof(p));
   int n_maps = 0;
+  const int b_box = pair ? BN / 2 : BN;
   for (int s = 0; s < n_seg; ++s) {
     const sp_gemm_prepared_segment& g = segs[s];
     SP_REQUIRE(g.Kp > 0 && g.Kp % md.bk == 0 && g.A != nullptr && g.B != nullptr, SP_ERR_INVALID, "bad prepared segment %d", s);
@@ -644,18 +811,24 @@ static int launch_prepared(int n_seg, const sp_gemm_prepared_segment* segs, floa
     const int ia_hi = n_maps++, ib_hi = n_maps++;
     int rc = make_map(&p.maps[ia_hi], a_hi, M, g.Kp, BM, md.elem);
     if (rc) return rc;
-    rc = make_map(&p.maps[ib_hi], b_hi, N, g.Kp, BN, md.elem);
+    rc = make_map(&p.maps[ib_hi], b_hi, N, g.Kp, b_box, md.elem);
     if (rc) return rc;
     if (md.copies == 2) {
       const int ia_lo = n_maps++, ib_lo = n_maps++;
       rc = make_map(&p.maps[ia_lo], a_hi + M * g.Kp * md.elem, M, g.Kp, BM, md.elem);
       if (rc) return rc;
-      rc = make_map(&p.maps[ib_lo], b_hi + N * g.Kp * md.elem, N, g.Kp, BN, md.elem);
+      rc = make_map(&p.maps[ib_lo], b_hi + N * g.Kp * md.elem, N, g.Kp, b_box, md.elem);
       if (rc) return rc;
-      // small cross terms first, dominant term last
-      sg.a_map[0] = ia_lo; sg.b_map[0] = ib_hi;
-      sg.a_map[1] = ia_hi; sg.b_map[1] = ib_lo;
-      sg.a_map[2] = ia_hi; sg.b_map[2] = ib_hi;
+      if (pair) {
+        // the pair kernel indexes the copies: [0] = hi, [1] = lo
+        sg.a_map[0] = ia_hi; sg.b_map[0] = ib_hi;
+        sg.a_map[1] = ia_lo; sg.b_map[1] = ib_lo;
+      } else {
+        // per-term operand pairs: small cross terms first, dominant term last
+        sg.a_map[0] = ia_lo; sg.b_map[0] = ib_hi;
+        sg.a_map[1] = ia_hi; sg.b_map[1] = ib_lo;
+        sg.a_map[2] = ia_hi; sg.b_map[2] = ib_hi;
+      }
     } else {
       sg.a_map[0] = ia_hi; sg.b_map[0] = ib_hi;
     }
@@ -673,10 +846,25 @@ static int launch_prepared(int n_seg, const sp_gemm_prepared_segment* segs, floa
   p.col_bias = col_bias;
   p.part_val = part_val;
   p.part_idx = part_idx;
-  const int tiles = p.m_blocks * p.n_blocks;
-  const int grid = std::min(tiles, num_sms());
-  if (md.kind == 0) gemm_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);
-  else gemm_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);
+  if (pair) {
+    const int tiles = (p.m_blocks + 1) / 2 * p.n_blocks;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3(static_cast<unsigned>(2 * std::min(tiles, max_clusters)));
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = PAIR_SMEM_BYTES;
+    cfg.stream = stream;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (md.kind == 0) SP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<0, true>, p));
+    else SP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<1, true>, p));
+  } else {
+    const int tiles = p.m_blocks * p.n_blocks;
+    const int grid = std::min(tiles, num_sms());
+    if (md.kind == 0) gemm_kernel<0, false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);
+    else gemm_kernel<1, false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);
+  }
   SP_CUDA_CHECK(cudaGetLastError());
   return SP_OK;
 }

@@ -479,3 +479,37 @@ def test_general_expression_outside_the_static_catalogue():
     got = e.sum(axis=0).optimized().glom()
     np.testing.assert_allclose(got, (np.abs(x - y).astype(np.float64) * x + np.maximum(y, 0.5)).sum(axis=0), rtol=2e-5, atol=1e-4)
     Assert.all_eq(((X - Y) / (sp.abs(Y) + 1) - (X * X - 3)).optimized().glom(), (x - y) / (np.abs(y) + 1) - (x * x - 3))
+
+
+@pytest.mark.parametrize('M,N,K', [(256, 256, 64), (129, 70, 200), (384, 520, 1000), (1000, 1300, 2500), (2048, 1024, 4096)])
+def test_gemm_cta_pair_matches_single_cta(M, N, K):
+  """The cta_group::2 kernel (256 x 256 tile per CTA pair) and the one-CTA kernel issue the same MMAs on the same
+  chunks in the same order: results must agree bit for bit -- ragged edges, several segments, accumulate --
+  and both must meet the fp32 bar against float64."""
+  import torch
+  from spartan_b200 import device_ops, blob_ctx
+  from spartan_b200._lib import lib, check
+  ctx = blob_ctx.get()
+  g = torch.Generator(device='cpu'); g.manual_seed(M * 7 + N)
+  A = torch.randn(M, K, generator=g).to(ctx.device); B = torch.randn(K, N, generator=g).to(ctx.device)
+  C0 = torch.randn(M, N, generator=g).to(ctx.device)
+  ref = A.double().cpu().numpy() @ B.double().cpu().numpy()
+  k1 = (K // 3 + 3) // 4 * 4
+  segs = [(A[:, :k1].contiguous(), B[:k1].contiguous()), (A[:, k1:].contiguous(), B[k1:].contiguous())]
+  try:
+    for prec in ('bf16x3', 'tf32x3', 'tf32x1'):
+      out = {}
+      for variant in (1, 2):
+        check(lib.sp_gemm_set_variant(variant), 'sp_gemm_set_variant')
+        C = torch.empty(M, N, device=ctx.device)
+        device_ops.gemm([(A, B)], C, precision=prec)
+        Cs = C0.clone()
+        device_ops.gemm(segs, Cs, accumulate=True, precision=prec)
+        out[variant] = (C.cpu().numpy(), Cs.cpu().numpy())
+      Assert.all_eq(out[1][0], out[2][0])
+      Assert.all_eq(out[1][1], out[2][1])
+      if prec != 'tf32x1':
+        assert np.abs(out[2][0] - ref).max() <= 1e-5 * np.abs(ref).max()
+        assert np.abs(out[2][1] - (ref + C0.cpu().numpy())).max() <= 2e-5 * np.abs(ref).max()
+  finally:
+    check(lib.sp_gemm_set_variant(0), 'sp_gemm_set_variant')

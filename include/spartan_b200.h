@@ -273,6 +273,24 @@ int sp_gemm_prepare_b(const float* B, int64_t ldb, int64_t K, int64_t N, int pre
                       int64_t k_offset, int64_t out_bytes, void* stream);
 int sp_gemm_prepared(int n_seg, const sp_gemm_prepared_segment* segs, float* C, int64_t ldc, int64_t M, int64_t N,
                      int accumulate, int precision, void* stream);
+/* Row-range forms for a pipelined dot (host strips arrive one by one over PCIe while earlier strips are being
+ * contracted): a strip is prepared straight into its rows of a full-size prepared operand
+ * [copies][rows_total][Kp], and a contraction addresses any contiguous row range of such an operand.
+ * `out` / A / B point at the first row of the range inside copy 0; copy 1 (the lo halves of the split modes)
+ * starts *_copy_stride bytes later (= rows_total * Kp * element bytes). */
+typedef struct {
+  const void* A;
+  int64_t a_copy_stride;
+  const void* B;
+  int64_t b_copy_stride;
+  int64_t Kp;
+} sp_gemm_prepared_view;
+int sp_gemm_prepare_a_rows(const float* A, int64_t lda, int64_t M, int64_t K, int precision, void* out,
+                           int64_t copy_stride, int64_t Kp, int64_t k_offset, void* stream);
+int sp_gemm_prepare_b_rows(const float* B, int64_t ldb, int64_t K, int64_t N, int precision, void* out,
+                           int64_t copy_stride, int64_t Kp, int64_t k_offset, void* stream);
+int sp_gemm_prepared_views(int n_seg, const sp_gemm_prepared_view* segs, float* C, int64_t ldc, int64_t M, int64_t N,
+                           int accumulate, int precision, void* stream);
 /* Fused row-argmin epilogue over prepared operands (no C is stored): for every row and every 128-column half tile,
  * part_val[row][p] = min_j (col_bias[j] - 2 * (A.B)[row, j]) and part_idx[row][p] = arg min (ties: smallest j);
  * p < sp_gemm_argmin_parts(N).  k-means assignment: col_bias = |c_j|^2 (k_means_.py:61-66). */

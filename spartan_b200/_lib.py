@@ -51,6 +51,11 @@ class sp_gemm_prepared_segment(ctypes.Structure):
   _fields_ = [('A', ctypes.c_void_p), ('B', ctypes.c_void_p), ('Kp', ctypes.c_int64)]
 
 
+class sp_gemm_prepared_view(ctypes.Structure):
+  _fields_ = [('A', ctypes.c_void_p), ('a_copy_stride', ctypes.c_int64), ('B', ctypes.c_void_p),
+              ('b_copy_stride', ctypes.c_int64), ('Kp', ctypes.c_int64)]
+
+
 class sp_gemm_segment(ctypes.Structure):
   _fields_ = [('A', ctypes.c_void_p), ('lda', ctypes.c_int64), ('B', ctypes.c_void_p), ('ldb', ctypes.c_int64),
               ('K', ctypes.c_int64)]
@@ -88,6 +93,9 @@ _SIGS = {
   'sp_gemm_prepare_a': (_int, [_vp, _i64, _i64, _i64, _int, _vp, _i64, _i64, _i64, _vp]),
   'sp_gemm_prepare_b': (_int, [_vp, _i64, _i64, _i64, _int, _vp, _i64, _i64, _i64, _vp]),
   'sp_gemm_prepared': (_int, [_int, ctypes.POINTER(sp_gemm_prepared_segment), _vp, _i64, _i64, _i64, _int, _int, _vp]),
+  'sp_gemm_prepare_a_rows': (_int, [_vp, _i64, _i64, _i64, _int, _vp, _i64, _i64, _i64, _vp]),
+  'sp_gemm_prepare_b_rows': (_int, [_vp, _i64, _i64, _i64, _int, _vp, _i64, _i64, _i64, _vp]),
+  'sp_gemm_prepared_views': (_int, [_int, ctypes.POINTER(sp_gemm_prepared_view), _vp, _i64, _i64, _i64, _int, _int, _vp]),
   'sp_gemm_argmin_parts': (_i64, [_i64]),
   'sp_gemm_prepared_argmin': (_int, [_int, ctypes.POINTER(sp_gemm_prepared_segment), _i64, _i64, _vp, _vp, _vp, _int, _vp]),
   'sp_gemm_f32_workspace_bytes': (_i64, [_i64, _i64, _int, _i64p, _int]),

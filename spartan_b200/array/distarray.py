@@ -149,6 +149,7 @@ class DistArrayImpl(DistArray):
     self.blob_to_ex = dict((v, k) for k, v in tiles.items())
     self.slab = None                        # this rank's tiles as one HBM allocation (or None)
     self.slab_axes = None                   # per-axis sorted (lo, hi) intervals covered by the slab
+    self.block_events = None                # [(region, CUDA event)] left by a producer that finished block by block
 
   def __del__(self):
     try:
@@ -302,6 +303,7 @@ class DistArrayImpl(DistArray):
     Assert.eq(tuple(region.shape), tuple(data.shape), 'Size of extent does not match size of data')
     ctx = self.ctx
     me = ctx.worker_id
+    self.block_events = None
     if (host and self.reducer_fn is None and self.slab is not None and len(self.shape) > 0
         and tuple(region.shape) == self.shape and data.dtype == self.dtype):
       # whole-array upload: one H2D copy per contiguous block of this rank's slab instead of one per tile
@@ -352,6 +354,20 @@ class DistArrayImpl(DistArray):
     contiguous slab block; asynchronous when ``out`` is pinned: synchronise before reading).  Returns bytes."""
     ctx = self.ctx
     total = 0
+    if self.block_events and self.slab is not None and ctx.device.type == 'cuda':
+      # the producer (a streamed dot) finished the array block by block: copy each block out on a side stream as soon
+      # as its event fires, while later blocks are still being computed on the main stream
+      main = torch.cuda.current_stream(ctx.device)
+      d2h = ctx.side_stream('d2h')
+      events, self.block_events = self.block_events, None
+      with torch.cuda.stream(d2h):
+        for region, ev in events:
+          d2h.wait_event(ev)
+          view = self.slab_view(region)
+          device_ops.download_rect(out[region.to_slice()], view)
+          total += view.numel() * view.element_size()
+      main.wait_stream(d2h)
+      return total
     if self.slab is not None and self.shape:
       for block in self.local_blocks():
         view = self.slab_view(block)

@@ -51,6 +51,7 @@ class BlobCtx(object):
     self._next_id = [0] * self.num_workers    # per-worker id sequence, identical on every rank
     self._rr = 0
     self._scratch = {}
+    self._side_streams = {}
     self.kernel_launches = 0                  # launches of this library's kernels (bench.py "gpu_launches")
 
   # ------------------------------------------------------------------ reference surface
@@ -110,6 +111,13 @@ class BlobCtx(object):
     if self.device.type != 'cuda':
       raise SpartanError('no CUDA device: spartan_b200 has no CPU fallback for compute kernels')
     return torch.cuda.current_stream(self.device).cuda_stream
+
+  def side_stream(self, name):
+    """A second CUDA stream of this rank (H2D / D2H copies that overlap kernels on the main stream)."""
+    st = self._side_streams.get(name)
+    if st is None:
+      st = self._side_streams[name] = torch.cuda.Stream(self.device)
+    return st
 
   def empty(self, shape, dtype):
     return torch.empty(tuple(int(s) for s in shape), dtype=torch_dtype(dtype), device=self.device)

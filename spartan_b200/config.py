@@ -12,6 +12,11 @@ class Flags(object):
     # tensor-core mode of dot(): 'bf16x3' (default: 16-bit-mantissa split, 3 bf16 passes), 'tf32x3' (22-bit),
     # 'tf32x1' (fastest, 11-bit operands), 'simt' (CUDA cores, plain IEEE fp32)
     self.dot_precision = 'bf16x3'
+    # dot(from_numpy(a), from_numpy(b)) on one GPU: pipeline the PCIe upload of host operands with the contraction
+    # (row strips of A / column strips of B of this many rows / columns) when the operands are at least this large
+    self.dot_stream_host_operands = True
+    self.dot_stream_strip = 4096
+    self.dot_stream_min_bytes = 256 << 20
 
   def __repr__(self):
     return 'FLAGS(%s)' % ', '.join('%s=%r' % kv for kv in sorted(self.__dict__.items()))

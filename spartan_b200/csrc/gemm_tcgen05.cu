@@ -718,17 +718,28 @@ static int check_prep(const void* out, int64_t out_bytes, int64_t rows, int64_t 
   return SP_OK;
 }
 
-// A strip [M, K] (leading dim lda) -> out[copies][M][Kp] at depth offset k_offset (columns k_offset .. k_offset+K).
-// The caller zero-fills the buffer when the strips it writes do not cover [0, Kp).
-extern "C" int sp_gemm_prepare_a(const float* A, int64_t lda, int64_t M, int64_t K, int precision, void* out,
-                                 int64_t Kp, int64_t k_offset, int64_t out_bytes, void* stream_) {
+static int check_prep_rows(const void* out, int64_t copy_stride, int64_t rows, int64_t Kp, int precision, Mode* md) {
+  SP_REQUIRE(mode_of(precision, md), SP_ERR_INVALID, "unknown precision %d", precision);
+  SP_REQUIRE(Kp > 0 && Kp % md->bk == 0, SP_ERR_INVALID, "Kp=%lld is not a multiple of the k-block %d", (long long)Kp, md->bk);
+  SP_REQUIRE(out != nullptr && (reinterpret_cast<uint64_t>(out) % 128) == 0, SP_ERR_INVALID,
+             "prepared operand buffer must be 128-byte aligned");
+  SP_REQUIRE(md->copies == 1 || (copy_stride >= rows * Kp * md->elem && copy_stride % 128 == 0), SP_ERR_INVALID,
+             "bad copy stride %lld", (long long)copy_stride);
+  return SP_OK;
+}
+
+// Row-range forms: `out` points at the first destination row inside copy 0 of a larger prepared operand
+// [copies][rows_total][Kp]; copy 1 (the lo halves) starts copy_stride bytes after copy 0.  They let a pipelined
+// dot prepare one strip at a time into a full-size operand and contract any row range of it.
+extern "C" int sp_gemm_prepare_a_rows(const float* A, int64_t lda, int64_t M, int64_t K, int precision, void* out,
+                                      int64_t copy_stride, int64_t Kp, int64_t k_offset, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   Mode md;
-  int rc = check_prep(out, out_bytes, M, Kp, precision, &md);
+  int rc = check_prep_rows(out, copy_stride, M, Kp, precision, &md);
   if (rc) return rc;
   SP_REQUIRE(k_offset >= 0 && k_offset % 4 == 0 && k_offset + K <= Kp, SP_ERR_INVALID, "bad k_offset %lld", (long long)k_offset);
   uint8_t* hi = static_cast<uint8_t*>(out) + k_offset * md.elem;
-  uint8_t* lo = md.copies == 2 ? hi + M * Kp * md.elem : nullptr;
+  uint8_t* lo = md.copies == 2 ? hi + copy_stride : nullptr;
   // rows of the destination are Kp apart; the kernel pads K up to a multiple of 4 within its strip
   const int64_t Kq = std::min<int64_t>(round_up(K, 4), Kp - k_offset);
   const int64_t total = M * (Kq / 4);
@@ -742,16 +753,15 @@ extern "C" int sp_gemm_prepare_a(const float* A, int64_t lda, int64_t M, int64_t
   return SP_OK;
 }
 
-// B strip [K, N] (leading dim ldb) -> transposed out[copies][N][Kp] at depth offset k_offset.
-extern "C" int sp_gemm_prepare_b(const float* B, int64_t ldb, int64_t K, int64_t N, int precision, void* out,
-                                 int64_t Kp, int64_t k_offset, int64_t out_bytes, void* stream_) {
+extern "C" int sp_gemm_prepare_b_rows(const float* B, int64_t ldb, int64_t K, int64_t N, int precision, void* out,
+                                      int64_t copy_stride, int64_t Kp, int64_t k_offset, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   Mode md;
-  int rc = check_prep(out, out_bytes, N, Kp, precision, &md);
+  int rc = check_prep_rows(out, copy_stride, N, Kp, precision, &md);
   if (rc) return rc;
   SP_REQUIRE(k_offset >= 0 && k_offset + K <= Kp, SP_ERR_INVALID, "bad k_offset %lld", (long long)k_offset);
   uint8_t* hi = static_cast<uint8_t*>(out) + k_offset * md.elem;
-  uint8_t* lo = md.copies == 2 ? hi + N * Kp * md.elem : nullptr;
+  uint8_t* lo = md.copies == 2 ? hi + copy_stride : nullptr;
   dim3 grid(static_cast<unsigned>((N + 31) / 32), static_cast<unsigned>((K + 31) / 32));
   dim3 block(32, 8);
   const int Ni = static_cast<int>(N), Ki = static_cast<int>(K);
@@ -762,7 +772,26 @@ extern "C" int sp_gemm_prepare_b(const float* B, int64_t ldb, int64_t K, int64_t
   return SP_OK;
 }
 
-static int launch_prepared(int n_seg, const sp_gemm_prepared_segment* segs, float* C, int64_t ldc, int64_t M, int64_t N,
+// A strip [M, K] (leading dim lda) -> out[copies][M][Kp] at depth offset k_offset (columns k_offset .. k_offset+K).
+// The caller zero-fills the buffer when the strips it writes do not cover [0, Kp).
+extern "C" int sp_gemm_prepare_a(const float* A, int64_t lda, int64_t M, int64_t K, int precision, void* out,
+                                 int64_t Kp, int64_t k_offset, int64_t out_bytes, void* stream_) {
+  Mode md;
+  int rc = check_prep(out, out_bytes, M, Kp, precision, &md);
+  if (rc) return rc;
+  return sp_gemm_prepare_a_rows(A, lda, M, K, precision, out, M * Kp * md.elem, Kp, k_offset, stream_);
+}
+
+// B strip [K, N] (leading dim ldb) -> transposed out[copies][N][Kp] at depth offset k_offset.
+extern "C" int sp_gemm_prepare_b(const float* B, int64_t ldb, int64_t K, int64_t N, int precision, void* out,
+                                 int64_t Kp, int64_t k_offset, int64_t out_bytes, void* stream_) {
+  Mode md;
+  int rc = check_prep(out, out_bytes, N, Kp, precision, &md);
+  if (rc) return rc;
+  return sp_gemm_prepare_b_rows(B, ldb, K, N, precision, out, N * Kp * md.elem, Kp, k_offset, stream_);
+}
+
+static int launch_prepared(int n_seg, const sp_gemm_prepared_view* segs, float* C, int64_t ldc, int64_t M, int64_t N,
                            int accumulate, int precision, int epi_mode, const float* col_bias, float* part_val,
                            int* part_idx, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -801,8 +830,10 @@ static int launch_prepared(int n_seg, const sp_gemm_prepared_segment* segs, floa
   int n_maps = 0;
   const int b_box = pair ? BN / 2 : BN;
   for (int s = 0; s < n_seg; ++s) {
-    const sp_gemm_prepared_segment& g = segs[s];
+    const sp_gemm_prepared_view& g = segs[s];
     SP_REQUIRE(g.Kp > 0 && g.Kp % md.bk == 0 && g.A != nullptr && g.B != nullptr, SP_ERR_INVALID, "bad prepared segment %d", s);
+    SP_REQUIRE(md.copies == 1 || (g.a_copy_stride >= M * g.Kp * md.elem && g.b_copy_stride >= N * g.Kp * md.elem), SP_ERR_INVALID,
+               "prepared segment %d: copy stride smaller than the row range", s);
     const uint8_t* a_hi = static_cast<const uint8_t*>(g.A);
     const uint8_t* b_hi = static_cast<const uint8_t*>(g.B);
     Segment& sg = p.segs[s];
@@ -815,9 +846,9 @@ static int launch_prepared(int n_seg, const sp_gemm_prepared_segment* segs, floa
     if (rc) return rc;
     if (md.copies == 2) {
       const int ia_lo = n_maps++, ib_lo = n_maps++;
-      rc = make_map(&p.maps[ia_lo], a_hi + M * g.Kp * md.elem, M, g.Kp, BM, md.elem);
+      rc = make_map(&p.maps[ia_lo], a_hi + g.a_copy_stride, M, g.Kp, BM, md.elem);
       if (rc) return rc;
-      rc = make_map(&p.maps[ib_lo], b_hi + N * g.Kp * md.elem, N, g.Kp, b_box, md.elem);
+      rc = make_map(&p.maps[ib_lo], b_hi + g.b_copy_stride, N, g.Kp, b_box, md.elem);
       if (rc) return rc;
       if (pair) {
         // the pair kernel indexes the copies: [0] = hi, [1] = lo
@@ -869,10 +900,33 @@ static int launch_prepared(int n_seg, const sp_gemm_prepared_segment* segs, floa
   return SP_OK;
 }
 
+static int to_views(int n_seg, const sp_gemm_prepared_segment* segs, int64_t M, int64_t N, int precision,
+                    sp_gemm_prepared_view* out) {
+  Mode md;
+  SP_REQUIRE(mode_of(precision, &md), SP_ERR_INVALID, "unknown precision %d", precision);
+  SP_REQUIRE(n_seg >= 1 && n_seg <= 8, SP_ERR_INVALID, "%d segments (limit 8 per launch)", n_seg);
+  for (int s = 0; s < n_seg; ++s) {
+    out[s].A = segs[s].A; out[s].B = segs[s].B; out[s].Kp = segs[s].Kp;
+    out[s].a_copy_stride = M * segs[s].Kp * md.elem;
+    out[s].b_copy_stride = N * segs[s].Kp * md.elem;
+  }
+  return SP_OK;
+}
+
 // C[M,N] (+)= sum_s A_s . B_s over PREPARED operands (sp_gemm_prepare_a / _b), one launch.
 extern "C" int sp_gemm_prepared(int n_seg, const sp_gemm_prepared_segment* segs, float* C, int64_t ldc, int64_t M,
                                 int64_t N, int accumulate, int precision, void* stream_) {
   SP_REQUIRE(C != nullptr, SP_ERR_INVALID, "sp_gemm_prepared: null C");
+  sp_gemm_prepared_view v[8];
+  int rc = to_views(n_seg, segs, M, N, precision, v);
+  if (rc) return rc;
+  return launch_prepared(n_seg, v, C, ldc, M, N, accumulate, precision, 0, nullptr, nullptr, nullptr, stream_);
+}
+
+// Same over row ranges of larger prepared operands (sp_gemm_prepare_a_rows / _b_rows).
+extern "C" int sp_gemm_prepared_views(int n_seg, const sp_gemm_prepared_view* segs, float* C, int64_t ldc, int64_t M,
+                                      int64_t N, int accumulate, int precision, void* stream_) {
+  SP_REQUIRE(C != nullptr, SP_ERR_INVALID, "sp_gemm_prepared_views: null C");
   return launch_prepared(n_seg, segs, C, ldc, M, N, accumulate, precision, 0, nullptr, nullptr, nullptr, stream_);
 }
 
@@ -884,7 +938,10 @@ extern "C" int sp_gemm_prepared_argmin(int n_seg, const sp_gemm_prepared_segment
                                        const float* col_bias, float* part_val, int32_t* part_idx, int precision,
                                        void* stream_) {
   SP_REQUIRE(col_bias && part_val && part_idx, SP_ERR_INVALID, "sp_gemm_prepared_argmin: null pointer");
-  return launch_prepared(n_seg, segs, nullptr, 0, M, N, 0, precision, 1, col_bias, part_val, part_idx, stream_);
+  sp_gemm_prepared_view v[8];
+  int rc = to_views(n_seg, segs, M, N, precision, v);
+  if (rc) return rc;
+  return launch_prepared(n_seg, v, nullptr, 0, M, N, 0, precision, 1, col_bias, part_val, part_idx, stream_);
 }
 
 extern "C" int64_t sp_gemm_f32_workspace_bytes(int64_t M, int64_t N, int n_seg, const int64_t* seg_k, int precision) {

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from . import blob_ctx
-from ._lib import (lib, check, sp_program, sp_operand, sp_gemm_segment, sp_gemm_prepared_segment, i64arr, SpartanError, OP,
+from ._lib import (lib, check, sp_program, sp_operand, sp_gemm_segment, sp_gemm_prepared_segment, sp_gemm_prepared_view, i64arr, SpartanError, OP,
                    SP_F32, SP_F64, SP_I32, SP_I64, SP_U8, SP_BOOL, SP_RED_SUM, SP_RED_MIN, SP_RED_MAX, SP_RED_PROD,
                    SP_RED_ALL, SP_RED_ANY, SP_FILL_CONST, SP_FILL_IOTA, SP_FILL_RAND, SP_FILL_RANDN,
                    SP_GEMM_TF32X1, SP_GEMM_TF32X3, SP_GEMM_SIMT, SP_GEMM_BF16X3, SP_GEMM_MAX_SEGMENTS)
@@ -386,6 +386,56 @@ def gemm_prepared(segments, C, accumulate, precision):
                                _stream()), 'sp_gemm_prepared')
     _count_launch()
     acc = True
+
+
+class PreparedOperand(object):
+  """A full-size prepared GEMM operand [copies][rows][Kp] that is filled strip by strip (rows of A, columns of B)
+  and contracted over arbitrary row ranges -- the device side of a dot whose operands are still arriving."""
+
+  def __init__(self, rows, K, precision, key):
+    ctx = blob_ctx.get()
+    self.rows, self.K, self.precision = int(rows), int(K), precision
+    self.Kp = gemm_kpad(K, precision)
+    nbytes = gemm_prepared_bytes(self.rows, self.Kp, precision)
+    self.buf = ctx.scratch(nbytes, key)[:nbytes]
+    self.row_bytes = int(lib.sp_gemm_prepared_bytes(1, self.Kp, _PRECISIONS[precision]))
+    self.copies = 1 if precision == 'tf32x1' else 2
+    self.row_bytes //= self.copies
+    self.copy_stride = self.rows * self.row_bytes
+    if self.Kp != (self.K + 3) // 4 * 4:
+      self.buf.zero_()
+
+  def row_ptr(self, r0):
+    return self.buf.data_ptr() + int(r0) * self.row_bytes
+
+  def prepare_a(self, A, r0):
+    """rows [r0, r0 + A.shape[0]) <- the fp32 strip A [m, K]."""
+    _require_cuda(A)
+    assert A.dim() == 2 and A.stride(1) == 1 and A.dtype == torch.float32 and A.shape[1] == self.K
+    check(lib.sp_gemm_prepare_a_rows(A.data_ptr(), A.stride(0), A.shape[0], self.K, _PRECISIONS[self.precision],
+                                     self.row_ptr(r0), self.copy_stride, self.Kp, 0, _stream()), 'sp_gemm_prepare_a_rows')
+    _count_launch()
+
+  def prepare_b(self, B, c0):
+    """rows [c0, c0 + B.shape[1]) of the transposed operand <- the fp32 strip B [K, n]."""
+    _require_cuda(B)
+    assert B.dim() == 2 and B.stride(1) == 1 and B.dtype == torch.float32 and B.shape[0] == self.K
+    check(lib.sp_gemm_prepare_b_rows(B.data_ptr(), B.stride(0), self.K, B.shape[1], _PRECISIONS[self.precision],
+                                     self.row_ptr(c0), self.copy_stride, self.Kp, 0, _stream()), 'sp_gemm_prepare_b_rows')
+    _count_launch()
+
+
+def gemm_prepared_rows(pa, r0, r1, pb, c0, c1, C, accumulate=False):
+  """C[r1-r0, c1-c0] (+)= A[r0:r1, :] . B[:, c0:c1] over row ranges of two PreparedOperands."""
+  _require_cuda(C)
+  assert tuple(C.shape) == (r1 - r0, c1 - c0) and C.stride(1) == 1 and pa.Kp == pb.Kp and pa.precision == pb.precision
+  v = (sp_gemm_prepared_view * 1)()
+  v[0].A = pa.row_ptr(r0); v[0].a_copy_stride = pa.copy_stride
+  v[0].B = pb.row_ptr(c0); v[0].b_copy_stride = pb.copy_stride
+  v[0].Kp = pa.Kp
+  check(lib.sp_gemm_prepared_views(1, v, C.data_ptr(), C.stride(0), r1 - r0, c1 - c0, int(bool(accumulate)),
+                                   _PRECISIONS[pa.precision], _stream()), 'sp_gemm_prepared_views')
+  _count_launch()
 
 
 # ------------------------------------------------------------------------------------ host <-> device rectangles

@@ -22,7 +22,8 @@ from .. import blob_ctx, comm, device_ops
 from ..array import distarray, extent
 from ..config import FLAGS
 from .._lib import SpartanError
-from .base import Expr, lazify
+from .base import Expr, lazify, eval_cache
+from .write_array import WriteArrayExpr
 
 
 def _runs(intervals):
@@ -65,6 +66,102 @@ class DotExpr(Expr):
     if len(a) > 1 and len(b) > 1:
       return (a[0], b[1])
     raise ValueError('vector x matrix dot is not defined by the reference (tests/test_dot.py:45-53)')
+
+  # ------------------------------------------------------------------ host operands: upload || contract || read back
+  def evaluate(self):
+    cache = self.cache()
+    if cache is not None:
+      return cache
+    ctx = blob_ctx.get()
+    if self._streamable(ctx):
+      value = self._evaluate_streamed(ctx)
+      if self.needs_cache:
+        eval_cache.set(self.expr_id, value)
+      return value
+    return Expr.evaluate(self)
+
+  def _streamable(self, ctx):
+    """Both operands are host arrays that have not been uploaded yet (``from_numpy`` nodes, write_array.py:424-445),
+    large enough for PCIe time to matter, on one GPU: the upload is then pipelined with the contraction instead of
+    running in front of it."""
+    if not FLAGS.dot_stream_host_operands or ctx.num_workers != 1 or ctx.device.type != 'cuda':
+      return False
+    if FLAGS.dot_precision == 'simt':
+      return False
+    a, b = self.matrix_a, self.matrix_b
+    for e in (a, b):
+      if not isinstance(e, WriteArrayExpr) or e.cache() is not None:
+        return False
+      npa = e.npa
+      if npa.ndim != 2 or npa.dtype != np.float32 or npa.shape[0] == 0 or npa.strides[1] != npa.itemsize:
+        return False
+    if a.npa.shape[1] != b.npa.shape[0] or a.npa.shape[1] == 0 or b.npa.shape[1] == 0:
+      return False
+    return a.npa.nbytes + b.npa.nbytes >= FLAGS.dot_stream_min_bytes
+
+  def _evaluate_streamed(self, ctx):
+    """C = A . B with A and B still in host memory.  A is cut into row strips and B into column strips; strip s of
+    each is uploaded on a copy stream while the compute stream contracts what has already arrived: after A_s lands,
+    C[rows_s, columns of strips < s]; after B_s lands, C[rows of strips <= s, columns_s] (an L-shaped frontier, the
+    order that makes the most output computable per byte uploaded).  Every C element is still produced by one
+    contraction over the full K in the order of the resident path, so results are bit-identical to it.  Each launch
+    leaves an event behind; ``DistArrayImpl.read_local_into`` uses them to start the D2H copy of a finished block
+    while later blocks are still being computed.  The operand arrays end up resident and cached exactly as
+    ``from_numpy(...).evaluate()`` would leave them."""
+    ea, eb = self.matrix_a, self.matrix_b
+    a_np, b_np = ea.npa, eb.npa
+    M, K = a_np.shape
+    N = b_np.shape[1]
+    precision = FLAGS.dot_precision
+    av = distarray.create(a_np.shape, np.float32, tile_hint=ea.tile_hint)
+    bv = distarray.create(b_np.shape, np.float32, tile_hint=eb.tile_hint)
+    target = distarray.create((M, N), np.float32, reducer=np.add, tile_hint=self.tile_hint or (M, N))
+    if av.slab is None or bv.slab is None or target.slab is None:
+      raise SpartanError('streamed dot expects slab-backed arrays on a single rank')
+    pa = device_ops.PreparedOperand(M, K, precision, 'dot_stream_a')
+    pb = device_ops.PreparedOperand(N, K, precision, 'dot_stream_b')
+    strip = int(FLAGS.dot_stream_strip)
+    ra = [(r, min(M, r + strip)) for r in range(0, M, strip)]
+    cb = [(c, min(N, c + strip)) for c in range(0, N, strip)]
+    main = torch.cuda.current_stream(ctx.device)
+    copy = ctx.side_stream('h2d')
+    copy.wait_stream(main)              # recycled allocations may still be in use by work queued on the main stream
+    C = target.slab
+    done = []
+
+    def contract(r0, r1, c0, c1):
+      device_ops.gemm_prepared_rows(pa, r0, r1, pb, c0, c1, C[r0:r1, c0:c1])
+      done.append((extent.create((r0, c0), (r1, c1), (M, N)), main.record_event()))
+
+    for s in range(max(len(ra), len(cb))):
+      ev_a = ev_b = None
+      with torch.cuda.stream(copy):
+        if s < len(ra):
+          r0, r1 = ra[s]
+          device_ops.upload_rect(av.slab[r0:r1], a_np[r0:r1])
+          ev_a = copy.record_event()
+        if s < len(cb):
+          c0, c1 = cb[s]
+          device_ops.upload_rect(bv.slab[:, c0:c1], b_np[:, c0:c1])
+          ev_b = copy.record_event()
+      if ev_a is not None:
+        main.wait_event(ev_a)
+        pa.prepare_a(av.slab[r0:r1], r0)
+        ncols = cb[min(s, len(cb)) - 1][1] if s > 0 else 0      # columns whose strips (< s) are prepared already
+        if ncols:
+          contract(r0, r1, 0, ncols)
+      if ev_b is not None:
+        main.wait_event(ev_b)
+        pb.prepare_b(bv.slab[:, c0:c1], c0)
+        contract(0, ra[min(s, len(ra) - 1)][1], c0, c1)         # rows whose strips (<= s) are prepared
+    for arr in (av, bv, target):
+      for tid in arr.tiles.values():
+        ctx.tile(tid).valid = True
+    target.block_events = done
+    for e, v in ((ea, av), (eb, bv)):
+      if e.needs_cache:
+        eval_cache.set(e.expr_id, v)
+    return target
 
   def _allgather_path(self, ctx, av, bv, target, shape, M, N, K, dtype, precision):
     """Multi-GPU fast path for the regular placement (every rank owns whole column blocks of A, B and C, e.g.

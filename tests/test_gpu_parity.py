@@ -513,3 +513,42 @@ def test_gemm_cta_pair_matches_single_cta(M, N, K):
         assert np.abs(out[2][1] - (ref + C0.cpu().numpy())).max() <= 2e-5 * np.abs(ref).max()
   finally:
     check(lib.sp_gemm_set_variant(0), 'sp_gemm_set_variant')
+
+
+@pytest.mark.parametrize('M,N,K,strip', [(1024, 768, 512, 256), (700, 900, 333, 256), (512, 2048, 640, 512),
+                                         (2048, 300, 1000, 512)])
+@pytest.mark.parametrize('prec', ['bf16x3', 'tf32x3'])
+def test_streamed_dot_matches_resident(M, N, K, strip, prec):
+  """dot(from_numpy(a), from_numpy(b)) with the PCIe upload pipelined against the contraction (strips of A rows /
+  B columns, L-shaped frontier) must give the bits of the resident path -- ragged strips, unequal strip counts,
+  unaligned K -- read back both block by block (read_local_into, event driven) and through glom; the operand
+  arrays must be left resident and cached like from_numpy(...).evaluate() leaves them."""
+  import torch
+  from spartan_b200.expr.base import eval_cache
+  rng = np.random.default_rng(M + N + K)
+  a = rng.standard_normal((M, K), dtype=np.float32); b = rng.standard_normal((K, N), dtype=np.float32)
+  old = (sp.FLAGS.dot_stream_host_operands, sp.FLAGS.dot_stream_strip, sp.FLAGS.dot_stream_min_bytes, sp.FLAGS.dot_precision)
+  try:
+    sp.FLAGS.dot_precision = prec
+    sp.FLAGS.dot_stream_host_operands = False
+    want = sp.dot(sp.from_numpy(a), sp.from_numpy(b)).glom()
+    sp.FLAGS.dot_stream_host_operands = True
+    sp.FLAGS.dot_stream_strip = strip
+    sp.FLAGS.dot_stream_min_bytes = 0
+    ea, eb = sp.from_numpy(a, tile_hint=(256, 256)), sp.from_numpy(b)
+    e = sp.dot(ea, eb, tile_hint=(256, 256))
+    c = e.evaluate()
+    assert c.block_events, 'the streamed path did not run'
+    out = torch.empty((M, N), dtype=torch.float32, pin_memory=True)
+    nbytes = c.read_local_into(out.numpy())
+    torch.cuda.current_stream().synchronize()
+    assert nbytes == M * N * 4 and c.block_events is None
+    Assert.all_eq(out.numpy(), want)
+    Assert.all_eq(c.glom(), want)
+    Assert.all_eq(ea.evaluate().glom(), a)          # cached by the streamed evaluation, resident and complete
+    Assert.all_eq(eb.evaluate().glom(), b)
+    assert eval_cache.get(ea.expr_id) is not None
+    ref = a.astype(np.float64) @ b.astype(np.float64)
+    assert np.abs(want - ref).max() <= 1e-5 * np.abs(ref).max()
+  finally:
+    (sp.FLAGS.dot_stream_host_operands, sp.FLAGS.dot_stream_strip, sp.FLAGS.dot_stream_min_bytes, sp.FLAGS.dot_precision) = old

@@ -300,6 +300,12 @@ int sp_gemm_prepared_argmin(int n_seg, const sp_gemm_prepared_segment* segs, int
 int sp_gemm_f32(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
                 int64_t N, int64_t K, int accumulate, int precision, void* workspace, int64_t workspace_bytes,
                 void* stream);
+/* Operands that are transposed VIEWS (transpose.py:27-67; tests/test_transpose.py:27-37 dot(A, transpose(B))):
+ * a_trans != 0: A is passed as At [K, M] row-major; b_trans != 0: B is passed as Bt [N, K] row-major.  No transpose is
+ * materialised -- the operand preparation reads the view's layout directly. */
+int sp_gemm_f32_ex(const float* A, int64_t lda, int a_trans, const float* B, int64_t ldb, int b_trans, float* C,
+                   int64_t ldc, int64_t M, int64_t N, int64_t K, int accumulate, int precision, void* workspace,
+                   int64_t workspace_bytes, void* stream);
 /* ------------------------------------------------------------------------
  * Application kernels on the hot path (BASELINE configs 4, 5).
  * ------------------------------------------------------------------------ */

@@ -1,3 +1,4 @@
 """ORACLE -- test infrastructure only (see oracle/README.md).  Never imported by spartan_b200/."""
 from . import extent, distarray, expr            # noqa: F401
+from . import views                               # noqa: F401  (installs Expr.__getitem__ / transpose / reshape)
 from .distarray import initialize                 # noqa: F401

@@ -113,6 +113,10 @@ class LocalReduceExpr(FnCallExpr):
 
 
 # ----------------------------------------------------------------------------------- base.py
+class newaxis(object):
+  pass
+
+
 class NotShapeable(Exception):
   pass
 

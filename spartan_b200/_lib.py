@@ -101,6 +101,7 @@ _SIGS = {
   'sp_gemm_f32_workspace_bytes': (_i64, [_i64, _i64, _int, _i64p, _int]),
   'sp_gemm_f32_segments': (_int, [_int, ctypes.POINTER(sp_gemm_segment), _vp, _i64, _i64, _i64, _int, _int, _vp, _i64, _vp]),
   'sp_gemm_f32': (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp, _i64, _vp]),
+  'sp_gemm_f32_ex': (_int, [_vp, _i64, _int, _vp, _i64, _int, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp, _i64, _vp]),
   'sp_kmeans_workspace_bytes': (_i64, [_i64, _i64, _i64]),
   'sp_kmeans_assign': (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),
   'sp_spmv_csr': (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _int, _int, _vp]),

@@ -546,7 +546,7 @@ def as_array(data):
 def largest_value(vals):
   """distarray.py:636-642: the input with the most elements drives the map.  Distributed arrays are preferred
   over values every rank holds, so an empty distributed array still drives (and yields an empty result)."""
-  dist = [v for v in vals if isinstance(v, DistArrayImpl)]
+  dist = [v for v in vals if isinstance(v, DistArrayImpl) or getattr(v, 'is_view', False)]
   return max(dist or vals, key=lambda v: v.real_size())
 
 

@@ -992,6 +992,41 @@ extern "C" int sp_gemm_f32_segments(int n_seg, const sp_gemm_segment* segs, floa
   return sp_gemm_prepared(n_seg, ps, C, ldc, M, N, accumulate, precision, stream_);
 }
 
+// C (+)= op(A) . op(B) for operands that may be TRANSPOSED VIEWS (spartan/expr/operator/transpose.py:27-67):
+// a_trans != 0: A is given as At [K, M] row-major (lda = its leading dimension); b_trans != 0: B is given as
+// Bt [N, K] row-major.  Nothing is materialised: a K-major Bt is exactly what the tensor path consumes (it goes
+// through the A-style preparation), an M-major At goes through the transposing B-style preparation.
+extern "C" int sp_gemm_f32_ex(const float* A, int64_t lda, int a_trans, const float* B, int64_t ldb, int b_trans,
+                               float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int accumulate, int precision,
+                               void* workspace, int64_t workspace_bytes, void* stream_) {
+  Mode md;
+  SP_REQUIRE(mode_of(precision, &md), SP_ERR_INVALID, "sp_gemm_f32_ex: unknown precision %d", precision);
+  SP_REQUIRE(M > 0 && N > 0 && K > 0 && A && B && C, SP_ERR_INVALID, "sp_gemm_f32_ex: bad arguments");
+  const int64_t need = sp_gemm_f32_workspace_bytes(M, N, 1, &K, precision);
+  SP_REQUIRE(workspace != nullptr && workspace_bytes >= need, SP_ERR_INVALID,
+             "sp_gemm_f32_ex: workspace %lld B < required %lld B", (long long)workspace_bytes, (long long)need);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uint64_t>(workspace) + 1023) & ~1023ull);
+  const int64_t Kp = round_up(K, md.bk);
+  const int64_t a_bytes = round_up(M * Kp * md.elem * md.copies, 1024);
+  const int64_t b_bytes = round_up(N * Kp * md.elem * md.copies, 1024);
+  uint8_t* a_buf = ws;
+  uint8_t* b_buf = ws + a_bytes;
+  if (Kp != K) {
+    SP_CUDA_CHECK(cudaMemsetAsync(a_buf, 0, a_bytes, stream));
+    SP_CUDA_CHECK(cudaMemsetAsync(b_buf, 0, b_bytes, stream));
+  }
+  int rc = a_trans ? sp_gemm_prepare_b(A, lda, K, M, precision, a_buf, Kp, 0, a_bytes, stream_)
+                   : sp_gemm_prepare_a(A, lda, M, K, precision, a_buf, Kp, 0, a_bytes, stream_);
+  if (rc) return rc;
+  rc = b_trans ? sp_gemm_prepare_a(B, ldb, N, K, precision, b_buf, Kp, 0, b_bytes, stream_)
+               : sp_gemm_prepare_b(B, ldb, K, N, precision, b_buf, Kp, 0, b_bytes, stream_);
+  if (rc) return rc;
+  sp_gemm_prepared_segment seg;
+  seg.A = a_buf; seg.B = b_buf; seg.Kp = Kp;
+  return sp_gemm_prepared(1, &seg, C, ldc, M, N, accumulate, precision, stream_);
+}
+
 extern "C" int sp_gemm_f32(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
                             int64_t M, int64_t N, int64_t K, int accumulate, int precision, void* workspace,
                             int64_t workspace_bytes, void* stream) {

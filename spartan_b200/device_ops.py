@@ -174,21 +174,22 @@ def run_map_reduce(prog, inputs, in_shape, axis, red_op, out, accumulate, index=
   # collapse outer and inner groups independently (the reduced axis stays its own dim)
   o_shape, o_str = collapse(outer_shape, [st[:axis] for st in in_strides] + [list(out.stride())[:axis]])
   i_shape, i_str = collapse(inner_shape, [st[axis + 1:] for st in in_strides] + [list(out.stride())[axis:]])
-  if len(i_shape) > 1:
-    raise SpartanError('reduction with a non-collapsible inner block is not supported')
-  d2 = i_shape[0] if i_shape else 1
+  d2 = i_shape[-1] if i_shape else 1
+  no = len(o_str) - 1            # position of the output in the stride lists (after inputs [+ index])
+  # what does not collapse (strided views: slices, transposes) is looped over on the host: leading outer dims and,
+  # for an inner block that is not one contiguous run per operand, its leading dims
   for offs in _leading_loops(o_shape, o_str, 1):
-    d0 = o_shape[-1] if o_shape else 1
-    st3 = []
-    for i in range(n_in):
-      st3.append([o_str[i][-1] if o_shape else 0, in_strides[i][axis], i_str[i][0] if i_shape else 0])
-    no = len(o_str) - 1          # position of the output in the stride lists (after inputs [+ index])
-    out_stride = [o_str[no][-1] if o_shape else 0, 0, i_str[no][0] if i_shape else 0]
-    if index is not None:
-      _set_index(prog, index[0] + offs[n_in], [o_str[n_in][-1] if o_shape else 0, in_strides[n_in][axis],
-                                               i_str[n_in][0] if i_shape else 0])
-    _launch_reduce(ctx, prog, inputs, st3, offs[:n_in], out, out_stride, offs[no], [d0, in_shape[axis], d2], red_op,
-                   accumulate)
+    for ioffs in _leading_loops(i_shape, i_str, 1):
+      d0 = o_shape[-1] if o_shape else 1
+      st3 = []
+      for i in range(n_in):
+        st3.append([o_str[i][-1] if o_shape else 0, in_strides[i][axis], i_str[i][-1] if i_shape else 0])
+      out_stride = [o_str[no][-1] if o_shape else 0, 0, i_str[no][-1] if i_shape else 0]
+      if index is not None:
+        _set_index(prog, index[0] + offs[n_in] + ioffs[n_in],
+                   [o_str[n_in][-1] if o_shape else 0, in_strides[n_in][axis], i_str[n_in][-1] if i_shape else 0])
+      _launch_reduce(ctx, prog, inputs, st3, [a + b for a, b in zip(offs[:n_in], ioffs[:n_in])], out, out_stride,
+                     offs[no] + ioffs[no], [d0, in_shape[axis], d2], red_op, accumulate)
 
 
 def _launch_reduce(ctx, prog, inputs, st3, in_offs, out, out_stride, out_off, dims, red_op, accumulate):
@@ -342,6 +343,54 @@ def gemm(segments, C, accumulate=False, precision='tf32x3'):
                                    ws.data_ptr(), ws.numel(), _stream()), 'sp_gemm_f32_segments')
     _count_launch(1 + 2 * len(chunk))
     acc = True
+
+
+def materialize(t):
+  """A dense row-major copy of a strided device view (through the library's own rectangle-copy kernel)."""
+  if t.is_contiguous():
+    return t
+  out = torch.empty(tuple(t.shape), dtype=t.dtype, device=t.device)
+  copy_rect(out, t)
+  return out
+
+
+def _matrix_layout(t):
+  """(tensor, leading dimension, transposed flag) of a 2-D operand: row-major as is, a transposed view of a row-major
+  matrix by flag, anything else through one explicit copy."""
+  r, c = t.shape
+  s0, s1 = t.stride()
+  if c == 1 or s1 == 1:
+    if s1 != 1:
+      t = t.as_strided((r, c), (s0, 1))
+    return t, (s0 if r > 1 else max(1, c)), 0
+  if r == 1 or s0 == 1:
+    return t, (s1 if c > 1 else max(1, r)), 1
+  t = materialize(t)
+  return t, t.stride(0), 0
+
+
+def gemm_views(A, B, C, accumulate=False, precision='bf16x3'):
+  """C (+)= A @ B where A and/or B may be transposed views (stride(0) == 1): float32 goes through sp_gemm_f32_ex with
+  no materialised transpose; the exact CUDA-core dtypes copy the view first."""
+  _require_cuda(A, B, C)
+  M, N = C.shape
+  K = A.shape[1]
+  assert A.shape[0] == M and tuple(B.shape) == (K, N) and (C.stride(1) == 1 or N == 1)
+  if M == 0 or N == 0:
+    return
+  prec = _PRECISIONS[precision]
+  if C.dtype != torch.float32 or prec == SP_GEMM_SIMT or K == 0:
+    return gemm([(materialize(A), materialize(B))], C, accumulate, precision)
+  A, lda, at = _matrix_layout(A)
+  B, ldb, bt = _matrix_layout(B)
+  if not at and not bt:
+    return gemm([(A, B)], C, accumulate, precision)
+  ctx = blob_ctx.get()
+  need = lib.sp_gemm_f32_workspace_bytes(M, N, 1, i64arr([K]), prec)
+  ws = ctx.scratch(need, 'gemm')
+  check(lib.sp_gemm_f32_ex(A.data_ptr(), lda, at, B.data_ptr(), ldb, bt, C.data_ptr(), C.stride(0), M, N, K,
+                           int(bool(accumulate)), prec, ws.data_ptr(), ws.numel(), _stream()), 'sp_gemm_f32_ex')
+  _count_launch(3)
 
 
 # ------------------------------------------------------------------------------------ split-form gemm (multi-GPU)

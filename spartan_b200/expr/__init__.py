@@ -22,6 +22,9 @@ from .ndarray import ndarray, NdArrayExpr
 from .optimize import optimize, MapMapFusion, ReduceMapFusion
 from .reduce import reduce, ReduceExpr, ArgReduceExpr
 from .write_array import from_numpy, WriteArrayExpr
+from .slice import SliceExpr
+from .transpose import transpose, TransposeExpr
+from .reshape import reshape, ravel, ReshapeExpr
 from .program import NotDeviceMappable
 from . import local
 import sys as _sys
@@ -41,6 +44,11 @@ Expr.mean = mean
 Expr.min = min
 Expr.prod = prod
 Expr.sum = sum
+Expr.ravel = ravel
+Expr.flatten = ravel
+Expr.reshape = reshape
+Expr.transpose = transpose
+Expr.T = property(transpose)
 
 
 class operator(object):

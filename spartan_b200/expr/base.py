@@ -155,6 +155,45 @@ class Expr(object):
   def __rdiv__(self, other): return _map(other, self, fn=np.divide)
   __rtruediv__ = __rdiv__
 
+  def __getitem__(self, idx):
+    """base.py:401-448: basic slices give a SliceExpr; integer indices and ``newaxis`` additionally drop / insert
+    unit dimensions through a ReshapeExpr.  Boolean / integer-array indexing (FilterExpr) needs data-dependent
+    output sizes and is not part of the device path."""
+    from .slice import SliceExpr
+    from .reshape import ReshapeExpr
+    if not isinstance(idx, (int, tuple, slice)):
+      from .program import NotDeviceMappable
+      raise NotDeviceMappable('indexing with %r (filter.py) is not supported on the device path' % type(idx).__name__)
+    del_dim = [x for x in range(len(idx)) if isinstance(idx[x], int)] if isinstance(idx, tuple) else []
+    has_newaxis = isinstance(idx, tuple) and any(x is newaxis for x in idx)
+    if not (isinstance(idx, int) or del_dim or has_newaxis):
+      return SliceExpr(src=self, idx=idx)
+    if isinstance(idx, tuple):
+      sl = tuple(slice(x, None, None) if (isinstance(x, int) and x == -1) else x for x in idx if x is not newaxis)
+    else:
+      sl = slice(idx, None, None) if idx == -1 else idx
+    ret = SliceExpr(src=self, idx=sl)
+    new_shape = []
+    if isinstance(idx, tuple):
+      shape_ptr = idx_ptr = 0
+      while shape_ptr < len(ret.shape) or idx_ptr < len(idx):
+        if idx_ptr < len(idx) and idx[idx_ptr] is newaxis:
+          new_shape.append(1)
+        else:
+          new_shape.append(ret.shape[shape_ptr])
+          shape_ptr += 1
+        idx_ptr += 1
+      # positions of the integer indices in the shape WITH the inserted axes
+      drop, pos = [], 0
+      for x in idx:
+        if isinstance(x, int):
+          drop.append(pos)
+        pos += 1
+      new_shape = [s for i, s in enumerate(new_shape) if i not in drop]
+    else:
+      new_shape = list(ret.shape)[1:]
+    return ReshapeExpr(array=ret, new_shape=tuple(new_shape))
+
   def __setitem__(self, k, val):
     raise Exception('Expressions are read-only.')
 

@@ -316,8 +316,6 @@ class DotExpr(Expr):
           continue
         A = cast(as2d(a_cache[(r0, r1)], r1 - r0 if a_nd > 1 else 1, K))
         B = cast(as2d(b_cache[(c0, c1)], K, c1 - c0 if b_nd > 1 else 1))
-        if A.stride(-1) != 1: A = A.contiguous()
-        if B.stride(-1) != 1: B = B.contiguous()
         if len(shape) == 2:
           creg = extent.create((r0, c0), (r1, c1), shape)
         else:
@@ -326,7 +324,7 @@ class DotExpr(Expr):
         C2 = Cv.reshape(A.shape[0], B.shape[1])
         if C2.data_ptr() != Cv.data_ptr() or C2.stride(-1) != 1:
           raise SpartanError('dot target block is not addressable as a row-major view')
-        device_ops.gemm([(A, B)], C2, accumulate=False, precision=precision)
+        device_ops.gemm_views(A, B, C2, accumulate=False, precision=precision)   # transposed views: no copy
     for tid in target.tiles.values():
       if ctx.is_local(tid):
         ctx.tile(tid).valid = True

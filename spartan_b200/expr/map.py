@@ -107,7 +107,7 @@ class MapExpr(Expr):
     i = children.index(largest)
     children[0], children[i] = children[i], children[0]
     child_to_var[0], child_to_var[i] = child_to_var[i], child_to_var[0]
-    if not isinstance(largest, distarray.DistArrayImpl):
+    if not (isinstance(largest, distarray.DistArrayImpl) or getattr(largest, 'is_view', False)):
       raise program.NotDeviceMappable('a map needs at least one distributed (non-broadcast) input')
 
     loc_kernel = getattr(self.op.fn, 'device_location_kernel', None) \

@@ -91,7 +91,7 @@ class ReduceExpr(Expr):
     i = children.index(largest)
     children[0], children[i] = children[i], children[0]
     child_to_var[0], child_to_var[i] = child_to_var[i], child_to_var[0]
-    if not isinstance(largest, distarray.DistArrayImpl):
+    if not (isinstance(largest, distarray.DistArrayImpl) or getattr(largest, 'is_view', False)):
       raise program.NotDeviceMappable('a reduction needs a distributed (non-broadcast) input')
 
     spec = getattr(op.fn, 'device_reduce', None)

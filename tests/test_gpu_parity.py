@@ -552,3 +552,100 @@ def test_streamed_dot_matches_resident(M, N, K, strip, prec):
     assert np.abs(want - ref).max() <= 1e-5 * np.abs(ref).max()
   finally:
     (sp.FLAGS.dot_stream_host_operands, sp.FLAGS.dot_stream_strip, sp.FLAGS.dot_stream_min_bytes, sp.FLAGS.dot_precision) = old
+
+
+# ------------------------------------------------------------------ views: tests/test_slice.py, test_transpose.py, test_reshape.py
+@pytest.mark.parametrize('hint', [None, (4, 4), (3, 10)])
+def test_slice_reference_cases(hint):
+  """tests/test_slice.py:25-80 on the device: slices are zero-copy strided operands of the fused kernels."""
+  T = 10
+  # the reference's _arange_mapper (creation.py:135-141) numbers a tile as one contiguous run, which is only right for
+  # full-row tiles; with a grid hint the device (np.arange(n).reshape(shape), the documented result) is checked alone
+  for m in ((sp, oexpr) if hint != (4, 4) else (sp,)):
+    x = m.arange((T, T), tile_hint=hint)
+    nx = np.arange(T * T).reshape(T, T)
+    Assert.all_eq(x[5:8, 5:8].evaluate().glom(), nx[5:8, 5:8])                          # test_slice_get
+    Assert.all_eq((x[5:8, 5:8] + 1).glom(), nx[5:8, 5:8] + 1)                           # test_slice_map
+    Assert.all_eq((x[2:9, 1:3] * x[1:8, 5:7]).optimized().glom(), nx[2:9, 1:3] * nx[1:8, 5:7])
+    x3 = m.arange((10, 10, 10), dtype=np.int64); n3 = np.arange(1000).reshape((10, 10, 10))
+    Assert.all_eq((x3[:, :, 0] + 13).glom().reshape(10, 10), n3[:, :, 0] + 13)          # test_slice_map2
+    Assert.all_eq(x3[:, :, 0].sum().glom(), n3[:, :, 0].sum())                          # test_slice_reduce
+    Assert.all_eq(x3[2:7, :, 3:9].sum(axis=1).glom(), n3[2:7, :, 3:9].sum(axis=1))
+    a = m.arange((T,), dtype=np.int64); na = np.arange(T)
+    Assert.all_eq((a[1:] - a[:-1]).glom(), na[1:] - na[:-1])                            # test_slice_sub
+    Assert.all_eq((a[1:] - a[:-1]).optimized().glom(), na[1:] - na[:-1])
+  assert sp.extent.from_slice((slice(None), slice(None), 0), [100, 100, 100]).shape == (100, 100, 1)
+
+
+def test_getitem_integer_and_newaxis():
+  """base.py:401-448: integer indices drop their dimension (NumPy semantics; the reference's sequential pops mis-handle
+  several integers and a bare integer keeps a unit dimension -- the evident intent is implemented)."""
+  n3 = np.arange(4 * 5 * 6, dtype=np.float32).reshape(4, 5, 6)
+  x = sp.from_numpy(n3, tile_hint=(2, 5, 3))
+  Assert.all_eq(x[1].glom(), n3[1])
+  Assert.all_eq(x[:, 2].glom(), n3[:, 2])
+  Assert.all_eq(x[1, :, 4].glom(), n3[1, :, 4])
+  Assert.all_eq(x[-1].glom(), n3[-1])
+  Assert.all_eq(x[:, sp.newaxis, 2:4].glom(), n3[:, np.newaxis, 2:4])
+  Assert.all_eq((x[1] * 2 + x[3]).optimized().glom(), n3[1] * 2 + n3[3])
+  Assert.all_eq(x[1:3].sum(axis=0).glom(), n3[1:3].sum(axis=0))
+
+
+@pytest.mark.parametrize('hint', [None, (500, 200), (64, 1347)])
+def test_transpose_reference_cases(hint):
+  """tests/test_transpose.py:9-37."""
+  t2 = np.transpose(np.reshape(np.arange(3721 * 1347), (3721, 1347)))
+  Assert.all_eq(sp.transpose(sp.arange((3721, 1347), tile_hint=hint)).glom(), t2)                        # transpose1
+  t3 = np.transpose(np.reshape(np.arange(101 * 102 * 103), (101, 102, 103)))
+  Assert.all_eq(sp.transpose(sp.arange((101, 102, 103))).glom(), t3)                                     # transpose2
+  rng = np.random.RandomState(0)
+  n1 = rng.random_sample((401, 97)); n2 = rng.random_sample((401, 97))
+  got = sp.dot(sp.from_numpy(n1), sp.transpose(sp.from_numpy(n2))).glom()                                # transpose_dot (f64: exact path)
+  assert np.all(np.isclose(np.dot(n1, np.transpose(n2)), got))
+  f1, f2 = n1.astype(np.float32), n2.astype(np.float32)
+  for a, b, ref in ((sp.from_numpy(f1), sp.transpose(sp.from_numpy(f2)), f1.astype(np.float64) @ f2.T.astype(np.float64)),
+                    (sp.transpose(sp.from_numpy(f1)), sp.from_numpy(f2), f1.T.astype(np.float64) @ f2.astype(np.float64)),
+                    (sp.from_numpy(f1).T, sp.from_numpy(f2.T.copy()).T, f1.T.astype(np.float64) @ f2.astype(np.float64))):
+    got = sp.dot(a, b).glom()            # fp32: tensor-core path reads the transposed views in place (sp_gemm_f32_ex)
+    assert got.dtype == np.float32 and np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+  x = rng.random_sample((300, 200)).astype(np.float32); y = rng.random_sample((200, 300)).astype(np.float32)
+  got, want = both(lambda m: (m.transpose(m.from_numpy(x)) * 2 + m.from_numpy(y)).sum(axis=0).optimized())
+  np.testing.assert_allclose(got, want, rtol=1e-5)
+  Assert.all_eq((sp.from_numpy(x).T - sp.from_numpy(y)).glom(), x.T - y)
+
+
+def test_reshape_reference_cases():
+  """tests/test_reshape.py:9-88,98-121 (dense)."""
+  Assert.all_eq(sp.reshape(sp.arange((10, 10)), (100,)).glom(), sp.arange((100,)).glom())                # reshape1
+  b = sp.reshape(sp.arange((1000,), tile_hint=[100]), (10, 100)).evaluate()                              # reshape2
+  sp.reshape(b, (1000,)).evaluate()
+  d = sp.reshape(sp.reshape(sp.reshape(sp.arange((100, 100)), (10000,)), (10000, 1)), (1, 10000))
+  Assert.all_eq(d.glom(), sp.arange((1, 10000)).glom())                                                   # reshape3
+  f = sp.arange((10000,))
+  for shp in ((10, 1000), (1000, 10), (20, 500), (500, 20), (1, 10000)):
+    f = sp.reshape(f, shp)
+  Assert.all_eq(f.glom(), sp.arange((1, 10000)).glom())                                                   # reshape4
+  for n, s1, s2 in ((35511, (133, 267), (267, 133)), (12319, (127, 97), (97, 127))):                      # reshape5, 6
+    d = sp.reshape(sp.reshape(sp.reshape(sp.arange((n,)), s1), s2), (1, n))
+    Assert.all_eq(d.glom(), sp.arange((1, n)).glom())
+  targets = [(23, 120, 100), (12, 230, 100), (276000, 1), (1, 276000)]                                    # reshape7
+  for src in ((100, 23, 120), (12, 23, 1000), (1, 276000), (276000, 1), (276000,)):
+    a = sp.arange(src)
+    for shp in targets:
+      Assert.all_eq(sp.reshape(a, shp).glom(), np.arange(276000).reshape(shp))
+  rng = np.random.RandomState(1)                                                                          # reshape_dot
+  n1 = rng.random_sample((357, 93)); n2 = rng.random_sample((31, 357))
+  Assert.all_eq(np.dot(np.reshape(n1, (1071, 31)), n2),
+                sp.dot(sp.reshape(sp.from_numpy(n1), (1071, 31)), sp.from_numpy(n2)).glom(), 10e-9)
+  n1 = rng.random_sample((357, 718)); n2 = rng.random_sample((718,))
+  Assert.all_eq(np.dot(n1, np.reshape(n2, (718, 1))),
+                sp.dot(sp.from_numpy(n1), sp.reshape(sp.from_numpy(n2), (718, 1))).glom(), 10e-9)
+  n1 = rng.random_sample((718,)); n2 = rng.random_sample((1, 357))
+  Assert.all_eq(np.dot(np.reshape(n1, (718, 1)), n2),
+                sp.dot(sp.reshape(sp.from_numpy(n1), (718, 1)), sp.from_numpy(n2)).glom(), 10e-9)
+  # maps and reductions over reshaped / ravelled operands, tiled bases
+  x = rng.random_sample((60, 70)).astype(np.float32)
+  sx = sp.from_numpy(x, tile_hint=(16, 32))
+  Assert.all_eq((sp.reshape(sx, (70, 60)) * 3).glom(), x.reshape(70, 60) * 3)
+  Assert.all_eq((sp.ravel(sx) + 1).glom(), x.ravel() + 1)
+  np.testing.assert_allclose(sp.reshape(sx, (4, 15, 70)).sum(axis=1).glom(), x.reshape(4, 15, 70).sum(axis=1), rtol=1e-5)

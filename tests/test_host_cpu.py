@@ -216,3 +216,54 @@ def test_optimized_expressions_leave_no_reference_cycles():
       assert gc.collect() == 0
   finally:
     gc.enable()
+
+
+@pytest.mark.parametrize('W', [1, 3, 8])
+def test_view_tile_tables_match_oracle(W):
+  """Slice / Transpose / Reshape report their tiles in view coordinates; the extents must be exactly the ones the
+  reference's mappers hand to a kernel (slice.py:9-39, transpose.py:19-24, reshape.py:32-44), restated by the oracle."""
+  from spartan_b200 import blob_ctx
+  from spartan_b200.array import views
+  from spartan_oracle import views as oviews
+  old = blob_ctx._global_ctx[0]
+  blob_ctx.set(blob_ctx.BlobCtx(0, W, 'cpu'))
+  spartan_oracle.initialize(W)
+  try:
+    def table(v):
+      return sorted((ex.ul, ex.lr, tuple(ex.array_shape)) for ex in v.tiles)
+
+    def otable(v):
+      out = v.foreach_tile(lambda ex: [(ex.ul, ex.lr, tuple(ex.array_shape))], {})
+      return sorted(t for r in out for t in r)
+
+    cases = [((10, 10), None, np.index_exp[5:8, 5:8]), ((10, 10), (4, 4), np.index_exp[5:8, 5:8]),
+             ((10, 10, 10), None, np.index_exp[:, :, 0]), ((100, 37), (16, 10), np.index_exp[3:77, 9:30]),
+             ((1000,), (100,), np.index_exp[1:]), ((1000,), (100,), np.index_exp[:-1])]
+    for shape, hint, idx in cases:
+      base = pdist.create(shape, np.float32, tile_hint=hint)
+      obase = odist.create(shape, np.float32, tile_hint=hint)
+      v, ov = views.Slice(base, idx), oviews.Slice(obase, idx)
+      assert v.shape == tuple(ov.shape)
+      assert table(v) == otable(ov), (shape, hint, idx)
+      owners = dict(((ex.ul, ex.lr), tid.worker) for ex, tid in base.tiles.items())
+      for ex, tid in v.tiles.items():                     # a view tile lives where the base tile that backs it lives
+        b = pex.compute_slice(v.slice, ex.to_slice())
+        hit = [w for (ul, lr), w in owners.items() if all(u <= bu and bl <= l for u, bu, bl, l in zip(ul, b.ul, b.lr, lr))]
+        assert hit == [tid.worker]
+    for shape, hint in [((372, 134), None), ((31, 32, 33), None), ((50, 60), (16, 16))]:
+      base = pdist.create(shape, np.float32, tile_hint=hint)
+      obase = odist.create(shape, np.float32, tile_hint=hint)
+      v, ov = views.Transpose(base), oviews.Transpose(obase)
+      assert v.shape == tuple(ov.shape) and tuple(v.tile_shape()) == tuple(ov.tile_shape())
+      # the reference hands the kernel the BASE extent reversed (transpose.py:19-24): same rectangles, view shape
+      assert [(ul, lr) for ul, lr, _ in table(v)] == sorted((ex.ul[::-1], ex.lr[::-1]) for ex in obase.tiles)
+    for shape, new in [((10, 10), (100,)), ((1000,), (10, 100)), ((100, 23, 120), (12, 230, 100)), ((60, 70), (60, 70, 1)),
+                       ((276000,), (1, 276000))]:
+      base = pdist.create(shape, np.float32)
+      obase = odist.create(shape, np.float32)
+      v, ov = views.Reshape(base, new), oviews.Reshape(obase, new)
+      assert v._same_tiles == ov._same_tiles and tuple(v.tile_shape()) == tuple(ov.tile_shape())
+      assert table(v) == otable(ov), (shape, new)
+  finally:
+    blob_ctx._global_ctx[0] = old
+    blob_ctx._local.ctx = old

@@ -247,3 +247,60 @@ def test_fusion_structure():
   all_eq(opt.glom(), e.glom())
   all_eq(opt.glom(), np.full((8,), 24, np.float32))
   assert opt.glom().dtype == np.float32
+
+
+# ---- tests/test_slice.py:25-80 (the shuffle variant needs the shuffle operator, outside the hot path)
+def test_slice_reference_cases():
+  T = 10
+  x = expr.arange((T, T)); nx = np.arange(T * T).reshape(T, T)
+  all_eq(x[5:8, 5:8].evaluate().glom(), nx[5:8, 5:8])                       # test_slice_get
+  all_eq(expr.map(x[5:8, 5:8], lambda tile: tile + 1).glom(), nx[5:8, 5:8] + 1)   # test_slice_map
+  x3 = expr.arange((10, 10, 10), dtype=np.int64); n3 = np.arange(1000).reshape((10, 10, 10))
+  all_eq(expr.map(x3[:, :, 0], lambda tile: tile + 13).glom().reshape(10, 10), n3[:, :, 0] + 13)   # test_slice_map2
+  xr = expr.arange((T, T, T), dtype=np.int64); nr = np.arange(T ** 3).reshape((T, T, T))
+  all_eq(xr[:, :, 0].sum().glom(), nr[:, :, 0].sum())                       # test_slice_reduce
+  a = expr.arange((T,), dtype=np.int64); na = np.arange(T)
+  all_eq((a[1:] - a[:-1]).glom(), na[1:] - na[:-1])                         # test_slice_sub
+  all_eq((a[1:] - a[:-1]).optimized().glom(), na[1:] - na[:-1])
+  assert extent.from_slice((slice(None), slice(None), 0), [100, 100, 100]).shape == (100, 100, 1)   # test_from_slice
+
+
+# ---- tests/test_transpose.py:9-37 (dense cases)
+def test_transpose_reference_cases():
+  all_eq(expr.transpose(expr.arange((372, 134))).glom(), np.transpose(np.arange(372 * 134).reshape(372, 134)))
+  all_eq(expr.transpose(expr.arange((31, 32, 33))).glom(), np.transpose(np.arange(31 * 32 * 33).reshape(31, 32, 33)))
+  rng = np.random.RandomState(0)
+  n1 = rng.random_sample((401, 97)); n2 = rng.random_sample((401, 97))
+  got = expr.dot(expr.from_numpy(n1), expr.transpose(expr.from_numpy(n2))).glom()
+  assert np.all(np.isclose(np.dot(n1, np.transpose(n2)), got))
+
+
+# ---- tests/test_reshape.py:9-88,98-121 (dense cases)
+def test_reshape_reference_cases():
+  all_eq(expr.reshape(expr.arange((10, 10)), (100,)).glom(), expr.arange((100,)).glom())          # reshape1
+  b = expr.reshape(expr.arange((1000,), tile_hint=[100]), (10, 100)).evaluate()                   # reshape2
+  expr.reshape(b, (1000,)).evaluate()
+  d = expr.reshape(expr.reshape(expr.reshape(expr.arange((100, 100)), (10000,)), (10000, 1)), (1, 10000))
+  all_eq(d.glom(), expr.arange((1, 10000)).glom())                                                  # reshape3
+  f = expr.arange((10000,))
+  for shp in ((10, 1000), (1000, 10), (20, 500), (500, 20), (1, 10000)):
+    f = expr.reshape(f, shp)
+  all_eq(f.glom(), expr.arange((1, 10000)).glom())                                                  # reshape4
+  for n, s1, s2 in ((35511, (133, 267), (267, 133)), (12319, (127, 97), (97, 127))):               # reshape5, 6
+    d = expr.reshape(expr.reshape(expr.reshape(expr.arange((n,)), s1), s2), (1, n))
+    all_eq(d.glom(), expr.arange((1, n)).glom())
+  targets = [(23, 120, 100), (12, 230, 100), (276000, 1), (1, 276000)]                             # reshape7
+  for src in ((100, 23, 120), (12, 23, 1000), (1, 276000), (276000, 1), (276000,)):
+    a = expr.arange(src)
+    for shp in targets:
+      all_eq(expr.reshape(a, shp).glom(), np.arange(276000).reshape(shp))
+  rng = np.random.RandomState(1)                                                                    # reshape_dot
+  n1 = rng.random_sample((357, 93)); n2 = rng.random_sample((31, 357))
+  all_eq(np.dot(np.reshape(n1, (1071, 31)), n2),
+         expr.dot(expr.reshape(expr.from_numpy(n1), (1071, 31)), expr.from_numpy(n2)).glom(), 10e-9)
+  n1 = rng.random_sample((357, 718)); n2 = rng.random_sample((718,))
+  all_eq(np.dot(n1, np.reshape(n2, (718, 1))),
+         expr.dot(expr.from_numpy(n1), expr.reshape(expr.from_numpy(n2), (718, 1))).glom(), 10e-9)
+  n1 = rng.random_sample((718,)); n2 = rng.random_sample((1, 357))
+  all_eq(np.dot(np.reshape(n1, (718, 1)), n2),
+         expr.dot(expr.reshape(expr.from_numpy(n1), (718, 1)), expr.from_numpy(n2)).glom(), 10e-9)

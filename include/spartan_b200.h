@@ -20,8 +20,17 @@
 #ifndef SPARTAN_B200_H_
 #define SPARTAN_B200_H_
 
+#ifdef __CUDACC_RTC__ /* compiled at run time by NVRTC (csrc/jit.cu): no system headers there */
+typedef signed char int8_t;
+typedef unsigned char uint8_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+#else
 #include <stddef.h>
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -184,6 +193,17 @@ typedef struct {
 /* out[d0,d1,d2] = program(in...), out written with strides out->stride, cast to out->dtype. */
 int sp_map(const sp_program* prog, int n_in, const sp_operand* in, const sp_operand* out, const int64_t dims[3],
            void* stream);
+
+/* Run-time specialisation (csrc/jit.cu): a fused chain outside the library's static catalogue is compiled ONCE, by
+ * NVRTC for sm_100a, into a straight-line instance of the same streaming kernel -- the counterpart of the reference's
+ * per-expression code generation (local.py:58-152 `codegen`).  Large launches only; the interpreter runs everything
+ * else and is the fallback when libnvrtc is missing.  sp_jit_compile_check compiles (never loads) the specialisation of
+ * `prog` -- usable without a GPU; returns the cubin size. */
+int sp_jit_enable(int on);
+int sp_jit_set_nvrtc_path(const char* path);
+int sp_jit_stats(int64_t* compiled, int64_t* launches, int64_t* failures);
+const char* sp_jit_last_log(void);
+int64_t sp_jit_compile_check(const sp_program* prog, int n_in, int mode);
 
 typedef enum {
   SP_RED_SUM = 0,  /* mathematics.py:126 _sum_local;  combiner np.add */

@@ -82,6 +82,11 @@ _SIGS = {
   'sp_map_reduce_scratch_bytes': (_i64, [_i64p, _int]),
   'sp_map_reduce': (_int, [ctypes.POINTER(sp_program), _int, ctypes.POINTER(sp_operand), ctypes.POINTER(sp_operand),
                            _i64p, _int, _int, _vp, _i64, _vp]),
+  'sp_jit_enable': (_int, [_int]),
+  'sp_jit_set_nvrtc_path': (_int, [ctypes.c_char_p]),
+  'sp_jit_stats': (_int, [_i64p, _i64p, _i64p]),
+  'sp_jit_last_log': (ctypes.c_char_p, []),
+  'sp_jit_compile_check': (_i64, [ctypes.POINTER(sp_program), _int, _int]),
   'sp_combine': (_int, [_vp, _vp, _int, _i64, _int, _vp]),
   'sp_copy_rect': (_int, [_vp, _i64p, _vp, _i64p, _i64p, _int, _vp]),
   'sp_gemm_set_chunk_kblocks': (_int, [_int]),

@@ -6,7 +6,12 @@
 // accumulator (see "the interpreter" below); dispatch cost is amortised over V elements.
 #pragma once
 #include "sp_common.h"
+#ifdef __CUDACC_RTC__
+#define CUDART_INF_F __int_as_float(0x7f800000)
+#define CUDART_INF __longlong_as_double(0x7ff0000000000000LL)
+#else
 #include <math_constants.h>
+#endif
 
 namespace sp {
 
@@ -153,6 +158,7 @@ enum AOp : int {
 enum ASrc : int { S_IN0 = 0, S_CONST = 8, S_TMP = 9, S_INDEX = 10, S_NONE = 11 };
 constexpr int kMaxTmp = 4;
 
+#ifndef __CUDACC_RTC__   // host-side lowering
 struct PostfixNode { int op, arg, l, r; };
 
 inline int aop_binary(int sp_op, bool reversed) {
@@ -268,6 +274,8 @@ inline bool lower_program(const sp_program* prog, DevProgram<T>* out) {
   lw.emit(stack[0]);
   return lw.ok;
 }
+
+#endif  // !__CUDACC_RTC__
 
 #define SP_B(x) ((x) ? T(1) : T(0))
 

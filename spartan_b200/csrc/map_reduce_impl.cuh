@@ -269,6 +269,12 @@ static int launch_stream_as(const DevProgram<T>& dp, const DevOperands<NI>& ops,
   return SP_OK;
 }
 
+namespace jit {
+int launch_stream_specialised(int dtype, int ni, int mode, const uint8_t* op, const uint8_t* src, const uint8_t* arg, int n,
+                              void** params, int grid, int threads, int smem_bytes, cudaStream_t stream);
+}
+constexpr int64_t kJitMinBytes = 1 << 20;
+
 // Index of the statically compiled program equal to `dp`, or -1.
 template <typename T>
 static int match_static(const DevProgram<T>& dp) {
@@ -278,9 +284,12 @@ static int match_static(const DevProgram<T>& dp) {
   return -1;
 }
 
+// Returns SP_OK when a kernel was launched, < 0 on error, and kNotLaunched when `interp_ok` is false and there is no
+// compiled (static or run-time specialised) instance for this program.
+constexpr int kNotLaunched = 1;
 template <typename T, int NI, int MODE>
 static int launch_stream(const DevProgram<T>& dp, const DevOperands<NI>& ops, const stream::Plan& plan, int red_op,
-                         T* scratch, cudaStream_t stream_) {
+                         T* scratch, cudaStream_t stream_, bool interp_ok = true) {
   // statically compiled programs exist for the float / double two-operand kernels
   if constexpr (NI == 2 && !std::is_same<T, long long>::value) {
     switch (match_static<T>(dp)) {
@@ -290,6 +299,18 @@ static int launch_stream(const DevProgram<T>& dp, const DevOperands<NI>& ops, co
       default: break;
     }
   }
+  // any other fused chain: specialise the same kernel for it at run time (jit.cu) when the launch is large enough
+  // for the one-off compile to pay; otherwise, or if NVRTC is unavailable, interpret it
+  if (plan.d0 * plan.d1 * plan.d2 * static_cast<int64_t>(sizeof(T)) >= kJitMinBytes) {
+    const int grid = static_cast<int>(std::min<int64_t>(plan.n_units, num_sms()));
+    int red = red_op;
+    void* params[] = {const_cast<DevProgram<T>*>(&dp), const_cast<DevOperands<NI>*>(&ops),
+                      const_cast<stream::Plan*>(&plan), &red, &scratch};
+    const int rc = jit::launch_stream_specialised(TypeTag<T>::dtype, NI, MODE, dp.op, dp.src, dp.arg, dp.n_ops, params,
+                                                  grid, stream::kThreads, stream::kSmemBytes, stream_);
+    if (rc != 0) return rc < 0 ? rc : SP_OK;
+  }
+  if (!interp_ok) return kNotLaunched;
   return launch_stream_as<T, NI, MODE, DynamicProgram>(dp, ops, plan, red_op, scratch, stream_);
 }
 
@@ -321,14 +342,20 @@ static int launch_map_v(const sp_program* prog, int n_in, const sp_operand* in, 
   ops.out = make_operand<T, V>(*out, 2, dims);
   if (ops.out.kind == kSplat) ops.out.kind = kGeneric;
   if (dims[0] * dims[1] * dims[2] == 0) return SP_OK;
-  if (V == 32 / sizeof(T)) {     // the streaming kernel uses the 32-byte-per-lane vector width
+  {
+    // The streaming kernel works on 32-byte-per-lane vectors.  With up to two operands any program may run on it
+    // (interpreted if need be); with more operands the interpreter's register footprint would spill, so only a
+    // compiled instance is used there.
+    const bool interp_ok = (V == 32 / sizeof(T));
     int64_t sd[3] = {dims[0], dims[1], dims[2]};
     DevOperands<NI> sops = ops;
     DevProgram<T> sdp = dp;
     if (reshape_flat<T, NI>(sops, sd)) sdp.index_stride[1] = sd[2] * sdp.index_stride[2];   // i2 = i1' * row + i2'
     stream::Plan plan;
-    if (plan_stream<T, NI>(sops, sd, true, 0, &plan))
-      return launch_stream<T, NI, 0>(sdp, sops, plan, 0, nullptr, stream);
+    if (plan_stream<T, NI>(sops, sd, true, 0, &plan)) {
+      const int rc = launch_stream<T, NI, 0>(sdp, sops, plan, 0, nullptr, stream, interp_ok);
+      if (rc != kNotLaunched) return rc;
+    }
   }
   Dims3 d{dims[0], dims[1], dims[2]};
   const int64_t d2v = (dims[2] + V - 1) / V;
@@ -414,19 +441,22 @@ static int launch_reduce_v(const sp_program* prog, int n_in, const sp_operand* i
   const int64_t n_out = dims[0] * dims[2];
   if (n_out == 0) return SP_OK;
   T* sc = static_cast<T*>(scratch);
-  if (!p.row && V == 32 / sizeof(T)) {
+  if (!p.row) {
+    const bool interp_ok = (V == 32 / sizeof(T));      // see launch_map_v
     stream::Plan plan;
     if (plan_stream<T, NI>(ops, dims, false, kStreamReduceRows, &plan)) {
       const int64_t sneed = plan.n_chunks * dims[0] * dims[2] * static_cast<int64_t>(sizeof(T));
       SP_REQUIRE(scratch_bytes >= sneed, SP_ERR_INVALID, "sp_map_reduce: scratch %lld B < required %lld B",
                  (long long)scratch_bytes, (long long)sneed);
-      int rc = launch_stream<T, NI, 1>(dp, ops, plan, red_op, sc, stream);
-      if (rc) return rc;
-      const int fb = static_cast<int>(std::min<int64_t>((n_out + 255) / 256, 4096));
-      finalize_kernel<T><<<fb, 256, 0, stream>>>(sc, n_out, static_cast<int>(plan.n_chunks), n_out, 1, o, dims[2], red_op,
-                                                 accumulate);
-      SP_CUDA_CHECK(cudaGetLastError());
-      return SP_OK;
+      int rc = launch_stream<T, NI, 1>(dp, ops, plan, red_op, sc, stream, interp_ok);
+      if (rc < 0) return rc;
+      if (rc != kNotLaunched) {
+        const int fb = static_cast<int>(std::min<int64_t>((n_out + 255) / 256, 4096));
+        finalize_kernel<T><<<fb, 256, 0, stream>>>(sc, n_out, static_cast<int>(plan.n_chunks), n_out, 1, o, dims[2],
+                                                   red_op, accumulate);
+        SP_CUDA_CHECK(cudaGetLastError());
+        return SP_OK;
+      }
     }
   }
   if (p.row) {

@@ -4,6 +4,10 @@
 // return 0 on success, a negative sp_status on failure; the message of the
 // most recent failure on the calling thread is available from sp_last_error().
 #pragma once
+#ifdef __CUDACC_RTC__
+// Run-time compilation of a fused kernel (jit.cu): device code only, headers come from memory.
+#include "spartan_b200.h"
+#else
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -49,3 +53,4 @@ inline size_t dtype_size(int dt) {
 int num_sms();
 
 }  // namespace sp
+#endif  // !__CUDACC_RTC__

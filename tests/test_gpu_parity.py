@@ -649,3 +649,55 @@ def test_reshape_reference_cases():
   Assert.all_eq((sp.reshape(sx, (70, 60)) * 3).glom(), x.reshape(70, 60) * 3)
   Assert.all_eq((sp.ravel(sx) + 1).glom(), x.ravel() + 1)
   np.testing.assert_allclose(sp.reshape(sx, (4, 15, 70)).sum(axis=1).glom(), x.reshape(4, 15, 70).sum(axis=1), rtol=1e-5)
+
+
+def _jit_stats():
+  import ctypes
+  from spartan_b200._lib import lib
+  c, l, f = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+  lib.sp_jit_stats(ctypes.byref(c), ctypes.byref(l), ctypes.byref(f))
+  return c.value, l.value, f.value
+
+
+@pytest.mark.parametrize('dtype', [np.float32, np.float64, np.int64])
+def test_runtime_specialised_kernels_match_interpreter(dtype):
+  """A fused chain outside the static catalogue on a large array is compiled once by NVRTC into a straight-line
+  instance of the streaming kernel (csrc/jit.cu; the reference's per-expression codegen, local.py:58-152).  It runs the
+  same exec_op code as the interpreter, so results must be bit-identical to the interpreted run and to NumPy
+  (+,-,*,abs,max round once per operation under -fmad=false)."""
+  from spartan_b200._lib import lib
+  rng = np.random.RandomState(5)
+  shape = (2048, 1024)
+  if dtype == np.int64:
+    x = rng.randint(-1000, 1000, size=shape).astype(dtype); y = rng.randint(-1000, 1000, size=shape).astype(dtype)
+    z = rng.randint(-1000, 1000, size=shape).astype(dtype)
+    c = 3
+  else:
+    x = rng.randn(*shape).astype(dtype); y = rng.randn(*shape).astype(dtype); z = rng.randn(*shape).astype(dtype)
+    c = dtype(0.5)
+  X, Y, Z = sp.from_numpy(x), sp.from_numpy(y), sp.from_numpy(z)
+
+  def build():
+    return [(sp.abs(X - Y) * X + sp.maximum(Y, c)).optimized(),               # 2 operands, one temporary
+            ((X + Y) * Z - X * c + Y * Y - Z).optimized(),                    # 3 operands (NI = 8 kernel)
+            (sp.abs(X - Y) * X + sp.maximum(Y, c)).sum(axis=0).optimized(),   # map+reduce
+            ((X - Z) * (Y + Z)).max(axis=0).optimized()]
+  want = [np.abs(x - y) * x + np.maximum(y, c), (x + y) * z - x * c + y * y - z]
+  try:
+    lib.sp_jit_enable(0)
+    interp = [e.glom() for e in build()]
+    lib.sp_jit_enable(1)
+    c0, l0, f0 = _jit_stats()
+    jit = [e.glom() for e in build()]
+    jit2 = [e.glom() for e in build()]          # second run: cache hits, no new compiles
+    c1, l1, f1 = _jit_stats()
+  finally:
+    lib.sp_jit_enable(1)
+  assert f1 == f0, 'run-time specialisation failed: %s' % lib.sp_jit_last_log().decode()
+  assert l1 - l0 == 8 and c1 - c0 <= 4, (c0, c1, l0, l1)
+  for a, b, c_ in zip(interp, jit, jit2):
+    Assert.all_eq(a, b)
+    Assert.all_eq(b, c_)
+  Assert.all_eq(jit[0], want[0])
+  Assert.all_eq(jit[1], want[1])
+  Assert.all_eq(jit[3], ((x - z) * (y + z)).max(axis=0))

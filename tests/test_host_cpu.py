@@ -267,3 +267,15 @@ def test_view_tile_tables_match_oracle(W):
   finally:
     blob_ctx._global_ctx[0] = old
     blob_ctx._local.ctx = old
+
+
+def test_runtime_specialisation_compiles_without_gpu():
+  """csrc/jit.cu: the fused chain |x-y|*x + max(y, c) is lowered and compiled by NVRTC for sm_100a from the kernel
+  headers embedded in the library (no GPU needed to compile; loading and running it is covered by the -m gpu tests)."""
+  from spartan_b200 import device_ops
+  ops = [('IN', 0), ('IN', 1), ('SUB', 0), ('ABS', 0), ('IN', 0), ('MUL', 0), ('IN', 1), ('CONST', 0), ('MAX', 0), ('ADD', 0)]
+  p = device_ops.make_program(ops, _lib.SP_F32, [0.5])
+  n = _lib.lib.sp_jit_compile_check(ctypes.byref(p), 2, 1)
+  if n < 0 and 'not found' in _lib.lib.sp_jit_last_log().decode():
+    pytest.skip('libnvrtc not present on this machine')
+  assert n > 10000, _lib.last_error()

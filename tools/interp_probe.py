@@ -27,6 +27,8 @@ CASES = [
   ("10-op chain map", lambda: (((x + y) * z - x) * 0.5 + y * y - z * 2 + 1), 4 * nb),
 ]
 
+from spartan_b200._lib import lib
+jit_on = os.environ.get('SPARTAN_JIT', '1') != '0'
 out = []
 for name, build, nbytes in CASES:
   e = build().optimized()
@@ -39,8 +41,8 @@ for name, build, nbytes in CASES:
   for _ in range(n): build().optimized().evaluate()
   ev1.record(); torch.cuda.synchronize()
   ms = ev0.elapsed_time(ev1) / n
-  line = {"expr": name, "ms": round(ms, 3), "GBps": round(nbytes / ms / 1e6, 1)}
+  line = {"expr": name, "jit": jit_on, "ms": round(ms, 3), "GBps": round(nbytes / ms / 1e6, 1)}
   print(json.dumps(line), flush=True)
   out.append(line)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(out, open(os.path.join(ROOT, "gpurun_out", "interp_probe.json"), "w"), indent=1)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", "interp_probe_%s.json" % ("jit" if jit_on else "interp")), "w"), indent=1)

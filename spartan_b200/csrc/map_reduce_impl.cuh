@@ -241,8 +241,11 @@ static bool plan_stream(const DevOperands<NI>& ops, const int64_t dims[3], bool 
     if (ops.in[i].kind == kVec) plan->stream_slot[i] = n_stream++;
   }
   if (n_stream == 0 || n_stream > 8) return false;
-  int rb = stream::kStageBytes / stream::kPanelBytes;       // 8 rows of one operand fill a stage
-  while (rb * n_stream > stream::kStageBytes / stream::kPanelBytes) rb >>= 1;
+  // rows per stage: 16+ warp-items (rows x 4 segments) per stage whenever a stage of <= 64 KiB can hold them
+  const int rb = n_stream == 1 ? 8 : n_stream <= 4 ? 4 : 2;
+  plan->stage_bytes = n_stream * rb * stream::kPanelBytes;
+  // 4 x 32 KiB measured best for one and two operands (6 stages cost ~7% on the two-operand map+reduce)
+  plan->n_stages = std::min(4, stream::kRingBytes / plan->stage_bytes);
   plan->d0 = dims[0]; plan->d1 = dims[1]; plan->d2 = dims[2];
   plan->n_panels = static_cast<int>((row_bytes + stream::kPanelBytes - 1) / stream::kPanelBytes);
   plan->rb = rb;

@@ -3,10 +3,10 @@
 // The simple kernels in map_reduce_impl.cuh keep only ~32 KB of loads in flight per SM (the
 // interpreter's register footprint caps occupancy), which is less than half of what HBM3e needs.
 // Here the loads are decoupled from the interpreter: one producer warp issues 1 KiB
-// cp.async.bulk copies (TMA engine, SASS UBLKCP) into a 4 x 32 KiB shared-memory ring guarded by
-// mbarriers, sixteen consumer warps read the ring with conflict-free 16-byte LDS, run the bytecode
+// cp.async.bulk copies (TMA engine, SASS UBLKCP) into a 192 KiB shared-memory ring (3-6 stages of 32-64 KiB,
+// sized so that a stage carries 16 warp-items whatever the operand count) guarded by mbarriers, sixteen consumer warps read the ring with conflict-free 16-byte LDS, run the bytecode
 // and either store the result (map) or fold it into per-thread accumulators (reduce).  Up to
-// 128 KiB per SM is in flight regardless of register pressure.  One CTA per SM, persistent over
+// 192 KiB per SM is in flight regardless of register pressure.  One CTA per SM, persistent over
 // work units.
 //
 // Work unit = RC consecutive rows x one 4 KiB-wide column panel; one bulk copy moves one row of a panel
@@ -25,15 +25,16 @@
 namespace sp {
 namespace stream {
 
-constexpr int kStages = 4;
-constexpr int kStageBytes = 32 * 1024;
+constexpr int kRingBytes = 192 * 1024;         // shared-memory ring; a stage holds rb rows x one panel of every streamed operand
+constexpr int kMaxStages = 8;
+constexpr int kMaxStageBytes = 64 * 1024;
 constexpr int kSegBytes = 1024;               // what one consumer warp handles per pass (32 lanes x 32 B)
 constexpr int kPanelBytes = 4096;             // one bulk copy = one row x one panel (1 KiB copies starve the TMA unit)
 constexpr int kSegsPerPanel = kPanelBytes / kSegBytes;
 constexpr int kConsumerWarps = 16;
 constexpr int kThreads = 32 * (1 + kConsumerWarps);
 constexpr int kRedBytes = kConsumerWarps * 32 * 32;   // [warps][32 lanes][V * sizeof(T) = 32 B]
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + kRedBytes + 128;
+constexpr int kSmemBytes = kRingBytes + 1024 /*align*/ + kRedBytes + 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -70,7 +71,9 @@ struct Plan {
   int64_t n_chunks;          // ceil(d1 / rc)      (reduce: per d0)    map: rows = d0*d1 flattened is NOT assumed
   int64_t n_units;           // d0 * n_chunks * n_panels
   int n_stream;              // streamed operands
-  int rb;                    // rows per stage  (n_stream * rb * kPanelBytes <= kStageBytes)
+  int rb;                    // rows per stage  (n_stream * rb * kPanelBytes = stage_bytes <= kMaxStageBytes)
+  int stage_bytes;
+  int n_stages;              // kRingBytes / stage_bytes, at most kMaxStages
   int stream_slot[SP_MAX_OPERANDS];   // operand -> slot in the stage, or -1 (loaded directly)
 };
 
@@ -104,15 +107,17 @@ stream_kernel(const DevProgram<T> prog, const DevOperands<NI> ops, const Plan pl
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + kStages * kStageBytes + kRedBytes;
-  T* red_smem = reinterpret_cast<T*>(smem_gen + kStages * kStageBytes);   // [warps][32 lanes][V]
+  const uint32_t bar_base = smem_base + kRingBytes + kRedBytes;
+  T* red_smem = reinterpret_cast<T*>(smem_gen + kRingBytes);   // [warps][32 lanes][V]
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  const int n_stages = plan.n_stages;
+  const int stage_bytes = plan.stage_bytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < n_stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), kConsumerWarps);
     }
@@ -151,10 +156,10 @@ stream_kernel(const DevProgram<T> prog, const DevOperands<NI> ops, const Plan pl
         if (my_op >= 0 && slot < plan.n_stream && r_in < rows) {
           const DevOperand& o = ops.in[my_op];
           const T* src = static_cast<const T*>(o.ptr) + i0 * o.stride[0] + (row0 + r_in) * o.stride[1] + col0;
-          const uint32_t dst = smem_base + stage * kStageBytes + (slot * rb + r_in) * kPanelBytes;
+          const uint32_t dst = smem_base + stage * stage_bytes + (slot * rb + r_in) * kPanelBytes;
           bulk_g2s(dst, src, seg_bytes, full_bar(stage));
         }
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -185,7 +190,7 @@ stream_kernel(const DevProgram<T> prog, const DevOperands<NI> ops, const Plan pl
         if (row0 >= row_end) break;
         const int rows = static_cast<int>(min(static_cast<int64_t>(rb), row_end - row0));
         mbar_wait(full_bar(stage), phase);
-        const uint8_t* sbase = smem_gen + stage * kStageBytes;
+        const uint8_t* sbase = smem_gen + stage * stage_bytes;
         for (int item = cw; item < rows * kSegsPerPanel; item += kConsumerWarps) {
           const int r = item / kSegsPerPanel;                // item % kSegsPerPanel == q for every item of this warp
           T in[NI][V];
@@ -235,7 +240,7 @@ stream_kernel(const DevProgram<T> prog, const DevOperands<NI> ops, const Plan pl
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty_bar(stage));
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
       if (MODE == 1) {
         // fold the 8 consumer warps (fixed order), warp 0 of the consumers writes the unit's partial

@@ -160,6 +160,28 @@ def run_map_reduce(prog, inputs, in_shape, axis, red_op, out, accumulate, index=
     if len(shape) == 0:
       shape, strides = [1], [[0] for _ in in_strides]
     first = True
+    if len(shape) == 1 and shape[0] >= _FLAT_REDUCE_MIN and all(st[0] in (0, 1) for st in strides):
+      # A long contiguous run: fold it as rows of _FLAT_REDUCE_COLS elements down to one row (the streaming
+      # column-reduce kernel, HBM-bound), then fold that row; the ragged tail goes through the generic path below.
+      cols = _FLAT_REDUCE_COLS
+      rows = shape[0] // cols
+      st3 = [[0, st[0] * cols, st[0]] for st in strides]
+      if index is not None:
+        _set_index(prog, index[0], st3[n_in])
+      row = torch.empty((cols,), dtype=_TORCH_OF_COMPUTE[prog.compute_dtype], device=out.device)
+      _launch_reduce(ctx, prog, inputs, st3[:n_in], [0] * n_in, row, [0, 0, 1], 0, [1, rows, cols], red_op, False)
+      ident = make_program([('IN', 0)], prog.compute_dtype)
+      _launch_reduce(ctx, ident, [row], [[0, 1, 0]], [0], out, [0, 0, 0], 0, [1, cols, 1], red_op, accumulate)
+      first = False
+      done = rows * cols
+      if done == shape[0]:
+        return
+      tail_offs = [st[0] * done for st in strides]
+      if index is not None:
+        _set_index(prog, index[0] + tail_offs[n_in], [0, strides[n_in][0], 0])
+      _launch_reduce(ctx, prog, inputs, [[0, st[0], 0] for st in strides[:n_in]], tail_offs[:n_in], out, [0, 0, 0], 0,
+                     [1, shape[0] - done, 1], red_op, True)
+      return
     for offs in _leading_loops(shape, strides, 1):
       dims = [1, shape[-1], 1]
       st3 = [[0, st[-1], 0] for st in strides]
@@ -190,6 +212,11 @@ def run_map_reduce(prog, inputs, in_shape, axis, red_op, out, accumulate, index=
                    [o_str[n_in][-1] if o_shape else 0, in_strides[n_in][axis], i_str[n_in][-1] if i_shape else 0])
       _launch_reduce(ctx, prog, inputs, st3, [a + b for a, b in zip(offs[:n_in], ioffs[:n_in])], out, out_stride,
                      offs[no] + ioffs[no], [d0, in_shape[axis], d2], red_op, accumulate)
+
+
+_FLAT_REDUCE_COLS = 8192          # elements per row when a flat reduction is re-viewed as a column reduction
+_FLAT_REDUCE_MIN = 1 << 20
+_TORCH_OF_COMPUTE = {SP_F32: torch.float32, SP_F64: torch.float64, SP_I64: torch.int64}
 
 
 def _launch_reduce(ctx, prog, inputs, st3, in_offs, out, out_stride, out_off, dims, red_op, accumulate):

@@ -91,7 +91,7 @@ class MapMapFusion(OptimizePass):
         key = make_var()
         combined_op.add_dep(LocalInput(idx=key))
         child_to_var.append(key)
-    if not program.fits_one_kernel(combined_op):
+    if not program.fits_one_kernel(combined_op, children, child_to_var):
       return expr.visit(self)       # too deep / too many operands for one kernel: keep the children as nodes
     return expr_like(expr, children=ListExpr(vals=children), child_to_var=child_to_var, op=combined_op)
 

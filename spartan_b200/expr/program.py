@@ -134,12 +134,27 @@ def tree_cost(op):
   return depth, names
 
 
-def fits_one_kernel(op):
-  """True when the tree can run as ONE fused kernel: stack depth and operand count within the
-  evaluator's register budget.  Fusion passes stop fusing at this boundary; the un-fused child is then
-  evaluated (once, cached by expression id) into a temporary array."""
+def fits_one_kernel(op, children=None, child_to_var=None):
+  """True when the tree can run as ONE fused kernel: stack depth, distinct array operands and scalar constants within
+  the evaluator's budget.  Fusion passes stop fusing at this boundary; the un-fused child is then evaluated (once,
+  cached by expression id) into a temporary array.  With ``children`` / ``child_to_var`` given, an array that is used
+  several times counts once (it is bound to one kernel operand, map.bind_operands) and Python scalars count as
+  immediates, not operands."""
   depth, names = tree_cost(op)
-  return depth <= SP_MAX_STACK and len(names) <= SP_MAX_OPERANDS
+  if depth > SP_MAX_STACK:
+    return False
+  if children is None:
+    return len(names) <= SP_MAX_OPERANDS
+  arrays, consts = set(), 0
+  for child, var in zip(children, child_to_var):
+    if var not in names:
+      continue
+    val = getattr(child, 'val', None)
+    if type(child).__name__ == 'AsArray' and (np.isscalar(val) or getattr(val, 'shape', None) == ()):
+      consts += 1
+    else:
+      arrays.add(child.expr_id)
+  return len(arrays) <= SP_MAX_OPERANDS and consts <= SP_MAX_CONSTS
 
 
 def _analyse(node, operands):

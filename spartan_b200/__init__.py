@@ -15,6 +15,7 @@ from . import expr
 from .array import distarray, extent, tile
 from . import sparse
 from .examples.kmeans import KMeans
+from .replay import replayable, Replayable
 
 
 def initialize(argv=None, device=None):

@@ -317,10 +317,13 @@ static int launch_stream(const DevProgram<T>& dp, const DevOperands<NI>& ops, co
   return launch_stream_as<T, NI, MODE, DynamicProgram>(dp, ops, plan, red_op, scratch, stream_);
 }
 
+#ifndef SP_FLAT_ROW_BYTES
+#define SP_FLAT_ROW_BYTES 16384
+#endif
 // A flat contiguous map (d0 = d1 = 1) is re-viewed as rows of `kFlatRow` elements so the ring carries full stages.
 template <typename T, int NI>
 static bool reshape_flat(DevOperands<NI>& ops, int64_t dims[3]) {
-  constexpr int64_t kFlatRow = 16384 / sizeof(T);
+  constexpr int64_t kFlatRow = (SP_FLAT_ROW_BYTES) / sizeof(T);
   if (dims[0] * dims[1] != 1 || dims[2] < kFlatRow * 8 || dims[2] % kFlatRow != 0) return false;
   for (int i = 0; i < ops.n_in; ++i)
     if (ops.in[i].stride[2] != 0 && ops.in[i].stride[2] != 1) return false;

@@ -66,6 +66,32 @@ def blockwise_ok(largest, children):
   return True
 
 
+def slabwise_operands(largest, children, child_to_var, used_vars, free_axes=None):
+  """When every array operand of a map / reduce is tiled and placed exactly like ``largest`` (or is ``largest``), the
+  rank's whole share can be processed as ONE launch over the slabs themselves -- slab coordinates line up across
+  operands, and an element-wise result does not care which global rows / columns a slab position stands for.
+  ``free_axes`` lists the axes along which the slab may be a non-contiguous selection of the array (None = any axis,
+  the case of a map; for a reduction only the reduced axis).  Returns the slab tensors in ``used_vars`` order, or None."""
+  if largest.slab is None or not isinstance(largest, distarray.DistArrayImpl) or not largest.shape:
+    return None
+  for d, ivs in enumerate(largest.slab_axes):
+    if free_axes is not None and d not in free_axes and not (len(ivs) >= 1 and ivs[0][0] == 0 and
+                                                             ivs[-1][1] == largest.shape[d] and
+                                                             all(a[1] == b[0] for a, b in zip(ivs, ivs[1:]))):
+      return None
+  slabs = {}
+  for child, var in zip(children, child_to_var):
+    if var not in used_vars:
+      continue
+    if child is largest:
+      slabs[var] = largest.slab
+    elif isinstance(child, distarray.DistArrayImpl) and largest.same_layout(child):
+      slabs[var] = child.slab
+    else:
+      return None
+  return [slabs[v] for v in used_vars]
+
+
 def tile_mapper(ex, children, child_to_var, op, compiled, output):
   """Runs for each tile of a map (map.py:48-88): one fused kernel launch on the owning GPU."""
   ctx = blob_ctx.get()
@@ -126,8 +152,16 @@ class MapExpr(Expr):
     compiled = program.compile_tree(self.op, bind_operands(children, child_to_var))
     output = distarray.create_like(largest, compiled.out_dtype)
     if blockwise_ok(largest, children) and output.slab is not None:
-      # one fused launch per contiguous block of this rank's share (the tiling is the reference's unit of
-      # RPC dispatch, not a unit of work the GPU needs)
+      # one fused launch per rank when all operands share the layout, else one per contiguous block of this rank's
+      # share (the tiling is the reference's unit of RPC dispatch, not a unit of work the GPU needs)
+      slabs = slabwise_operands(largest, children, child_to_var, compiled.used_vars)
+      if slabs is not None and output.slab.shape == largest.slab.shape:
+        if output.slab.numel():
+          device_ops.run_map(compiled.program, slabs, output.slab)
+        for tid in output.tiles.values():
+          if ctx.is_local(tid):
+            ctx.tile(tid).valid = True
+        return output
       for block in largest.local_blocks():
         values = get_local_values(block, children, child_to_var, compiled.used_vars, ctx.worker_id)
         device_ops.run_map(compiled.program, [values[v] for v in compiled.used_vars], output.slab_view(block))

@@ -20,7 +20,7 @@ from .._lib import SpartanError, SP_FILL_CONST, SP_F64, SP_I64
 from . import program
 from .base import Expr, ListExpr, as_array
 from .local import make_var, LocalReduceExpr, LocalInput
-from .map import bind_operands, get_local_values, blockwise_ok
+from .map import bind_operands, get_local_values, blockwise_ok, slabwise_operands
 
 
 class _DtypeOf(object):
@@ -111,7 +111,16 @@ class ReduceExpr(Expr):
     shape = tuple(extent.shape_for_reduction(largest.shape, axis))
     acc = ctx.empty(shape, dtype)
     acc.fill_(tile.identity_of(red_op, dtype))     # exact for int64 extremes (a double immediate is not)
-    if blockwise_ok(largest, children):
+    nd = len(largest.shape)
+    free = None if axis is None else [axis + nd if axis < 0 else axis]
+    slabs = slabwise_operands(largest, children, child_to_var, compiled.used_vars, free) \
+      if blockwise_ok(largest, children) else None
+    if slabs is not None:
+      # the rank's whole share in one fused launch: a selection of rows / columns along the reduced axis folds into
+      # the same accumulator whatever global positions it stands for
+      if largest.slab.numel():
+        device_ops.run_map_reduce(compiled.program, slabs, tuple(largest.slab.shape), axis, red_op, acc, accumulate=True)
+    elif blockwise_ok(largest, children):
       for block in largest.local_blocks():       # one fused launch per contiguous block of this rank's slab
         _reduce_mapper(block, children, child_to_var, op, axis, None, compiled=compiled, red_op=red_op, acc=acc,
                        owner=ctx.worker_id)

@@ -51,6 +51,16 @@ def _worker(rank, world, port, q):
     got = (sp.from_numpy(x, tile_hint=(128, 2048)) + sp.from_numpy(y, tile_hint=(1024, 256))).glom()
     assert np.array_equal(got, x + y)
     assert sp.ones((4096, 4096)).sum().glom() == 16777216.0
+    # a captured evaluation (kernels + ncclAllReduce in one CUDA graph) replayed on updated inputs
+    from spartan_b200.expr.base import lazify
+    X = sp.from_numpy(x, tile_hint=(128, 2048)).evaluate(); Y = sp.from_numpy(y, tile_hint=(128, 2048)).evaluate()
+    rep = sp.replayable(lambda: (lazify(X) * 2 + lazify(Y)).sum(axis=0).optimized().evaluate())
+    for _ in range(3):
+      got = rep().glom()
+    np.testing.assert_allclose(got, (x.astype(np.float64) * 2 + y).sum(axis=0), rtol=1e-5)
+    x2 = rng.random((1024, 2048), dtype=np.float32)
+    X.update(sp.extent.from_shape(X.shape), x2)
+    np.testing.assert_allclose(rep().glom(), (x2.astype(np.float64) * 2 + y).sum(axis=0), rtol=1e-5)
     dist.barrier()
     q.put((rank, 'ok'))
   except Exception:

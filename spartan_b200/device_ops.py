@@ -492,13 +492,33 @@ class PreparedOperand(object):
                                      self.row_ptr(r0), self.copy_stride, self.Kp, 0, _stream()), 'sp_gemm_prepare_a_rows')
     _count_launch()
 
-  def prepare_b(self, B, c0):
-    """rows [c0, c0 + B.shape[1]) of the transposed operand <- the fp32 strip B [K, n]."""
+  def prepare_b(self, B, c0, k_offset=0):
+    """rows [c0, c0 + B.shape[1]) of the transposed operand, depth [k_offset, k_offset + B.shape[0]) <- the fp32 strip
+    B [k, n]."""
     _require_cuda(B)
-    assert B.dim() == 2 and B.stride(1) == 1 and B.dtype == torch.float32 and B.shape[0] == self.K
-    check(lib.sp_gemm_prepare_b_rows(B.data_ptr(), B.stride(0), self.K, B.shape[1], _PRECISIONS[self.precision],
-                                     self.row_ptr(c0), self.copy_stride, self.Kp, 0, _stream()), 'sp_gemm_prepare_b_rows')
+    assert B.dim() == 2 and B.stride(1) == 1 and B.dtype == torch.float32 and k_offset + B.shape[0] <= self.K
+    check(lib.sp_gemm_prepare_b_rows(B.data_ptr(), B.stride(0), B.shape[0], B.shape[1], _PRECISIONS[self.precision],
+                                     self.row_ptr(c0), self.copy_stride, self.Kp, int(k_offset), _stream()),
+          'sp_gemm_prepare_b_rows')
     _count_launch()
+
+
+def gemm_prepared_views(views, C, accumulate, precision):
+  """C (+)= sum over views (A ptr, A copy stride, B ptr, B copy stride, Kp) of A.B -- row ranges of larger prepared
+  operands (at most 8 per launch)."""
+  _require_cuda(C)
+  M, N = C.shape
+  assert C.stride(1) == 1 or N == 1
+  acc = accumulate
+  for lo in range(0, len(views), SP_GEMM_MAX_SEGMENTS):
+    chunk = views[lo:lo + SP_GEMM_MAX_SEGMENTS]
+    v = (sp_gemm_prepared_view * len(chunk))()
+    for i, (a, astr, b, bstr, Kp) in enumerate(chunk):
+      v[i].A = a; v[i].a_copy_stride = int(astr); v[i].B = b; v[i].b_copy_stride = int(bstr); v[i].Kp = int(Kp)
+    check(lib.sp_gemm_prepared_views(len(chunk), v, C.data_ptr(), C.stride(0), M, N, int(bool(acc)),
+                                     _PRECISIONS[precision], _stream()), 'sp_gemm_prepared_views')
+    _count_launch()
+    acc = True
 
 
 def gemm_prepared_rows(pa, r0, r1, pb, c0, c1, C, accumulate=False):

@@ -49,6 +49,32 @@ def _owned_runs(array, worker):
   return _runs(axes[0]), _runs(axes[1])
 
 
+def _regular_layout(av, bv, target, W, M, K):
+  """The placement the multi-GPU fast paths need: every rank owns whole column blocks of A, B and C (full height),
+  equally wide, and the B columns a rank needs for its C columns are its own -- e.g. round-robin over an evenly
+  divisible tile grid.  Returns per-rank (A axes, B axes, C runs) or None."""
+  a_axes, c_runs, b_axes = [], [], []
+  for w in range(W):
+    la = [ex for ex, tid in av.tiles.items() if tid.worker == w]
+    lb = [ex for ex, tid in bv.tiles.items() if tid.worker == w]
+    pa = distarray._product_layout(la, 2)
+    pb = distarray._product_layout(lb, 2)
+    rc = _owned_runs(target, w)
+    if pa is None or pb is None or rc is None or not rc[0]:
+      return None
+    if _runs(pa[0]) != [(0, M)] or _runs(pb[0]) != [(0, K)] or rc[0] != [(0, M)]:
+      return None                       # every rank must hold full columns of A and B and full-height C blocks
+    if a_axes and sum(b - a for a, b in pa[1]) != sum(b - a for a, b in a_axes[0][1]):
+      return None                       # equal slab widths (all-gather needs equal contributions)
+    # the B columns this rank needs (= its C columns) must be local to it
+    bcols = pb[1]
+    for c0, c1 in rc[1]:
+      if not any(a <= c0 and c1 <= b for a, b in _runs(bcols)):
+        return None
+    a_axes.append(pa); b_axes.append(pb); c_runs.append(rc)
+  return a_axes, b_axes, c_runs
+
+
 class DotExpr(Expr):
   """dot.py:95-158 (the node the reference defines but no longer constructs -- Q11 -- is the natural
   home of the GEMM evaluator)."""
@@ -84,7 +110,7 @@ class DotExpr(Expr):
     """Both operands are host arrays that have not been uploaded yet (``from_numpy`` nodes, write_array.py:424-445),
     large enough for PCIe time to matter, on one GPU: the upload is then pipelined with the contraction instead of
     running in front of it."""
-    if not FLAGS.dot_stream_host_operands or ctx.num_workers != 1 or ctx.device.type != 'cuda':
+    if not FLAGS.dot_stream_host_operands or ctx.device.type != 'cuda':
       return False
     if FLAGS.dot_precision == 'simt':
       return False
@@ -115,6 +141,8 @@ class DotExpr(Expr):
     precision = FLAGS.dot_precision
     av = distarray.create(a_np.shape, np.float32, tile_hint=ea.tile_hint)
     bv = distarray.create(b_np.shape, np.float32, tile_hint=eb.tile_hint)
+    if ctx.num_workers > 1:
+      return self._evaluate_streamed_ranks(ctx, av, bv, M, N, K, precision)
     target = distarray.create((M, N), np.float32, reducer=np.add, tile_hint=self.tile_hint or (M, N))
     if av.slab is None or bv.slab is None or target.slab is None:
       raise SpartanError('streamed dot expects slab-backed arrays on a single rank')
@@ -163,6 +191,89 @@ class DotExpr(Expr):
         eval_cache.set(e.expr_id, v)
     return target
 
+  def _evaluate_streamed_ranks(self, ctx, av, bv, M, N, K, precision):
+    """The streamed dot on several GPUs (regular placement, see _regular_layout): every rank uploads only its own
+    column blocks.  Its B block goes first; A then arrives in row strips, and for each strip
+        copy stream:  H2D of the strip's owned columns
+        comm stream:  split/round the strip (sp_gemm_prepare_a_rows) and ncclAllGather the prepared strip
+        main stream:  C[strip, mine] = sum over source ranks p of  A_p[strip, :] . B[k_p, mine]   (one launch, W segments)
+    run concurrently for different strips; a finished strip of C can be read back (read_local_into) while later
+    strips are in flight.  Any other placement uploads the operands whole and takes the resident path."""
+    import torch.distributed as dist
+    ea, eb = self.matrix_a, self.matrix_b
+    a_np, b_np = ea.npa, eb.npa
+    W, me = ctx.num_workers, ctx.worker_id
+    target = distarray.create((M, N), np.float32, reducer=np.add, tile_hint=self.tile_hint or (M, N))
+    layout = _regular_layout(av, bv, target, W, M, K) \
+      if (av.slab is not None and bv.slab is not None and target.slab is not None) else None
+    if layout is not None and any(_runs(layout[1][w][1]) != layout[2][w][1] for w in range(W)):
+      layout = None                     # a rank's B columns must be exactly its C columns (the slabs are used whole)
+    if layout is None:
+      for e, v, npa in ((ea, av, a_np), (eb, bv, b_np)):
+        v.update(extent.from_shape(npa.shape), npa)
+        if e.needs_cache:
+          eval_cache.set(e.expr_id, v)
+      return Expr.evaluate(self)
+    a_axes, b_axes, c_runs = layout
+    ka, nb = av.slab.shape[1], bv.slab.shape[1]
+    main = torch.cuda.current_stream(ctx.device)
+    copy, commst = ctx.side_stream('h2d'), ctx.side_stream('dot_comm')
+    copy.wait_stream(main); commst.wait_stream(main)
+
+    def upload_cols(slab, host, r0, r1, col_intervals):
+      off = 0
+      for c0, c1 in col_intervals:
+        device_ops.upload_rect(slab[r0:r1, off:off + (c1 - c0)], host[r0:r1, c0:c1])
+        off += c1 - c0
+
+    # B[:, mine]: up first, prepared once per source rank p as the rows k_p of the transposed operand
+    with torch.cuda.stream(copy):
+      upload_cols(bv.slab, b_np, 0, K, b_axes[me][1])
+      ev_b = copy.record_event()
+    main.wait_event(ev_b)
+    pbs = []
+    for p in range(W):
+      pb = device_ops.PreparedOperand(nb, ka, precision, 'dot_ms_b%d' % p)
+      off = 0
+      for a, b in a_axes[p][1]:
+        pb.prepare_b(bv.slab[a:b, :], 0, k_offset=off)
+        off += b - a
+      pbs.append(pb)
+    ev_pb = main.record_event()
+    strip = int(FLAGS.dot_stream_strip)
+    done = []
+    for i, r0 in enumerate(range(0, M, strip)):
+      r1 = min(M, r0 + strip)
+      with torch.cuda.stream(copy):
+        upload_cols(av.slab, a_np, r0, r1, a_axes[me][1])
+        ev_a = copy.record_event()
+      mine = device_ops.PreparedOperand(r1 - r0, ka, precision, 'dot_ms_mine%d' % i)
+      nbytes = mine.buf.numel()
+      gathered = ctx.scratch(W * nbytes, 'dot_ms_gath%d' % i)[:W * nbytes]
+      with torch.cuda.stream(commst):
+        commst.wait_event(ev_a)
+        if i == 0:
+          commst.wait_event(ev_pb)        # scratch buffers recycled from an earlier evaluation: main-stream readers first
+        mine.prepare_a(av.slab[r0:r1, :], 0)
+        dist.all_gather_into_tensor(gathered, mine.buf)
+        ev_g = commst.record_event()
+      main.wait_event(ev_g)
+      views = [(gathered.data_ptr() + p * nbytes, mine.copy_stride, pbs[p].row_ptr(0), pbs[p].copy_stride, mine.Kp)
+               for p in range(W)]
+      device_ops.gemm_prepared_views(views, target.slab[r0:r1, :], False, precision)
+      ev_c = main.record_event()
+      for c0, c1 in c_runs[me][1]:
+        done.append((extent.create((r0, c0), (r1, c1), (M, N)), ev_c))
+    for arr in (av, bv, target):
+      for tid in arr.tiles.values():
+        if ctx.is_local(tid):
+          ctx.tile(tid).valid = True
+    target.block_events = done
+    for e, v in ((ea, av), (eb, bv)):
+      if e.needs_cache:
+        eval_cache.set(e.expr_id, v)
+    return target
+
   def _allgather_path(self, ctx, av, bv, target, shape, M, N, K, dtype, precision):
     """Multi-GPU fast path for the regular placement (every rank owns whole column blocks of A, B and C, e.g.
     round-robin over an evenly divisible tile grid): ONE NCCL all-gather moves the A slabs, then every rank
@@ -178,25 +289,10 @@ class DotExpr(Expr):
       return False
     if av.dtype != np.float32 or bv.dtype != np.float32:
       return False
-    a_axes, c_runs, b_axes = [], [], []
-    for w in range(W):
-      la = [ex for ex, tid in av.tiles.items() if tid.worker == w]
-      lb = [ex for ex, tid in bv.tiles.items() if tid.worker == w]
-      pa = distarray._product_layout(la, 2)
-      pb = distarray._product_layout(lb, 2)
-      rc = _owned_runs(target, w)
-      if pa is None or pb is None or rc is None or not rc[0]:
-        return False
-      if _runs(pa[0]) != [(0, M)] or _runs(pb[0]) != [(0, K)] or rc[0] != [(0, M)]:
-        return False                      # every rank must hold full columns of A and B and full-height C blocks
-      if a_axes and sum(b - a for a, b in pa[1]) != sum(b - a for a, b in a_axes[0][1]):
-        return False                      # equal slab widths (all-gather needs equal contributions)
-      # the B columns this rank needs (= its C columns) must be local to it
-      bcols = pb[1]
-      for c0, c1 in rc[1]:
-        if not any(a <= c0 and c1 <= b for a, b in _runs(bcols)):
-          return False
-      a_axes.append(pa); b_axes.append(pb); c_runs.append(rc)
+    layout = _regular_layout(av, bv, target, W, M, K)
+    if layout is None:
+      return False
+    a_axes, b_axes, c_runs = layout
     if av.slab is None or bv.slab is None or target.slab is None:
       return False
 

@@ -51,6 +51,32 @@ def _worker(rank, world, port, q):
     got = (sp.from_numpy(x, tile_hint=(128, 2048)) + sp.from_numpy(y, tile_hint=(1024, 256))).glom()
     assert np.array_equal(got, x + y)
     assert sp.ones((4096, 4096)).sum().glom() == 16777216.0
+    # dot over host operands with the upload pipelined against the contraction (per-strip prepare + all-gather + GEMM
+    # on three streams); checked against float64 and the resident multi-GPU path, through glom and block-wise read-back
+    sp.FLAGS.dot_precision = 'bf16x3'
+    for (M, K, N, hint, strip) in [(1024, 1024, 1024, (256, 256), 256), (768, 512, 1024, (128, 128), 200)]:
+      a = rng.standard_normal((M, K), dtype=np.float32); b = rng.standard_normal((K, N), dtype=np.float32)
+      sp.FLAGS.dot_stream_host_operands = False
+      want = sp.dot(sp.from_numpy(a, tile_hint=hint), sp.from_numpy(b, tile_hint=hint), tile_hint=hint).glom()
+      sp.FLAGS.dot_stream_host_operands = True; sp.FLAGS.dot_stream_min_bytes = 0; sp.FLAGS.dot_stream_strip = strip
+      c = sp.dot(sp.from_numpy(a, tile_hint=hint), sp.from_numpy(b, tile_hint=hint), tile_hint=hint).evaluate()
+      assert c.block_events, 'the streamed multi-rank path did not run'
+      out = torch.zeros((M, N), dtype=torch.float32, pin_memory=True)
+      nbytes = c.read_local_into(out.numpy())
+      torch.cuda.current_stream().synchronize()
+      assert nbytes == M * N * 4 // world
+      full = c.glom()
+      # (the resident path contracts its own K segment first, the streamed one walks the source ranks in order:
+      #  same products, different fp32 summation order)
+      ref = a.astype(np.float64) @ b.astype(np.float64)
+      assert np.abs(full - ref).max() <= 1e-5 * np.abs(ref).max()
+      assert np.abs(full - want).max() <= 2e-6 * np.abs(ref).max()
+      mine = np.zeros((M, N), bool)
+      for ex, tid in c.tiles.items():
+        if tid.worker == rank:
+          mine[ex.to_slice()] = True
+      assert np.array_equal(out.numpy()[mine], full[mine])
+    sp.FLAGS.dot_stream_min_bytes = 256 << 20; sp.FLAGS.dot_stream_strip = 4096
     # a captured evaluation (kernels + ncclAllReduce in one CUDA graph) replayed on updated inputs
     from spartan_b200.expr.base import lazify
     X = sp.from_numpy(x, tile_hint=(128, 2048)).evaluate(); Y = sp.from_numpy(y, tile_hint=(128, 2048)).evaluate()

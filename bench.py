@@ -287,7 +287,8 @@ def run_b200(args):
       e2e = {'value': flops / ms_e / 1e6, 'unit': 'GFLOP/s', 'ms_per_step': ms_e,
              'h2d_bytes_per_step': int(2 * ne * ne * 4 // world), 'd2h_bytes_per_step': int(out_bytes[0]),
              'note': 'sp.dot(sp.from_numpy(a), sp.from_numpy(b)).evaluate() + read-back of C; pinned host buffers; '
-                     'bytes are per rank'}
+                     'bytes are per rank; upload, contraction and read-back are pipelined strip by strip '
+                     '(FLAGS.dot_stream_host_operands)'}
       del a_host, b_host, out_host
 
   # ---------------- fused map+reduce workload (configs[2])
@@ -343,7 +344,7 @@ def run_b200(args):
           'roofline': {'bound': 'hbm', 'achieved': gbs / world, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                        'frac': gbs / world / peaks['hbm_gbs'],
                        'traffic': measured_traffic('stream_kernel_mapreduce_2p30') if (world == 1 and args.mr_log2 == 30) else None,
-                       'peak_source': peaks['source']},
+                       'peak_source': peaks['source'] + ' copy bandwidth (read+write); a read-only stream can exceed it'},
           'max_rel_err_vs_fp64': mr_par}
     holder.pop('rep', None)
 

@@ -17,6 +17,7 @@ class Flags(object):
     self.dot_stream_host_operands = True
     self.dot_stream_strip = 4096
     self.dot_stream_min_bytes = 256 << 20
+    self.checkpoint_path = '/tmp/spartan/checkpoint'     # config.py:96 default checkpoint directory
 
   def __repr__(self):
     return 'FLAGS(%s)' % ', '.join('%s=%r' % kv for kv in sorted(self.__dict__.items()))

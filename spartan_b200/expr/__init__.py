@@ -25,6 +25,7 @@ from .write_array import from_numpy, WriteArrayExpr
 from .slice import SliceExpr
 from .transpose import transpose, TransposeExpr
 from .reshape import reshape, ravel, ReshapeExpr
+from .fio import save, load, checkpoint, LoadExpr, CheckpointExpr
 from .program import NotDeviceMappable
 from . import local
 import sys as _sys

@@ -728,3 +728,25 @@ def test_replayable_evaluation_tracks_input_updates():
   np.testing.assert_allclose(got[0], (x2.astype(np.float64) * 2 + y).sum(axis=0), rtol=1e-5)
   Assert.all_eq(got[1], np.abs(x2 - y) * x2 + y * y)
   np.testing.assert_allclose(got[2], (x2.astype(np.float64) * y).sum(), rtol=1e-5)
+
+
+@pytest.mark.parametrize('iszip', [False, True])
+def test_save_load_checkpoint_roundtrip(tmp_path, iszip):
+  """tests/test_fio.py:24-31: save / load round trips straight out of and into HBM, the files readable by the
+  reference's loader (oracle restatement); checkpoint() writes once and load_data() restores."""
+  rng = np.random.RandomState(8)
+  x = rng.rand(300, 200).astype(np.float32)
+  t1 = sp.from_numpy(x, tile_hint=(64, 50))
+  assert sp.save(t1, 'fiotest1', str(tmp_path), iszip) is True
+  Assert.all_eq(t1.glom(), sp.load('fiotest1', str(tmp_path), iszip).glom())
+  Assert.all_eq(spartan_oracle.fio.load('fiotest1', str(tmp_path), iszip).glom(), x)
+  np.testing.assert_allclose((sp.load('fiotest1', str(tmp_path), iszip) * 2 + t1).sum(axis=0).optimized().glom(),
+                             (x.astype(np.float64) * 2 + x).sum(axis=0), rtol=1e-5)
+  old = sp.FLAGS.checkpoint_path
+  try:
+    sp.FLAGS.checkpoint_path = str(tmp_path / 'ckpt')
+    c = sp.expr.checkpoint(t1 + 1)
+    Assert.all_eq(c.glom(), x + 1)
+    Assert.all_eq(c.load_data().glom(), x + 1)
+  finally:
+    sp.FLAGS.checkpoint_path = old

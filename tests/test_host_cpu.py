@@ -279,3 +279,43 @@ def test_runtime_specialisation_compiles_without_gpu():
   if n < 0 and 'not found' in _lib.lib.sp_jit_last_log().decode():
     pytest.skip('libnvrtc not present on this machine')
   assert n > 10000, _lib.last_error()
+
+
+@pytest.mark.parametrize('W', [1, 3])
+@pytest.mark.parametrize('iszip', [False, True])
+def test_tile_files_interchange_with_the_reference_format(tmp_path, W, iszip):
+  """fio.py:46-232: arrays saved by the product load through the oracle's restatement of the reference loader and the
+  other way round, and the tile files are the same bytes (tests/test_fio.py:24-31 round trips)."""
+  from spartan_b200 import blob_ctx
+  old = blob_ctx._global_ctx[0]
+  blob_ctx.set(blob_ctx.BlobCtx(0, 1, 'cpu'))         # one product rank owns every tile here; W tiles the oracle side
+  spartan_oracle.initialize(W)
+  try:
+    rng = np.random.RandomState(3)
+    for case, (shape, hint, dtype) in enumerate([((100, 37), (16, 10), np.float32), ((50,), None, np.int64),
+                                                ((12, 8, 6), (5, 8, 3), np.float64)]):
+      x = (rng.rand(*shape) * 100).astype(dtype)
+      d1, d2 = str(tmp_path / ('product%d' % case)), str(tmp_path / ('oracle%d' % case))
+      arr = pdist.create(shape, dtype, tile_hint=hint)
+      arr.update(pex.from_shape(shape), x)
+      assert sp.save(arr, 'a', d1, iszip) is True
+      assert np.array_equal(spartan_oracle.fio.load('a', d1, iszip).glom(), x)            # product -> reference loader
+      oarr = odist.create(shape, dtype, tile_hint=hint)
+      oarr.update(oex.from_shape(shape), x)
+      assert spartan_oracle.fio.save(oarr, 'a', d2, iszip) is True
+      back = sp.load('a', d2, iszip).evaluate()                                           # reference writer -> product
+      assert back.dtype == np.dtype(dtype) and np.array_equal(back.glom(), x)
+      if hint is not None or W == 1:
+        names = sorted(os.listdir(os.path.join(d2, 'a')))
+        assert names == sorted(os.listdir(os.path.join(d1, 'a')))
+        for n in names:
+          opener = bz2_open if (iszip and n.endswith('bz2')) else open
+          assert opener(os.path.join(d1, 'a', n), 'rb').read() == opener(os.path.join(d2, 'a', n), 'rb').read(), n
+  finally:
+    blob_ctx._global_ctx[0] = old
+    blob_ctx._local.ctx = old
+
+
+def bz2_open(path, mode):
+  import bz2
+  return bz2.BZ2File(path, mode)

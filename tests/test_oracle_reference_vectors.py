@@ -304,3 +304,12 @@ def test_reshape_reference_cases():
   n1 = rng.random_sample((718,)); n2 = rng.random_sample((1, 357))
   all_eq(np.dot(np.reshape(n1, (718, 1)), n2),
          expr.dot(expr.reshape(expr.from_numpy(n1), (718, 1)), expr.from_numpy(n2)).glom(), 10e-9)
+
+
+# ---- tests/test_fio.py:24-31 (dense save / load round trips, zipped and not)
+def test_fio_reference_roundtrip(tmp_path):
+  from spartan_oracle import fio
+  t1 = expr.arange((123, 45), dtype=np.float64) if False else expr.from_numpy(np.random.RandomState(0).rand(123, 45))
+  for iszip in (False, True):
+    assert fio.save(t1, 'fiotest1', str(tmp_path), iszip) is True
+    all_eq(t1.glom(), fio.load('fiotest1', str(tmp_path), iszip).glom())

@@ -30,6 +30,15 @@ for hint in [(rows, cols), (rows, cols // 8)]:
   print(json.dumps({'case': 'sp x*y map', 'tile_hint': hint, 'ms': round(ms, 3), 'GBps': round(3 * nb / ms / 1e6, 1)}), flush=True)
   ms = timeit(lambda: (x * 2).optimized().evaluate())
   print(json.dumps({'case': 'sp x*2 map', 'tile_hint': hint, 'ms': round(ms, 3), 'GBps': round(2 * nb / ms / 1e6, 1)}), flush=True)
+  # the same steps replayed from a CUDA graph: what the kernels do without the Python host between launches
+  for name, fn, nbytes in [('x*2+y map', lambda: (x * 2 + y).optimized().evaluate(), 3 * nb),
+                           ('x*2 map', lambda: (x * 2).optimized().evaluate(), 2 * nb),
+                           ('(x*2+y).sum(0)', lambda: (x * 2 + y).sum(axis=0).optimized().evaluate(), 2 * nb),
+                           ('(x*2+y).sum()', lambda: (x * 2 + y).sum().optimized().evaluate(), 2 * nb)]:
+    rep = sp.replayable(fn)
+    ms = timeit(rep, n=20)
+    print(json.dumps({'case': 'sp replay ' + name, 'tile_hint': hint, 'ms': round(ms, 3), 'GBps': round(nbytes / ms / 1e6, 1)}), flush=True)
+    del rep
 a = torch.rand(rows, cols, device='cuda'); b = torch.rand(rows, cols, device='cuda'); c = torch.empty_like(a)
 ms = timeit(lambda: torch.add(a, b, alpha=1.0, out=c))
 print(json.dumps({'case': 'torch.add(out=)', 'ms': round(ms, 3), 'GBps': round(3 * nb / ms / 1e6, 1)}), flush=True)

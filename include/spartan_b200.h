@@ -273,6 +273,10 @@ int sp_gemm_set_chunk_kblocks(int k_blocks);
 /* Test / tuning hook: kernel variant of the tensor-core paths. 0 = choose by shape (default), 1 = one CTA per
  * 128 x 256 tile, 2 = CTA pairs (tcgen05 cta_group::2) on 256 x 256 tiles. Results are identical bit for bit. */
 int sp_gemm_set_variant(int variant);
+/* Test / tuning hook: 1 = the CTA pairs of a launch check in at every tile round (bounded wait) so their K loops stay
+ * within a few k-blocks of each other and shared operand tiles are served from L2; 0 = free running. */
+int sp_gemm_set_round_sync(int on);
+int sp_gemm_set_tuning(int sync_k_blocks, int group_m); /* extra check-ins inside a tile; tile rows per rasterisation group */
 int64_t sp_gemm_f32_workspace_bytes(int64_t M, int64_t N, int n_seg, const int64_t* seg_k, int precision);
 int sp_gemm_f32_segments(int n_seg, const sp_gemm_segment* segs, float* C, int64_t ldc, int64_t M, int64_t N,
                          int accumulate, int precision, void* workspace, int64_t workspace_bytes, void* stream);

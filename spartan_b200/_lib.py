@@ -91,6 +91,8 @@ _SIGS = {
   'sp_copy_rect': (_int, [_vp, _i64p, _vp, _i64p, _i64p, _int, _vp]),
   'sp_gemm_set_chunk_kblocks': (_int, [_int]),
   'sp_gemm_set_variant': (_int, [_int]),
+  'sp_gemm_set_round_sync': (_int, [_int]),
+  'sp_gemm_set_tuning': (_int, [_int, _int]),
   'sp_upload_2d': (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _vp]),
   'sp_download_2d': (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _vp]),
   'sp_gemm_kpad': (_i64, [_i64, _int]),

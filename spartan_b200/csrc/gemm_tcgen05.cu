@@ -84,6 +84,11 @@ struct Params {
   const float* col_bias;
   float* part_val;
   int* part_idx;
+  // pair kernel: round counter that keeps the clusters' K loops within a few k-blocks of each other, so that the operand
+  // tiles several clusters share are still in L2 when the next one asks for them (nullptr = free running)
+  unsigned int* round_sync;
+  int sync_kb;           // additional check-ins every sync_kb k-blocks inside a tile (0 = only at tile starts)
+  int group_m;           // tile rasterisation: tile rows per group
 };
 
 // ----------------------------------------------------------------------------
@@ -263,14 +268,26 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt, int m, int n) {
          (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
-__device__ __forceinline__ void tile_coords(int tile, int m_blocks, int n_blocks, int& m_blk, int& n_blk) {
-  const int tiles_per_group = GROUP_M * n_blocks;
+__device__ __forceinline__ void tile_coords(int tile, int m_blocks, int n_blocks, int group_m, int& m_blk, int& n_blk) {
+  const int tiles_per_group = group_m * n_blocks;
   const int group = tile / tiles_per_group;
-  const int first_m = group * GROUP_M;
-  const int rows_in_group = min(GROUP_M, m_blocks - first_m);
+  const int first_m = group * group_m;
+  const int rows_in_group = min(group_m, m_blocks - first_m);
   const int in_group = tile - group * tiles_per_group;
   m_blk = first_m + in_group % rows_in_group;
   n_blk = in_group / rows_in_group;
+}
+
+// One check-in of the soft round barrier: `participants` clusters pass this point; wait (bounded) until all have.
+__device__ __forceinline__ void round_checkin(unsigned int* counter, unsigned int& target, int participants) {
+  target += static_cast<unsigned int>(participants);
+  atomicAdd(counter, 1u);
+  for (int spin = 0; spin < 20000; ++spin) {
+    unsigned int seen;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    if (seen >= target) break;
+    __nanosleep(64);
+  }
 }
 
 // ----------------------------------------------------------------------------
@@ -348,13 +365,22 @@ gemm_kernel(const __grid_constant__ Params p) {
       if (lane == 0) {
         int stage = 0;
         uint32_t phase = 0;
+        unsigned int round_target = 0;
         for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
           int m_blk, n_blk;
-          tile_coords(tile, m_tiles, p.n_blocks, m_blk, n_blk);
+          tile_coords(tile, m_tiles, p.n_blocks, p.group_m, m_blk, n_blk);
+          if constexpr (PAIR) {
+            // Soft round barrier (leaders only; the peer is throttled through the ring): every cluster with a tile in
+            // this round checks in, then waits -- for a bounded time, so nothing can deadlock -- until all have.
+            if (p.round_sync != nullptr && rank == 0 && tile != first_tile)
+              round_checkin(p.round_sync, round_target, min(tile_step, num_tiles - (tile - first_tile)));
+          }
           for (int s = 0; s < p.n_segs; ++s) {
             const Segment seg = p.segs[s];
             for (int kb = 0; kb < seg.k_blocks; ++kb) {
               if constexpr (PAIR) {
+                if (p.round_sync != nullptr && rank == 0 && p.sync_kb > 0 && kb > 0 && kb % p.sync_kb == 0)
+                  round_checkin(p.round_sync, round_target, min(tile_step, num_tiles - (tile - first_tile)));
                 mbar_wait(empty_bar(stage), phase ^ 1);
                 // the leader's barrier counts the bytes of both CTAs' loads of this stage
                 if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * stage_bytes);
@@ -470,7 +496,7 @@ gemm_kernel(const __grid_constant__ Params p) {
     uint32_t acc_phase = 0;
     for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
       int m_blk, n_blk;
-      tile_coords(tile, m_tiles, p.n_blocks, m_blk, n_blk);
+      tile_coords(tile, m_tiles, p.n_blocks, p.group_m, m_blk, n_blk);
       if constexpr (PAIR) m_blk = m_blk * 2 + static_cast<int>(rank);     // this CTA's 128-row block
       float sum[128];
 #pragma unroll
@@ -675,6 +701,10 @@ static bool mode_of(int precision, Mode* m) {
 
 static int g_chunk_override = 0;
 static int g_variant = 0;      // 0: choose, 1: one CTA per tile, 2: CTA pairs
+static int g_sync_kb = 0;
+static int g_group_m = 8;       // 256-row tile rows per rasterisation group (pair kernel); the one-CTA kernel uses twice as many 128-row blocks
+static int g_round_sync = 1;   // pair kernel: keep the clusters' tile rounds in step (L2 reuse of shared operand tiles)
+static unsigned int* g_round_counter = nullptr;
 
 }  // namespace gemm
 }  // namespace sp
@@ -693,6 +723,19 @@ extern "C" int sp_gemm_set_chunk_kblocks(int kb) {
 extern "C" int sp_gemm_set_variant(int variant) {
   SP_REQUIRE(variant >= 0 && variant <= 2, SP_ERR_INVALID, "bad gemm variant %d", variant);
   g_variant = variant;
+  return SP_OK;
+}
+
+// Test / tuning hook: 1 = the CTA pairs of one launch start every tile round together (soft barrier), 0 = free running.
+extern "C" int sp_gemm_set_round_sync(int on) {
+  g_round_sync = on ? 1 : 0;
+  return SP_OK;
+}
+// Test / tuning hooks: extra check-ins every `sync_kb` k-blocks (0 = tile starts only); tile rows per rasterisation group.
+extern "C" int sp_gemm_set_tuning(int sync_kb, int group_m) {
+  SP_REQUIRE(sync_kb >= 0 && group_m >= 1 && group_m <= 1024, SP_ERR_INVALID, "bad tuning values");
+  g_sync_kb = sync_kb;
+  g_group_m = group_m;
   return SP_OK;
 }
 
@@ -873,12 +916,19 @@ static int launch_prepared(int n_seg, const sp_gemm_prepared_view* segs, float* 
   p.accumulate = accumulate;
   p.C = C;
   p.ldc = ldc;
+  p.group_m = pair ? g_group_m : 2 * g_group_m;
+  p.sync_kb = g_sync_kb;
   p.epi_mode = epi_mode;
   p.col_bias = col_bias;
   p.part_val = part_val;
   p.part_idx = part_idx;
   if (pair) {
     const int tiles = (p.m_blocks + 1) / 2 * p.n_blocks;
+    if (g_round_sync && tiles > max_clusters) {
+      if (g_round_counter == nullptr) SP_CUDA_CHECK(cudaMalloc(&g_round_counter, sizeof(unsigned int)));
+      SP_CUDA_CHECK(cudaMemsetAsync(g_round_counter, 0, sizeof(unsigned int), stream));
+      p.round_sync = g_round_counter;
+    }
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;

@@ -750,3 +750,28 @@ def test_save_load_checkpoint_roundtrip(tmp_path, iszip):
     Assert.all_eq(c.load_data().glom(), x + 1)
   finally:
     sp.FLAGS.checkpoint_path = old
+
+
+def test_gemm_round_sync_is_bit_identical():
+  """The soft round barrier of the CTA-pair GEMM (clusters check in at every tile round so shared operand tiles stay in
+  L2) only changes WHEN tiles start: more tiles than clusters, ragged edges, accumulate -- same bits with it on and off."""
+  import torch
+  from spartan_b200 import device_ops, blob_ctx
+  from spartan_b200._lib import lib, check
+  ctx = blob_ctx.get()
+  g = torch.Generator(device='cpu'); g.manual_seed(5)
+  M, N, K = 3000, 3500, 700
+  A = torch.randn(M, K, generator=g).to(ctx.device); B = torch.randn(K, N, generator=g).to(ctx.device)
+  C0 = torch.randn(M, N, generator=g).to(ctx.device)
+  out = {}
+  try:
+    for on in (0, 1):
+      check(lib.sp_gemm_set_round_sync(on), 'sp_gemm_set_round_sync')
+      C = C0.clone()
+      device_ops.gemm([(A, B)], C, accumulate=True, precision='bf16x3')
+      out[on] = C.cpu().numpy()
+  finally:
+    check(lib.sp_gemm_set_round_sync(1), 'sp_gemm_set_round_sync')
+  Assert.all_eq(out[0], out[1])
+  ref = C0.double().cpu().numpy() + A.double().cpu().numpy() @ B.double().cpu().numpy()
+  assert np.abs(out[1] - ref).max() <= 1e-5 * np.abs(ref).max()

@@ -191,6 +191,7 @@ stream_kernel(const DevProgram<T> prog, const DevOperands<NI> ops, const Plan pl
         const int rows = static_cast<int>(min(static_cast<int64_t>(rb), row_end - row0));
         mbar_wait(full_bar(stage), phase);
         const uint8_t* sbase = smem_gen + stage * stage_bytes;
+        bool released = false;
         for (int item = cw; item < rows * kSegsPerPanel; item += kConsumerWarps) {
           const int r = item / kSegsPerPanel;                // item % kSegsPerPanel == q for every item of this warp
           T in[NI][V];
@@ -213,6 +214,13 @@ stream_kernel(const DevProgram<T> prog, const DevOperands<NI> ops, const Plan pl
                                         in[i]);
               }
             }
+          }
+          // The operands of this warp's last item of the stage are in registers: hand the stage back to the producer
+          // now, so the refill is in flight while the program runs and the results are stored.
+          if (item + kConsumerWarps >= rows * kSegsPerPanel) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_bar(stage));
+            released = true;
           }
           T res[V], idx[V];
           if (prog.uses_index) {       // two halves of the lane's vector sit EPS/2 elements apart
@@ -238,8 +246,10 @@ stream_kernel(const DevProgram<T> prog, const DevOperands<NI> ops, const Plan pl
             for (int v = 0; v < V; ++v) acc[v] = red_apply<T>(red_op, acc[v], res[v]);
           }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty_bar(stage));
+        if (!released) {               // a warp without an item in this stage
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty_bar(stage));
+        }
         if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
       if (MODE == 1) {

@@ -149,8 +149,17 @@ class DotExpr(Expr):
     pa = device_ops.PreparedOperand(M, K, precision, 'dot_stream_a')
     pb = device_ops.PreparedOperand(N, K, precision, 'dot_stream_b')
     strip = int(FLAGS.dot_stream_strip)
-    ra = [(r, min(M, r + strip)) for r in range(0, M, strip)]
-    cb = [(c, min(N, c + strip)) for c in range(0, N, strip)]
+
+    def strips(n):
+      # equal strips, the last one halved: what can only start after the final byte has arrived (and must be read back
+      # after the final launch) is half as large
+      out = [(r, min(n, r + strip)) for r in range(0, n, strip)]
+      lo, hi = out[-1]
+      if len(out) > 1 and hi - lo >= 1024:
+        mid = lo + ((hi - lo) // 2 + 255) // 256 * 256
+        out[-1:] = [(lo, mid), (mid, hi)]
+      return out
+    ra, cb = strips(M), strips(N)
     main = torch.cuda.current_stream(ctx.device)
     copy = ctx.side_stream('h2d')
     copy.wait_stream(main)              # recycled allocations may still be in use by work queued on the main stream
@@ -181,7 +190,13 @@ class DotExpr(Expr):
       if ev_b is not None:
         main.wait_event(ev_b)
         pb.prepare_b(bv.slab[:, c0:c1], c0)
-        contract(0, ra[min(s, len(ra) - 1)][1], c0, c1)         # rows whose strips (<= s) are prepared
+        rows = ra[min(s, len(ra) - 1)][1]                       # rows whose strips (<= s) are prepared
+        if s == max(len(ra), len(cb)) - 1 and rows >= 2048:
+          half = (rows // 2 + 255) // 256 * 256                 # final launch in two: read-back of the first half overlaps
+          contract(0, half, c0, c1)
+          contract(half, rows, c0, c1)
+        else:
+          contract(0, rows, c0, c1)
     for arr in (av, bv, target):
       for tid in arr.tiles.values():
         ctx.tile(tid).valid = True

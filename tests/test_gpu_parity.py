@@ -516,7 +516,7 @@ def test_gemm_cta_pair_matches_single_cta(M, N, K):
 
 
 @pytest.mark.parametrize('M,N,K,strip', [(1024, 768, 512, 256), (700, 900, 333, 256), (512, 2048, 640, 512),
-                                         (2048, 300, 1000, 512)])
+                                         (2048, 300, 1000, 512), (2304, 4400, 300, 1024)])
 @pytest.mark.parametrize('prec', ['bf16x3', 'tf32x3'])
 def test_streamed_dot_matches_resident(M, N, K, strip, prec):
   """dot(from_numpy(a), from_numpy(b)) with the PCIe upload pipelined against the contraction (strips of A rows /

@@ -278,16 +278,22 @@ __device__ __forceinline__ void tile_coords(int tile, int m_blocks, int n_blocks
   n_blk = in_group / rows_in_group;
 }
 
-// One check-in of the soft round barrier: `participants` clusters pass this point; wait (bounded) until all have.
-__device__ __forceinline__ void round_checkin(unsigned int* counter, unsigned int& target, int participants) {
+// One check-in of the soft round barrier: `participants` clusters pass this point; wait until all have -- for at most
+// ~100 us (in step, clusters arrive within a few us of each other).  A cluster that times out stops waiting for the rest
+// of the launch (it keeps checking in): when not every cluster of the grid is resident -- another kernel, e.g. an NCCL
+// collective, holds some SMs -- the barrier costs one time-out per cluster instead of one per round, and nothing can
+// deadlock.
+__device__ __forceinline__ void round_checkin(unsigned int* counter, unsigned int& target, int participants, bool& wait) {
   target += static_cast<unsigned int>(participants);
   atomicAdd(counter, 1u);
-  for (int spin = 0; spin < 20000; ++spin) {
+  if (!wait) return;
+  for (int spin = 0; spin < 160; ++spin) {
     unsigned int seen;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
-    if (seen >= target) break;
-    __nanosleep(64);
+    if (seen >= target) return;
+    __nanosleep(256);
   }
+  wait = false;
 }
 
 // ----------------------------------------------------------------------------
@@ -366,6 +372,7 @@ gemm_kernel(const __grid_constant__ Params p) {
         int stage = 0;
         uint32_t phase = 0;
         unsigned int round_target = 0;
+        bool round_wait = true;
         for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
           int m_blk, n_blk;
           tile_coords(tile, m_tiles, p.n_blocks, p.group_m, m_blk, n_blk);
@@ -373,14 +380,14 @@ gemm_kernel(const __grid_constant__ Params p) {
             // Soft round barrier (leaders only; the peer is throttled through the ring): every cluster with a tile in
             // this round checks in, then waits -- for a bounded time, so nothing can deadlock -- until all have.
             if (p.round_sync != nullptr && rank == 0 && tile != first_tile)
-              round_checkin(p.round_sync, round_target, min(tile_step, num_tiles - (tile - first_tile)));
+              round_checkin(p.round_sync, round_target, min(tile_step, num_tiles - (tile - first_tile)), round_wait);
           }
           for (int s = 0; s < p.n_segs; ++s) {
             const Segment seg = p.segs[s];
             for (int kb = 0; kb < seg.k_blocks; ++kb) {
               if constexpr (PAIR) {
                 if (p.round_sync != nullptr && rank == 0 && p.sync_kb > 0 && kb > 0 && kb % p.sync_kb == 0)
-                  round_checkin(p.round_sync, round_target, min(tile_step, num_tiles - (tile - first_tile)));
+                  round_checkin(p.round_sync, round_target, min(tile_step, num_tiles - (tile - first_tile)), round_wait);
                 mbar_wait(empty_bar(stage), phase ^ 1);
                 // the leader's barrier counts the bytes of both CTAs' loads of this stage
                 if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * stage_bytes);

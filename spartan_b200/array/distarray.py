@@ -23,7 +23,7 @@ import torch
 from . import extent, tile
 from .. import blob_ctx, comm, device_ops
 from .._lib import lib, check, i64arr, SpartanError
-from ..core import TileId, LocalKernelResult
+from ..core import TileId
 from ..util import Assert
 
 DEFAULT_TILE_SIZE = 100000   # distarray.py:20

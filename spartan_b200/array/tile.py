@@ -8,10 +8,9 @@ reduce" rule (tile.pyx:250-283) for every combiner it uses (add, multiply, minim
 logical_and, logical_or).
 """
 import numpy as np
-import torch
 
 from .. import device_ops
-from .._lib import SpartanError, SP_RED_SUM, SP_RED_MIN, SP_RED_MAX, SP_RED_PROD, SP_RED_ALL, SP_RED_ANY, SP_FILL_CONST
+from .._lib import SpartanError, SP_RED_SUM, SP_RED_MIN, SP_RED_MAX, SP_RED_PROD, SP_RED_ALL, SP_RED_ANY
 
 TYPE_EMPTY, TYPE_DENSE, TYPE_MASKED, TYPE_SPARSE = 0, 1, 2, 3
 

@@ -84,7 +84,8 @@ extern "C" int sp_extent_drop_axis(int ndim, const int64_t* ul, const int64_t* l
 extern "C" int64_t sp_extent_to_global(int ndim, const int64_t* ul, const int64_t* lr, const int64_t* array_shape,
                                        int64_t idx, int axis) {
   if (axis != SP_AXIS_NONE) return idx + ul[axis];
-  int64_t shape[SP_MAX_DIM], local[SP_MAX_DIM], glob[SP_MAX_DIM];
+  if (ndim < 0 || ndim > SP_MAX_DIM) return -1;
+  int64_t shape[SP_MAX_DIM] = {0}, local[SP_MAX_DIM] = {0}, glob[SP_MAX_DIM] = {0};
   for (int i = 0; i < ndim; ++i) {
     shape[i] = lr[i] - ul[i];
     if (shape[i] == 0) shape[i] = 1;   // extent.pyx:66-72

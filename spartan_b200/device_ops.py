@@ -12,7 +12,7 @@ import torch
 from . import blob_ctx
 from ._lib import (lib, check, sp_program, sp_operand, sp_gemm_segment, sp_gemm_prepared_segment, sp_gemm_prepared_view, i64arr, SpartanError, OP,
                    SP_F32, SP_F64, SP_I32, SP_I64, SP_U8, SP_BOOL, SP_RED_SUM, SP_RED_MIN, SP_RED_MAX, SP_RED_PROD,
-                   SP_RED_ALL, SP_RED_ANY, SP_FILL_CONST, SP_FILL_IOTA, SP_FILL_RAND, SP_FILL_RANDN,
+                   SP_RED_ALL, SP_RED_ANY,
                    SP_GEMM_TF32X1, SP_GEMM_TF32X3, SP_GEMM_SIMT, SP_GEMM_BF16X3, SP_GEMM_MAX_SEGMENTS)
 
 _SP_DTYPE = {torch.float32: SP_F32, torch.float64: SP_F64, torch.int32: SP_I32, torch.int64: SP_I64,

@@ -9,7 +9,7 @@ SURVEY.md section 9 Q7).  Empty clusters are re-seeded on the host exactly like 
 import numpy as np
 import torch
 
-from .. import blob_ctx, comm, device_ops
+from .. import blob_ctx, comm
 from .._lib import lib, check, SP_RED_SUM, SpartanError
 from ..array import distarray, extent
 from ..expr.base import Expr, evaluate

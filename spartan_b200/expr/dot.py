@@ -18,7 +18,7 @@ summation order is fixed.
 import numpy as np
 import torch
 
-from .. import blob_ctx, comm, device_ops
+from .. import blob_ctx, device_ops
 from ..array import distarray, extent
 from ..config import FLAGS
 from .._lib import SpartanError

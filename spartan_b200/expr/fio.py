@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from .. import blob_ctx, comm, device_ops
-from ..array import distarray, extent
+from ..array import distarray
 from ..config import FLAGS
 from .._lib import SpartanError
 from .base import Expr, lazify, evaluate

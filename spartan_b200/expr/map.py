@@ -7,15 +7,10 @@ with one NumPy call (and one temporary) per node, the tree is compiled once per 
 (program.py) and each tile is ONE launch of the fused CUDA map kernel writing straight into the
 output tile in HBM.
 """
-import collections
-
-import numpy as np
-
 from .. import blob_ctx, device_ops, util
-from ..array import distarray, extent
+from ..array import distarray
 from ..array.distarray import Broadcast, broadcast, LocalWrapper
 from ..core import LocalKernelResult
-from ..util import Assert
 from . import program
 from .base import ListExpr, Expr, as_array
 from .local import LocalInput, LocalMapExpr, LocalMapLocationExpr, make_var

@@ -2,7 +2,7 @@
 import numpy as np
 
 from ..array import distarray
-from .base import Expr, expr_like
+from .base import Expr
 
 
 class NdArrayExpr(Expr):

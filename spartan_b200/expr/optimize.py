@@ -6,12 +6,10 @@ CollapsedCachedExpressions.  A map is only fused into its consumer if its local 
 device (program.tree_is_mappable); otherwise it stays a separate node, exactly like an un-fusable
 child in the reference.
 """
-from .. import util
 from ..config import FLAGS
-from ..util import Assert
 from . import program
 from .base import Expr, Val, AsArray, ListExpr, expr_like
-from .local import LocalInput, LocalMapExpr, LocalMapLocationExpr, LocalReduceExpr, make_var
+from .local import LocalInput, LocalMapLocationExpr, LocalReduceExpr, make_var
 from .map import MapExpr
 from .ndarray import NdArrayExpr
 from .reduce import ReduceExpr

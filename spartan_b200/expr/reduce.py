@@ -14,9 +14,9 @@ import numpy as np
 
 from .. import blob_ctx, comm, device_ops
 from ..array import distarray, extent, tile
-from ..array.distarray import Broadcast, broadcast
+from ..array.distarray import broadcast
 from ..core import LocalKernelResult
-from .._lib import SpartanError, SP_FILL_CONST, SP_F64, SP_I64
+from .._lib import SP_F64, SP_I64
 from . import program
 from .base import Expr, ListExpr, as_array
 from .local import make_var, LocalReduceExpr, LocalInput

@@ -1,7 +1,8 @@
 """Definitions of expressions and optimisations (reference: spartan/expr/__init__.py:26-142)."""
 from .builtins import astype, size
 from .builtins import empty, empty_like
-from .builtins import zeros, zeros_like, ones, ones_like, full, full_like, arange
+from .builtins import zeros, zeros_like, ones, ones_like, full, full_like, arange, eye, identity
+from .diag import diagonal, diagflat, diag, DiagonalExpr, DiagFlatExpr
 from .builtins import all, any, equal, not_equal, greater, greater_equal, less, less_equal
 from .builtins import logical_and, logical_or, logical_xor
 from .builtins import add, sub, multiply, divide, true_divide, floor_divide
@@ -9,7 +10,7 @@ from .builtins import reciprocal, negative, fmod, mod, remainder
 from .builtins import power, ln, log, square, sqrt, exp
 from .builtins import abs, maximum, minimum, sum, prod
 from .builtins import rand, randn
-from .builtins import max, min, mean
+from .builtins import max, min, mean, std
 from .builtins import count_nonzero, count_zero, argmin, argmax
 from .dot import dot, DotExpr
 
@@ -44,6 +45,8 @@ Expr.max = max
 Expr.mean = mean
 Expr.min = min
 Expr.prod = prod
+Expr.std = std
+Expr.diagonal = diagonal
 Expr.sum = sum
 Expr.ravel = ravel
 Expr.flatten = ravel

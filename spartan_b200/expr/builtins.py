@@ -11,7 +11,7 @@ import numpy as np
 from .. import blob_ctx, device_ops
 from ..array import extent
 from .._lib import (SP_RED_SUM, SP_RED_MIN, SP_RED_MAX, SP_RED_PROD, SP_RED_ALL, SP_RED_ANY, SP_FILL_CONST,
-                    SP_FILL_IOTA, SP_FILL_RAND, SP_FILL_RANDN, SpartanError)
+                    SP_FILL_IOTA, SP_FILL_RAND, SP_FILL_RANDN, SP_I64, SpartanError)
 from . import program
 from .base import Expr
 from .map import map, map_with_location
@@ -84,6 +84,34 @@ def full(shape, fill_value, dtype=np.float32, tile_hint=None):
 def full_like(array, fill_value, dtype=None, tile_hint=None):
   return full(array.shape, fill_value, array.dtype if dtype is None else dtype,
               _hint_of(array) if tile_hint is None else tile_hint)
+
+
+def _eye_mapper(tile, ex, k=None, dtype=None):
+  """creation.py:51-53 (host form, never called)."""
+  raise SpartanError('host evaluation is not available')
+
+
+def _eye_kernel(out, ex, k=None, dtype=None):
+  """Tile of np.eye: 1 where (global column - global row) == k.  The reference offsets the tile's k by its first ROW only
+  (creation.py:52), which is right for the row tilings it produces by default; the column offset is honoured here too."""
+  prog = device_ops.make_program([('INDEX', 0), ('CONST', 0), ('EQ', 0)], SP_I64, [0])
+  device_ops.run_map(prog, [], out, index=(int(ex.ul[1]) - int(ex.ul[0]) - int(k or 0), [-1, 1]))
+
+
+_eye_mapper.device_location_kernel = _eye_kernel
+_eye_mapper.result_dtype = lambda in_dtype, kw: np.dtype(kw.get('dtype') or in_dtype)
+
+
+def eye(N, M=None, k=0, dtype=np.float32, tile_hint=None):
+  """creation.py:56-60."""
+  if M is None:
+    M = N
+  return map_with_location(ndarray((N, M), dtype, tile_hint), _eye_mapper, fn_kw={'k': k, 'dtype': dtype})
+
+
+def identity(n, dtype=np.float32, tile_hint=None):
+  """creation.py:63-64."""
+  return eye(n, dtype=dtype, tile_hint=tile_hint)
 
 
 def _arange_mapper(tile, ex, start, stop, step, dtype=None):
@@ -303,6 +331,12 @@ def mean(x, axis=None):
   if axis is None:
     return true_divide(sum(x, axis), float(np.prod(x.shape)))
   return true_divide(sum(x, axis), float(x.shape[axis]))
+
+
+def std(a, axis=None):
+  """Standard deviation (statistics.py:86-102): sqrt(mean(a**2) - mean(a)**2) in float64, like the reference."""
+  a_casted = astype(a, np.float64)
+  return sqrt(sub(mean(power(a_casted, 2), axis), power(mean(a_casted, axis), 2)))
 
 
 # ------------------------------------------------------------------------------------ logic.py

@@ -775,3 +775,40 @@ def test_gemm_round_sync_is_bit_identical():
   Assert.all_eq(out[0], out[1])
   ref = C0.double().cpu().numpy() + A.double().cpu().numpy() @ B.double().cpu().numpy()
   assert np.abs(out[1] - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+# ------------------------------------------------------------------ tests/test_creation.py:10-16,65-92, test_statistics.py:32-70
+@pytest.mark.parametrize('hint', [None, (16, 4), (7, 10)])
+def test_eye_identity_diag(hint):
+  """eye / identity as an extent-aware fill (INDEX leaf), diagonal / diagflat / diag as strided rectangle copies."""
+  Assert.all_eq(sp.eye(100, 10, tile_hint=hint).glom(), np.eye(100, 10))
+  Assert.all_eq(sp.eye(40, 60, k=3, tile_hint=hint).glom(), np.eye(40, 60, k=3))
+  Assert.all_eq(sp.eye(40, 60, k=-5, dtype=np.float64, tile_hint=hint).glom(), np.eye(40, 60, k=-5))
+  Assert.all_eq(sp.identity(100).glom(), np.identity(100))
+  got, want = both(lambda m: m.eye(100, 10))
+  Assert.all_eq(got, want)
+  rng = np.random.RandomState(2)
+  for shp in ((2, 2), (15, 10), (16, 16), (10, 33)):
+    x = rng.randn(*shp)
+    Assert.all_eq(sp.diagonal(sp.from_numpy(x, tile_hint=hint if hint and shp[0] > 2 else None)).glom(), np.diagonal(x))
+    Assert.all_eq(oexpr.diagonal(oexpr.from_numpy(x)).glom(), np.diagonal(x))
+  x = rng.randn(57, 57)
+  Assert.all_eq(sp.diag(sp.from_numpy(x)).glom(), np.diag(x))
+  Assert.all_eq(sp.diag(sp.diag(sp.from_numpy(x))).glom(), np.diag(np.diag(x)))
+  xf = rng.randn(300).astype(np.float32)
+  Assert.all_eq(sp.diagflat(sp.from_numpy(xf, tile_hint=(64,)), tile_hint=(128, 100)).glom(), np.diagflat(xf))
+
+
+def test_std_reference_cases():
+  rng = np.random.RandomState(4)
+  for shp in ((10,), (10, 10), (17, 17)):
+    x = rng.randn(*shp)
+    got, want = both(lambda m: m.std(m.from_numpy(x)))
+    assert abs(got - np.std(x)) < 1e-6 and abs(got - want) < 1e-6       # Assert.float_close
+  for shp in ((10, 10), (15, 13), (13, 15), (17, 17)):
+    x = rng.randn(*shp)
+    for axis in (0, 1):
+      got, want = both(lambda m: m.std(m.from_numpy(x), axis))
+      assert np.allclose(got, np.std(x, axis)) and np.allclose(got, want)
+  xb = rng.rand(600, 4096).astype(np.float32)
+  np.testing.assert_allclose(sp.std(sp.from_numpy(xb, tile_hint=(128, 4096)), 0).optimized().glom(), np.std(xb.astype(np.float64), 0), rtol=1e-6)

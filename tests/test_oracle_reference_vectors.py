@@ -313,3 +313,30 @@ def test_fio_reference_roundtrip(tmp_path):
   for iszip in (False, True):
     assert fio.save(t1, 'fiotest1', str(tmp_path), iszip) is True
     all_eq(t1.glom(), fio.load('fiotest1', str(tmp_path), iszip).glom())
+
+
+# ---- tests/test_creation.py:10-16 (eye / identity), :65-92 (diagonal / diag)
+def test_creation_eye_diag_reference_cases():
+  all_eq(expr.eye(100, 10).glom(), np.eye(100, 10))
+  all_eq(expr.identity(100).glom(), np.identity(100))
+  rng = np.random.RandomState(2)
+  for shp in ((2, 2), (15, 10), (16, 16)):
+    x = rng.randn(*shp)
+    all_eq(expr.diagonal(expr.from_numpy(x)).glom(), np.diagonal(x))
+  dim = random.randint(1, 99)
+  x = rng.randn(dim, dim)
+  all_eq(expr.diag(expr.from_numpy(x)).glom(), np.diag(x))
+  all_eq(expr.diag(expr.diag(expr.from_numpy(x))).glom(), np.diag(np.diag(x)))
+
+
+# ---- tests/test_statistics.py:32-70 (std; Assert.float_close / all_close)
+def test_std_reference_cases():
+  rng = np.random.RandomState(4)
+  for shp in ((10,), (10, 10), (17, 17)):
+    x = rng.randn(*shp)
+    assert abs(expr.std(expr.from_numpy(x)).glom() - np.std(x)) < 1e-6
+  for shp in ((10, 10), (15, 13), (13, 15), (17, 17)):
+    x = rng.randn(*shp)
+    sx = expr.from_numpy(x)
+    assert np.allclose(expr.std(sx, 0).glom(), np.std(x, 0))
+    assert np.allclose(expr.std(sx, 1).glom(), np.std(x, 1))

@@ -165,6 +165,39 @@ def run_reference(args):
   print(json.dumps(out), flush=True)
 
 
+def cpu_map_reduce_baseline(log2_elems=27, tiles=8):
+  """The reference's CPU path for configs[2] on a bounded sample: per row tile the NumPy chain of tile_mapper +
+  _reduce_mapper ((x*2) -> (+y) -> .sum(axis=0), one temporary per ufunc; map.py:48-88, reduce.py:21-70), tiles evaluated
+  by a pool of `tiles` threads (emulates num_workers=8; NumPy releases the GIL), partials merged with np.add
+  (tile.pyx:263-283)."""
+  from concurrent.futures import ThreadPoolExecutor
+  cols = 32768
+  rows = (1 << log2_elems) // cols
+  rng = np.random.default_rng(2)
+  x = rng.random((rows, cols), dtype=np.float32); y = rng.random((rows, cols), dtype=np.float32)
+  trow = rows // tiles
+
+  def tile_fn(i):
+    xs, ys = x[i * trow:(i + 1) * trow], y[i * trow:(i + 1) * trow]
+    return (xs * np.float32(2) + ys).sum(axis=0)
+
+  def run(pool):
+    parts = list(pool.map(tile_fn, range(tiles))) if pool else [tile_fn(i) for i in range(tiles)]
+    out = parts[0]
+    for p in parts[1:]:
+      out = np.add(out, p)
+    return out
+  nbytes = 2.0 * 4.0 * rows * cols
+  t0 = time.perf_counter(); run(None); t_single = time.perf_counter() - t0
+  with ThreadPoolExecutor(tiles) as pool:
+    run(pool)
+    t0 = time.perf_counter(); run(pool); t_pool = time.perf_counter() - t0
+  return {'value': nbytes / t_pool / 1e9, 'unit': 'GB/s', 'cores': min(tiles, os.cpu_count() or 1), 'kind': 'port',
+          'single_thread_gbs': nbytes / t_single / 1e9,
+          'sample': '(x*2+y).sum(axis=0) over 2^%d fp32 elements in %d row tiles, NumPy ufunc chain per tile, '
+                    '%d tile threads' % (log2_elems, tiles, tiles)}
+
+
 # ----------------------------------------------------------------------------------------------- b200 arm
 def timed(fn, steps, warmup, sync, maxreduce):
   import torch
@@ -347,6 +380,8 @@ def run_b200(args):
                        'peak_source': peaks['source'] + ' copy bandwidth (read+write); a read-only stream can exceed it'},
           'max_rel_err_vs_fp64': mr_par}
     holder.pop('rep', None)
+    if rank == 0 and world == 1 and not args.skip_cpu:
+      mr['cpu_baseline'] = cpu_map_reduce_baseline()
 
   # ---------------- CPU baseline (rank 0, N=1): the oracle's np.dot on a bounded sample
   cpu = None

@@ -69,6 +69,35 @@ def _worker(rank, world, port, q):
     flags = torch.tensor([rank == 0, True, False])
     comm.allreduce(flags, _lib.SP_RED_ANY); assert flags.tolist() == [True, True, False]
 
+    # 3b. tile files: every rank writes / reads only the tiles it owns, rank 0 writes the array-wide file; the result
+    # loads identically on both ranks and through the oracle's restatement of the reference loader
+    import tempfile
+    from spartan_oracle import fio as ofio
+    import spartan_oracle
+    spartan_oracle.initialize(world)
+    base = [tempfile.mkdtemp(prefix='sp_fio_') if rank == 0 else None]
+    dist.broadcast_object_list(base, src=0)
+    for iszip in (False, True):
+      x = rng.randn(70, 33).astype(np.float32)
+      arr = sp.from_numpy(x, tile_hint=(16, 33)).evaluate()
+      assert sp.save(arr, 'w2', base[0], iszip) is True
+      names = sorted(n for n in os.listdir(os.path.join(base[0], 'w2')) if n.endswith('bz2') == iszip and 'dist' not in n)
+      assert len(names) == len(arr.tiles), names              # one file per tile, written by its owner
+      assert np.array_equal(sp.load('w2', base[0], iszip).glom(), x)
+      assert np.array_equal(ofio.load('w2', base[0], iszip).glom(), x)
+      dist.barrier()
+
+    # 3c. views: both ranks derive the same view tile tables, and every view tile lives on the rank of the base tile
+    from spartan_b200.array import views
+    arr = distarray.create((64, 48), np.float32, tile_hint=(16, 16))
+    for v in (views.Slice(arr, np.index_exp[5:40, 10:33]), views.Transpose(arr), views.Reshape(arr, (48, 64)),
+              views.Reshape(arr, (64, 48, 1))):
+      table = [(e.ul, e.lr, tuple(e.array_shape), t.worker) for e, t in v.tiles.items()]
+      gathered = [None] * world
+      dist.all_gather_object(gathered, table)
+      assert all(g == gathered[0] for g in gathered), 'ranks disagree on a view tile table'
+      assert all(0 <= w < world for _, _, _, w in table)
+
     # 4. compute without a GPU must fail loudly on every rank, not fall back
     try:
       (sp.from_numpy(np.ones((4, 4), np.float32)) + 1).glom()

@@ -319,3 +319,70 @@ def test_tile_files_interchange_with_the_reference_format(tmp_path, W, iszip):
 def bz2_open(path, mode):
   import bz2
   return bz2.BZ2File(path, mode)
+
+
+def test_view_fetch_semantics_match_numpy_on_host_tensors():
+  """The extent translation of Slice / Transpose / Reshape (and Expr.__getitem__ shapes) against NumPy on random cases.
+  With one rank every fetch is a zero-copy torch view of the slab, so this runs on CPU tensors without any kernel."""
+  from spartan_b200 import blob_ctx
+  from spartan_b200.array import views
+  old = blob_ctx._global_ctx[0]
+  blob_ctx.set(blob_ctx.BlobCtx(0, 1, 'cpu'))
+  try:
+    rng = np.random.RandomState(12)
+    for _ in range(60):
+      nd = int(rng.randint(1, 4))
+      shape = tuple(int(s) for s in rng.randint(1, 9, size=nd))
+      hint = tuple(int(rng.randint(1, s + 1)) for s in shape)
+      x = rng.rand(*shape).astype(np.float32)
+      arr = pdist.create(shape, np.float32, tile_hint=hint)
+      arr.update(pex.from_shape(shape), x)
+      # random basic slice
+      idx = tuple(slice(int(a), int(a + rng.randint(1, s - a + 1))) for s, a in ((s, rng.randint(0, s)) for s in shape))
+      v = views.Slice(arr, idx)
+      assert np.array_equal(v.glom(), x[idx]), (shape, hint, idx)
+      t = views.Transpose(arr)
+      assert np.array_equal(t.glom(), x.T)
+      assert np.array_equal(views.Slice(t, tuple(reversed(idx))).glom(), x.T[tuple(reversed(idx))])
+      # reshape of the (contiguous) base to a random factorisation
+      n = int(np.prod(shape))
+      divs = [d for d in range(1, n + 1) if n % d == 0]
+      a = int(divs[rng.randint(len(divs))])
+      for new in ((n,), (a, n // a), (n // a, a, 1)):
+        r = views.Reshape(arr, new)
+        assert np.array_equal(r.glom(), x.reshape(new)), (shape, new)
+        for ex in r.tiles:                                  # every view tile on its own, incl. partial-row extents
+          assert np.array_equal(r.fetch(ex).numpy(), x.reshape(new)[ex.to_slice()])
+    # shapes produced by Expr.__getitem__ (NumPy semantics for integers and newaxis)
+    e = sp.ndarray((4, 5, 6), dtype=np.float32)
+    ref = np.zeros((4, 5, 6), np.float32)
+    for idx in (1, -1, np.index_exp[:, 2], np.index_exp[1, :, 4], np.index_exp[1:3], np.index_exp[:, sp.newaxis, 2:4],
+                np.index_exp[0, 1], np.index_exp[:, :, -1]):
+      np_idx = tuple(np.newaxis if i is sp.newaxis else i for i in idx) if isinstance(idx, tuple) else idx
+      assert tuple(e[idx].shape) == ref[np_idx].shape, idx
+  finally:
+    blob_ctx._global_ctx[0] = old
+    blob_ctx._local.ctx = old
+
+
+def test_fusion_counts_distinct_operands():
+  """A chain that uses three arrays ten times is ONE kernel (an array used several times is one operand, Python scalars
+  are immediates); nine distinct arrays are not (SP_MAX_OPERANDS = 8)."""
+  from spartan_b200 import blob_ctx
+  old = blob_ctx._global_ctx[0]
+  blob_ctx.set(blob_ctx.BlobCtx(0, 1, 'cpu'))
+  try:
+    x, y, z = (sp.ndarray((64, 64), dtype=np.float32) for _ in range(3))
+    e = (((x + y) * z - x) * 0.5 + y * y - z * 2 + 1).optimized()
+    assert isinstance(e, sp.MapExpr) and not any(isinstance(c, sp.MapExpr) for c in e.children)
+    ids = set(c.expr_id for c in e.children if isinstance(c, sp.NdArrayExpr))
+    assert ids == {x.expr_id, y.expr_id, z.expr_id}
+    many = [sp.ndarray((8, 8), dtype=np.float32) for _ in range(9)]
+    s = many[0]
+    for m in many[1:]:
+      s = s + m
+    opt = s.optimized()
+    assert any(isinstance(c, sp.MapExpr) for c in opt.children)      # split: the ninth operand does not fit
+  finally:
+    blob_ctx._global_ctx[0] = old
+    blob_ctx._local.ctx = old

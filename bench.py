@@ -406,7 +406,9 @@ def run_b200(args):
                         'unit': 'TFLOP/s', 'frac': tf / peaks['bf16_tflops_sustained'],
                         'traffic': measured_traffic('gemm_kernel_bf16x3_dot32768') if (world == 1 and n == 32768 and args.precision == 'bf16x3') else None,
                         'executed_mma_frac': tf * (3 if 'x3' in args.precision else 1) / (peaks['bf16_tflops_sustained'] / (2 if args.precision.startswith('tf32') else 1)),
-                        'peak_source': peaks['source'] + ' bf16 sustained (tf32 runs at half the bf16 rate)',
+                        'peak_source': peaks['source'] + ' bf16 sustained (tf32 runs at half the bf16 rate); executed_mma_frac '
+                                       'counts the 3 MMA passes of the split modes and can exceed 1: the sustained cuBLAS '
+                                       'figure is itself limited by the power cap',
                         'per_gpu': True},
            'clocks': clocks, 'gpu_launches': launches, 'parity': parity, 'e2e': e2e, 'map_reduce': mr,
            'cpu_baseline': cpu}

@@ -2,6 +2,9 @@
 ``num_workers`` becomes the number of GPU ranks (one process per GPU)."""
 
 
+import os
+
+
 class Flags(object):
   def __init__(self):
     self.optimization = True            # optimize.py:1101
@@ -17,6 +20,8 @@ class Flags(object):
     self.dot_stream_host_operands = True
     self.dot_stream_strip = 4096
     self.dot_stream_min_bytes = 256 << 20
+    # fraction of K uploaded as (A[:, k-strip], B[k-strip, :]) pairs and contracted K-split before the frontier (0 = none)
+    self.dot_stream_k_head = float(os.environ.get('SPARTAN_DOT_K_HEAD', '0'))
     self.checkpoint_path = '/tmp/spartan/checkpoint'     # config.py:96 default checkpoint directory
 
   def __repr__(self):

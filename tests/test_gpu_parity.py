@@ -519,6 +519,17 @@ def test_gemm_cta_pair_matches_single_cta(M, N, K):
                                          (2048, 300, 1000, 512), (2304, 4400, 300, 1024)])
 @pytest.mark.parametrize('prec', ['bf16x3', 'tf32x3'])
 def test_streamed_dot_matches_resident(M, N, K, strip, prec):
+  _streamed_dot_case(M, N, K, strip, prec, 0.0)
+
+
+@pytest.mark.parametrize('M,N,K,strip', [(1024, 768, 512, 256), (1024, 768, 2048, 256), (700, 900, 1333, 256)])
+def test_streamed_dot_with_k_split_head(M, N, K, strip):
+  """FLAGS.dot_stream_k_head: the leading half of K is contracted K-split (rank-`strip` updates of all of C), the rest by
+  the frontier with accumulate -- same result up to fp32 summation order."""
+  _streamed_dot_case(M, N, K, strip, 'bf16x3', 0.5)
+
+
+def _streamed_dot_case(M, N, K, strip, prec, k_head):
   """dot(from_numpy(a), from_numpy(b)) with the PCIe upload pipelined against the contraction (strips of A rows /
   B columns, L-shaped frontier) must give the bits of the resident path -- ragged strips, unequal strip counts,
   unaligned K -- read back both block by block (read_local_into, event driven) and through glom; the operand
@@ -528,7 +539,9 @@ def test_streamed_dot_matches_resident(M, N, K, strip, prec):
   rng = np.random.default_rng(M + N + K)
   a = rng.standard_normal((M, K), dtype=np.float32); b = rng.standard_normal((K, N), dtype=np.float32)
   old = (sp.FLAGS.dot_stream_host_operands, sp.FLAGS.dot_stream_strip, sp.FLAGS.dot_stream_min_bytes, sp.FLAGS.dot_precision)
+  old_head = sp.FLAGS.dot_stream_k_head
   try:
+    sp.FLAGS.dot_stream_k_head = k_head
     sp.FLAGS.dot_precision = prec
     sp.FLAGS.dot_stream_host_operands = False
     want = sp.dot(sp.from_numpy(a), sp.from_numpy(b)).glom()
@@ -543,8 +556,14 @@ def test_streamed_dot_matches_resident(M, N, K, strip, prec):
     nbytes = c.read_local_into(out.numpy())
     torch.cuda.current_stream().synchronize()
     assert nbytes == M * N * 4 and c.block_events is None
-    Assert.all_eq(out.numpy(), want)
-    Assert.all_eq(c.glom(), want)
+    if k_head == 0:
+      Assert.all_eq(out.numpy(), want)
+      Assert.all_eq(c.glom(), want)
+    else:
+      Assert.all_eq(out.numpy(), c.glom())
+      ref64 = a.astype(np.float64) @ b.astype(np.float64)
+      assert np.abs(c.glom() - want).max() <= 2e-6 * np.abs(ref64).max()
+      assert np.abs(c.glom() - ref64).max() <= 1e-5 * np.abs(ref64).max()
     Assert.all_eq(ea.evaluate().glom(), a)          # cached by the streamed evaluation, resident and complete
     Assert.all_eq(eb.evaluate().glom(), b)
     assert eval_cache.get(ea.expr_id) is not None
@@ -552,6 +571,7 @@ def test_streamed_dot_matches_resident(M, N, K, strip, prec):
     assert np.abs(want - ref).max() <= 1e-5 * np.abs(ref).max()
   finally:
     (sp.FLAGS.dot_stream_host_operands, sp.FLAGS.dot_stream_strip, sp.FLAGS.dot_stream_min_bytes, sp.FLAGS.dot_precision) = old
+    sp.FLAGS.dot_stream_k_head = old_head
 
 
 # ------------------------------------------------------------------ views: tests/test_slice.py, test_transpose.py, test_reshape.py

@@ -386,3 +386,35 @@ def test_fusion_counts_distinct_operands():
   finally:
     blob_ctx._global_ctx[0] = old
     blob_ctx._local.ctx = old
+
+
+def test_tile_file_bytes_match_golden(tmp_path):
+  """tests/golden/fio_vectors.json (made by tests/golden/make_fio_vectors.py): the product writes exactly these bytes and
+  both loaders read them back."""
+  import base64, json
+  from spartan_b200 import blob_ctx
+  gold = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'fio_vectors.json')))
+  old = blob_ctx._global_ctx[0]
+  blob_ctx.set(blob_ctx.BlobCtx(0, 1, 'cpu'))
+  spartan_oracle.initialize(1)
+  try:
+    for case in gold['cases']:
+      shape, hint, dtype = tuple(case['shape']), tuple(case['tile_hint']), np.dtype(case['dtype'])
+      x = np.array(case['data'], dtype=dtype).reshape(shape)
+      arr = pdist.create(shape, dtype, tile_hint=hint)
+      arr.update(pex.from_shape(shape), x)
+      assert sp.save(arr, case['prefix'], str(tmp_path), False) is True
+      d = os.path.join(str(tmp_path), case['prefix'])
+      assert sorted(os.listdir(d)) == sorted(case['files'])
+      for fn, b64 in case['files'].items():
+        assert open(os.path.join(d, fn), 'rb').read() == base64.b64decode(b64), fn
+      # a directory holding only the golden bytes loads through both loaders
+      g = os.path.join(str(tmp_path), 'golden_' + case['prefix'], case['prefix'])
+      os.makedirs(g)
+      for fn, b64 in case['files'].items():
+        open(os.path.join(g, fn), 'wb').write(base64.b64decode(b64))
+      assert np.array_equal(sp.load(case['prefix'], os.path.dirname(g), False).glom(), x)
+      assert np.array_equal(spartan_oracle.fio.load(case['prefix'], os.path.dirname(g), False).glom(), x)
+  finally:
+    blob_ctx._global_ctx[0] = old
+    blob_ctx._local.ctx = old

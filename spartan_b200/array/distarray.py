@@ -24,7 +24,7 @@ from . import extent, tile
 from .. import blob_ctx, comm, device_ops
 from .._lib import lib, check, i64arr, SpartanError
 from ..core import TileId
-from ..util import Assert
+from ..util import require_type, require_equal, require_unique
 
 DEFAULT_TILE_SIZE = 100000   # distarray.py:20
 
@@ -44,7 +44,7 @@ def compute_extents(shape, tile_hint=None, num_shards=-1):
   if n == 0:
     return collections.OrderedDict([(extent.create([], [], ()), 0)])
   if tile_hint is not None:
-    Assert.eq(len(tile_hint), n, '#dimensions in tile hint does not match shape %s vs %s' % (tile_hint, shape))
+    require_equal(len(tile_hint), n, '#dimensions in tile hint does not match shape %s vs %s' % (tile_hint, shape))
   hint = None if tile_hint is None else i64arr(tile_hint)
   total = check(lib.sp_compute_extents(n, i64arr(shape), hint, int(num_shards), None, None, None), 'compute_extents')
   ul = (ctypes.c_int64 * max(1, total * n))(); lr = (ctypes.c_int64 * max(1, total * n))()
@@ -144,7 +144,7 @@ class DistArrayImpl(DistArray):
     self.sparse = False
     self.bad_tiles = []
     self.ctx = blob_ctx.get()
-    Assert.isinstance(tiles, dict)
+    require_type(tiles, dict)
     self.tiles = tiles                      # extent -> TileId, ALL tiles of the array (every rank knows them)
     self.blob_to_ex = dict((v, k) for k, v in tiles.items())
     self.slab = None                        # this rank's tiles as one HBM allocation (or None)
@@ -247,8 +247,8 @@ class DistArrayImpl(DistArray):
     ``dst`` = rank that needs the data (default: the caller, which then must own every overlapping
     tile).  With dst given the call is collective: every rank calls it with the same arguments, owners
     of overlapping tiles send their rectangles over NCCL, and only rank ``dst`` gets a tensor back."""
-    Assert.isinstance(region, extent.TileExtent)
-    Assert.eq(region.array_shape, self.shape)
+    require_type(region, extent.TileExtent)
+    require_equal(region.array_shape, self.shape)
     ctx = self.ctx
     me = ctx.worker_id
     want = me if dst is None else dst
@@ -296,11 +296,11 @@ class DistArrayImpl(DistArray):
     """distarray.py:372-422.  ``data`` is either a host ndarray that every rank holds (each rank
     uploads the parts that land in its own tiles) or a device tensor, in which case every tile it
     overlaps must be local to the caller."""
-    Assert.isinstance(region, extent.TileExtent)
+    require_type(region, extent.TileExtent)
     host = isinstance(data, np.ndarray)
     if not host and not torch.is_tensor(data):
       data = np.asarray(data); host = True
-    Assert.eq(tuple(region.shape), tuple(data.shape), 'Size of extent does not match size of data')
+    require_equal(tuple(region.shape), tuple(data.shape), 'Size of extent does not match size of data')
     ctx = self.ctx
     me = ctx.worker_id
     self.block_events = None
@@ -471,7 +471,7 @@ def create_like(src, dtype, reducer=None):
 def from_table(extents):
   """distarray.py:519-550: shape = max extent corner, dtype from the (local) tiles."""
   ctx = blob_ctx.get()
-  Assert.no_duplicates(extents)
+  require_unique(extents)
   if not extents:
     return DistArrayImpl(shape=(), dtype=np.float64, tiles=extents, reducer_fn=None)
   shape = extent.find_shape(list(extents.keys()))
@@ -555,7 +555,7 @@ class Broadcast(DistArray):
   """NumPy broadcasting as a view (spartan/expr/operator/broadcast.py:28-109)."""
 
   def __init__(self, base, shape):
-    Assert.isinstance(base, DistArray)
+    require_type(base, DistArray)
     self.base = base.base if isinstance(base, Broadcast) else base
     self.shape = tuple(shape)
     self.tiles = self.base.tiles

@@ -19,7 +19,7 @@ import numpy as np
 from . import extent
 from .. import blob_ctx, comm, device_ops
 from ..core import TileId
-from ..util import Assert
+from ..util import require_type, require_equal, require_unique
 from . import distarray
 from .distarray import DistArray, _tile_mapper
 
@@ -96,7 +96,7 @@ class Slice(ViewArray):
     ViewArray.__init__(self)
     if not isinstance(idx, extent.TileExtent):
       idx = extent.from_slice(idx, darray.shape)
-    Assert.isinstance(darray, DistArray)
+    require_type(darray, DistArray)
     if idx is None:
       raise ValueError('empty slice')
     self.base = darray
@@ -126,7 +126,7 @@ class Transpose(ViewArray):
 
   def __init__(self, base):
     ViewArray.__init__(self)
-    Assert.isinstance(base, DistArray)
+    require_type(base, DistArray)
     self.base = base
     self.shape = tuple(base.shape[::-1])
     self.dtype = base.dtype
@@ -166,7 +166,7 @@ class Reshape(ViewArray):
 
   def __init__(self, base, shape, tile_hint=None):
     ViewArray.__init__(self)
-    Assert.isinstance(base, DistArray)
+    require_type(base, DistArray)
     shape = tuple(int(s) for s in shape)
     if int(np.prod(shape, dtype=np.int64)) != int(np.prod(base.shape, dtype=np.int64)):
       raise ValueError('total size of new array must be unchanged: %s -> %s' % (base.shape, shape))

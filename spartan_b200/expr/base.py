@@ -14,7 +14,7 @@ import numpy as np
 from .. import blob_ctx
 from ..array import distarray
 from ..config import FLAGS
-from ..util import Assert
+from ..util import require_type, require_equal, require_unique
 
 
 class newaxis(object):
@@ -343,7 +343,7 @@ def evaluate(node):
   """base.py:679-690."""
   if isinstance(node, Expr):
     return node.evaluate()
-  Assert.isinstance(node, (np.ndarray, distarray.DistArray))
+  require_type(node, (np.ndarray, distarray.DistArray))
   return node
 
 

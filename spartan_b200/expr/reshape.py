@@ -1,6 +1,6 @@
 """Reshape operation and expr (reference: spartan/expr/operator/reshape.py:196-239)."""
 from ..array.views import Reshape
-from ..util import Assert
+from ..util import require_type, require_equal, require_unique
 from .base import Expr, lazify
 
 
@@ -30,7 +30,7 @@ def reshape(array, *args, **kargs):
     new_shape = tuple(args[0])
   else:
     new_shape = tuple(args)
-  Assert.isinstance(new_shape, tuple)
+  require_type(new_shape, tuple)
   return ReshapeExpr(array=lazify(array), new_shape=new_shape, tile_hint=kargs.get('tile_hint'))
 
 

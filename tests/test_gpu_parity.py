@@ -11,7 +11,7 @@ import spartan_oracle
 from spartan_oracle import expr as oexpr
 
 import spartan_b200 as sp
-from spartan_b200.util import Assert
+from helpers import all_eq
 
 TEST_SIZE = 50
 
@@ -40,12 +40,12 @@ def test_ones_sum_golden():
 
 # ------------------------------------------------------------------ tests/test_maptiles.py:12-62
 def test_map_chains():
-  Assert.all_eq((sp.ones((20, 20)) + sp.ones((20, 20))).glom(), 2 * np.ones((20, 20)))
+  all_eq((sp.ones((20, 20)) + sp.ones((20, 20))).glom(), 2 * np.ones((20, 20)))
   a = sp.ones((10, 10)); b = sp.ones((10, 10)); c = sp.ones((10, 10))
-  Assert.all_eq((a + b + c).glom(), np.ones((10, 10)) * 3)
+  all_eq((a + b + c).glom(), np.ones((10, 10)) * 3)
   many = (a + b + a + b + a + b + a + b + a + b)
-  Assert.all_eq(many.glom(), np.ones((10, 10)) * 10)
-  Assert.all_eq(many.optimized().glom(), np.ones((10, 10)) * 10)
+  all_eq(many.glom(), np.ones((10, 10)) * 10)
+  all_eq(many.optimized().glom(), np.ones((10, 10)) * 10)
   assert many.glom().dtype == np.float32
 
 
@@ -58,16 +58,16 @@ def test_ln():
 
 def test_broadcast():
   a = sp.ones((2, 1)); b = sp.ones((2, 5))
-  Assert.all_eq((a / b).glom(), np.ones((2, 5)))
-  Assert.all_eq((b / a).glom(), np.ones((2, 5)))
+  all_eq((a / b).glom(), np.ones((2, 5)))
+  all_eq((b / a).glom(), np.ones((2, 5)))
 
 
 def test_maximum_and_scalar_broadcast():
   # tests/test_elementwise.py:9-22 -- exact (max is exact in any precision)
   rng = np.random.RandomState(0)
   np_a = rng.randn(10, 10); np_b = rng.randn(10, 10)
-  Assert.all_eq(sp.maximum(sp.from_numpy(np_a), sp.from_numpy(np_b)).glom(), np.maximum(np_a, np_b))
-  Assert.all_eq(sp.maximum(sp.from_numpy(np_a), 0).glom(), np.maximum(np_a, 0))
+  all_eq(sp.maximum(sp.from_numpy(np_a), sp.from_numpy(np_b)).glom(), np.maximum(np_a, np_b))
+  all_eq(sp.maximum(sp.from_numpy(np_a), 0).glom(), np.maximum(np_a, 0))
 
 
 @pytest.mark.parametrize('shape', [(1,), (7,), (33, 5), (128, 257), (3, 4, 5), (1000, 1)])
@@ -84,7 +84,7 @@ def test_elementwise_bit_exact(shape, dtype):
     got = build(sp, sp.from_numpy(x), sp.from_numpy(y)).optimized().glom()
     ref = build(oexpr, oexpr.from_numpy(x), oexpr.from_numpy(y)).optimized().glom()
     assert got.dtype == ref.dtype, (got.dtype, ref.dtype)
-    Assert.all_eq(got, ref)
+    all_eq(got, ref)
 
 
 def test_compare_logic_astype():
@@ -95,7 +95,7 @@ def test_compare_logic_astype():
     got = build(sp, sp.from_numpy(x), sp.from_numpy(y)).glom()
     ref = build(oexpr, oexpr.from_numpy(x), oexpr.from_numpy(y)).glom()
     assert got.dtype == ref.dtype
-    Assert.all_eq(got, ref)
+    all_eq(got, ref)
 
 
 def test_transcendentals_tolerance():
@@ -113,7 +113,7 @@ def test_row_and_column_vector_broadcast():
   rng = np.random.RandomState(4)
   x = rng.randn(96, 40).astype(np.float32); r = rng.randn(1, 40).astype(np.float32); c = rng.randn(96, 1).astype(np.float32)
   got = (sp.from_numpy(x) * sp.from_numpy(r) + sp.from_numpy(c)).optimized().glom()
-  Assert.all_eq(got, x * r + c)
+  all_eq(got, x * r + c)
 
 
 # ------------------------------------------------------------------ tests/test_reduce.py:14-107
@@ -121,20 +121,20 @@ def test_sum_3d_int64_exact():
   nx = np.arange(TEST_SIZE ** 3, dtype=np.int64).reshape((TEST_SIZE,) * 3)
   for axis in [None, 0, 1, 2]:
     x = sp.arange((TEST_SIZE, TEST_SIZE, TEST_SIZE), dtype=np.int64)
-    Assert.all_eq(x.sum(axis).glom(), nx.sum(axis))
+    all_eq(x.sum(axis).glom(), nx.sum(axis))
 
 
 def test_sum_2d_1d():
   nx = np.arange(TEST_SIZE * TEST_SIZE, dtype=np.int64).reshape((TEST_SIZE, TEST_SIZE))
   for axis in [None, 0, 1]:
-    Assert.all_eq(sp.arange((TEST_SIZE, TEST_SIZE), dtype=np.int64).sum(axis).glom(), nx.sum(axis))
-  Assert.all_eq(sp.arange((TEST_SIZE,), dtype=np.int64).sum().glom(), np.arange(TEST_SIZE).sum())
+    all_eq(sp.arange((TEST_SIZE, TEST_SIZE), dtype=np.int64).sum(axis).glom(), nx.sum(axis))
+  all_eq(sp.arange((TEST_SIZE,), dtype=np.int64).sum().glom(), np.arange(TEST_SIZE).sum())
 
 
 def test_simple_sum():
   for axis in [0, 1, None]:
     a = sp.ones((TEST_SIZE, TEST_SIZE)) + sp.ones((TEST_SIZE, TEST_SIZE))
-    Assert.all_eq(a.sum(axis=axis).glom(), 2 * np.ones((TEST_SIZE, TEST_SIZE)).sum(axis))
+    all_eq(a.sum(axis=axis).glom(), 2 * np.ones((TEST_SIZE, TEST_SIZE)).sum(axis))
 
 
 def test_count_nonzero_zero():
@@ -154,40 +154,40 @@ def test_reductions_vs_oracle(shape, axis):
   for name in ('sum', 'min', 'max'):
     got = getattr(sp, name)(sp.from_numpy(xi), axis).glom(); ref = getattr(oexpr, name)(oexpr.from_numpy(xi), axis).glom()
     assert got.dtype == ref.dtype
-    Assert.all_eq(np.asarray(got), np.asarray(ref))                       # integers: bit-exact
+    all_eq(np.asarray(got), np.asarray(ref))                       # integers: bit-exact
     got = getattr(sp, name)(sp.from_numpy(xf), axis).glom(); ref = getattr(oexpr, name)(oexpr.from_numpy(xf), axis).glom()
     assert got.dtype == ref.dtype == np.float32
     if name == 'sum':     # different (tree) summation order: 1e-5 relative, the north-star tolerance
       np.testing.assert_allclose(got, ref, rtol=1e-5)
     else:
-      Assert.all_eq(np.asarray(got), np.asarray(ref))
+      all_eq(np.asarray(got), np.asarray(ref))
   small = rng.randint(1, 3, size=shape).astype(np.int32)
   got = sp.prod(sp.from_numpy(small), axis).glom(); ref = oexpr.prod(oexpr.from_numpy(small), axis).glom()
   assert got.dtype == ref.dtype == np.int64
-  Assert.all_eq(np.asarray(got), np.asarray(ref))
+  all_eq(np.asarray(got), np.asarray(ref))
   b = rng.randint(0, 2, size=shape).astype(np.int32)
   for name in ('all', 'any'):
     got = getattr(sp, name)(sp.from_numpy(b), axis).glom(); ref = getattr(oexpr, name)(oexpr.from_numpy(b), axis).glom()
     assert got.dtype == np.bool_
-    Assert.all_eq(np.asarray(got), np.asarray(ref))
+    all_eq(np.asarray(got), np.asarray(ref))
 
 
 def test_min_max_prod_logic_reference():
   # tests/test_statistics.py:16-30, tests/test_mathematics.py:9-15, tests/test_logic.py:9-23
   src = np.asarray([1, 1, 1, 2, 2, 5, 5, 10])
-  Assert.all_eq(sp.max(sp.from_numpy(src)).glom(), np.max(src))
-  Assert.all_eq(sp.min(sp.from_numpy(src)).glom(), np.min(src))
+  all_eq(sp.max(sp.from_numpy(src)).glom(), np.max(src))
+  all_eq(sp.min(sp.from_numpy(src)).glom(), np.min(src))
   src = np.arange(100).reshape(10, 10)
-  Assert.all_eq(sp.min(sp.from_numpy(src), axis=1).glom(), np.min(src, axis=1))
+  all_eq(sp.min(sp.from_numpy(src), axis=1).glom(), np.min(src, axis=1))
   nA = np.arange(40000, dtype=np.int32).reshape(100, 400)
   got = sp.from_numpy(nA).prod().glom()
   assert got.dtype == np.int64
-  Assert.all_eq(got, nA.astype(np.int64).prod())
+  all_eq(got, nA.astype(np.int64).prod())
   nC = (nA.T.copy() // 1000)
   C = sp.from_numpy(nA.T.copy()) / 1000          # Python-2 era integer divide floors
-  Assert.all_eq(C.glom(), nC)
-  Assert.all_eq(sp.all(C).glom(), np.all(nC))
-  Assert.all_eq(sp.any(C).glom(), np.any(nC))
+  all_eq(C.glom(), nC)
+  all_eq(sp.all(C).glom(), np.all(nC))
+  all_eq(sp.any(C).glom(), np.any(nC))
 
 
 def test_fused_map_reduce_vs_oracle():
@@ -222,24 +222,24 @@ def test_optimization_reduced():
 
 # ------------------------------------------------------------------ creation (tests/test_creation.py:17-68)
 def test_arange():
-  Assert.raises_exception(ValueError, sp.arange)
-  Assert.all_eq(sp.arange((10,)).glom(), np.arange(10))
-  Assert.all_eq(sp.arange((3, 5)).glom(), np.arange(15).reshape((3, 5)))
-  Assert.all_eq(sp.arange((10,), -1).glom(), np.arange(-1, 9))
-  Assert.all_eq(sp.arange((3, 5), -1).glom(), np.arange(-1, 14).reshape((3, 5)))
-  Assert.all_eq(sp.arange((10,), step=2).glom(), np.arange(0, 20, 2))
-  Assert.all_eq(sp.arange((3, 5), 1, step=2).glom(), np.arange(1, 31, 2).reshape((3, 5)))
-  Assert.all_eq(sp.arange(stop=10).glom(), np.arange(10))
-  Assert.all_eq(sp.arange(-1, 19, 2).glom(), np.arange(-1, 19, 2))
-  Assert.all_eq(sp.arange((64, 48), dtype=np.int64, tile_hint=(16, 16)).glom(), np.arange(64 * 48).reshape(64, 48))
+  pytest.raises(ValueError, sp.arange)
+  all_eq(sp.arange((10,)).glom(), np.arange(10))
+  all_eq(sp.arange((3, 5)).glom(), np.arange(15).reshape((3, 5)))
+  all_eq(sp.arange((10,), -1).glom(), np.arange(-1, 9))
+  all_eq(sp.arange((3, 5), -1).glom(), np.arange(-1, 14).reshape((3, 5)))
+  all_eq(sp.arange((10,), step=2).glom(), np.arange(0, 20, 2))
+  all_eq(sp.arange((3, 5), 1, step=2).glom(), np.arange(1, 31, 2).reshape((3, 5)))
+  all_eq(sp.arange(stop=10).glom(), np.arange(10))
+  all_eq(sp.arange(-1, 19, 2).glom(), np.arange(-1, 19, 2))
+  all_eq(sp.arange((64, 48), dtype=np.int64, tile_hint=(16, 16)).glom(), np.arange(64 * 48).reshape(64, 48))
 
 
 def test_from_numpy_roundtrip_and_tilings():
   rng = np.random.RandomState(6)
   for shape, hint in [((37, 53), None), ((37, 53), (10, 53)), ((37, 53), (37, 7)), ((37, 53), (8, 9)), ((5,), (2,)), ((2, 3, 4), (1, 3, 2))]:
     x = rng.randn(*shape)
-    Assert.all_eq(sp.from_numpy(x, tile_hint=hint).glom(), x)
-    Assert.all_eq((sp.from_numpy(x, tile_hint=hint) + 1).glom(), x + 1)
+    all_eq(sp.from_numpy(x, tile_hint=hint).glom(), x)
+    all_eq((sp.from_numpy(x, tile_hint=hint) + 1).glom(), x + 1)
 
 
 def test_rand_properties():
@@ -248,7 +248,7 @@ def test_rand_properties():
   b = sp.rand(512, 256, seed=7, dtype=np.float32, tile_hint=(64, 64)).glom()
   c = sp.rand(512, 256, seed=8, dtype=np.float32).glom()
   assert a.dtype == np.float32 and a.min() >= 0.0 and a.max() < 1.0
-  Assert.all_eq(a, b)
+  all_eq(a, b)
   assert not np.array_equal(a, c)
   assert abs(a.mean() - 0.5) < 5e-3 and abs(a.var() - 1 / 12.0) < 5e-3
   n = sp.randn(512, 256, seed=9, dtype=np.float32).glom()
@@ -258,20 +258,20 @@ def test_rand_properties():
 
 # ------------------------------------------------------------------ dot (tests/test_dot.py:8-103, test_matmul.py:12-22)
 def test_dot_reference_cases_exact():
-  Assert.all_eq(sp.dot(sp.arange((132, 100)), sp.arange((100, 77))).glom(),
+  all_eq(sp.dot(sp.arange((132, 100)), sp.arange((100, 77))).glom(),
                 np.dot(np.arange(13200.).reshape(132, 100), np.arange(7700.).reshape(100, 77)))
-  Assert.all_eq(sp.dot(sp.arange((67, 100)), sp.arange((100, 77))).glom(),
+  all_eq(sp.dot(sp.arange((67, 100)), sp.arange((100, 77))).glom(),
                 np.dot(np.arange(6700.).reshape(67, 100), np.arange(7700.).reshape(100, 77)))
-  Assert.all_eq(sp.dot(sp.arange((77, 100)), np.arange(8800.).reshape(100, 88)).glom(),
+  all_eq(sp.dot(sp.arange((77, 100)), np.arange(8800.).reshape(100, 88)).glom(),
                 np.dot(np.arange(7700.).reshape(77, 100), np.arange(8800.).reshape(100, 88)))
-  Assert.all_eq(sp.dot(sp.arange(stop=100), sp.arange(stop=100)).glom(), np.asarray([np.dot(np.arange(100.), np.arange(100.))]))
-  Assert.all_eq(sp.dot(sp.arange((100, 77)), sp.arange(stop=77)).glom(), np.dot(np.arange(7700.).reshape(100, 77), np.arange(77.)))
-  Assert.all_eq(sp.dot(sp.arange((77, 100)), sp.arange(stop=100)).glom(), np.dot(np.arange(7700.).reshape(77, 100), np.arange(100.)))
-  Assert.all_eq(sp.dot(sp.arange((77, 100)), np.arange(100.)).glom(), np.dot(np.arange(7700.).reshape(77, 100), np.arange(100.)))
+  all_eq(sp.dot(sp.arange(stop=100), sp.arange(stop=100)).glom(), np.asarray([np.dot(np.arange(100.), np.arange(100.))]))
+  all_eq(sp.dot(sp.arange((100, 77)), sp.arange(stop=77)).glom(), np.dot(np.arange(7700.).reshape(100, 77), np.arange(77.)))
+  all_eq(sp.dot(sp.arange((77, 100)), sp.arange(stop=100)).glom(), np.dot(np.arange(7700.).reshape(77, 100), np.arange(100.)))
+  all_eq(sp.dot(sp.arange((77, 100)), np.arange(100.)).glom(), np.dot(np.arange(7700.).reshape(77, 100), np.arange(100.)))
   x = sp.arange((100, 50), dtype=np.int64).astype(np.float64); y = sp.arange((50, 100), dtype=np.int64).astype(np.float64)
-  Assert.all_eq(sp.dot(x, y).glom(), np.dot(np.arange(5000.).reshape(100, 50), np.arange(5000.).reshape(50, 100)))
+  all_eq(sp.dot(x, y).glom(), np.dot(np.arange(5000.).reshape(100, 50), np.arange(5000.).reshape(50, 100)))
   xi = sp.arange((40, 30), dtype=np.int64); yi = sp.arange((30, 20), dtype=np.int64)
-  Assert.all_eq(sp.dot(xi, yi).glom(), np.dot(np.arange(1200).reshape(40, 30), np.arange(600).reshape(30, 20)))
+  all_eq(sp.dot(xi, yi).glom(), np.dot(np.arange(1200).reshape(40, 30), np.arange(600).reshape(30, 20)))
 
 
 @pytest.mark.parametrize('M,N,K,hint', [(256, 512, 384, None), (300, 700, 1000, (128, 256)), (1024, 1024, 2048, (512, 512)),
@@ -335,7 +335,7 @@ def test_streaming_map_bit_exact(shape, dtype):
     got = build(sp, *[sp.from_numpy(a) for a in (x, y, z, row, col)]).optimized().glom()
     ref = build(oexpr, *[oexpr.from_numpy(a) for a in (x, y, z, row, col)]).optimized().glom()
     assert got.dtype == ref.dtype
-    Assert.all_eq(got, ref)
+    all_eq(got, ref)
 
 
 @pytest.mark.parametrize('shape', [(1000, 1024), (129, 4100), (4096, 512), (5, 300, 256)])
@@ -348,13 +348,13 @@ def test_streaming_reduce_axis0(shape):
   for name in ('sum', 'min', 'max'):
     got = getattr(sp, name)(sp.from_numpy(xi) * 3 - sp.from_numpy(yi), axis).optimized().glom()
     ref = getattr(oexpr, name)(oexpr.from_numpy(xi) * 3 - oexpr.from_numpy(yi), axis).optimized().glom()
-    Assert.all_eq(got, ref)
+    all_eq(got, ref)
   got = (sp.from_numpy(xf) * 2 + sp.from_numpy(yf)).sum(axis=axis).optimized().glom()
   ref = (xf.astype(np.float64) * 2 + yf).sum(axis=axis)
   np.testing.assert_allclose(got, ref, rtol=1e-5)
   got = sp.from_numpy(xd).sum(axis=axis).glom()
   np.testing.assert_allclose(got, xd.sum(axis=axis), rtol=1e-12)
-  Assert.all_eq(sp.max(sp.from_numpy(xf), axis).glom(), xf.max(axis=axis))
+  all_eq(sp.max(sp.from_numpy(xf), axis).glom(), xf.max(axis=axis))
 
 
 def test_gemm_split_form_matches_one_call():
@@ -381,17 +381,17 @@ def test_gemm_split_form_matches_one_call():
 # ------------------------------------------------------------------ tests/test_reduce.py:38-90 argmin / argmax
 def test_argmin_argmax_reference_cases():
   nx1 = np.arange(TEST_SIZE, dtype=np.int64)
-  Assert.all_eq(sp.arange((TEST_SIZE,), dtype=np.int64).argmin().glom(), nx1.argmin())
-  Assert.all_eq(sp.arange((TEST_SIZE,), dtype=np.int64).argmax().glom(), nx1.argmax())
+  all_eq(sp.arange((TEST_SIZE,), dtype=np.int64).argmin().glom(), nx1.argmin())
+  all_eq(sp.arange((TEST_SIZE,), dtype=np.int64).argmax().glom(), nx1.argmax())
   nx2 = np.arange(TEST_SIZE * TEST_SIZE, dtype=np.int64).reshape((TEST_SIZE, TEST_SIZE))
   x2 = sp.arange((TEST_SIZE, TEST_SIZE), dtype=np.int64)
-  Assert.all_eq(x2.argmin(axis=1).glom(), nx2.argmin(axis=1))
-  Assert.all_eq(x2.argmax(axis=1).glom(), nx2.argmax(axis=1))
+  all_eq(x2.argmin(axis=1).glom(), nx2.argmin(axis=1))
+  all_eq(x2.argmax(axis=1).glom(), nx2.argmax(axis=1))
   nx3 = np.arange(TEST_SIZE ** 3, dtype=np.int64).reshape((TEST_SIZE,) * 3)
   for axis in [None, 0, 1, 2]:
     x3 = sp.arange((TEST_SIZE,) * 3, dtype=np.int64)
-    Assert.all_eq(x3.argmin(axis).glom(), nx3.argmin(axis))
-    Assert.all_eq(x3.argmax(axis).glom(), nx3.argmax(axis))
+    all_eq(x3.argmin(axis).glom(), nx3.argmin(axis))
+    all_eq(x3.argmax(axis).glom(), nx3.argmax(axis))
 
 
 @pytest.mark.parametrize('shape,hint', [((257, 129), None), ((64, 4100), (16, 4100)), ((300, 700), (100, 128)), ((5, 6, 7), None)])
@@ -400,8 +400,8 @@ def test_argmin_argmax_random(shape, hint):
   rng = np.random.RandomState(13)
   for x in (rng.randn(*shape).astype(np.float32), rng.randint(-5, 5, size=shape).astype(np.int64)):
     for axis in [None] + list(range(len(shape))):
-      Assert.all_eq(np.asarray(sp.argmin(sp.from_numpy(x, tile_hint=hint), axis).glom()), np.asarray(x.argmin(axis)))
-      Assert.all_eq(np.asarray(sp.argmax(sp.from_numpy(x, tile_hint=hint), axis).glom()), np.asarray(x.argmax(axis)))
+      all_eq(np.asarray(sp.argmin(sp.from_numpy(x, tile_hint=hint), axis).glom()), np.asarray(x.argmin(axis)))
+      all_eq(np.asarray(sp.argmax(sp.from_numpy(x, tile_hint=hint), axis).glom()), np.asarray(x.argmax(axis)))
 
 
 # ------------------------------------------------------------------ k-means and SpMV (reference parity unpinned)
@@ -464,7 +464,7 @@ def test_zero_dim_and_empty_arrays():
     assert (z + 1).glom().shape == shape
     assert sp.sum(z).glom() == 0.0
   assert sp.sum(sp.zeros((0, 5)), axis=0).glom().shape == (5,)
-  Assert.all_eq(sp.sum(sp.zeros((0, 5)), axis=0).glom(), np.zeros((5,), np.float32))
+  all_eq(sp.sum(sp.zeros((0, 5)), axis=0).glom(), np.zeros((5,), np.float32))
 
 
 def test_general_expression_outside_the_static_catalogue():
@@ -475,10 +475,10 @@ def test_general_expression_outside_the_static_catalogue():
     x = rng.randn(*shape).astype(np.float32); y = rng.randn(*shape).astype(np.float32)
     X, Y = sp.from_numpy(x), sp.from_numpy(y)
     e = (sp.abs(X - Y) * X + sp.maximum(Y, 0.5))
-    Assert.all_eq(e.optimized().glom(), np.abs(x - y) * x + np.maximum(y, np.float32(0.5)))
+    all_eq(e.optimized().glom(), np.abs(x - y) * x + np.maximum(y, np.float32(0.5)))
     got = e.sum(axis=0).optimized().glom()
     np.testing.assert_allclose(got, (np.abs(x - y).astype(np.float64) * x + np.maximum(y, 0.5)).sum(axis=0), rtol=2e-5, atol=1e-4)
-    Assert.all_eq(((X - Y) / (sp.abs(Y) + 1) - (X * X - 3)).optimized().glom(), (x - y) / (np.abs(y) + 1) - (x * x - 3))
+    all_eq(((X - Y) / (sp.abs(Y) + 1) - (X * X - 3)).optimized().glom(), (x - y) / (np.abs(y) + 1) - (x * x - 3))
 
 
 @pytest.mark.parametrize('M,N,K', [(256, 256, 64), (129, 70, 200), (384, 520, 1000), (1000, 1300, 2500), (2048, 1024, 4096)])
@@ -506,8 +506,8 @@ def test_gemm_cta_pair_matches_single_cta(M, N, K):
         Cs = C0.clone()
         device_ops.gemm(segs, Cs, accumulate=True, precision=prec)
         out[variant] = (C.cpu().numpy(), Cs.cpu().numpy())
-      Assert.all_eq(out[1][0], out[2][0])
-      Assert.all_eq(out[1][1], out[2][1])
+      all_eq(out[1][0], out[2][0])
+      all_eq(out[1][1], out[2][1])
       if prec != 'tf32x1':
         assert np.abs(out[2][0] - ref).max() <= 1e-5 * np.abs(ref).max()
         assert np.abs(out[2][1] - (ref + C0.cpu().numpy())).max() <= 2e-5 * np.abs(ref).max()
@@ -557,15 +557,15 @@ def _streamed_dot_case(M, N, K, strip, prec, k_head):
     torch.cuda.current_stream().synchronize()
     assert nbytes == M * N * 4 and c.block_events is None
     if k_head == 0:
-      Assert.all_eq(out.numpy(), want)
-      Assert.all_eq(c.glom(), want)
+      all_eq(out.numpy(), want)
+      all_eq(c.glom(), want)
     else:
-      Assert.all_eq(out.numpy(), c.glom())
+      all_eq(out.numpy(), c.glom())
       ref64 = a.astype(np.float64) @ b.astype(np.float64)
       assert np.abs(c.glom() - want).max() <= 2e-6 * np.abs(ref64).max()
       assert np.abs(c.glom() - ref64).max() <= 1e-5 * np.abs(ref64).max()
-    Assert.all_eq(ea.evaluate().glom(), a)          # cached by the streamed evaluation, resident and complete
-    Assert.all_eq(eb.evaluate().glom(), b)
+    all_eq(ea.evaluate().glom(), a)          # cached by the streamed evaluation, resident and complete
+    all_eq(eb.evaluate().glom(), b)
     assert eval_cache.get(ea.expr_id) is not None
     ref = a.astype(np.float64) @ b.astype(np.float64)
     assert np.abs(want - ref).max() <= 1e-5 * np.abs(ref).max()
@@ -584,16 +584,16 @@ def test_slice_reference_cases(hint):
   for m in ((sp, oexpr) if hint != (4, 4) else (sp,)):
     x = m.arange((T, T), tile_hint=hint)
     nx = np.arange(T * T).reshape(T, T)
-    Assert.all_eq(x[5:8, 5:8].evaluate().glom(), nx[5:8, 5:8])                          # test_slice_get
-    Assert.all_eq((x[5:8, 5:8] + 1).glom(), nx[5:8, 5:8] + 1)                           # test_slice_map
-    Assert.all_eq((x[2:9, 1:3] * x[1:8, 5:7]).optimized().glom(), nx[2:9, 1:3] * nx[1:8, 5:7])
+    all_eq(x[5:8, 5:8].evaluate().glom(), nx[5:8, 5:8])                          # test_slice_get
+    all_eq((x[5:8, 5:8] + 1).glom(), nx[5:8, 5:8] + 1)                           # test_slice_map
+    all_eq((x[2:9, 1:3] * x[1:8, 5:7]).optimized().glom(), nx[2:9, 1:3] * nx[1:8, 5:7])
     x3 = m.arange((10, 10, 10), dtype=np.int64); n3 = np.arange(1000).reshape((10, 10, 10))
-    Assert.all_eq((x3[:, :, 0] + 13).glom().reshape(10, 10), n3[:, :, 0] + 13)          # test_slice_map2
-    Assert.all_eq(x3[:, :, 0].sum().glom(), n3[:, :, 0].sum())                          # test_slice_reduce
-    Assert.all_eq(x3[2:7, :, 3:9].sum(axis=1).glom(), n3[2:7, :, 3:9].sum(axis=1))
+    all_eq((x3[:, :, 0] + 13).glom().reshape(10, 10), n3[:, :, 0] + 13)          # test_slice_map2
+    all_eq(x3[:, :, 0].sum().glom(), n3[:, :, 0].sum())                          # test_slice_reduce
+    all_eq(x3[2:7, :, 3:9].sum(axis=1).glom(), n3[2:7, :, 3:9].sum(axis=1))
     a = m.arange((T,), dtype=np.int64); na = np.arange(T)
-    Assert.all_eq((a[1:] - a[:-1]).glom(), na[1:] - na[:-1])                            # test_slice_sub
-    Assert.all_eq((a[1:] - a[:-1]).optimized().glom(), na[1:] - na[:-1])
+    all_eq((a[1:] - a[:-1]).glom(), na[1:] - na[:-1])                            # test_slice_sub
+    all_eq((a[1:] - a[:-1]).optimized().glom(), na[1:] - na[:-1])
   assert sp.extent.from_slice((slice(None), slice(None), 0), [100, 100, 100]).shape == (100, 100, 1)
 
 
@@ -602,22 +602,22 @@ def test_getitem_integer_and_newaxis():
   several integers and a bare integer keeps a unit dimension -- the evident intent is implemented)."""
   n3 = np.arange(4 * 5 * 6, dtype=np.float32).reshape(4, 5, 6)
   x = sp.from_numpy(n3, tile_hint=(2, 5, 3))
-  Assert.all_eq(x[1].glom(), n3[1])
-  Assert.all_eq(x[:, 2].glom(), n3[:, 2])
-  Assert.all_eq(x[1, :, 4].glom(), n3[1, :, 4])
-  Assert.all_eq(x[-1].glom(), n3[-1])
-  Assert.all_eq(x[:, sp.newaxis, 2:4].glom(), n3[:, np.newaxis, 2:4])
-  Assert.all_eq((x[1] * 2 + x[3]).optimized().glom(), n3[1] * 2 + n3[3])
-  Assert.all_eq(x[1:3].sum(axis=0).glom(), n3[1:3].sum(axis=0))
+  all_eq(x[1].glom(), n3[1])
+  all_eq(x[:, 2].glom(), n3[:, 2])
+  all_eq(x[1, :, 4].glom(), n3[1, :, 4])
+  all_eq(x[-1].glom(), n3[-1])
+  all_eq(x[:, sp.newaxis, 2:4].glom(), n3[:, np.newaxis, 2:4])
+  all_eq((x[1] * 2 + x[3]).optimized().glom(), n3[1] * 2 + n3[3])
+  all_eq(x[1:3].sum(axis=0).glom(), n3[1:3].sum(axis=0))
 
 
 @pytest.mark.parametrize('hint', [None, (500, 200), (64, 1347)])
 def test_transpose_reference_cases(hint):
   """tests/test_transpose.py:9-37."""
   t2 = np.transpose(np.reshape(np.arange(3721 * 1347), (3721, 1347)))
-  Assert.all_eq(sp.transpose(sp.arange((3721, 1347), tile_hint=hint)).glom(), t2)                        # transpose1
+  all_eq(sp.transpose(sp.arange((3721, 1347), tile_hint=hint)).glom(), t2)                        # transpose1
   t3 = np.transpose(np.reshape(np.arange(101 * 102 * 103), (101, 102, 103)))
-  Assert.all_eq(sp.transpose(sp.arange((101, 102, 103))).glom(), t3)                                     # transpose2
+  all_eq(sp.transpose(sp.arange((101, 102, 103))).glom(), t3)                                     # transpose2
   rng = np.random.RandomState(0)
   n1 = rng.random_sample((401, 97)); n2 = rng.random_sample((401, 97))
   got = sp.dot(sp.from_numpy(n1), sp.transpose(sp.from_numpy(n2))).glom()                                # transpose_dot (f64: exact path)
@@ -631,43 +631,43 @@ def test_transpose_reference_cases(hint):
   x = rng.random_sample((300, 200)).astype(np.float32); y = rng.random_sample((200, 300)).astype(np.float32)
   got, want = both(lambda m: (m.transpose(m.from_numpy(x)) * 2 + m.from_numpy(y)).sum(axis=0).optimized())
   np.testing.assert_allclose(got, want, rtol=1e-5)
-  Assert.all_eq((sp.from_numpy(x).T - sp.from_numpy(y)).glom(), x.T - y)
+  all_eq((sp.from_numpy(x).T - sp.from_numpy(y)).glom(), x.T - y)
 
 
 def test_reshape_reference_cases():
   """tests/test_reshape.py:9-88,98-121 (dense)."""
-  Assert.all_eq(sp.reshape(sp.arange((10, 10)), (100,)).glom(), sp.arange((100,)).glom())                # reshape1
+  all_eq(sp.reshape(sp.arange((10, 10)), (100,)).glom(), sp.arange((100,)).glom())                # reshape1
   b = sp.reshape(sp.arange((1000,), tile_hint=[100]), (10, 100)).evaluate()                              # reshape2
   sp.reshape(b, (1000,)).evaluate()
   d = sp.reshape(sp.reshape(sp.reshape(sp.arange((100, 100)), (10000,)), (10000, 1)), (1, 10000))
-  Assert.all_eq(d.glom(), sp.arange((1, 10000)).glom())                                                   # reshape3
+  all_eq(d.glom(), sp.arange((1, 10000)).glom())                                                   # reshape3
   f = sp.arange((10000,))
   for shp in ((10, 1000), (1000, 10), (20, 500), (500, 20), (1, 10000)):
     f = sp.reshape(f, shp)
-  Assert.all_eq(f.glom(), sp.arange((1, 10000)).glom())                                                   # reshape4
+  all_eq(f.glom(), sp.arange((1, 10000)).glom())                                                   # reshape4
   for n, s1, s2 in ((35511, (133, 267), (267, 133)), (12319, (127, 97), (97, 127))):                      # reshape5, 6
     d = sp.reshape(sp.reshape(sp.reshape(sp.arange((n,)), s1), s2), (1, n))
-    Assert.all_eq(d.glom(), sp.arange((1, n)).glom())
+    all_eq(d.glom(), sp.arange((1, n)).glom())
   targets = [(23, 120, 100), (12, 230, 100), (276000, 1), (1, 276000)]                                    # reshape7
   for src in ((100, 23, 120), (12, 23, 1000), (1, 276000), (276000, 1), (276000,)):
     a = sp.arange(src)
     for shp in targets:
-      Assert.all_eq(sp.reshape(a, shp).glom(), np.arange(276000).reshape(shp))
+      all_eq(sp.reshape(a, shp).glom(), np.arange(276000).reshape(shp))
   rng = np.random.RandomState(1)                                                                          # reshape_dot
   n1 = rng.random_sample((357, 93)); n2 = rng.random_sample((31, 357))
-  Assert.all_eq(np.dot(np.reshape(n1, (1071, 31)), n2),
+  all_eq(np.dot(np.reshape(n1, (1071, 31)), n2),
                 sp.dot(sp.reshape(sp.from_numpy(n1), (1071, 31)), sp.from_numpy(n2)).glom(), 10e-9)
   n1 = rng.random_sample((357, 718)); n2 = rng.random_sample((718,))
-  Assert.all_eq(np.dot(n1, np.reshape(n2, (718, 1))),
+  all_eq(np.dot(n1, np.reshape(n2, (718, 1))),
                 sp.dot(sp.from_numpy(n1), sp.reshape(sp.from_numpy(n2), (718, 1))).glom(), 10e-9)
   n1 = rng.random_sample((718,)); n2 = rng.random_sample((1, 357))
-  Assert.all_eq(np.dot(np.reshape(n1, (718, 1)), n2),
+  all_eq(np.dot(np.reshape(n1, (718, 1)), n2),
                 sp.dot(sp.reshape(sp.from_numpy(n1), (718, 1)), sp.from_numpy(n2)).glom(), 10e-9)
   # maps and reductions over reshaped / ravelled operands, tiled bases
   x = rng.random_sample((60, 70)).astype(np.float32)
   sx = sp.from_numpy(x, tile_hint=(16, 32))
-  Assert.all_eq((sp.reshape(sx, (70, 60)) * 3).glom(), x.reshape(70, 60) * 3)
-  Assert.all_eq((sp.ravel(sx) + 1).glom(), x.ravel() + 1)
+  all_eq((sp.reshape(sx, (70, 60)) * 3).glom(), x.reshape(70, 60) * 3)
+  all_eq((sp.ravel(sx) + 1).glom(), x.ravel() + 1)
   np.testing.assert_allclose(sp.reshape(sx, (4, 15, 70)).sum(axis=1).glom(), x.reshape(4, 15, 70).sum(axis=1), rtol=1e-5)
 
 
@@ -716,11 +716,11 @@ def test_runtime_specialised_kernels_match_interpreter(dtype):
   assert f1 == f0, 'run-time specialisation failed: %s' % lib.sp_jit_last_log().decode()
   assert l1 - l0 == 8 and c1 - c0 <= 4, (c0, c1, l0, l1)
   for a, b, c_ in zip(interp, jit, jit2):
-    Assert.all_eq(a, b)
-    Assert.all_eq(b, c_)
-  Assert.all_eq(jit[0], want[0])
-  Assert.all_eq(jit[1], want[1])
-  Assert.all_eq(jit[3], ((x - z) * (y + z)).max(axis=0))
+    all_eq(a, b)
+    all_eq(b, c_)
+  all_eq(jit[0], want[0])
+  all_eq(jit[1], want[1])
+  all_eq(jit[3], ((x - z) * (y + z)).max(axis=0))
 
 
 def test_replayable_evaluation_tracks_input_updates():
@@ -741,12 +741,12 @@ def test_replayable_evaluation_tracks_input_updates():
   for _ in range(3):
     got = [r.glom() for r in rep()]
   for e, g in zip(eager, got):
-    Assert.all_eq(e, g)
+    all_eq(e, g)
   x2 = rng.rand(2048, 1024).astype(np.float32)
   X.update(sp.extent.from_shape(X.shape), x2)          # new data in the same device array
   got = [r.glom() for r in rep()]
   np.testing.assert_allclose(got[0], (x2.astype(np.float64) * 2 + y).sum(axis=0), rtol=1e-5)
-  Assert.all_eq(got[1], np.abs(x2 - y) * x2 + y * y)
+  all_eq(got[1], np.abs(x2 - y) * x2 + y * y)
   np.testing.assert_allclose(got[2], (x2.astype(np.float64) * y).sum(), rtol=1e-5)
 
 
@@ -758,16 +758,16 @@ def test_save_load_checkpoint_roundtrip(tmp_path, iszip):
   x = rng.rand(300, 200).astype(np.float32)
   t1 = sp.from_numpy(x, tile_hint=(64, 50))
   assert sp.save(t1, 'fiotest1', str(tmp_path), iszip) is True
-  Assert.all_eq(t1.glom(), sp.load('fiotest1', str(tmp_path), iszip).glom())
-  Assert.all_eq(spartan_oracle.fio.load('fiotest1', str(tmp_path), iszip).glom(), x)
+  all_eq(t1.glom(), sp.load('fiotest1', str(tmp_path), iszip).glom())
+  all_eq(spartan_oracle.fio.load('fiotest1', str(tmp_path), iszip).glom(), x)
   np.testing.assert_allclose((sp.load('fiotest1', str(tmp_path), iszip) * 2 + t1).sum(axis=0).optimized().glom(),
                              (x.astype(np.float64) * 2 + x).sum(axis=0), rtol=1e-5)
   old = sp.FLAGS.checkpoint_path
   try:
     sp.FLAGS.checkpoint_path = str(tmp_path / 'ckpt')
     c = sp.expr.checkpoint(t1 + 1)
-    Assert.all_eq(c.glom(), x + 1)
-    Assert.all_eq(c.load_data().glom(), x + 1)
+    all_eq(c.glom(), x + 1)
+    all_eq(c.load_data().glom(), x + 1)
   finally:
     sp.FLAGS.checkpoint_path = old
 
@@ -792,7 +792,7 @@ def test_gemm_round_sync_is_bit_identical():
       out[on] = C.cpu().numpy()
   finally:
     check(lib.sp_gemm_set_round_sync(1), 'sp_gemm_set_round_sync')
-  Assert.all_eq(out[0], out[1])
+  all_eq(out[0], out[1])
   ref = C0.double().cpu().numpy() + A.double().cpu().numpy() @ B.double().cpu().numpy()
   assert np.abs(out[1] - ref).max() <= 1e-5 * np.abs(ref).max()
 
@@ -801,22 +801,22 @@ def test_gemm_round_sync_is_bit_identical():
 @pytest.mark.parametrize('hint', [None, (16, 4), (7, 10)])
 def test_eye_identity_diag(hint):
   """eye / identity as an extent-aware fill (INDEX leaf), diagonal / diagflat / diag as strided rectangle copies."""
-  Assert.all_eq(sp.eye(100, 10, tile_hint=hint).glom(), np.eye(100, 10))
-  Assert.all_eq(sp.eye(40, 60, k=3, tile_hint=hint).glom(), np.eye(40, 60, k=3))
-  Assert.all_eq(sp.eye(40, 60, k=-5, dtype=np.float64, tile_hint=hint).glom(), np.eye(40, 60, k=-5))
-  Assert.all_eq(sp.identity(100).glom(), np.identity(100))
+  all_eq(sp.eye(100, 10, tile_hint=hint).glom(), np.eye(100, 10))
+  all_eq(sp.eye(40, 60, k=3, tile_hint=hint).glom(), np.eye(40, 60, k=3))
+  all_eq(sp.eye(40, 60, k=-5, dtype=np.float64, tile_hint=hint).glom(), np.eye(40, 60, k=-5))
+  all_eq(sp.identity(100).glom(), np.identity(100))
   got, want = both(lambda m: m.eye(100, 10))
-  Assert.all_eq(got, want)
+  all_eq(got, want)
   rng = np.random.RandomState(2)
   for shp in ((2, 2), (15, 10), (16, 16), (10, 33)):
     x = rng.randn(*shp)
-    Assert.all_eq(sp.diagonal(sp.from_numpy(x, tile_hint=hint if hint and shp[0] > 2 else None)).glom(), np.diagonal(x))
-    Assert.all_eq(oexpr.diagonal(oexpr.from_numpy(x)).glom(), np.diagonal(x))
+    all_eq(sp.diagonal(sp.from_numpy(x, tile_hint=hint if hint and shp[0] > 2 else None)).glom(), np.diagonal(x))
+    all_eq(oexpr.diagonal(oexpr.from_numpy(x)).glom(), np.diagonal(x))
   x = rng.randn(57, 57)
-  Assert.all_eq(sp.diag(sp.from_numpy(x)).glom(), np.diag(x))
-  Assert.all_eq(sp.diag(sp.diag(sp.from_numpy(x))).glom(), np.diag(np.diag(x)))
+  all_eq(sp.diag(sp.from_numpy(x)).glom(), np.diag(x))
+  all_eq(sp.diag(sp.diag(sp.from_numpy(x))).glom(), np.diag(np.diag(x)))
   xf = rng.randn(300).astype(np.float32)
-  Assert.all_eq(sp.diagflat(sp.from_numpy(xf, tile_hint=(64,)), tile_hint=(128, 100)).glom(), np.diagflat(xf))
+  all_eq(sp.diagflat(sp.from_numpy(xf, tile_hint=(64,)), tile_hint=(128, 100)).glom(), np.diagflat(xf))
 
 
 def test_std_reference_cases():

@@ -315,6 +315,13 @@ int sp_gemm_prepare_b_rows(const float* B, int64_t ldb, int64_t K, int64_t N, in
                            int64_t copy_stride, int64_t Kp, int64_t k_offset, void* stream);
 int sp_gemm_prepared_views(int n_seg, const sp_gemm_prepared_view* segs, float* C, int64_t ldc, int64_t M, int64_t N,
                            int accumulate, int precision, void* stream);
+/* Gated form for the multi-GPU dot (dot.py:195-238; join_mapper's remote strip fetches, map.py:243-286): segment s is
+ * read only after *ready_flag[s] has reached ready_value[s] (NULL flag = not gated).  Peers push operand strips into this
+ * GPU's memory and write the flag behind them (sp_peer_push); the contraction runs on what is present and picks up the
+ * rest as it lands, in one launch.  A gate closed for ~4 s is given up and counted in *gate_status (device word or NULL). */
+int sp_gemm_prepared_views_gated(int n_seg, const sp_gemm_prepared_view* segs, const uint32_t* const* ready_flag,
+                                 const uint32_t* ready_value, uint32_t* gate_status, float* C, int64_t ldc, int64_t M,
+                                 int64_t N, int accumulate, int precision, void* stream);
 /* Fused row-argmin epilogue over prepared operands (no C is stored): for every row and every 128-column half tile,
  * part_val[row][p] = min_j (col_bias[j] - 2 * (A.B)[row, j]) and part_idx[row][p] = arg min (ties: smallest j);
  * p < sp_gemm_argmin_parts(N).  k-means assignment: col_bias = |c_j|^2 (k_means_.py:61-66). */
@@ -354,6 +361,30 @@ int sp_spmv_csr(const int64_t* rowptr, const int32_t* colidx, const float* value
  * float64 / int64 operands: tests/test_dot.py:8-103, tests/test_matmul.py:12-22). */
 int sp_gemm_simt(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t M, int64_t N,
                  int64_t K, int dtype, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Peer memory: the cross-rank tile movement of the path (one process per GPU).
+ * Replaces the strip fetches / partial-tile updates the reference sends over its RPC layer
+ * (join_mapper map.py:243-286 -> DistArrayImpl.fetch distarray.py:294-367 -> Worker.get worker.py:188-217).
+ * A rank allocates symmetric buffers (sp_peer_alloc: cudaMalloc'ed, zero-filled), exports them (sp_peer_export writes
+ * sp_peer_handle_bytes() bytes the host exchanges by any means) and opens its peers' (sp_peer_import / sp_peer_close).
+ * sp_peer_push moves `bytes` from a local buffer to n destinations with the copy engines over NVLink and writes, behind
+ * each copy in stream order, the 4-byte word at flag_src into flag_dst[i] (may be NULL) -- the word a consumer polls
+ * (sp_gemm_prepared_views_gated, sp_wait_u32).  sp_write_u32 / sp_wait_u32 are the stream-side set / wait of such a
+ * word (wait gives up after timeout_ms and increments *status, a device uint32 or NULL).
+ * ------------------------------------------------------------------------ */
+int sp_peer_alloc(int64_t bytes, void** out);
+int sp_peer_free(void* p);
+int sp_peer_handle_bytes(void);
+int sp_peer_export(void* p, void* handle_out);
+int sp_peer_import(const void* handle, void** out);
+int sp_peer_close(void* p);
+int sp_peer_push(int n, void* const* dst, const void* src, int64_t bytes, void* const* flag_dst, const void* flag_src,
+                 void* stream);
+int sp_peer_push_2d(int n, void* const* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width_bytes,
+                    int64_t rows, void* const* flag_dst, const void* flag_src, void* stream);
+int sp_write_u32(void* p, uint32_t value, void* stream);
+int sp_wait_u32(const void* flag, uint32_t value, int64_t timeout_ms, void* status, void* stream);
 
 #ifdef __cplusplus
 }

@@ -103,6 +103,18 @@ _SIGS = {
   'sp_gemm_prepare_a_rows': (_int, [_vp, _i64, _i64, _i64, _int, _vp, _i64, _i64, _i64, _vp]),
   'sp_gemm_prepare_b_rows': (_int, [_vp, _i64, _i64, _i64, _int, _vp, _i64, _i64, _i64, _vp]),
   'sp_gemm_prepared_views': (_int, [_int, ctypes.POINTER(sp_gemm_prepared_view), _vp, _i64, _i64, _i64, _int, _int, _vp]),
+  'sp_gemm_prepared_views_gated': (_int, [_int, ctypes.POINTER(sp_gemm_prepared_view), ctypes.POINTER(_vp),
+                                          ctypes.POINTER(ctypes.c_uint32), _vp, _vp, _i64, _i64, _i64, _int, _int, _vp]),
+  'sp_peer_alloc': (_int, [_i64, ctypes.POINTER(_vp)]),
+  'sp_peer_free': (_int, [_vp]),
+  'sp_peer_handle_bytes': (_int, []),
+  'sp_peer_export': (_int, [_vp, _vp]),
+  'sp_peer_import': (_int, [_vp, ctypes.POINTER(_vp)]),
+  'sp_peer_close': (_int, [_vp]),
+  'sp_peer_push': (_int, [_int, ctypes.POINTER(_vp), _vp, _i64, ctypes.POINTER(_vp), _vp, _vp]),
+  'sp_peer_push_2d': (_int, [_int, ctypes.POINTER(_vp), _i64, _vp, _i64, _i64, _i64, ctypes.POINTER(_vp), _vp, _vp]),
+  'sp_write_u32': (_int, [_vp, ctypes.c_uint32, _vp]),
+  'sp_wait_u32': (_int, [_vp, ctypes.c_uint32, _i64, _vp, _vp]),
   'sp_gemm_argmin_parts': (_i64, [_i64]),
   'sp_gemm_prepared_argmin': (_int, [_int, ctypes.POINTER(sp_gemm_prepared_segment), _i64, _i64, _vp, _vp, _vp, _int, _vp]),
   'sp_gemm_f32_workspace_bytes': (_i64, [_i64, _i64, _int, _i64p, _int]),

@@ -16,6 +16,7 @@ largest_value, good_tile_shape, compute_extents) and of spartan/expr/operator/br
 """
 import collections
 import ctypes
+import itertools
 
 import numpy as np
 import torch
@@ -27,6 +28,7 @@ from ..core import TileId
 from ..util import require_type, require_equal, require_unique
 
 DEFAULT_TILE_SIZE = 100000   # distarray.py:20
+_serials = itertools.count(1)
 
 
 def good_tile_shape(shape, num_shards=-1):
@@ -150,9 +152,11 @@ class DistArrayImpl(DistArray):
     self.slab = None                        # this rank's tiles as one HBM allocation (or None)
     self.slab_axes = None                   # per-axis sorted (lo, hi) intervals covered by the slab
     self.block_events = None                # [(region, CUDA event)] left by a producer that finished block by block
+    self.serial = next(_serials)            # identity of this array for caches of derived data (never reused)
 
   def __del__(self):
     try:
+      device_ops.prepared_cache.drop(self.serial)
       self.ctx.destroy_all(list(self.tiles.values()))
     except Exception:
       pass
@@ -304,6 +308,7 @@ class DistArrayImpl(DistArray):
     ctx = self.ctx
     me = ctx.worker_id
     self.block_events = None
+    ctx.touch()
     if (host and self.reducer_fn is None and self.slab is not None and len(self.shape) > 0
         and tuple(region.shape) == self.shape and data.dtype == self.dtype):
       # whole-array upload: one H2D copy per contiguous block of this rank's slab instead of one per tile

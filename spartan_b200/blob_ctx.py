@@ -53,6 +53,21 @@ class BlobCtx(object):
     self._scratch = {}
     self._side_streams = {}
     self.kernel_launches = 0                  # launches of this library's kernels (bench.py "gpu_launches")
+    self.data_epoch = 0                       # bumped whenever an existing array may have changed in place
+    self._peer = None
+    self.push_done = None                     # event after the last copy-engine push of this rank
+
+  @property
+  def peer(self):
+    """Peer memory of the job (spartan_b200/peer.py), created on first use."""
+    if self._peer is None:
+      from .peer import PeerMemory
+      self._peer = PeerMemory(self)
+    return self._peer
+
+  def touch(self):
+    """Some array was modified in place: derived copies (prepared GEMM operands) are stale."""
+    self.data_epoch += 1
 
   # ------------------------------------------------------------------ reference surface
   def is_master(self):
@@ -89,6 +104,7 @@ class BlobCtx(object):
 
   def update(self, tile_id, subslice, data, reducer, wait=True):
     """blob_ctx.py:163-179 -> Tile.merge; local tiles only."""
+    self.data_epoch += 1
     return self._blobs[tile_id].update(subslice, data, reducer)
 
   def destroy_all(self, tile_ids):
@@ -168,5 +184,9 @@ def initialize(device=None):
 
 
 def shutdown():
+  ctx = _global_ctx[0]
+  if ctx is not None and ctx._peer is not None:
+    ctx._peer.close()
+    ctx._peer = None
   _global_ctx[0] = None
   _local.ctx = None

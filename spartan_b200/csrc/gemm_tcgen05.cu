@@ -89,6 +89,11 @@ struct Params {
   unsigned int* round_sync;
   int sync_kb;           // additional check-ins every sync_kb k-blocks inside a tile (0 = only at tile starts)
   int group_m;           // tile rasterisation: tile rows per group
+  // gated segments (multi-GPU dot): segment s may only be read once *seg_flag[s] has reached seg_flag_value[s] -- the word
+  // a peer's copy engine writes after it has pushed the operand strip of that segment into this GPU's memory (peer.cu)
+  const unsigned int* seg_flag[8];
+  unsigned int seg_flag_value[8];
+  unsigned int* gate_status;   // incremented when a gate times out (the launch then finishes on whatever is there)
 };
 
 // ----------------------------------------------------------------------------
@@ -296,6 +301,28 @@ __device__ __forceinline__ void round_checkin(unsigned int* counter, unsigned in
   wait = false;
 }
 
+// Gate of a K segment whose operand strip is pushed into this GPU's memory by a peer (peer.cu: data copy, then a flag word,
+// both by the copy engine, in stream order).  The TMA thread polls the flag with a system-scope acquire load; the fence
+// orders that generic-proxy read before the async-proxy (TMA) reads of the strip.  Bounded: after ~4 s the launch goes on
+// and reports through gate_status, so a lost peer cannot hang the GPU.
+__device__ __forceinline__ void gate_wait(const unsigned int* flag, unsigned int value, unsigned int* status) {
+  unsigned long long t0 = 0;
+  for (unsigned int spin = 0;; ++spin) {
+    unsigned int seen;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+    if (static_cast<int>(seen - value) >= 0) break;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (spin == 0) t0 = t;
+    if (t - t0 > 4000000000ull) {
+      if (status != nullptr) atomicAdd(status, 1u);
+      break;
+    }
+    __nanosleep(128);
+  }
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+
 // ----------------------------------------------------------------------------
 // The kernel.  KIND 0: tf32 operands (BK = 32 elements), KIND 1: bf16 (BK = 64).
 // PAIR false: one CTA per 128 x 256 tile, a pipeline stage = the (A, Bt) tiles of one precision term.
@@ -373,6 +400,7 @@ gemm_kernel(const __grid_constant__ Params p) {
         uint32_t phase = 0;
         unsigned int round_target = 0;
         bool round_wait = true;
+        unsigned int gate_seen = 0;      // segments whose gate this CTA has passed
         for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
           int m_blk, n_blk;
           tile_coords(tile, m_tiles, p.n_blocks, p.group_m, m_blk, n_blk);
@@ -384,6 +412,10 @@ gemm_kernel(const __grid_constant__ Params p) {
           }
           for (int s = 0; s < p.n_segs; ++s) {
             const Segment seg = p.segs[s];
+            if (p.seg_flag[s] != nullptr && !((gate_seen >> s) & 1u)) {
+              gate_wait(p.seg_flag[s], p.seg_flag_value[s], p.gate_status);
+              gate_seen |= 1u << s;
+            }
             for (int kb = 0; kb < seg.k_blocks; ++kb) {
               if constexpr (PAIR) {
                 if (p.round_sync != nullptr && rank == 0 && p.sync_kb > 0 && kb > 0 && kb % p.sync_kb == 0)
@@ -841,9 +873,15 @@ extern "C" int sp_gemm_prepare_b(const float* B, int64_t ldb, int64_t K, int64_t
   return sp_gemm_prepare_b_rows(B, ldb, K, N, precision, out, N * Kp * md.elem, Kp, k_offset, stream_);
 }
 
+struct Gates {
+  const uint32_t* const* flags;    // per segment: word to poll (NULL = not gated)
+  const uint32_t* values;          // per segment: value the word must reach
+  uint32_t* status;                // time-out counter (device memory) or NULL
+};
+
 static int launch_prepared(int n_seg, const sp_gemm_prepared_view* segs, float* C, int64_t ldc, int64_t M, int64_t N,
                            int accumulate, int precision, int epi_mode, const float* col_bias, float* part_val,
-                           int* part_idx, void* stream_) {
+                           int* part_idx, void* stream_, const Gates* gates = nullptr) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   Mode md;
   SP_REQUIRE(mode_of(precision, &md), SP_ERR_INVALID, "sp_gemm_prepared: unknown precision %d", precision);
@@ -915,6 +953,13 @@ static int launch_prepared(int n_seg, const sp_gemm_prepared_view* segs, float* 
     }
   }
   p.n_segs = n_seg;
+  if (gates != nullptr) {
+    for (int s = 0; s < n_seg; ++s) {
+      p.seg_flag[s] = gates->flags ? gates->flags[s] : nullptr;
+      p.seg_flag_value[s] = gates->values ? gates->values[s] : 0u;
+    }
+    p.gate_status = gates->status;
+  }
   p.chunk_kb = g_chunk_override > 0 ? g_chunk_override : md.chunk_kb;
   p.M = static_cast<int>(M);
   p.N = static_cast<int>(N);
@@ -985,6 +1030,19 @@ extern "C" int sp_gemm_prepared_views(int n_seg, const sp_gemm_prepared_view* se
                                       int64_t N, int accumulate, int precision, void* stream_) {
   SP_REQUIRE(C != nullptr, SP_ERR_INVALID, "sp_gemm_prepared_views: null C");
   return launch_prepared(n_seg, segs, C, ldc, M, N, accumulate, precision, 0, nullptr, nullptr, nullptr, stream_);
+}
+
+// Same, with gated segments: segment s is read only after *ready_flag[s] has reached ready_value[s] (wrap-safe compare;
+// ready_flag[s] == NULL: not gated).  The flags are words in this GPU's memory that peers write behind the operand strips
+// they push (sp_peer_push): the contraction starts on the strips that are present and picks the others up as they land,
+// inside ONE launch -- the device side of the dot row x column shuffle (dot.py:195-238, map.py:243-286 join_mapper).
+// A gate that stays closed for ~4 s is given up and counted in *gate_status (device uint32, may be NULL).
+extern "C" int sp_gemm_prepared_views_gated(int n_seg, const sp_gemm_prepared_view* segs, const uint32_t* const* ready_flag,
+                                            const uint32_t* ready_value, uint32_t* gate_status, float* C, int64_t ldc,
+                                            int64_t M, int64_t N, int accumulate, int precision, void* stream_) {
+  SP_REQUIRE(C != nullptr, SP_ERR_INVALID, "sp_gemm_prepared_views_gated: null C");
+  Gates g{ready_flag, ready_value, gate_status};
+  return launch_prepared(n_seg, segs, C, ldc, M, N, accumulate, precision, 0, nullptr, nullptr, nullptr, stream_, &g);
 }
 
 // Fused row-argmin epilogue (k-means assignment, k_means_.py:61-66): for every row and every 128-column half tile

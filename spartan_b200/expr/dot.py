@@ -21,7 +21,7 @@ import torch
 from .. import blob_ctx, device_ops
 from ..array import distarray, extent
 from ..config import FLAGS
-from .._lib import SpartanError
+from .._lib import SpartanError, SP_GEMM_MAX_SEGMENTS
 from .base import Expr, lazify, eval_cache
 from .write_array import WriteArrayExpr
 
@@ -254,6 +254,10 @@ class DotExpr(Expr):
       return Expr.evaluate(self)
     a_axes, b_axes, c_runs = layout
     ka, nb = av.slab.shape[1], bv.slab.shape[1]
+    strip = int(FLAGS.dot_stream_strip)
+    n_strips = -(-M // strip)
+    if W <= SP_GEMM_MAX_SEGMENTS and 2 * n_strips * W <= 2048 and ctx.peer.available():
+      return self._evaluate_streamed_peer(ctx, av, bv, target, a_axes, b_axes, c_runs, M, N, K, precision)
     main = torch.cuda.current_stream(ctx.device)
     copy, commst = ctx.side_stream('h2d'), ctx.side_stream('dot_comm')
     copy.wait_stream(main); commst.wait_stream(main)
@@ -285,13 +289,15 @@ class DotExpr(Expr):
       with torch.cuda.stream(copy):
         upload_cols(av.slab, a_np, r0, r1, a_axes[me][1])
         ev_a = copy.record_event()
-      mine = device_ops.PreparedOperand(r1 - r0, ka, precision, 'dot_ms_mine%d' % i)
-      nbytes = mine.buf.numel()
-      gathered = ctx.scratch(W * nbytes, 'dot_ms_gath%d' % i)[:W * nbytes]
       with torch.cuda.stream(commst):
         commst.wait_event(ev_a)
         if i == 0:
           commst.wait_event(ev_pb)        # scratch buffers recycled from an earlier evaluation: main-stream readers first
+        # constructed on the stream that fills it: the zero-fill of a padded operand (K/W not a multiple of the k-block)
+        # must be ordered before prepare_a and the gather, not behind the previous strip's GEMM on the main stream
+        mine = device_ops.PreparedOperand(r1 - r0, ka, precision, 'dot_ms_mine%d' % i)
+        nbytes = mine.buf.numel()
+        gathered = ctx.scratch(W * nbytes, 'dot_ms_gath%d' % i)[:W * nbytes]
         mine.prepare_a(av.slab[r0:r1, :], 0)
         dist.all_gather_into_tensor(gathered, mine.buf)
         ev_g = commst.record_event()
@@ -311,6 +317,167 @@ class DotExpr(Expr):
       if e.needs_cache:
         eval_cache.set(e.expr_id, v)
     return target
+
+  def _evaluate_streamed_peer(self, ctx, av, bv, target, a_axes, b_axes, c_runs, M, N, K, precision):
+    """The streamed multi-GPU dot over peer memory.  Per A row strip i, every rank
+        copy stream:  H2D of the strip's owned columns (all strips are queued up front; PCIe never waits for compute)
+        main stream:  split/round the strip straight into slot [i][me] of its symmetric gather buffer
+        push stream:  copy-engine push of that slot into slot [i][me] of every peer + the epoch word behind it
+        main stream:  ONE gated launch  C[strip, mine] = sum_p A_p[strip, :] . B[k_p, mine]  that starts on the local
+                      segment and picks each peer's segment up when its flag arrives
+    with the strip loop software-pipelined on the main stream (prepare i+1 is queued before contract i), so the only SM
+    work between two contractions is one short preparation kernel and nothing on the SMs ever waits for a collective."""
+    ea, eb = self.matrix_a, self.matrix_b
+    a_np, b_np = ea.npa, eb.npa
+    W, me = ctx.num_workers, ctx.worker_id
+    peer = ctx.peer
+    ka, nb = av.slab.shape[1], bv.slab.shape[1]
+    strip = int(FLAGS.dot_stream_strip)
+    strips = [(r0, min(M, r0 + strip)) for r0 in range(0, M, strip)]
+    S = len(strips)
+    Kp = device_ops.gemm_kpad(ka, precision)
+    part = device_ops.gemm_prepared_bytes(strip, Kp, precision)         # bytes of one (strip, source rank) slot
+    rb = device_ops.gemm_row_bytes(Kp, precision)
+    main = torch.cuda.current_stream(ctx.device)
+    copy, push = ctx.side_stream('h2d'), ctx.side_stream('peer_push')
+    copy.wait_stream(main)
+    if ctx.push_done is not None:
+      main.wait_event(ctx.push_done)
+    gather = peer.buffer('dot_stream_gather', 2 * S * W * part)
+    f0 = peer.flag_range('dot_stream_gather', 2048)
+    epoch, esrc = peer.next_epoch('dot_stream_gather')
+    half = epoch & 1
+
+    def slot(i, p):
+      return (half * S + i) * W + p
+
+    def upload_cols(slab, host, r0, r1, col_intervals):
+      off = 0
+      for c0, c1 in col_intervals:
+        device_ops.upload_rect(slab[r0:r1, off:off + (c1 - c0)], host[r0:r1, c0:c1])
+        off += c1 - c0
+
+    with torch.cuda.stream(copy):
+      upload_cols(bv.slab, b_np, 0, K, b_axes[me][1])
+      ev_b = copy.record_event()
+      ev_a = []
+      for r0, r1 in strips:
+        upload_cols(av.slab, a_np, r0, r1, a_axes[me][1])
+        ev_a.append(copy.record_event())
+
+    order = [(me + j) % W for j in range(W)]
+
+    def prepare_and_push(i):
+      r0, r1 = strips[i]
+      main.wait_event(ev_a[i])
+      mine = device_ops.PreparedOperand(r1 - r0, ka, precision, None,
+                                        buf=gather.tensor[slot(i, me) * part:(slot(i, me) + 1) * part])
+      mine.prepare_a(av.slab[r0:r1, :], 0)
+      ev = main.record_event()
+      with torch.cuda.stream(push):
+        push.wait_event(ev)
+        dsts = [(me - j) % W for j in range(1, W)]           # ring order: the peer that needs this slot first goes first
+        peer.push([gather.ptrs[d] + slot(i, me) * part for d in dsts], mine.buf.data_ptr(), mine.nbytes,
+                  [peer.flag_ptr(d, f0 + slot(i, me)) for d in dsts], esrc)
+        ctx.push_done = push.record_event()
+      return mine
+
+    # B[:, mine]: prepared once per source rank p as the rows k_p of the transposed operand
+    main.wait_event(ev_b)
+    pbs = []
+    for p in range(W):
+      pb = device_ops.PreparedOperand(nb, ka, precision, 'dot_ms_b%d' % p)
+      off = 0
+      for a, b in a_axes[p][1]:
+        pb.prepare_b(bv.slab[a:b, :], 0, k_offset=off)
+        off += b - a
+      pbs.append(pb)
+    done = []
+    mines = {0: prepare_and_push(0)}
+    for i, (r0, r1) in enumerate(strips):
+      if i + 1 < S:
+        mines[i + 1] = prepare_and_push(i + 1)
+      mine = mines.pop(i)
+      views, flags = [], []
+      for p in order:
+        a_ptr = gather.local_ptr + slot(i, p) * part
+        views.append((a_ptr, (r1 - r0) * rb, pbs[p].row_ptr(0), pbs[p].copy_stride, Kp))
+        flags.append(0 if p == me else peer.flag_ptr(me, f0 + slot(i, p)))
+      device_ops.gemm_prepared_views_gated(views, flags, [epoch] * W, peer.status.data_ptr(), target.slab[r0:r1, :],
+                                           False, precision)
+      ev_c = main.record_event()
+      for c0, c1 in c_runs[me][1]:
+        done.append((extent.create((r0, c0), (r1, c1), (M, N)), ev_c))
+    for arr in (av, bv, target):
+      for tid in arr.tiles.values():
+        if ctx.is_local(tid):
+          ctx.tile(tid).valid = True
+    target.block_events = done
+    for e, v in ((ea, av), (eb, bv)):
+      if e.needs_cache:
+        eval_cache.set(e.expr_id, v)
+    return target
+
+  def _peer_gather_path(self, ctx, av, bv, target, shape, M, N, K, dtype, precision):
+    """Multi-GPU dot over peer memory for the regular placement (every rank owns whole column blocks of A, B and C):
+    every rank prepares its own A slab once (cached while A is unchanged), its copy engines push the prepared slab into
+    the symmetric gather buffer of every peer -- ring order, an epoch word behind each copy -- and ONE gated tcgen05
+    launch per C block contracts  C[:, mine] = sum_p A_p . B[k_p, mine]  starting with the local segment and taking
+    each peer's segment as its flag arrives.  The exchange costs no SM and is hidden behind the segments already present;
+    the gather buffer is double-buffered by epoch so a fast rank never overwrites a slab a slow peer is still reading.
+    Returns False when the placement is not of this form or CUDA IPC is unavailable (NCCL path follows)."""
+    W, me = ctx.num_workers, ctx.worker_id
+    if W == 1 or W > SP_GEMM_MAX_SEGMENTS or len(shape) != 2 or dtype != np.float32 or precision == 'simt':
+      return False
+    if not (isinstance(av, distarray.DistArrayImpl) and isinstance(bv, distarray.DistArrayImpl)):
+      return False
+    if av.dtype != np.float32 or bv.dtype != np.float32:
+      return False
+    if av.slab is None or bv.slab is None or target.slab is None:
+      return False
+    layout = _regular_layout(av, bv, target, W, M, K)
+    if layout is None or not ctx.peer.available():
+      return False
+    a_axes, b_axes, c_runs = layout
+    peer = ctx.peer
+    width = av.slab.shape[1]
+    Kp = device_ops.gemm_kpad(width, precision)
+    a_bytes = device_ops.gemm_prepared_bytes(M, Kp, precision)
+    rb = device_ops.gemm_row_bytes(Kp, precision)
+    main = torch.cuda.current_stream(ctx.device)
+    push = ctx.side_stream('peer_push')
+    if ctx.push_done is not None:
+      main.wait_event(ctx.push_done)        # an earlier push may still be reading the buffer about to be re-prepared
+    mine = device_ops.cached_operand(av, ('a_slab',), M, width, precision, lambda op: op.prepare_a(av.slab, 0))
+    gather = peer.buffer('dot_gather', 2 * W * a_bytes)
+    f0 = peer.flag_range('dot_gather', 2 * W)
+    epoch, esrc = peer.next_epoch('dot_gather')
+    half = epoch & 1
+    ev = main.record_event()
+    with torch.cuda.stream(push):
+      push.wait_event(ev)
+      dsts = [(me - j) % W for j in range(1, W)]
+      peer.push([gather.ptrs[d] + (half * W + me) * a_bytes for d in dsts], mine.buf.data_ptr(), mine.nbytes,
+                [peer.flag_ptr(d, f0 + half * W + me) for d in dsts], esrc)
+      ctx.push_done = push.record_event()
+    order = [(me + j) % W for j in range(W)]
+    for (r0, r1) in c_runs[me][0]:
+      for (c0, c1) in c_runs[me][1]:
+        views, flags = [], []
+        for p in order:
+          def fill(op, p=p):
+            off = 0
+            for a, b in a_axes[p][1]:
+              Bv = bv.fetch(extent.create((a, c0), (b, c1), bv.shape))       # zero-copy view of this rank's B slab
+              op.prepare_b(Bv, 0, k_offset=off)
+              off += b - a
+          pb = device_ops.cached_operand(bv, ('b_cols', c0, c1, p), c1 - c0, width, precision, fill)
+          a_ptr = mine.row_ptr(r0) if p == me else gather.local_ptr + (half * W + p) * a_bytes + r0 * rb
+          views.append((a_ptr, M * rb, pb.row_ptr(0), pb.copy_stride, Kp))
+          flags.append(0 if p == me else peer.flag_ptr(me, f0 + half * W + p))
+        Cv = target.fetch(extent.create((r0, c0), (r1, c1), shape))
+        device_ops.gemm_prepared_views_gated(views, flags, [epoch] * W, peer.status.data_ptr(), Cv, False, precision)
+    return True
 
   def _allgather_path(self, ctx, av, bv, target, shape, M, N, K, dtype, precision):
     """Multi-GPU fast path for the regular placement (every rank owns whole column blocks of A, B and C, e.g.
@@ -422,7 +589,8 @@ class DotExpr(Expr):
     def cast(t):
       return t if t.dtype == blob_ctx.torch_dtype(dtype) else t.to(blob_ctx.torch_dtype(dtype))
 
-    if self._allgather_path(ctx, av, bv, target, shape, M, N, K, dtype, precision):
+    if (self._peer_gather_path(ctx, av, bv, target, shape, M, N, K, dtype, precision) or
+        self._allgather_path(ctx, av, bv, target, shape, M, N, K, dtype, precision)):
       for tid in target.tiles.values():
         if ctx.is_local(tid):
           ctx.tile(tid).valid = True
@@ -458,6 +626,14 @@ class DotExpr(Expr):
         C2 = Cv.reshape(A.shape[0], B.shape[1])
         if C2.data_ptr() != Cv.data_ptr() or C2.stride(-1) != 1:
           raise SpartanError('dot target block is not addressable as a row-major view')
+        if (W == 1 and len(shape) == 2 and dtype == np.float32 and precision != 'simt' and K > 0
+            and isinstance(av, distarray.DistArrayImpl) and isinstance(bv, distarray.DistArrayImpl)
+            and A.stride(1) == 1 and B.stride(1) == 1 and FLAGS.dot_prepared_cache):
+          # operands prepared once while the arrays are unchanged (same kernels, same bits as the uncached call)
+          pa = device_ops.cached_operand(av, ('a_rows', r0, r1), r1 - r0, K, precision, lambda op, A=A: op.prepare_a(A, 0))
+          pb = device_ops.cached_operand(bv, ('b_cols', c0, c1), c1 - c0, K, precision, lambda op, B=B: op.prepare_b(B, 0))
+          device_ops.gemm_prepared_rows(pa, 0, r1 - r0, pb, 0, c1 - c0, C2, accumulate=False)
+          continue
         device_ops.gemm_views(A, B, C2, accumulate=False, precision=precision)   # transposed views: no copy
     for tid in target.tiles.values():
       if ctx.is_local(tid):

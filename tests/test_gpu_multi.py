@@ -19,10 +19,10 @@ def _free_port():
   s = socket.socket(); s.bind(('127.0.0.1', 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, use_peer):
   try:
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR='127.0.0.1',
-                      MASTER_PORT=str(port))
+                      MASTER_PORT=str(port), SPARTAN_PEER='1' if use_peer else '0')
     if ROOT not in sys.path:
       sys.path.insert(0, ROOT)
     import torch.distributed as dist
@@ -38,6 +38,34 @@ def _worker(rank, world, port, q):
         got = sp.dot(sp.from_numpy(a, tile_hint=hint), sp.from_numpy(b, tile_hint=hint), tile_hint=hint).glom()
         err = np.abs(got - ref).max() / np.abs(ref).max()
         assert err <= tol, (M, K, N, hint, prec, err)
+    # the regular placement goes over peer memory (copy-engine pushes + gated segments) when CUDA IPC works
+    peer_ok = ctx.peer.available()
+    assert peer_ok or not use_peer or os.environ.get('SPARTAN_ALLOW_NO_IPC'), 'CUDA IPC between the two ranks failed'
+    print('rank %d: peer memory %s' % (rank, 'available' if peer_ok else 'UNAVAILABLE (NCCL paths)'), flush=True)
+    from spartan_b200.expr.base import lazify as _lz
+    sp.FLAGS.dot_precision = 'bf16x3'
+    # K/W not a multiple of the k-block (zero-padded prepared operands), repeated evaluations over the same arrays
+    # (prepared-operand cache + the two halves of the gather buffer), then an in-place update (cache invalidation)
+    for (M, K, N, ha, hb, hc) in [(512, 1000, 512, (256, 500), (500, 256), (256, 256)),
+                                  (384, 2048, 768, (128, 256), (256, 128), (128, 128))]:
+      a = rng.standard_normal((M, K), dtype=np.float32); b = rng.standard_normal((K, N), dtype=np.float32)
+      Ad = sp.from_numpy(a, tile_hint=ha).evaluate(); Bd = sp.from_numpy(b, tile_hint=hb).evaluate()
+      ref = a.astype(np.float64) @ b.astype(np.float64)
+      outs = []
+      for _ in range(4):
+        outs.append(sp.dot(_lz(Ad), _lz(Bd), tile_hint=hc).glom())
+      for o in outs:
+        assert np.abs(o - ref).max() <= 1e-5 * np.abs(ref).max()
+        assert np.array_equal(o, outs[0])
+      a2 = rng.standard_normal((M, K), dtype=np.float32)
+      Ad.update(sp.extent.from_shape(Ad.shape), a2)
+      got = sp.dot(_lz(Ad), _lz(Bd), tile_hint=hc).glom()
+      ref2 = a2.astype(np.float64) @ b.astype(np.float64)
+      assert np.abs(got - ref2).max() <= 1e-5 * np.abs(ref2).max()
+      sp.FLAGS.dot_prepared_cache = False
+      again = sp.dot(_lz(Ad), _lz(Bd), tile_hint=hc).glom()
+      sp.FLAGS.dot_prepared_cache = True
+      assert np.array_equal(again, got)
     # fused map + reduce: partials combined by ncclAllReduce
     x = rng.random((1024, 2048), dtype=np.float32); y = rng.random((1024, 2048), dtype=np.float32)
     for hint in [(128, 2048), (256, 512), None]:
@@ -54,12 +82,15 @@ def _worker(rank, world, port, q):
     # dot over host operands with the upload pipelined against the contraction (per-strip prepare + all-gather + GEMM
     # on three streams); checked against float64 and the resident multi-GPU path, through glom and block-wise read-back
     sp.FLAGS.dot_precision = 'bf16x3'
-    for (M, K, N, hint, strip) in [(1024, 1024, 1024, (256, 256), 256), (768, 512, 1024, (128, 128), 200)]:
+    for (M, K, N, hint, strip) in [(1024, 1024, 1024, (256, 256), 256), (768, 512, 1024, (128, 128), 200),
+                                   (640, 1000, 512, None, 256), (1024, 1024, 1024, (256, 256), 256)]:
       a = rng.standard_normal((M, K), dtype=np.float32); b = rng.standard_normal((K, N), dtype=np.float32)
+      ha, hb = (hint, hint) if hint is not None else ((128, 500), (500, 256))     # K/W = 500: padded k-blocks
+      hint = hint or (128, 256)
       sp.FLAGS.dot_stream_host_operands = False
-      want = sp.dot(sp.from_numpy(a, tile_hint=hint), sp.from_numpy(b, tile_hint=hint), tile_hint=hint).glom()
+      want = sp.dot(sp.from_numpy(a, tile_hint=ha), sp.from_numpy(b, tile_hint=hb), tile_hint=hint).glom()
       sp.FLAGS.dot_stream_host_operands = True; sp.FLAGS.dot_stream_min_bytes = 0; sp.FLAGS.dot_stream_strip = strip
-      c = sp.dot(sp.from_numpy(a, tile_hint=hint), sp.from_numpy(b, tile_hint=hint), tile_hint=hint).evaluate()
+      c = sp.dot(sp.from_numpy(a, tile_hint=ha), sp.from_numpy(b, tile_hint=hb), tile_hint=hint).evaluate()
       assert c.block_events, 'the streamed multi-rank path did not run'
       out = torch.zeros((M, N), dtype=torch.float32, pin_memory=True)
       nbytes = c.read_local_into(out.numpy())
@@ -87,20 +118,25 @@ def _worker(rank, world, port, q):
     x2 = rng.random((1024, 2048), dtype=np.float32)
     X.update(sp.extent.from_shape(X.shape), x2)
     np.testing.assert_allclose(rep().glom(), (x2.astype(np.float64) * 2 + y).sum(axis=0), rtol=1e-5)
+    if peer_ok:
+      assert ctx.peer.gate_timeouts() == 0, 'a gated GEMM segment timed out waiting for its operand strip'
     dist.barrier()
     q.put((rank, 'ok'))
   except Exception:
     q.put((rank, traceback.format_exc()))
 
 
-def test_two_ranks_nccl():
+@pytest.mark.parametrize('use_peer', [True, False], ids=['peer-memory', 'nccl-only'])
+def test_two_ranks_nccl(use_peer):
+  """use_peer=False forces the NCCL all-gather implementations of the dot exchange (the fallback when CUDA IPC is not
+  available between the ranks)."""
   if torch.cuda.device_count() < 2:
     pytest.skip('needs 2 GPUs')
   world = 2
   ctx = mp.get_context('spawn')
   q = ctx.Queue()
   port = _free_port()
-  procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+  procs = [ctx.Process(target=_worker, args=(r, world, port, q, use_peer)) for r in range(world)]
   for p in procs: p.start()
   results = [q.get(timeout=600) for _ in range(world)]
   for p in procs: p.join(timeout=60)

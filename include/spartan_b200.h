@@ -346,11 +346,19 @@ int sp_gemm_f32_ex(const float* A, int64_t lda, int a_trans, const float* B, int
  *   sums[labels[i], :] += X_i                   (kmeans_center_mapper)
  * sums [k, d] and counts [k] are ACCUMULATED into (zero them before the first block); the caller divides and
  * all-reduces across GPUs.  Distances go through the tensor cores (bf16x3 split GEMM of X . centers^T). */
-#define SP_KMEANS_CHUNK_ROWS 262144
 int64_t sp_kmeans_workspace_bytes(int64_t n, int64_t d, int64_t k);
 int sp_kmeans_assign(const float* X, int64_t ldx, int64_t n, int64_t d, const float* centers, int64_t k,
                      int32_t* labels, float* sums, int64_t* counts, void* workspace, int64_t workspace_bytes,
                      void* stream);
+/* The same pass split in two, because the points of a run never change (k_means_.py:130-160 iterates over the same X):
+ * sp_kmeans_prepare_points lays X out once as the tensor cores consume it ([2][n][Kp] bf16 hi/lo,
+ * sp_kmeans_prepared_bytes bytes); sp_kmeans_assign_prepared is one iteration over it. */
+int64_t sp_kmeans_prepared_bytes(int64_t n, int64_t d);
+int sp_kmeans_prepare_points(const float* X, int64_t ldx, int64_t n, int64_t d, void* out, int64_t out_bytes, void* stream);
+int64_t sp_kmeans_assign_workspace_bytes(int64_t n, int64_t d, int64_t k);
+int sp_kmeans_assign_prepared(const void* Xprep, const float* X, int64_t ldx, int64_t n, int64_t d, const float* centers,
+                              int64_t k, int32_t* labels, float* sums, int64_t* counts, void* workspace,
+                              int64_t workspace_bytes, void* stream);
 /* y (+)= A x with A in CSR (dot.py:213-217 `tocsr().dot(dense)`; sparse.pyx:103-158 dot_coo_dense_unordered_map).
  * rowptr[n_rows + 1] int64, colidx int32, values fp32; x, y dense fp32.  avg_nnz_per_row (0 = unknown) picks the
  * number of threads that share a row. */

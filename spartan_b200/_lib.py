@@ -123,6 +123,10 @@ _SIGS = {
   'sp_gemm_f32_ex': (_int, [_vp, _i64, _int, _vp, _i64, _int, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp, _i64, _vp]),
   'sp_kmeans_workspace_bytes': (_i64, [_i64, _i64, _i64]),
   'sp_kmeans_assign': (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),
+  'sp_kmeans_prepared_bytes': (_i64, [_i64, _i64]),
+  'sp_kmeans_prepare_points': (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp]),
+  'sp_kmeans_assign_workspace_bytes': (_i64, [_i64, _i64, _i64]),
+  'sp_kmeans_assign_prepared': (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),
   'sp_spmv_csr': (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _int, _int, _vp]),
   'sp_gemm_simt': (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp]),
 }

@@ -98,57 +98,84 @@ spmv_csr_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ 
 using namespace sp;
 
 extern "C" int64_t sp_kmeans_workspace_bytes(int64_t n, int64_t d, int64_t k) {
-  const int64_t rows = std::min<int64_t>(n, SP_KMEANS_CHUNK_ROWS);
   const int64_t Kp = sp_gemm_kpad(d, SP_GEMM_BF16X3);
-  return sp_gemm_prepared_bytes(rows, Kp, SP_GEMM_BF16X3) + sp_gemm_prepared_bytes(k, Kp, SP_GEMM_BF16X3) +
-         rows * sp_gemm_argmin_parts(k) * 8 + k * 4 + 8192;
+  return sp_gemm_prepared_bytes(n, Kp, SP_GEMM_BF16X3) + sp_kmeans_assign_workspace_bytes(n, d, k) + 2048;
 }
 
-extern "C" int sp_kmeans_assign(const float* X, int64_t ldx, int64_t n, int64_t d, const float* centers, int64_t k,
-                                int32_t* labels, float* sums, int64_t* counts, void* workspace,
-                                int64_t workspace_bytes, void* stream_) {
+// Workspace of sp_kmeans_assign_prepared: prepared centres + per-row argmin candidates + centre norms.
+extern "C" int64_t sp_kmeans_assign_workspace_bytes(int64_t n, int64_t d, int64_t k) {
+  const int64_t Kp = sp_gemm_kpad(d, SP_GEMM_BF16X3);
+  return sp_gemm_prepared_bytes(k, Kp, SP_GEMM_BF16X3) + n * sp_gemm_argmin_parts(k) * 8 + k * 4 + 8192;
+}
+
+// The points as the tensor cores consume them: [2][n][Kp] bf16 (hi, lo), Kp = d rounded up to the k-block.  The points
+// of a k-means run never change, so this is done once per fit, not once per iteration.
+extern "C" int64_t sp_kmeans_prepared_bytes(int64_t n, int64_t d) {
+  return sp_gemm_prepared_bytes(n, sp_gemm_kpad(d, SP_GEMM_BF16X3), SP_GEMM_BF16X3);
+}
+
+extern "C" int sp_kmeans_prepare_points(const float* X, int64_t ldx, int64_t n, int64_t d, void* out, int64_t out_bytes,
+                                        void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  SP_REQUIRE(n >= 0 && d > 0 && k > 0 && k < (1ll << 31) && d < (1ll << 31), SP_ERR_INVALID, "sp_kmeans_assign: bad shape");
+  SP_REQUIRE(n >= 0 && d > 0 && d < (1ll << 31), SP_ERR_INVALID, "sp_kmeans_prepare_points: bad shape");
   if (n == 0) return SP_OK;
-  SP_REQUIRE(X && centers && labels && sums && counts, SP_ERR_INVALID, "sp_kmeans_assign: null pointer");
-  SP_REQUIRE(workspace != nullptr && workspace_bytes >= sp_kmeans_workspace_bytes(n, d, k), SP_ERR_INVALID,
-             "sp_kmeans_assign: workspace too small");
+  const int64_t Kp = sp_gemm_kpad(d, SP_GEMM_BF16X3);
+  if (Kp != (d + 3) / 4 * 4) SP_CUDA_CHECK(cudaMemsetAsync(out, 0, sp_kmeans_prepared_bytes(n, d), stream));
+  return sp_gemm_prepare_a(X, ldx, n, d, SP_GEMM_BF16X3, out, Kp, 0, out_bytes, stream);
+}
+
+// One assignment pass over points already prepared by sp_kmeans_prepare_points (Xprep) -- X itself is still read by the
+// accumulation (fp32 sums of the original values).
+extern "C" int sp_kmeans_assign_prepared(const void* Xprep, const float* X, int64_t ldx, int64_t n, int64_t d,
+                                         const float* centers, int64_t k, int32_t* labels, float* sums, int64_t* counts,
+                                         void* workspace, int64_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SP_REQUIRE(n >= 0 && d > 0 && k > 0 && k < (1ll << 31) && d < (1ll << 31) && n < (1ll << 31), SP_ERR_INVALID,
+             "sp_kmeans_assign_prepared: bad shape");
+  if (n == 0) return SP_OK;
+  SP_REQUIRE(Xprep && X && centers && labels && sums && counts, SP_ERR_INVALID, "sp_kmeans_assign_prepared: null pointer");
+  SP_REQUIRE(workspace != nullptr && workspace_bytes >= sp_kmeans_assign_workspace_bytes(n, d, k), SP_ERR_INVALID,
+             "sp_kmeans_assign_prepared: workspace too small");
   const int prec = SP_GEMM_BF16X3;
-  const int64_t rows = std::min<int64_t>(n, SP_KMEANS_CHUNK_ROWS);
   const int64_t Kp = sp_gemm_kpad(d, prec);
   uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uint64_t>(workspace) + 1023) & ~1023ull);
-  const int64_t a_bytes = (sp_gemm_prepared_bytes(rows, Kp, prec) + 1023) / 1024 * 1024;
   const int64_t b_bytes = (sp_gemm_prepared_bytes(k, Kp, prec) + 1023) / 1024 * 1024;
-  uint8_t* a_prep = ws;
-  uint8_t* b_prep = a_prep + a_bytes;
+  uint8_t* b_prep = ws;
   const int parts = static_cast<int>(sp_gemm_argmin_parts(k));
   float* part_val = reinterpret_cast<float*>(b_prep + b_bytes);
-  int32_t* part_idx = reinterpret_cast<int32_t*>(part_val + rows * parts);
-  float* cnorm = reinterpret_cast<float*>(part_idx + rows * parts);
-  if (Kp != (d + 3) / 4 * 4) {
-    SP_CUDA_CHECK(cudaMemsetAsync(a_prep, 0, a_bytes, stream));
-    SP_CUDA_CHECK(cudaMemsetAsync(b_prep, 0, b_bytes, stream));
-  }
+  int32_t* part_idx = reinterpret_cast<int32_t*>(part_val + n * parts);
+  float* cnorm = reinterpret_cast<float*>(part_idx + n * parts);
+  if (Kp != (d + 3) / 4 * 4) SP_CUDA_CHECK(cudaMemsetAsync(b_prep, 0, b_bytes, stream));
   // the centres are already "B transposed" ([k, d] = [N, K]): prepare them like an A operand
   int rc = sp_gemm_prepare_a(centers, d, k, d, prec, b_prep, Kp, 0, b_bytes, stream);
   if (rc) return rc;
   row_sqnorm_kernel<<<static_cast<unsigned>((k + 7) / 8), 256, 0, stream>>>(centers, d, static_cast<int>(k),
                                                                             static_cast<int>(d), cnorm);
-  for (int64_t r0 = 0; r0 < n; r0 += rows) {
-    const int64_t m = std::min<int64_t>(rows, n - r0);
-    rc = sp_gemm_prepare_a(X + r0 * ldx, ldx, m, d, prec, a_prep, Kp, 0, a_bytes, stream);
-    if (rc) return rc;
-    sp_gemm_prepared_segment seg;
-    seg.A = a_prep; seg.B = b_prep; seg.Kp = Kp;
-    rc = sp_gemm_prepared_argmin(1, &seg, m, k, cnorm, part_val, part_idx, prec, stream);   // no n x k matrix in HBM
-    if (rc) return rc;
-    const int blocks = static_cast<int>(std::min<int64_t>((m + 7) / 8, static_cast<int64_t>(num_sms()) * 8));
-    kmeans_label_accumulate_kernel<<<blocks, 256, 0, stream>>>(part_val, part_idx, parts, X + r0 * ldx, ldx, m,
-                                                               static_cast<int>(d), labels + r0, sums,
-                                                               reinterpret_cast<unsigned long long*>(counts));
-    SP_CUDA_CHECK(cudaGetLastError());
-  }
+  sp_gemm_prepared_segment seg;
+  seg.A = Xprep; seg.B = b_prep; seg.Kp = Kp;
+  rc = sp_gemm_prepared_argmin(1, &seg, n, k, cnorm, part_val, part_idx, prec, stream);   // no n x k matrix in HBM
+  if (rc) return rc;
+  const int blocks = static_cast<int>(std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(num_sms()) * 8));
+  kmeans_label_accumulate_kernel<<<blocks, 256, 0, stream>>>(part_val, part_idx, parts, X, ldx, n, static_cast<int>(d),
+                                                             labels, sums, reinterpret_cast<unsigned long long*>(counts));
+  SP_CUDA_CHECK(cudaGetLastError());
   return SP_OK;
+}
+
+// Convenience: prepare + assign in one call (the workspace also holds the prepared points).
+extern "C" int sp_kmeans_assign(const float* X, int64_t ldx, int64_t n, int64_t d, const float* centers, int64_t k,
+                                int32_t* labels, float* sums, int64_t* counts, void* workspace,
+                                int64_t workspace_bytes, void* stream_) {
+  SP_REQUIRE(n >= 0 && d > 0 && k > 0, SP_ERR_INVALID, "sp_kmeans_assign: bad shape");
+  if (n == 0) return SP_OK;
+  SP_REQUIRE(workspace != nullptr && workspace_bytes >= sp_kmeans_workspace_bytes(n, d, k), SP_ERR_INVALID,
+             "sp_kmeans_assign: workspace too small");
+  uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uint64_t>(workspace) + 1023) & ~1023ull);
+  const int64_t a_bytes = (sp_kmeans_prepared_bytes(n, d) + 1023) / 1024 * 1024;
+  int rc = sp_kmeans_prepare_points(X, ldx, n, d, ws, a_bytes, stream_);
+  if (rc) return rc;
+  return sp_kmeans_assign_prepared(ws, X, ldx, n, d, centers, k, labels, sums, counts, ws + a_bytes,
+                                   workspace_bytes - a_bytes - 1024, stream_);
 }
 
 extern "C" int sp_spmv_csr(const int64_t* rowptr, const int32_t* colidx, const float* values, int64_t n_rows,

@@ -9,7 +9,7 @@ SURVEY.md section 9 Q7).  Empty clusters are re-seeded on the host exactly like 
 import numpy as np
 import torch
 
-from .. import blob_ctx, comm
+from .. import blob_ctx, comm, device_ops
 from .._lib import lib, check, SP_RED_SUM, SpartanError
 from ..array import distarray, extent
 from ..expr.base import Expr, evaluate
@@ -40,19 +40,32 @@ class KMeans(object):
     labels = distarray.create((n,), np.int32, tile_hint=(tile_rows,))
     sums = torch.zeros((k, d), dtype=torch.float32, device=ctx.device)
     counts = torch.zeros((k,), dtype=torch.int64, device=ctx.device)
+    # this rank's row blocks, their label views and the points as the tensor cores consume them -- prepared once per
+    # array (the points do not change between iterations, nor between fits of an unchanged X)
+    blocks = []
+    for block in X.local_blocks():
+      x = X.fetch(block)
+      lab = labels.slab_view(extent.create((block.ul[0],), (block.lr[0],), (n,)))
+      if lab is None or not lab.is_contiguous():
+        raise SpartanError('KMeans.fit: the label tiles do not line up with the row blocks of X (tile rows %d)' % tile_rows)
+      m = x.shape[0]
+
+      def fill(op, x=x, m=m):
+        check(lib.sp_kmeans_prepare_points(x.data_ptr(), x.stride(0), m, d, op.buf.data_ptr(), op.buf.numel(),
+                                           ctx.stream_ptr()), 'sp_kmeans_prepare_points')
+        ctx.kernel_launches += 1
+      xp = device_ops.cached_operand(X, ('kmeans_points', block.ul[0], block.lr[0]), m, d, 'bf16x3', fill)
+      blocks.append((x, lab, m, xp))
     for it in range(self.n_iter):
       sums.zero_(); counts.zero_()
       c_dev = torch.from_numpy(centers).to(ctx.device)
-      for block in X.local_blocks():
-        x = X.fetch(block)
-        lab = labels.fetch(extent.create((block.ul[0],), (block.lr[0],), (n,)))
-        m = x.shape[0]
-        need = lib.sp_kmeans_workspace_bytes(m, d, k)
+      for x, lab, m, xp in blocks:
+        need = lib.sp_kmeans_assign_workspace_bytes(m, d, k)
         ws = ctx.scratch(need, 'kmeans')
-        check(lib.sp_kmeans_assign(x.data_ptr(), x.stride(0), m, d, c_dev.data_ptr(), k, lab.data_ptr(),
-                                   sums.data_ptr(), counts.data_ptr(), ws.data_ptr(), ws.numel(), ctx.stream_ptr()),
-              'sp_kmeans_assign')
-        ctx.kernel_launches += 6
+        check(lib.sp_kmeans_assign_prepared(xp.buf.data_ptr(), x.data_ptr(), x.stride(0), m, d, c_dev.data_ptr(), k,
+                                            lab.data_ptr(), sums.data_ptr(), counts.data_ptr(), ws.data_ptr(), ws.numel(),
+                                            ctx.stream_ptr()), 'sp_kmeans_assign_prepared')
+        ctx.kernel_launches += 4
       comm.allreduce(sums, SP_RED_SUM)
       comm.allreduce(counts, SP_RED_SUM)
       counts_h = counts.cpu().numpy().astype(np.float64)

@@ -360,10 +360,10 @@ int sp_kmeans_assign_prepared(const void* Xprep, const float* X, int64_t ldx, in
                               int64_t k, int32_t* labels, float* sums, int64_t* counts, void* workspace,
                               int64_t workspace_bytes, void* stream);
 /* y (+)= A x with A in CSR (dot.py:213-217 `tocsr().dot(dense)`; sparse.pyx:103-158 dot_coo_dense_unordered_map).
- * rowptr[n_rows + 1] int64, colidx int32, values fp32; x, y dense fp32.  avg_nnz_per_row (0 = unknown) picks the
- * number of threads that share a row. */
-int sp_spmv_csr(const int64_t* rowptr, const int32_t* colidx, const float* values, int64_t n_rows, const float* x,
-                float* y, int accumulate, int avg_nnz_per_row, void* stream);
+ * rowptr[n_rows + 1] int32 (rowptr_is_i64 == 0; use it whenever nnz < 2^31) or int64, colidx int32, values fp32; x, y
+ * dense fp32.  avg_nnz_per_row (0 = unknown) picks the number of threads that share a row. */
+int sp_spmv_csr(const void* rowptr, int rowptr_is_i64, const int32_t* colidx, const float* values, int64_t n_rows,
+                const float* x, float* y, int accumulate, int avg_nnz_per_row, void* stream);
 
 /* CUDA-core GEMM for dtypes the tensor path does not carry exactly (reference tests use
  * float64 / int64 operands: tests/test_dot.py:8-103, tests/test_matmul.py:12-22). */

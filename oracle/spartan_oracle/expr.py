@@ -963,6 +963,33 @@ def dot_outer_mapper(ex_a, tile_a, ex_b, tile_b):
   yield extent.create(ul, lr, shape), tile_a.dot(tile_b)
 
 
+def dot_grid_join_mapper(ex, arrays, target):
+  """The K-join of one tile of a GRID-tiled left operand, as the reference's dot means it:
+  join_mapper (map.py:243-286) re-partitions the A tile ``ex`` along K and fetches the matching rows of B; the
+  reference's change_partition_axis maps a grid tile to a 1-wide strip (extent.pyx:545-552, a defect), so the join
+  extent is restated as what the contraction needs -- A[R, Kk] joins B[Kk, :] -- and dot_map2_mapper's product
+  (dot.py:195-217) is a partial of C[R, :] that ``target.update`` np.add-merges tile by tile (tile.pyx:263-268)."""
+  a, b = arrays
+  tile_a = a.fetch(ex)
+  ex_b = extent.create((ex.ul[1], 0), (ex.lr[1], b.shape[1]), b.shape)
+  tile_b = b.fetch(ex_b)                                        # stitched from the B tiles of that row block
+  target_ex = extent.create((ex.ul[0], 0), (ex.lr[0], b.shape[1]), target.shape)
+  target.update(target_ex, tile_a.dot(tile_b), wait=False)
+  return []
+
+
+def dot_grid(a, b, tile_hint=None):
+  """2-D x 2-D dot for grid-tiled operands: one dot_grid_join_mapper per tile of ``a``, partials merged with np.add.
+  Eager (returns the target DistArray)."""
+  a, b = evaluate(a), evaluate(b)
+  if a.shape[1] != b.shape[0]:
+    raise ValueError('objects are not aligned')
+  shape = (a.shape[0], b.shape[1])
+  target = distarray.create(shape, np.result_type(a.dtype, b.dtype), reducer=np.add, tile_hint=tile_hint or shape)
+  a.foreach_tile(mapper_fn=dot_grid_join_mapper, kw=dict(arrays=(a, b), target=target))
+  return target
+
+
 def dot(a, b, tile_hint=None):
   """dot.py:243-299 routing.  Operands must be 1-D tiled (row or column strips): the reference's
   grid-tiled path contracts only #tiles k-indices and np.dot is what its

@@ -127,7 +127,7 @@ _SIGS = {
   'sp_kmeans_prepare_points': (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp]),
   'sp_kmeans_assign_workspace_bytes': (_i64, [_i64, _i64, _i64]),
   'sp_kmeans_assign_prepared': (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),
-  'sp_spmv_csr': (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _int, _int, _vp]),
+  'sp_spmv_csr': (_int, [_vp, _int, _vp, _vp, _i64, _vp, _vp, _int, _int, _vp]),
   'sp_gemm_simt': (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp]),
 }
 

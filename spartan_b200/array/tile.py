@@ -5,7 +5,9 @@ exists on the device; instead of a per-element mask the tile tracks ``valid`` (n
 written), and a first partial write under a reducer initialises the rest of the tile with the
 reducer's identity -- observably the same as the reference's "first write replaces, later writes
 reduce" rule (tile.pyx:250-283) for every combiner it uses (add, multiply, minimum, maximum,
-logical_and, logical_or).
+logical_and, logical_or) on every element that has been written.  The full-tile fast path keeps the
+reference's test (tile.pyx:263-268): a full-tile update reduces only if the tile's FIRST element has been
+written before, otherwise it replaces the whole tile -- ``origin_written`` tracks that one mask bit.
 """
 import numpy as np
 
@@ -49,8 +51,19 @@ class DeviceTile(object):
     self.shape = tuple(int(s) for s in shape)
     self.dtype = np.dtype(dtype)
     self.data = data            # torch tensor on the owning device (may be a view into an array slab)
-    self.valid = bool(valid)
+    self._valid = bool(valid)
+    self.origin_written = bool(valid)     # mask[0, 0, ...] of the reference's Tile (tile.pyx:264)
     self.type = TYPE_DENSE
+
+  @property
+  def valid(self):
+    return self._valid
+
+  @valid.setter
+  def valid(self, v):
+    """Set by producers that write whole tiles (kernels, uploads): every element is written, the first included."""
+    self._valid = bool(v)
+    self.origin_written = bool(v)
 
   def _alloc(self):
     if self.data is None:
@@ -83,19 +96,41 @@ def from_shape(shape, dtype, tile_type=TYPE_DENSE):
   return DeviceTile(shape, dtype, None, valid=False)
 
 
+def _covers_origin(subslice):
+  for sl in subslice:
+    if isinstance(sl, slice):
+      if (sl.start or 0) != 0:
+        return False
+    elif int(sl) != 0:
+      return False
+  return True
+
+
 def merge(old_tile, subslice, update, reducer):
   """tile.pyx:200-297, dense and 0-d paths, on the device."""
   red = reducer_op(reducer)
   data = old_tile._alloc()
   full = subslice is None or data.dim() == 0 or tuple(update.shape) == tuple(data.shape)
   region = data if full else data[subslice]
-  if not old_tile.valid:
-    if not full:
-      data.fill_(identity_of(red, old_tile.dtype) if red is not None else 0)
-    device_ops.copy_into(region, update)          # first write replaces (and casts to the tile dtype, :267)
+  valid = old_tile.valid
+  if full:
+    # tile.pyx:263-268: reduce when there is a reducer and the first element was written, else replace (with the cast
+    # to the tile dtype of :267); 0-d tiles: :212-217
+    if red is not None and valid and (old_tile.origin_written or data.dim() == 0):
+      device_ops.combine_into(region, update, red)
+    else:
+      device_ops.copy_into(region, update)
     old_tile.valid = True
+    old_tile.origin_written = True
+    return old_tile
+  if not valid:
+    data.fill_(identity_of(red, old_tile.dtype) if red is not None else 0)
+    device_ops.copy_into(region, update)          # first write replaces (:272-273)
+    old_tile._valid = True
   elif red is None:
     device_ops.copy_into(region, update)
   else:
     device_ops.combine_into(region, update, red)
+  if _covers_origin(subslice):
+    old_tile.origin_written = True
   return old_tile

@@ -20,8 +20,6 @@ class Flags(object):
     self.dot_stream_host_operands = True
     self.dot_stream_strip = 4096
     self.dot_stream_min_bytes = 256 << 20
-    # fraction of K uploaded as (A[:, k-strip], B[k-strip, :]) pairs and contracted K-split before the frontier (0 = none)
-    self.dot_stream_k_head = float(os.environ.get('SPARTAN_DOT_K_HEAD', '0'))
     # prepared (rounded / split / transposed) GEMM operands of unchanged arrays are kept between evaluations, up to this
     # many bytes (0 disables the cache)
     self.dot_prepared_cache = True

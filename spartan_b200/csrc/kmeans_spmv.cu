@@ -75,10 +75,10 @@ kmeans_label_accumulate_kernel(const float* __restrict__ part_val, const int* __
   }
 }
 
-// CSR SpMV: GROUP threads per row
-template <int GROUP>
+// CSR SpMV: GROUP threads per row; PTR = int32_t row pointers whenever nnz < 2^31 (4 B per row instead of 8)
+template <int GROUP, typename PTR>
 __global__ void __launch_bounds__(256)
-spmv_csr_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
+spmv_csr_kernel(const PTR* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
                 int64_t n_rows, const float* __restrict__ x, float* __restrict__ y, int accumulate) {
   const int g = threadIdx.x % GROUP;
   const int64_t groups = static_cast<int64_t>(gridDim.x) * (blockDim.x / GROUP);
@@ -86,10 +86,21 @@ spmv_csr_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ 
        row += groups) {
     const int64_t lo = rowptr[row], hi = rowptr[row + 1];
     float s = 0.f;
-    for (int64_t p = lo + g; p < hi; p += GROUP) s += val[p] * __ldg(x + col[p]);
+    for (int64_t p = lo + g; p < hi; p += GROUP) s += __ldcs(val + p) * __ldg(x + __ldcs(col + p));
 #pragma unroll
     for (int o = GROUP / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, GROUP);
     if (g == 0) y[row] = accumulate ? y[row] + s : s;
+  }
+}
+
+template <typename PTR>
+static void launch_spmv(int group, int blocks, const PTR* rowptr, const int32_t* colidx, const float* values,
+                        int64_t n_rows, const float* x, float* y, int accumulate, cudaStream_t stream) {
+  switch (group) {
+    case 2: spmv_csr_kernel<2, PTR><<<blocks, 256, 0, stream>>>(rowptr, colidx, values, n_rows, x, y, accumulate); break;
+    case 4: spmv_csr_kernel<4, PTR><<<blocks, 256, 0, stream>>>(rowptr, colidx, values, n_rows, x, y, accumulate); break;
+    case 8: spmv_csr_kernel<8, PTR><<<blocks, 256, 0, stream>>>(rowptr, colidx, values, n_rows, x, y, accumulate); break;
+    default: spmv_csr_kernel<32, PTR><<<blocks, 256, 0, stream>>>(rowptr, colidx, values, n_rows, x, y, accumulate); break;
   }
 }
 
@@ -178,8 +189,8 @@ extern "C" int sp_kmeans_assign(const float* X, int64_t ldx, int64_t n, int64_t 
                                    workspace_bytes - a_bytes - 1024, stream_);
 }
 
-extern "C" int sp_spmv_csr(const int64_t* rowptr, const int32_t* colidx, const float* values, int64_t n_rows,
-                           const float* x, float* y, int accumulate, int avg_nnz_per_row, void* stream_) {
+extern "C" int sp_spmv_csr(const void* rowptr, int rowptr_is_i64, const int32_t* colidx, const float* values,
+                           int64_t n_rows, const float* x, float* y, int accumulate, int avg_nnz_per_row, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SP_REQUIRE(n_rows >= 0, SP_ERR_INVALID, "sp_spmv_csr: negative row count");
   if (n_rows == 0) return SP_OK;
@@ -189,12 +200,10 @@ extern "C" int sp_spmv_csr(const int64_t* rowptr, const int32_t* colidx, const f
   const int64_t groups_per_block = 256 / group;
   const int blocks = static_cast<int>(std::min<int64_t>((n_rows + groups_per_block - 1) / groups_per_block,
                                                         static_cast<int64_t>(num_sms()) * 16));
-  switch (group) {
-    case 2: spmv_csr_kernel<2><<<blocks, 256, 0, stream>>>(rowptr, colidx, values, n_rows, x, y, accumulate); break;
-    case 4: spmv_csr_kernel<4><<<blocks, 256, 0, stream>>>(rowptr, colidx, values, n_rows, x, y, accumulate); break;
-    case 8: spmv_csr_kernel<8><<<blocks, 256, 0, stream>>>(rowptr, colidx, values, n_rows, x, y, accumulate); break;
-    default: spmv_csr_kernel<32><<<blocks, 256, 0, stream>>>(rowptr, colidx, values, n_rows, x, y, accumulate); break;
-  }
+  if (rowptr_is_i64)
+    launch_spmv(group, blocks, static_cast<const int64_t*>(rowptr), colidx, values, n_rows, x, y, accumulate, stream);
+  else
+    launch_spmv(group, blocks, static_cast<const int32_t*>(rowptr), colidx, values, n_rows, x, y, accumulate, stream);
   SP_CUDA_CHECK(cudaGetLastError());
   return SP_OK;
 }

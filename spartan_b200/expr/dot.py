@@ -129,7 +129,7 @@ class DotExpr(Expr):
     """C = A . B with A and B still in host memory.  A is cut into row strips and B into column strips; strip s of
     each is uploaded on a copy stream while the compute stream contracts what has already arrived: after A_s lands,
     C[rows_s, columns of strips < s]; after B_s lands, C[rows of strips <= s, columns_s] (an L-shaped frontier, the
-    order that makes the most output computable per byte uploaded).  Without a K-split head every C element is still
+    order that makes the most output computable per byte uploaded).  Every C element is still
     produced by one contraction over the full K in the order of the resident path: bit-identical to it.  Each launch
     leaves an event behind; ``DistArrayImpl.read_local_into`` uses them to start the D2H copy of a finished block
     while later blocks are still being computed.  The operand arrays end up resident and cached exactly as
@@ -147,18 +147,8 @@ class DotExpr(Expr):
     if av.slab is None or bv.slab is None or target.slab is None:
       raise SpartanError('streamed dot expects slab-backed arrays on a single rank')
     strip = int(FLAGS.dot_stream_strip)
-    # Optional K-split head (FLAGS.dot_stream_k_head = fraction of K): with the L-shaped frontier alone only f^2 of the
-    # output is computable after a fraction f of the operands has arrived, so the contraction idles early and finishes
-    # late.  A pair (A[:, k-strip], B[k-strip, :]) makes a full rank-`strip` update of ALL of C computable at once, so
-    # the leading K columns go up as such pairs and are accumulated into C; the frontier then finishes the remaining K
-    # range with accumulate (every C element: head partial sums + one tail contraction -- a different fp32 summation
-    # order from the resident path, same tolerance).
-    n_head = int(float(FLAGS.dot_stream_k_head) * K / strip)
-    Kh = n_head * strip
-    if Kh <= 0 or K - Kh < strip:
-      Kh = n_head = 0
-    pa = device_ops.PreparedOperand(M, K - Kh, precision, 'dot_stream_a')
-    pb = device_ops.PreparedOperand(N, K - Kh, precision, 'dot_stream_b')
+    pa = device_ops.PreparedOperand(M, K, precision, 'dot_stream_a')
+    pb = device_ops.PreparedOperand(N, K, precision, 'dot_stream_b')
 
     def strips(n):
       # equal strips, the last one halved: what can only start after the final byte has arrived (and must be read back
@@ -177,42 +167,29 @@ class DotExpr(Expr):
     done = []
 
     def contract(r0, r1, c0, c1):
-      device_ops.gemm_prepared_rows(pa, r0, r1, pb, c0, c1, C[r0:r1, c0:c1], accumulate=Kh > 0)
+      device_ops.gemm_prepared_rows(pa, r0, r1, pb, c0, c1, C[r0:r1, c0:c1], accumulate=False)
       done.append((extent.create((r0, c0), (r1, c1), (M, N)), main.record_event()))
 
-    for i in range(n_head):                                     # K-split head: C (+)= A[:, k0:k1] . B[k0:k1, :]
-      k0, k1 = i * strip, (i + 1) * strip
-      with torch.cuda.stream(copy):
-        device_ops.upload_rect(av.slab[:, k0:k1], a_np[:, k0:k1])
-        device_ops.upload_rect(bv.slab[k0:k1, :], b_np[k0:k1, :])
-        ev = copy.record_event()
-      main.wait_event(ev)
-      pah = device_ops.PreparedOperand(M, k1 - k0, precision, 'dot_stream_head_a%d' % i)
-      pbh = device_ops.PreparedOperand(N, k1 - k0, precision, 'dot_stream_head_b%d' % i)
-      pah.prepare_a(av.slab[:, k0:k1], 0)
-      pbh.prepare_b(bv.slab[k0:k1, :], 0)
-      device_ops.gemm_prepared_rows(pah, 0, M, pbh, 0, N, C, accumulate=i > 0)
-
-    for s in range(max(len(ra), len(cb))):                      # L-shaped frontier over the K range [Kh, K)
+    for s in range(max(len(ra), len(cb))):                      # L-shaped frontier
       ev_a = ev_b = None
       with torch.cuda.stream(copy):
         if s < len(ra):
           r0, r1 = ra[s]
-          device_ops.upload_rect(av.slab[r0:r1, Kh:], a_np[r0:r1, Kh:])
+          device_ops.upload_rect(av.slab[r0:r1, :], a_np[r0:r1, :])
           ev_a = copy.record_event()
         if s < len(cb):
           c0, c1 = cb[s]
-          device_ops.upload_rect(bv.slab[Kh:, c0:c1], b_np[Kh:, c0:c1])
+          device_ops.upload_rect(bv.slab[:, c0:c1], b_np[:, c0:c1])
           ev_b = copy.record_event()
       if ev_a is not None:
         main.wait_event(ev_a)
-        pa.prepare_a(av.slab[r0:r1, Kh:], r0)
+        pa.prepare_a(av.slab[r0:r1, :], r0)
         ncols = cb[min(s, len(cb)) - 1][1] if s > 0 else 0      # columns whose strips (< s) are prepared already
         if ncols:
           contract(r0, r1, 0, ncols)
       if ev_b is not None:
         main.wait_event(ev_b)
-        pb.prepare_b(bv.slab[Kh:, c0:c1], c0)
+        pb.prepare_b(bv.slab[:, c0:c1], c0)
         rows = ra[min(s, len(ra) - 1)][1]                       # rows whose strips (<= s) are prepared
         if s == max(len(ra), len(cb)) - 1 and rows >= 2048:
           half = (rows // 2 + 255) // 256 * 256                 # final launch in two: read-back of the first half overlaps

@@ -19,42 +19,102 @@ from .array import distarray, extent
 from .expr.base import Expr, lazify
 
 
-class SparseStrips(object):
-  """Column strips of a scipy sparse matrix; strip i lives on rank i % num_workers."""
+def _strip_layout(n_cols, strip_width, num_workers):
+  """The reference's column strips, their round-robin owners, and the per-owner blocks of adjacent strips."""
+  strips = [(c0, min(n_cols, c0 + strip_width), i % num_workers) for i, c0 in enumerate(range(0, n_cols, strip_width))]
+  blocks = []
+  for c0, c1, owner in strips:
+    if blocks and blocks[-1][2] == owner and blocks[-1][1] == c0:
+      blocks[-1] = (blocks[-1][0], c1, owner)
+    else:
+      blocks.append((c0, c1, owner))
+  return strips, blocks
 
-  def __init__(self, matrix, strip_width=None):
+
+def _csr_from_coo_device(rows, cols, vals, n_rows, width):
+  """CSR (int32 rowptr when it fits, int32 column indices, fp32 values) of COO triples already on the device; entries are
+  ordered by (row, column); duplicates stay separate entries (their contributions add up in the product)."""
+  key = rows.to(torch.int64) * int(width) + cols.to(torch.int64)
+  key, order = torch.sort(key)
+  r = torch.div(key, int(width), rounding_mode='floor')
+  c = (key - r * int(width)).to(torch.int32)
+  counts = torch.bincount(r, minlength=n_rows)
+  rowptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=rows.device)
+  torch.cumsum(counts, 0, out=rowptr[1:])
+  return rowptr, c.contiguous(), vals[order].to(torch.float32).contiguous()
+
+
+class SparseStrips(object):
+  """Column strips of a sparse matrix; strip i lives on rank i % num_workers.  Built from a scipy matrix every rank
+  holds (``SparseStrips(matrix)``) or from COO triples generated on the device (``SparseStrips.from_device_coo``)."""
+
+  def __init__(self, matrix=None, strip_width=None, shape=None):
     ctx = blob_ctx.get()
-    matrix = sp_sparse.csc_matrix(matrix)
-    self.shape = matrix.shape
     self.dtype = np.dtype(np.float32)
     self.sparse = True
+    if matrix is None:
+      self.shape = tuple(shape)
+      self.strips, self.blocks, self.nnz = [], [], 0
+      return
+    matrix = sp_sparse.csc_matrix(matrix)
+    self.shape = matrix.shape
     n_rows, n_cols = self.shape
     if strip_width is None:
       strip_width = -(-n_cols // ctx.num_workers)
-    self.strips = []          # (c0, c1, owner): the reference's column strips and their round-robin owners
     self.nnz = int(matrix.nnz)
-    for i, c0 in enumerate(range(0, n_cols, strip_width)):
-      self.strips.append((c0, min(n_cols, c0 + strip_width), i % ctx.num_workers))
     # Adjacent strips of one owner are stored as ONE CSR block (one launch per contiguous block of the
     # rank's share, like the dense slabs): (c0, c1, owner, device CSR or None, nnz)
-    self.blocks = []
-    for c0, c1, owner in self.strips:
-      if self.blocks and self.blocks[-1][2] == owner and self.blocks[-1][1] == c0:
-        self.blocks[-1] = (self.blocks[-1][0], c1, owner)
-      else:
-        self.blocks.append((c0, c1, owner))
+    self.strips, blocks = _strip_layout(n_cols, strip_width, ctx.num_workers)
     built = []
-    for c0, c1, owner in self.blocks:
+    for c0, c1, owner in blocks:
       dev, nnz = None, 0
       if owner == ctx.worker_id:
         csr = matrix[:, c0:c1].tocsr()
         csr.sum_duplicates()
         nnz = int(csr.nnz)
-        dev = (torch.from_numpy(csr.indptr.astype(np.int64)).to(ctx.device),
-               torch.from_numpy(csr.indices.astype(np.int32)).to(ctx.device),
-               torch.from_numpy(csr.data.astype(np.float32)).to(ctx.device))
+        dev = _to_device_csr(csr.indptr, csr.indices, csr.data, ctx.device)
       built.append((c0, c1, owner, dev, nnz))
     self.blocks = built
+
+  @classmethod
+  def from_device_coo(cls, shape, strip_width, entries):
+    """``entries(c0, c1) -> (rows, cols, vals)`` device tensors of the strip's non-zeros (global column indices);
+    called only for the strips this rank owns, so every rank builds just its share (the reference's make_weights mapper
+    also runs once per tile on the tile's worker, tests/benchmark_pagerank.py:11-24)."""
+    ctx = blob_ctx.get()
+    self = cls(None, shape=shape)
+    n_rows, n_cols = self.shape
+    self.strips, blocks = _strip_layout(n_cols, strip_width, ctx.num_workers)
+    built = []
+    total = 0
+    for c0, c1, owner in blocks:
+      dev, nnz = None, 0
+      if owner == ctx.worker_id:
+        parts = [entries(s0, s1) for s0, s1, _ in self.strips if c0 <= s0 and s1 <= c1]
+        rows = torch.cat([p[0] for p in parts]); cols = torch.cat([p[1] for p in parts]) - c0
+        vals = torch.cat([p[2] for p in parts])
+        rowptr, col, val = _csr_from_coo_device(rows, cols, vals, n_rows, c1 - c0)
+        nnz = int(val.numel())
+        if nnz < 2 ** 31:
+          rowptr = rowptr.to(torch.int32)
+        dev = (rowptr, col, val)
+      total += nnz
+      built.append((c0, c1, owner, dev, nnz))
+    self.blocks = built
+    if ctx.num_workers > 1:
+      t = torch.tensor([total], dtype=torch.int64, device=ctx.device)
+      comm.allreduce(t, SP_RED_SUM)
+      total = int(t.item())
+    self.nnz = total
+    return self
+
+
+def _to_device_csr(indptr, indices, data, device):
+  """Row pointers as int32 whenever nnz < 2**31 (half the bytes the kernel streams per row)."""
+  ptr_dtype = np.int32 if int(indptr[-1]) < 2 ** 31 else np.int64
+  return (torch.from_numpy(np.ascontiguousarray(indptr.astype(ptr_dtype))).to(device),
+          torch.from_numpy(np.ascontiguousarray(indices.astype(np.int32))).to(device),
+          torch.from_numpy(np.ascontiguousarray(data.astype(np.float32))).to(device))
 
 
 class SparseStripsExpr(Expr):
@@ -72,6 +132,11 @@ class SparseStripsExpr(Expr):
 
   def _evaluate(self, ctx, deps):
     return self.val
+
+
+def from_device_coo(shape, strip_width, entries):
+  """A sparse matrix whose strips are generated on the device of their owner (see SparseStrips.from_device_coo)."""
+  return SparseStripsExpr(val=SparseStrips.from_device_coo(shape, strip_width, entries))
 
 
 def from_scipy(matrix, strip_width=None):
@@ -104,8 +169,9 @@ class SpMVExpr(Expr):
       if not xs.is_contiguous():
         xs = xs.contiguous()
       rowptr, col, val = dev
-      check(lib.sp_spmv_csr(rowptr.data_ptr(), col.data_ptr(), val.data_ptr(), n_rows, xs.data_ptr(), y.data_ptr(), 1,
-                            max(1, -(-nnz // max(1, n_rows))), ctx.stream_ptr()), 'sp_spmv_csr')
+      check(lib.sp_spmv_csr(rowptr.data_ptr(), 1 if rowptr.dtype == torch.int64 else 0, col.data_ptr(), val.data_ptr(),
+                            n_rows, xs.data_ptr(), y.data_ptr(), 1, max(1, -(-nnz // max(1, n_rows))), ctx.stream_ptr()),
+            'sp_spmv_csr')
       ctx.kernel_launches += 1
     comm.allreduce(y, SP_RED_SUM)                # the np.add merge of the strips' partial y (tile.pyx:263-268)
     out_shape = self.compute_shape()

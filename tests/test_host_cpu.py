@@ -182,7 +182,7 @@ def test_cabi_gemm_and_fill_argument_checks():
   assert lib.sp_fill(None, _lib.SP_F32, -1, 0, 0.0, 0.0, 0, 0, None) == -1
   assert lib.sp_fill(None, _lib.SP_F32, 0, 0, 0.0, 0.0, 0, 0, None) == 0          # empty fill is a no-op
   assert lib.sp_fill(None, _lib.SP_F32, 4, 0, 0.0, 0.0, 0, 0, None) == -1
-  assert lib.sp_spmv_csr(None, None, None, 0, None, None, 0, 0, None) == 0
+  assert lib.sp_spmv_csr(None, 1, None, None, 0, None, None, 0, 0, None) == 0
   assert lib.sp_kmeans_assign(None, 0, 4, 0, None, 1, None, None, None, None, 0, None) == -1
 
 

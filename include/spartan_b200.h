@@ -230,6 +230,12 @@ int sp_map_reduce(const sp_program* prog, int n_in, const sp_operand* in, const 
  * ncclAllReduce with the matching op instead. */
 int sp_combine(void* dst, const void* src, int dtype, int64_t n, int reduce_op, void* stream);
 
+/* Tile.merge on a partially written tile (tile.pyx:270-283): per element, dst = mask ? reducer(dst, src) : src, then
+ * mask = 1.  reduce_op < 0: no reducer.  3-D strided views (strides in elements); the reduction is evaluated in the
+ * NumPy result type of the two dtypes.  Pairs: equal dtypes, (f32,f64), (f64,f32), (i64,i32), (i32,i64). */
+int sp_merge_masked(void* dst, const int64_t dst_stride[3], int dst_dtype, const void* src, const int64_t src_stride[3],
+                    int src_dtype, uint8_t* mask, const int64_t mask_stride[3], const int64_t dims[3], int reduce_op,
+                    void* stream);
 /* Strided rectangle copy between tiles (DistArrayImpl.fetch stitching, distarray.py:294-367,
  * and update splitting, :372-422): copies dims[0..2] elements; strides in elements. */
 int sp_copy_rect(void* dst, const int64_t dst_stride[3], const void* src, const int64_t src_stride[3],

@@ -296,11 +296,46 @@ class DistArrayImpl(DistArray):
   def update_slice(self, slc, data):
     return self.update(extent.from_slice(slc, self.shape), data)
 
-  def update(self, region, data, wait=True):
+  def _update_from(self, region, data, src):
+    """Collective form of ``update``: ``data`` (a device tensor covering ``region``) lives on rank ``src``; every rank
+    calls this with the same region, pieces that land in tiles of other ranks travel point-to-point (cast to this
+    array's dtype) and are merged by the tile's owner -- the RPC ``update`` of the reference (blob_ctx.py:163-179)."""
+    ctx = self.ctx
+    me = ctx.worker_id
+    ctx.touch()
+    self.block_events = None
+    if len(self.shape) == 0:
+      pieces = [(next(iter(self.tiles.keys())), region)]
+    else:
+      pieces = list(extent.find_overlapping(self.tiles.keys(), region))
+    for dst_extent, inter in pieces:
+      tid = self.tiles[dst_extent]
+      src_slice = extent.offset_slice(region, inter)
+      dst_slice = extent.offset_slice(dst_extent, inter)
+      if len(self.shape) and not extent.all_nonzero_shape([s.stop - s.start for s in dst_slice]):
+        continue
+      full = len(self.shape) == 0 or tuple(inter.shape) == tuple(dst_extent.shape)
+      if tid.worker == src:
+        if me == src:
+          piece = data[src_slice] if data.dim() else data
+          ctx.update(tid, None if full else dst_slice, piece, self.reducer_fn)
+      elif me == src:
+        piece = (data[src_slice] if data.dim() else data).to(blob_ctx.torch_dtype(self.dtype)).contiguous()
+        comm.batch_p2p([('send', piece, tid.worker)])
+      elif me == tid.worker:
+        tmp = ctx.empty(inter.shape if len(self.shape) else (), self.dtype)
+        comm.batch_p2p([('recv', tmp, src)])
+        ctx.update(tid, None if full else dst_slice, tmp, self.reducer_fn)
+    return None
+
+  def update(self, region, data, wait=True, src=None):
     """distarray.py:372-422.  ``data`` is either a host ndarray that every rank holds (each rank
     uploads the parts that land in its own tiles) or a device tensor, in which case every tile it
-    overlaps must be local to the caller."""
+    overlaps must be local to the caller -- unless ``src`` names the rank that holds it: then the call is
+    collective and remote pieces are sent to their owners (see _update_from)."""
     require_type(region, extent.TileExtent)
+    if src is not None:
+      return self._update_from(region, data, src)
     host = isinstance(data, np.ndarray)
     if not host and not torch.is_tensor(data):
       data = np.asarray(data); host = True

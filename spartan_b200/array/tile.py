@@ -1,13 +1,12 @@
 """DeviceTile: one tile of a distributed array, resident in the HBM of its owning GPU.
 
-Counterpart of spartan/array/tile.pyx (Tile, from_data, from_shape, merge).  Only the dense mode
-exists on the device; instead of a per-element mask the tile tracks ``valid`` (nothing written yet /
-written), and a first partial write under a reducer initialises the rest of the tile with the
-reducer's identity -- observably the same as the reference's "first write replaces, later writes
-reduce" rule (tile.pyx:250-283) for every combiner it uses (add, multiply, minimum, maximum,
-logical_and, logical_or) on every element that has been written.  The full-tile fast path keeps the
-reference's test (tile.pyx:263-268): a full-tile update reduces only if the tile's FIRST element has been
-written before, otherwise it replaces the whole tile -- ``origin_written`` tracks that one mask bit.
+Counterpart of spartan/array/tile.pyx (Tile, from_data, from_shape, merge), dense mode.  The reference keeps a
+per-element mask so that the first write to an element replaces and later writes reduce (tile.pyx:250-283).  The
+same rule here: the mask is ``False`` (nothing written), ``True`` (every element written -- the state a kernel that
+produces the whole tile leaves) or, only once a tile has been written partially, a bool tensor next to the data; a
+tile that is first touched by a partial update is zero-filled like ``np.zeros`` in Tile._initialize (:115-127).  The
+full-tile fast path keeps the reference's test (:263-268): it reduces -- every element, the never-written zeros
+included -- if the tile's FIRST element has been written, otherwise it replaces the whole tile.
 """
 import numpy as np
 
@@ -51,18 +50,19 @@ class DeviceTile(object):
     self.shape = tuple(int(s) for s in shape)
     self.dtype = np.dtype(dtype)
     self.data = data            # torch tensor on the owning device (may be a view into an array slab)
-    self._valid = bool(valid)
-    self.origin_written = bool(valid)     # mask[0, 0, ...] of the reference's Tile (tile.pyx:264)
+    self.mask = bool(valid)     # False: nothing written; True: all written; bool tensor: partially written
+    self.origin_written = bool(valid)     # mask[0, 0, ...] (tile.pyx:264), tracked on the host
     self.type = TYPE_DENSE
 
   @property
   def valid(self):
-    return self._valid
+    """Something has been written to the tile."""
+    return self.mask is not False
 
   @valid.setter
   def valid(self, v):
     """Set by producers that write whole tiles (kernels, uploads): every element is written, the first included."""
-    self._valid = bool(v)
+    self.mask = bool(v)
     self.origin_written = bool(v)
 
   def _alloc(self):
@@ -108,29 +108,37 @@ def _covers_origin(subslice):
 
 def merge(old_tile, subslice, update, reducer):
   """tile.pyx:200-297, dense and 0-d paths, on the device."""
+  import torch
   red = reducer_op(reducer)
   data = old_tile._alloc()
-  full = subslice is None or data.dim() == 0 or tuple(update.shape) == tuple(data.shape)
-  region = data if full else data[subslice]
-  valid = old_tile.valid
-  if full:
-    # tile.pyx:263-268: reduce when there is a reducer and the first element was written, else replace (with the cast
-    # to the tile dtype of :267); 0-d tiles: :212-217
-    if red is not None and valid and (old_tile.origin_written or data.dim() == 0):
-      device_ops.combine_into(region, update, red)
+  if data.dim() == 0:                                     # :212-217
+    if red is not None and old_tile.valid:
+      device_ops.combine_into(data, update, red)
     else:
-      device_ops.copy_into(region, update)
+      device_ops.copy_into(data, update)
     old_tile.valid = True
-    old_tile.origin_written = True
     return old_tile
-  if not valid:
-    data.fill_(identity_of(red, old_tile.dtype) if red is not None else 0)
-    device_ops.copy_into(region, update)          # first write replaces (:272-273)
-    old_tile._valid = True
-  elif red is None:
-    device_ops.copy_into(region, update)
-  else:
-    device_ops.combine_into(region, update, red)
+  if subslice is None or tuple(update.shape) == tuple(data.shape):
+    # :263-268 -- reduce when there is a reducer and the first element was written, else replace (casting to the tile
+    # dtype, :267).  A partially written tile holds zeros where nothing was written; the reduce includes them.
+    if red is not None and old_tile.origin_written:
+      device_ops.combine_into(data, update, red)
+    else:
+      device_ops.copy_into(data, update)
+    old_tile.valid = True
+    return old_tile
+  # :270-283 partial region
+  if old_tile.mask is True:
+    region = data[subslice]
+    if red is None:
+      device_ops.copy_into(region, update)
+    else:
+      device_ops.combine_into(region, update, red)
+    return old_tile
+  if old_tile.mask is False:
+    data.zero_()                                          # Tile._initialize: np.zeros (:125-126)
+    old_tile.mask = torch.zeros(tuple(data.shape), dtype=torch.bool, device=data.device)
+  device_ops.merge_masked(data[subslice], update, old_tile.mask[subslice], red)
   if _covers_origin(subslice):
     old_tile.origin_written = True
   return old_tile

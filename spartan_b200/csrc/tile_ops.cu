@@ -191,6 +191,29 @@ __global__ void copy_rect_kernel(T* __restrict__ dst, int64_t ds0, int64_t ds1, 
   }
 }
 
+// Tile.merge on a partially written tile (tile.pyx:270-283): element by element, a first write replaces and a later
+// write reduces -- decided by the tile's mask, which is updated in the same pass.  The reduction is evaluated in CT, the
+// NumPy result type of (DT, ST), and stored back as DT, like `old_region[updated] = reducer(old_region[updated], update)`.
+template <typename DT, typename ST, typename CT>
+__global__ void merge_masked_kernel(DT* __restrict__ dst, int64_t ds0, int64_t ds1, int64_t ds2, const ST* __restrict__ src,
+                                    int64_t ss0, int64_t ss1, int64_t ss2, uint8_t* __restrict__ mask, int64_t ms0,
+                                    int64_t ms1, int64_t ms2, int64_t d0, int64_t d1, int64_t d2, int op) {
+  const int64_t total = d0 * d1 * d2;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t i2 = i % d2;
+    const int64_t t = i / d2;
+    const int64_t i1 = t % d1;
+    const int64_t i0 = t / d1;
+    const int64_t od = i0 * ds0 + i1 * ds1 + i2 * ds2;
+    const int64_t om = i0 * ms0 + i1 * ms1 + i2 * ms2;
+    const CT nv = static_cast<CT>(src[i0 * ss0 + i1 * ss1 + i2 * ss2]);
+    const bool written = mask[om] != 0;
+    dst[od] = (written && op >= 0) ? static_cast<DT>(combine_op<CT>(op, static_cast<CT>(dst[od]), nv)) : static_cast<DT>(nv);
+    mask[om] = 1;
+  }
+}
+
 static inline int grid_for(int64_t n) {
   const int64_t want = (n + 255) / 256;
   return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(num_sms()) * 16)));
@@ -344,5 +367,44 @@ extern "C" int sp_download_2d(void* dst_host, int64_t dst_pitch_bytes, const voi
   SP_CUDA_CHECK(cudaMemcpy2DAsync(dst_host, static_cast<size_t>(dst_pitch_bytes), src_device,
                                   static_cast<size_t>(src_pitch_bytes), static_cast<size_t>(width_bytes),
                                   static_cast<size_t>(rows), cudaMemcpyDeviceToHost, stream));
+  return SP_OK;
+}
+
+
+// Tile.merge, partial-region path (tile.pyx:270-283): dst[i] = mask[i] ? reducer(dst[i], src[i]) : src[i]; mask[i] = 1.
+// reduce_op < 0: no reducer (every element is replaced).  dst / src / mask are 3-D strided views (element strides).
+// Supported (dst, src) dtype pairs: equal dtypes, (f32, f64), (f64, f32), (i64, i32), (i32, i64); the host casts others.
+extern "C" int sp_merge_masked(void* dst, const int64_t dst_stride[3], int dst_dtype, const void* src,
+                               const int64_t src_stride[3], int src_dtype, uint8_t* mask, const int64_t mask_stride[3],
+                               const int64_t dims[3], int reduce_op, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SP_REQUIRE(dims[0] >= 0 && dims[1] >= 0 && dims[2] >= 0 && reduce_op <= SP_RED_ANY, SP_ERR_INVALID,
+             "sp_merge_masked: bad arguments");
+  const int64_t total = dims[0] * dims[1] * dims[2];
+  if (total == 0) return SP_OK;
+  SP_REQUIRE(dst && src && mask, SP_ERR_INVALID, "sp_merge_masked: null pointer");
+  const int g = grid_for(total);
+#define SP_MERGE(DT, ST, CT)                                                                                          \
+  merge_masked_kernel<DT, ST, CT><<<g, 256, 0, stream>>>(static_cast<DT*>(dst), dst_stride[0], dst_stride[1],          \
+      dst_stride[2], static_cast<const ST*>(src), src_stride[0], src_stride[1], src_stride[2], mask, mask_stride[0],   \
+      mask_stride[1], mask_stride[2], dims[0], dims[1], dims[2], reduce_op)
+  const int key = dst_dtype * 16 + src_dtype;
+  switch (key) {
+    case SP_F32 * 16 + SP_F32: SP_MERGE(float, float, float); break;
+    case SP_F32 * 16 + SP_F64: SP_MERGE(float, double, double); break;
+    case SP_F64 * 16 + SP_F64: SP_MERGE(double, double, double); break;
+    case SP_F64 * 16 + SP_F32: SP_MERGE(double, float, double); break;
+    case SP_I64 * 16 + SP_I64: SP_MERGE(long long, long long, long long); break;
+    case SP_I64 * 16 + SP_I32: SP_MERGE(long long, int32_t, long long); break;
+    case SP_I32 * 16 + SP_I32: SP_MERGE(int32_t, int32_t, int32_t); break;
+    case SP_I32 * 16 + SP_I64: SP_MERGE(int32_t, long long, long long); break;
+    case SP_U8 * 16 + SP_U8:
+    case SP_BOOL * 16 + SP_BOOL: SP_MERGE(uint8_t, uint8_t, uint8_t); break;
+    default:
+      set_error("sp_merge_masked: unsupported dtype pair (%d, %d)", dst_dtype, src_dtype);
+      return SP_ERR_UNSUPPORTED;
+  }
+#undef SP_MERGE
+  SP_CUDA_CHECK(cudaGetLastError());
   return SP_OK;
 }

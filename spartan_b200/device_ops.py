@@ -283,6 +283,32 @@ def combine_into(dst, src, red_op):
   run_map(prog, [dst, src], dst)
 
 
+_MERGE_PAIRS = {(torch.float32, torch.float64), (torch.float64, torch.float32), (torch.int64, torch.int32),
+                (torch.int32, torch.int64)}
+
+
+def merge_masked(dst, src, mask, red_op):
+  """dst = mask ? op(dst, src) : src element-wise, then mask = True (Tile.merge on a partially written tile,
+  tile.pyx:270-283).  ``dst`` / ``mask`` are views of the tile's data and of its bool mask over the same region, ``src``
+  the update (any strides).  red_op None: no reducer."""
+  _require_cuda(dst, src, mask)
+  assert tuple(dst.shape) == tuple(src.shape) == tuple(mask.shape) and mask.dtype == torch.bool
+  if dst.numel() == 0:
+    return
+  if src.dtype != dst.dtype and (dst.dtype, src.dtype) not in _MERGE_PAIRS:
+    tmp = torch.empty(tuple(src.shape), dtype=dst.dtype, device=dst.device)
+    copy_into(tmp, src)
+    src = tmp
+  shape, strides = collapse(tuple(dst.shape), [list(dst.stride()), list(src.stride()), list(mask.stride())])
+  for offs in _leading_loops(shape, strides, 3):
+    s3, st3 = _pad3(shape[-3:], [st[-3:] for st in strides])
+    check(lib.sp_merge_masked(dst.data_ptr() + offs[0] * dst.element_size(), i64arr(st3[0]), sp_dtype_of(dst),
+                              src.data_ptr() + offs[1] * src.element_size(), i64arr(st3[1]), sp_dtype_of(src),
+                              mask.data_ptr() + offs[2], i64arr(st3[2]), i64arr(s3),
+                              -1 if red_op is None else int(red_op), _stream()), 'sp_merge_masked')
+    _count_launch()
+
+
 # ------------------------------------------------------------------------------------ fill / copy
 def fill(t, kind, a=0.0, b=0.0, seed=0, offset=0):
   """In-place fill of a *contiguous* device tensor."""

@@ -18,7 +18,9 @@ from .base import Expr, evaluate, optimized_dag
 from .base import eager, lazify, as_array, glom
 from .base import NotShapeable, newaxis, Val, AsArray, ListExpr, TupleExpr
 from ..array.distarray import broadcast
-from .map import map, map_tiles, MapExpr, map_with_location, tile_mapper, map2, outer
+from .map import map, map_tiles, MapExpr, map_with_location, tile_mapper
+from .map2 import (map2, outer, Map2Expr, OuterProductExpr, DeviceTileFunction, device_tile_function, dot_map2_mapper,
+                   dot_outer_mapper, dot_as_join)
 from .ndarray import ndarray, NdArrayExpr
 from .optimize import optimize, MapMapFusion, ReduceMapFusion
 from .reduce import reduce, ReduceExpr, ArgReduceExpr

@@ -206,21 +206,4 @@ def map_with_location(inputs, fn, numpy_expr=None, fn_kw=None):
   return MapExpr(children=ListExpr(vals=children), child_to_var=child_to_var, op=op)
 
 
-def map2(arrays, axes=[], fn=None, fn_kw=None, shape=None, update_region=None, tile_hint=None, dtype=None,
-         reducer=None):
-  """The reference's axis-join map (map.py:337-375): ``fn`` is an arbitrary Python function over NumPy tiles
-  (``join_mapper`` fetches strips and calls it, map.py:243-286).  A Python callable cannot run on the GPU and
-  there is no CPU fallback; the joins the library itself is built from are provided as device operations
-  instead -- ``dot`` (dot.py:285-294), ``KMeans`` (k_means_.py:135-143) and sparse ``dot`` -- so this entry
-  point only explains where to go."""
-  raise program.NotDeviceMappable(
-    'map2() takes a Python tile function, which cannot run on the GPU (no CPU fallback). Use spartan_b200.dot, '
-    'spartan_b200.KMeans or spartan_b200.sparse for the joins the reference implements with map2; express '
-    'element-wise work with map() over NumPy ufuncs.')
-
-
-def outer(arrays, axes, fn, fn_kw=None, shape=None, tile_hint=None, reducer=None, dtype=None):
-  """The reference's tile cartesian join (outer.py:102-120); see ``map2``."""
-  raise program.NotDeviceMappable(
-    'outer() takes a Python tile function, which cannot run on the GPU (no CPU fallback); dot() covers the '
-    'rows > cols route the reference implements with outer (dot.py:285-289).')
+from .map2 import map2, outer          # noqa: E402,F401  (map.py:337-375, outer.py:102-120)

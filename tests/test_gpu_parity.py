@@ -426,6 +426,65 @@ def test_combiner_full_tile_before_first_element_replaces():
   all_eq(darr.glom(), 2 * whole)
 
 
+@pytest.mark.parametrize('M,K,N,ha,hb,hc', [(96, 64, 80, (24, 64), (16, 80), (48, 40)),      # rows > cols: outer route
+                                            (64, 200, 48, (16, 200), (50, 48), None),       # map2 route, A by rows
+                                            (40, 120, 70, (40, 30), (30, 70), (20, 35)),    # map2 route, A by columns
+                                            (300, 40, 70, (75, 40), (10, 70), (100, 70))])
+def test_dot_through_map2_and_outer_vs_oracle(M, K, N, ha, hb, hc):
+  """dot as an instance of the join operators, routed like dot.py:281-294 (outer for rows > cols, else map2 on
+  (axis 1, axis 0)): strips fetched by change_partition_axis, rank-k partials np.add-merged into the target.  The
+  oracle evaluates the same route with NumPy tiles; integer-valued float64 data makes the comparison exact."""
+  rng = np.random.default_rng(M + K)
+  a = rng.integers(-4, 5, size=(M, K)).astype(np.float64); b = rng.integers(-4, 5, size=(K, N)).astype(np.float64)
+  for workers in (1, 3):
+    spartan_oracle.initialize(workers)
+    want = oexpr.dot(oexpr.from_numpy(a, tile_hint=ha), oexpr.from_numpy(b, tile_hint=hb), tile_hint=hc).glom()
+    all_eq(want, a @ b)
+  got = sp.dot_as_join(sp.from_numpy(a, tile_hint=ha), sp.from_numpy(b, tile_hint=hb), tile_hint=hc).glom()
+  all_eq(got, want)
+  all_eq(sp.dot(sp.from_numpy(a, tile_hint=ha), sp.from_numpy(b, tile_hint=hb), tile_hint=hc).glom(), want)
+  # fp32 on the tensor cores through the same join
+  af, bf = a.astype(np.float32), b.astype(np.float32)
+  got = sp.dot_as_join(sp.from_numpy(af, tile_hint=ha), sp.from_numpy(bf, tile_hint=hb), tile_hint=hc).glom()
+  assert got.dtype == np.float32
+  all_eq(got, (a @ b).astype(np.float32))       # small integers: every mode is exact
+
+
+def test_map2_user_tile_function_with_reducer_target():
+  """A third join, not one the library hard-codes: per row strip, the column sums of x*y, merged with np.add into a
+  (cols,) target -- a device tile function built from the fused map+reduce kernel, against the oracle's map2 running the
+  NumPy version of the same function."""
+  from spartan_b200 import device_ops, _lib
+  from spartan_b200.array import extent as dext
+  from spartan_oracle import extent as oext
+  rng = np.random.default_rng(5)
+  x = rng.integers(-5, 6, size=(90, 40)).astype(np.float32); y = rng.integers(-5, 6, size=(90, 40)).astype(np.float32)
+
+  def target_extents(extents):
+    return [dext.create((0,), (extents[0].shape[1],), (extents[0].array_shape[1],))]
+
+  @sp.device_tile_function(target_extents)
+  def strip_colsum(extents, tiles):
+    import torch
+    out = torch.empty((tiles[0].shape[1],), dtype=torch.float32, device=tiles[0].device)
+    prog = device_ops.make_program([('IN', 0), ('IN', 1), ('MUL', 0)], _lib.SP_F32)
+    device_ops.run_map_reduce(prog, [tiles[0], tiles[1]], tuple(tiles[0].shape), 0, _lib.SP_RED_SUM, out, False)
+    return [out]
+
+  def strip_colsum_np(extents, tiles):
+    yield oext.create((0,), (extents[0].shape[1],), (extents[0].array_shape[1],)), (tiles[0] * tiles[1]).sum(axis=0)
+
+  spartan_oracle.initialize(3)
+  want = oexpr.map2((oexpr.from_numpy(x, tile_hint=(20, 40)), oexpr.from_numpy(y, tile_hint=(30, 40))), (0, 0),
+                    fn=strip_colsum_np, shape=(40,), reducer=np.add).glom()
+  got = sp.map2((sp.from_numpy(x, tile_hint=(20, 40)), sp.from_numpy(y, tile_hint=(30, 40))), (0, 0), fn=strip_colsum,
+                shape=(40,), reducer=np.add).glom()
+  all_eq(got, want)
+  all_eq(got, (x * y).sum(axis=0))
+  with pytest.raises(sp.NotDeviceMappable):
+    sp.map2([sp.from_numpy(x)], [0], fn=strip_colsum_np, shape=(40,))
+
+
 def test_dot_linearity_large():
   """Size-independent property at a shape the oracle would need minutes for: dot(A, B+C) = dot(A,B)+dot(A,C)
   and dot(A, e_j-columns) reproduces A columns exactly (identity is exact in TF32)."""

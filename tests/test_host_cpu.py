@@ -418,3 +418,31 @@ def test_tile_file_bytes_match_golden(tmp_path):
   finally:
     blob_ctx._global_ctx[0] = old
     blob_ctx._local.ctx = old
+
+
+def test_map2_join_extents_match_oracle_join_mapper():
+  """join_mapper's strip arithmetic (map.py:248-272, extent.pyx:501-570) is integer work: the extents the device map2
+  fetches must equal the ones the oracle's join_mapper hands to the tile function, for every tile."""
+  import spartan_oracle
+  from spartan_oracle import expr as oexpr, distarray as odist
+  from spartan_b200.expr.map2 import join_extents
+  from spartan_b200.array import distarray, extent
+  for workers in (1, 3, 8):
+    spartan_oracle.initialize(workers)
+    for shapes, hints, axes in [(((100, 60), (60, 77)), ((25, 60), (60, 20)), (1, 0)),
+                                (((64, 30), (30, 50)), ((64, 10), (6, 50)), (1, 0)),
+                                (((50, 8), (50,)), ((7, 8), (9,)), (0, 0)),
+                                (((33, 20), (33, 20)), ((10, 20), (33, 5)), ())]:
+      oarrs = [odist.create(s, np.float32, tile_hint=h) for s, h in zip(shapes, hints)]
+      seen = []
+      oexpr_fn = lambda extents, tiles, **kw: seen.append(extents if isinstance(extents, list) else [extents] * len(shapes)) or []
+      for ex in oarrs[0].tiles:
+        oexpr.join_mapper(ex, oarrs, axes, oexpr_fn, None, None)
+      got = []
+      for ex in distarray.compute_extents(shapes[0], hints[0], workers):
+        j = join_extents(extent.create(ex.ul, ex.lr, shapes[0]), list(shapes), axes)
+        if j is not None:
+          got.append(j)
+      assert len(got) == len(seen)
+      for a, b in zip(got, seen):
+        assert [(e.ul, e.lr, tuple(e.array_shape)) for e in a] == [(e.ul, e.lr, tuple(e.array_shape)) for e in b]

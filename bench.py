@@ -636,20 +636,21 @@ class Bench(object):
     c0 = c0.contiguous() if rank == 0 else torch.empty((k, d), dtype=torch.float32, device=ctx.device)
     self.comm.broadcast(c0, 0)
     c0 = c0.cpu().numpy()
-    km = sp.KMeans(n_clusters=k, n_iter=1)
+    iters = 5                                                # iterations per fit() in the timed steps
     res = {}
 
-    def step():
-      res['centers'], res['labels'] = km.fit(X, centers=c0)
+    def step(n_iter=iters):
+      res['centers'], res['labels'] = sp.KMeans(n_clusters=k, n_iter=n_iter).fit(X, centers=c0)
 
     device_ops.prepared_cache.clear()
-    step()                                                   # compiles nothing, sizes scratch, creates communicators
+    step(1)                                                  # sizes scratch, creates communicators
     device_ops.prepared_cache.clear()
-    ms_first = self.timed(step, 1, 0)                        # includes laying the points out for the tensor cores
-    steps = max(3, min(self.args.steps, 10))
+    ms_first = self.timed(lambda: step(1), 1, 0)             # a one-iteration fit incl. laying the points out for the tensor cores
+    steps = max(2, min(self.args.steps, 5))
     launches0 = ctx.kernel_launches
-    ms = self.timed(step, steps, 2)
-    launches = (ctx.kernel_launches - launches0) // (steps + 2)
+    ms = self.timed(step, steps, 1) / iters
+    launches = (ctx.kernel_launches - launches0) // ((steps + 1) * iters)
+    step(1)                                                  # parity below: the labels / centres of ONE iteration from c0
     flops = 2.0 * n * d * k
     tf = flops / ms / 1e9
     # parity at every N: labels of 2048 sampled points of every rank against float64 distances on the host; the counts
@@ -698,6 +699,7 @@ class Bench(object):
     km_out = {'config': 'k-means %d x %d fp32, k=%d: one iteration = assign (distance GEMM + argmin) + accumulate + '
                         'all-reduce of sums/counts + centre update on the host' % (n, d, k),
               'n_gpus': world, 'ms_per_iter': ms, 'ms_first_iter_incl_point_preparation': ms_first, 'steps': steps,
+              'iterations_per_step': iters,
               'value': tf, 'unit': 'TFLOP/s (2*n*d*k distance flops)', 'points_gbs': n * d * 4 / ms / 1e6,
               'gpu_launches_per_iter': launches,
               'roofline': {'bound': 'tensor', 'achieved': tf / world, 'peak': self.peaks['bf16_tflops_sustained'],

@@ -743,6 +743,7 @@ static int g_variant = 0;      // 0: choose, 1: one CTA per tile, 2: CTA pairs
 static int g_sync_kb = 0;
 static int g_group_m = 8;       // 256-row tile rows per rasterisation group (pair kernel); the one-CTA kernel uses twice as many 128-row blocks
 static int g_round_sync = 1;   // pair kernel: keep the clusters' tile rounds in step (L2 reuse of shared operand tiles)
+static int g_round_sync_min_kb = 64;   // round barrier only for contractions at least this many k-blocks deep
 static unsigned int* g_round_counter = nullptr;
 
 }  // namespace gemm
@@ -976,7 +977,12 @@ static int launch_prepared(int n_seg, const sp_gemm_prepared_view* segs, float* 
   p.part_idx = part_idx;
   if (pair) {
     const int tiles = (p.m_blocks + 1) / 2 * p.n_blocks;
-    if (g_round_sync && tiles > max_clusters) {
+    // The round barrier pays when a tile round lasts long enough for the clusters to drift apart (deep K: the operand
+    // tiles they share would fall out of L2); with a shallow K a round is a few microseconds and a grid-wide check-in per
+    // tile costs more than it saves (k-means: 4 k-blocks per tile, tensor pipe 62% busy with it, ncu r2c_apps).
+    int total_kb = 0;
+    for (int s = 0; s < n_seg; ++s) total_kb += p.segs[s].k_blocks;
+    if (g_round_sync && tiles > max_clusters && total_kb >= g_round_sync_min_kb) {
       if (g_round_counter == nullptr) SP_CUDA_CHECK(cudaMalloc(&g_round_counter, sizeof(unsigned int)));
       SP_CUDA_CHECK(cudaMemsetAsync(g_round_counter, 0, sizeof(unsigned int), stream));
       p.round_sync = g_round_counter;

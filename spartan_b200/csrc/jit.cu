@@ -252,10 +252,10 @@ extern "C" const char* sp_jit_last_log(void) {
 }
 
 // Compiles (does not load or run) the specialisation of `prog` for `n_in` operands: the build-time check that the
-// run-time path works on a machine without a GPU.  mode 0 = map, 1 = map+reduce.  Returns the cubin size.
+// run-time path works on a machine without a GPU.  mode 0 = map, 1 = map+reduce over the leading axis, 2 = map+reduce over the trailing axis.  Returns the cubin size.
 namespace sp { int lower_for_jit(const sp_program* prog, uint8_t* op, uint8_t* src, uint8_t* arg, int* n); }
 extern "C" int64_t sp_jit_compile_check(const sp_program* prog, int n_in, int mode) {
-  SP_REQUIRE(prog != nullptr && n_in >= 0 && n_in <= SP_MAX_OPERANDS && (mode == 0 || mode == 1), SP_ERR_INVALID,
+  SP_REQUIRE(prog != nullptr && n_in >= 0 && n_in <= SP_MAX_OPERANDS && (mode >= 0 && mode <= 2), SP_ERR_INVALID,
              "sp_jit_compile_check: bad arguments");
   uint8_t op[SP_MAX_PROGRAM], src[SP_MAX_PROGRAM], arg[SP_MAX_PROGRAM];
   int n = 0;

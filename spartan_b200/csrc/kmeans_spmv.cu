@@ -36,43 +36,57 @@ __global__ void row_sqnorm_kernel(const float* __restrict__ C, int64_t ldc, int 
 }
 
 // one warp per point: label = arg min over the per-half-tile candidates the GEMM epilogue emitted
-// (part_val / part_idx [n][parts]); then sums[label] += x_i, counts[label] += 1
+// (part_val / part_idx [n][parts]); then sums[label] += x_i, counts[label] += 1.
+// The point's row is loaded BEFORE the label is known (its address does not depend on it), so the row loads overlap the
+// candidate loads and the shuffles; 64 resident warps per SM keep the other points' atomics in flight meanwhile.
+template <bool VEC>
+__device__ __forceinline__ void kmeans_point(const float* __restrict__ part_val, const int* __restrict__ part_idx, int parts,
+                                             const float* __restrict__ X, int64_t ldx, int64_t i, int d, int lane,
+                                             int32_t* __restrict__ labels, float* __restrict__ sums,
+                                             unsigned long long* __restrict__ counts) {
+  const float* x = X + i * ldx;
+  float4 xv[2];
+  if (VEC) {                          // d == 256: two float4 per lane cover the row
+    xv[0] = __ldcs(reinterpret_cast<const float4*>(x) + lane);
+    xv[1] = __ldcs(reinterpret_cast<const float4*>(x) + 32 + lane);
+  }
+  float best = FLT_MAX;
+  int best_j = 0x7fffffff;
+  for (int j = lane; j < parts; j += 32) {
+    const float v = __ldcs(part_val + i * parts + j);
+    const int c = __ldcs(part_idx + i * parts + j);
+    if (v < best || (v == best && c < best_j)) { best = v; best_j = c; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
+    if (ob < best || (ob == best && oj < best_j)) { best = ob; best_j = oj; }
+  }
+  if (lane == 0) {
+    labels[i] = best_j;
+    atomicAdd(counts + best_j, 1ull);
+  }
+  float* dst = sums + static_cast<int64_t>(best_j) * d;
+  if (VEC) {
+    atomicAdd(reinterpret_cast<float4*>(dst) + lane, xv[0]);            // red.global.add.v4.f32 (sm_90+)
+    atomicAdd(reinterpret_cast<float4*>(dst) + 32 + lane, xv[1]);
+  } else if ((d & 3) == 0 && ((reinterpret_cast<uint64_t>(x) | reinterpret_cast<uint64_t>(dst)) & 15) == 0) {
+    for (int j = lane * 4; j < d; j += 128) atomicAdd(reinterpret_cast<float4*>(dst + j), *reinterpret_cast<const float4*>(x + j));
+  } else {
+    for (int j = lane; j < d; j += 32) atomicAdd(dst + j, x[j]);
+  }
+}
+
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 kmeans_label_accumulate_kernel(const float* __restrict__ part_val, const int* __restrict__ part_idx, int parts,
                                const float* __restrict__ X, int64_t ldx, int64_t n, int d,
                                int32_t* __restrict__ labels, float* __restrict__ sums, unsigned long long* __restrict__ counts) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = static_cast<int64_t>(gridDim.x) * (blockDim.x / 32);
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x / 32) + (threadIdx.x / 32); i < n; i += warps) {
-    float best = FLT_MAX;
-    int best_j = 0x7fffffff;
-    for (int j = lane; j < parts; j += 32) {
-      const float v = part_val[i * parts + j];
-      const int c = part_idx[i * parts + j];
-      if (v < best || (v == best && c < best_j)) { best = v; best_j = c; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ob = __shfl_down_sync(0xffffffffu, best, o);
-      const int oj = __shfl_down_sync(0xffffffffu, best_j, o);
-      if (ob < best || (ob == best && oj < best_j)) { best = ob; best_j = oj; }
-    }
-    best_j = __shfl_sync(0xffffffffu, best_j, 0);
-    if (lane == 0) {
-      labels[i] = best_j;
-      atomicAdd(counts + best_j, 1ull);
-    }
-    const float* x = X + i * ldx;
-    float* dst = sums + static_cast<int64_t>(best_j) * d;
-    if ((d & 3) == 0 && ((reinterpret_cast<uint64_t>(x) | reinterpret_cast<uint64_t>(dst)) & 15) == 0) {
-      for (int j = lane * 4; j < d; j += 128) {
-        const float4 v = *reinterpret_cast<const float4*>(x + j);
-        atomicAdd(reinterpret_cast<float4*>(dst + j), v);       // red.global.add.v4.f32 (sm_90+)
-      }
-    } else {
-      for (int j = lane; j < d; j += 32) atomicAdd(dst + j, x[j]);
-    }
-  }
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x / 32) + (threadIdx.x / 32); i < n; i += warps)
+    kmeans_point<VEC>(part_val, part_idx, parts, X, ldx, i, d, lane, labels, sums, counts);
 }
 
 // CSR SpMV: GROUP threads per row; PTR = int32_t row pointers whenever nnz < 2^31 (4 B per row instead of 8)
@@ -167,8 +181,13 @@ extern "C" int sp_kmeans_assign_prepared(const void* Xprep, const float* X, int6
   rc = sp_gemm_prepared_argmin(1, &seg, n, k, cnorm, part_val, part_idx, prec, stream);   // no n x k matrix in HBM
   if (rc) return rc;
   const int blocks = static_cast<int>(std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(num_sms()) * 8));
-  kmeans_label_accumulate_kernel<<<blocks, 256, 0, stream>>>(part_val, part_idx, parts, X, ldx, n, static_cast<int>(d),
-                                                             labels, sums, reinterpret_cast<unsigned long long*>(counts));
+  const bool vec = d == 256 && (ldx & 3) == 0 && ((reinterpret_cast<uint64_t>(X) | reinterpret_cast<uint64_t>(sums)) & 15) == 0;
+  if (vec)
+    kmeans_label_accumulate_kernel<true><<<blocks, 256, 0, stream>>>(part_val, part_idx, parts, X, ldx, n, static_cast<int>(d),
+                                                                     labels, sums, reinterpret_cast<unsigned long long*>(counts));
+  else
+    kmeans_label_accumulate_kernel<false><<<blocks, 256, 0, stream>>>(part_val, part_idx, parts, X, ldx, n, static_cast<int>(d),
+                                                                      labels, sums, reinterpret_cast<unsigned long long*>(counts));
   SP_CUDA_CHECK(cudaGetLastError());
   return SP_OK;
 }

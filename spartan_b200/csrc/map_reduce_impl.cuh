@@ -421,7 +421,10 @@ static int64_t reduce_scratch_elems(const int64_t dims[3]) {
   const ReducePlan p = plan_reduce<V>(dims);
   const int64_t simple = static_cast<int64_t>(p.splits) * dims[0] * dims[2];
   const int64_t streamed = stream_reduce_chunks<T>(dims) * dims[0] * dims[2];
-  return std::max(simple, streamed);
+  // trailing-axis reductions on the streaming kernel (MODE 2): one partial per (row, 4 KiB panel of the reduced axis)
+  const int64_t row_panels = (dims[1] * static_cast<int64_t>(sizeof(T)) + stream::kPanelBytes - 1) / stream::kPanelBytes;
+  const int64_t row_streamed = p.row ? row_panels * dims[0] : 0;
+  return std::max(std::max(simple, streamed), row_streamed);
 }
 
 template <typename T, int V, int NI>
@@ -466,6 +469,34 @@ static int launch_reduce_v(const sp_program* prog, int n_in, const sp_operand* i
     }
   }
   if (p.row) {
+    // Long contiguous rows: the streaming kernel with the reduced axis as its vector axis (MODE 2).  The iteration space
+    // (rows, cols, 1) becomes (1, rows, cols); operand and index strides move one slot to the right.
+    const bool interp_ok = (V == 32 / sizeof(T));
+    int64_t sd[3] = {1, dims[0], dims[1]};
+    DevOperands<NI> sops = ops;
+    for (int i = 0; i < n_in; ++i) {
+      sops.in[i].stride[2] = ops.in[i].stride[1];
+      sops.in[i].stride[1] = ops.in[i].stride[0];
+      sops.in[i].stride[0] = 0;
+    }
+    DevProgram<T> sdp = dp;
+    sdp.index_stride[2] = dp.index_stride[1];
+    sdp.index_stride[1] = dp.index_stride[0];
+    sdp.index_stride[0] = 0;
+    stream::Plan plan;
+    if (plan_stream<T, NI>(sops, sd, false, kStreamReduceRows, &plan)) {
+      const int64_t sneed = static_cast<int64_t>(plan.n_panels) * dims[0] * static_cast<int64_t>(sizeof(T));
+      SP_REQUIRE(scratch_bytes >= sneed, SP_ERR_INVALID, "sp_map_reduce: scratch %lld B < required %lld B",
+                 (long long)scratch_bytes, (long long)sneed);
+      int rc = launch_stream<T, NI, 2>(sdp, sops, plan, red_op, sc, stream, interp_ok);
+      if (rc < 0) return rc;
+      if (rc != kNotLaunched) {
+        const int fb = static_cast<int>(std::min<int64_t>((n_out + 255) / 256, 4096));
+        finalize_kernel<T><<<fb, 256, 0, stream>>>(sc, n_out, plan.n_panels, n_out, 1, o, 1, red_op, accumulate);
+        SP_CUDA_CHECK(cudaGetLastError());
+        return SP_OK;
+      }
+    }
     SP_REQUIRE(p.blocks_x < (1ll << 31), SP_ERR_INVALID, "sp_map_reduce: too many rows (%lld)", (long long)dims[0]);
     const int64_t nvec = (dims[1] + V - 1) / V;
     reduce_row_kernel<T, V, NI><<<static_cast<unsigned>(p.blocks_x), p.block, 0, stream>>>(dp, ops, d, nvec, p.splits,

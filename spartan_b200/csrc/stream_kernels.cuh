@@ -95,7 +95,10 @@ __device__ __forceinline__ void load_direct_split(const DevOperand& o, int64_t b
   }
 }
 
-// MODE 0: map (store), MODE 1: reduce over d1 (partials to scratch[chunk][d0][d2])
+// MODE 0: map (store), MODE 1: reduce over d1 (partials to scratch[chunk][d0][d2]),
+// MODE 2: reduce over d2, the vector axis (trailing-axis reductions): every (row, panel) of a unit is folded to one value
+//         -- lanes by shuffle, the panel's four segments through shared memory, in fixed order -- and written to
+//         scratch[panel][d0 * d1 rows]; finalize_kernel folds the panels of a row.
 template <typename T, int NI, int MODE, typename PROG>
 __global__ void __launch_bounds__(kThreads, 1)
 stream_kernel(const DevProgram<T> prog, const DevOperands<NI> ops, const Plan plan, const int red_op,
@@ -185,6 +188,11 @@ stream_kernel(const DevProgram<T> prog, const DevOperands<NI> ops, const Plan pl
 #pragma unroll
         for (int v = 0; v < V; ++v) acc[v] = red_identity<T>(red_op);
       }
+      if (MODE == 2) {
+        // a slot per (row of the unit, segment); rows no warp visits (ragged last unit) keep the identity
+        for (int i = threadIdx.x - 32; i < plan.rc * kSegsPerPanel; i += 32 * kConsumerWarps) red_smem[i] = red_identity<T>(red_op);
+        consumer_bar();
+      }
       for (int st = 0; st < stages_per_unit; ++st) {
         const int64_t row0 = chunk * plan.rc + static_cast<int64_t>(st) * rb;
         if (row0 >= row_end) break;
@@ -241,9 +249,20 @@ stream_kernel(const DevProgram<T> prog, const DevOperands<NI> ops, const Plan pl
             if (valid_b == H) *reinterpret_cast<int4*>(dst + col_b) = *reinterpret_cast<const int4*>(&res[H]);
             else
               for (int v = 0; v < valid_b; ++v) dst[col_b + v] = res[H + v];
-          } else {
+          } else if (MODE == 1) {
 #pragma unroll
             for (int v = 0; v < V; ++v) acc[v] = red_apply<T>(red_op, acc[v], res[v]);
+          } else {
+            // fold this lane's vector (elements past the end of the row hold no data), then the warp
+            T a = red_identity<T>(red_op);
+#pragma unroll
+            for (int v = 0; v < H; ++v) {
+              if (v < valid_a) a = red_apply<T>(red_op, a, res[v]);
+              if (v < valid_b) a = red_apply<T>(red_op, a, res[H + v]);
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) a = red_apply<T>(red_op, a, shfl_down_t<T>(a, d));
+            if (lane == 0) red_smem[(st * rb + r) * kSegsPerPanel + q] = a;
           }
         }
         if (!released) {               // a warp without an item in this stage
@@ -265,6 +284,18 @@ stream_kernel(const DevProgram<T> prog, const DevOperands<NI> ops, const Plan pl
           T* dst = scratch + (chunk * plan.d0 + i0) * plan.d2;
           for (int v = 0; v < valid_a; ++v) dst[col_a + v] = acc[v];
           for (int v = 0; v < valid_b; ++v) dst[col_b + v] = acc[H + v];
+        }
+        consumer_bar();
+      }
+      if (MODE == 2) {
+        consumer_bar();
+        const int rows_in_unit = static_cast<int>(row_end - chunk * plan.rc);
+        T* dst = scratch + (static_cast<int64_t>(panel) * plan.d0 + i0) * plan.d1 + chunk * plan.rc;
+        for (int r = threadIdx.x - 32; r < rows_in_unit; r += 32 * kConsumerWarps) {
+          T a = red_smem[r * kSegsPerPanel];
+#pragma unroll
+          for (int sg = 1; sg < kSegsPerPanel; ++sg) a = red_apply<T>(red_op, a, red_smem[r * kSegsPerPanel + sg]);
+          dst[r] = a;
         }
         consumer_bar();
       }

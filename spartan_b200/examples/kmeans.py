@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from .. import blob_ctx, comm, device_ops
-from .._lib import lib, check, SP_RED_SUM, SpartanError
+from .._lib import lib, check, SP_RED_SUM, SP_F64, SpartanError
 from ..array import distarray, extent
 from ..expr.base import Expr, evaluate
 
@@ -56,9 +56,10 @@ class KMeans(object):
         ctx.kernel_launches += 1
       xp = device_ops.cached_operand(X, ('kmeans_points', block.ul[0], block.lr[0]), m, d, 'bf16x3', fill)
       blocks.append((x, lab, m, xp))
+    c_dev = torch.from_numpy(centers).to(ctx.device)
+    div = device_ops.make_program([('IN', 0), ('IN', 1), ('DIV', 0)], SP_F64)
     for it in range(self.n_iter):
       sums.zero_(); counts.zero_()
-      c_dev = torch.from_numpy(centers).to(ctx.device)
       for x, lab, m, xp in blocks:
         need = lib.sp_kmeans_assign_workspace_bytes(m, d, k)
         ws = ctx.scratch(need, 'kmeans')
@@ -68,13 +69,19 @@ class KMeans(object):
         ctx.kernel_launches += 4
       comm.allreduce(sums, SP_RED_SUM)
       comm.allreduce(counts, SP_RED_SUM)
-      counts_h = counts.cpu().numpy().astype(np.float64)
-      centers_h = sums.cpu().numpy().astype(np.float64)
-      zcount = counts_h == 0                                     # k_means_.py:148-157
+      # Only the k counts go to the host -- to decide whether a centre lost all its points (k_means_.py:148-157); the
+      # new centres are sums / counts evaluated in float64 and stored as float32 (:159) by the map kernel, on the device.
+      counts_h = counts.cpu().numpy()
+      zcount = counts_h == 0
       if np.any(zcount):
-        counts_h[zcount] = 1
+        counts_f = counts_h.astype(np.float64)
+        centers_h = sums.cpu().numpy().astype(np.float64)
+        counts_f[zcount] = 1
         centers_h[zcount, :] = rng.randn(int(np.count_nonzero(zcount)), d)
-      centers = (centers_h / counts_h.reshape(k, 1)).astype(np.float32)   # k_means_.py:159
+        c_dev = torch.from_numpy((centers_h / counts_f.reshape(k, 1)).astype(np.float32)).to(ctx.device)
+      else:
+        device_ops.run_map(div, [sums, counts.reshape(k, 1)], c_dev)
+    centers = c_dev.cpu().numpy()
     for tid in labels.tiles.values():
       if ctx.is_local(tid):
         ctx.tile(tid).valid = True

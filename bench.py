@@ -493,7 +493,23 @@ class Bench(object):
           want = resident.fetch(sp.extent.create((sl[0].start, sl[1].start), (sl[0].stop, sl[1].stop), (n, n))).cpu().numpy()
           diff = max(diff, float(np.abs(out_np[sl] - want).max()))
           scale = max(scale, float(np.abs(want).max()))
-        e2e = {'value': flops / ms_e / 1e6, 'unit': 'GFLOP/s', 'ms_per_step': ms_e, 'steps': steps_e,
+        timeline = None
+        if world > 1 and os.environ.get('SPARTAN_BENCH_TRACE'):
+          sp.FLAGS.dot_trace = True
+          eval_cache.clear()
+          self.sync()
+          c = sp.dot(sp.from_numpy(a_np, tile_hint=(tile, tile)), sp.from_numpy(b_np, tile_hint=(tile, tile)),
+                     tile_hint=(tile, tile)).evaluate()
+          tr = getattr(c, 'trace', None)
+          c.read_local_into(out_np)
+          torch.cuda.synchronize()
+          mine = tr.report() if tr is not None else None
+          sp.FLAGS.dot_trace = False
+          gathered = [None] * world
+          self.dist.all_gather_object(gathered, mine)
+          timeline = {'rank0': gathered[0], 'rank%d' % (world - 1): gathered[-1]}
+          del c
+        e2e = {'value': flops / ms_e / 1e6, 'unit': 'GFLOP/s', 'ms_per_step': ms_e, 'steps': steps_e, 'timeline_ms': timeline,
                'h2d_bytes_per_step': int(2 * n * n * 4 // world), 'd2h_bytes_per_step': int(out_bytes[0]),
                'max_rel_diff_vs_resident': self.maxreduce(diff / scale),
                'note': 'sp.dot(sp.from_numpy(a), sp.from_numpy(b)).evaluate() + read-back of C; pinned host buffers; bytes '

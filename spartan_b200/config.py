@@ -22,6 +22,7 @@ class Flags(object):
     self.dot_stream_min_bytes = 256 << 20
     # prepared (rounded / split / transposed) GEMM operands of unchanged arrays are kept between evaluations, up to this
     # many bytes (0 disables the cache)
+    self.dot_trace = False              # record a CUDA-event timeline of streamed multi-GPU dots (diagnostic)
     self.dot_prepared_cache = True
     self.dot_prepared_cache_bytes = 48 << 30
     self.checkpoint_path = '/tmp/spartan/checkpoint'     # config.py:96 default checkpoint directory

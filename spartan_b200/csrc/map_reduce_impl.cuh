@@ -317,6 +317,52 @@ static int launch_stream(const DevProgram<T>& dp, const DevOperands<NI>& ops, co
   return launch_stream_as<T, NI, MODE, DynamicProgram>(dp, ops, plan, red_op, scratch, stream_);
 }
 
+// ---- direct map kernel (compiled programs only): see stream_kernels.cuh
+static int g_map_kernel = -1;     // 0 = ring (bulk-copy ring), 1 = direct; env SPARTAN_MAP_KERNEL=ring|direct, default direct
+static bool use_direct_map() {
+  if (g_map_kernel < 0) {
+    const char* e = getenv("SPARTAN_MAP_KERNEL");
+    g_map_kernel = (e && e[0] == 'r') ? 0 : 1;
+  }
+  return g_map_kernel == 1;
+}
+
+template <typename T, int NI, typename PROG>
+static int launch_direct_as(const DevProgram<T>& dp, const DevOperands<NI>& ops, const stream::Plan& plan, int64_t blocks,
+                            cudaStream_t stream_) {
+  stream::direct_map_kernel<T, NI, PROG><<<static_cast<unsigned>(blocks), stream::kDirectThreads, 0, stream_>>>(dp, ops, plan);
+  SP_CUDA_CHECK(cudaGetLastError());
+  return SP_OK;
+}
+
+// SP_OK when launched, kNotLaunched when there is no compiled instance of the program (or the shape does not fit).
+template <typename T, int NI>
+static int launch_direct(const DevProgram<T>& dp, const DevOperands<NI>& ops, const stream::Plan& plan, cudaStream_t stream_) {
+  constexpr int VEC = 16 / sizeof(T);
+  if (plan.d2 % VEC != 0) return kNotLaunched;
+  for (int i = 0; i < ops.n_in; ++i)
+    if (ops.in[i].kind == kGeneric) return kNotLaunched;
+  const int64_t row_vecs = plan.d2 / VEC;
+  const int64_t per_block = static_cast<int64_t>(stream::kDirectThreads) * stream::kDirectUnroll;
+  const int64_t blocks = plan.d0 * plan.d1 * ((row_vecs + per_block - 1) / per_block);
+  if (blocks <= 0 || blocks >= (1ll << 31)) return kNotLaunched;
+  if constexpr (NI == 2 && !std::is_same<T, long long>::value) {
+    switch (match_static<T>(dp)) {
+#define SP_LAUNCH(IDX, TYPE) case IDX: return launch_direct_as<T, NI, TYPE>(dp, ops, plan, blocks, stream_);
+      SP_STATIC_PROGRAMS(SP_LAUNCH)
+#undef SP_LAUNCH
+      default: break;
+    }
+  }
+  if (plan.d0 * plan.d1 * plan.d2 * static_cast<int64_t>(sizeof(T)) >= kJitMinBytes) {
+    void* params[] = {const_cast<DevProgram<T>*>(&dp), const_cast<DevOperands<NI>*>(&ops), const_cast<stream::Plan*>(&plan)};
+    const int rc = jit::launch_stream_specialised(TypeTag<T>::dtype, NI, 3, dp.op, dp.src, dp.arg, dp.n_ops, params,
+                                                  static_cast<int>(blocks), stream::kDirectThreads, 0, stream_);
+    if (rc != 0) return rc < 0 ? rc : SP_OK;
+  }
+  return kNotLaunched;
+}
+
 #ifndef SP_FLAT_ROW_BYTES
 #define SP_FLAT_ROW_BYTES 16384
 #endif
@@ -359,6 +405,10 @@ static int launch_map_v(const sp_program* prog, int n_in, const sp_operand* in, 
     if (reshape_flat<T, NI>(sops, sd)) sdp.index_stride[1] = sd[2] * sdp.index_stride[2];   // i2 = i1' * row + i2'
     stream::Plan plan;
     if (plan_stream<T, NI>(sops, sd, true, 0, &plan)) {
+      if (use_direct_map()) {
+        const int rc = launch_direct<T, NI>(sdp, sops, plan, stream);
+        if (rc != kNotLaunched) return rc;
+      }
       const int rc = launch_stream<T, NI, 0>(sdp, sops, plan, 0, nullptr, stream, interp_ok);
       if (rc != kNotLaunched) return rc;
     }

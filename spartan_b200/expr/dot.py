@@ -75,6 +75,25 @@ def _regular_layout(av, bv, target, W, M, K):
   return a_axes, b_axes, c_runs
 
 
+class _Trace(object):
+  """Timeline of one streamed evaluation (FLAGS.dot_trace): named CUDA events on the streams involved, reported as
+  milliseconds since the evaluation began.  A diagnostic; costs a few event records."""
+
+  def __init__(self, ctx, main):
+    self.t0 = torch.cuda.Event(enable_timing=True)
+    self.t0.record(main)
+    self.marks = []
+
+  def mark(self, name, stream):
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record(stream)
+    self.marks.append((name, ev))
+
+  def report(self):
+    torch.cuda.synchronize()
+    return [(name, round(self.t0.elapsed_time(ev), 3)) for name, ev in self.marks]
+
+
 class DotExpr(Expr):
   """dot.py:95-158 (the node the reference defines but no longer constructs -- Q11 -- is the natural
   home of the GEMM evaluator)."""
@@ -334,13 +353,17 @@ class DotExpr(Expr):
         device_ops.upload_rect(slab[r0:r1, off:off + (c1 - c0)], host[r0:r1, c0:c1])
         off += c1 - c0
 
+    trace = _Trace(ctx, main) if FLAGS.dot_trace else None
     with torch.cuda.stream(copy):
+      if trace: trace.mark('h2d begin', copy)
       upload_cols(bv.slab, b_np, 0, K, b_axes[me][1])
       ev_b = copy.record_event()
+      if trace: trace.mark('h2d B done', copy)
       ev_a = []
-      for r0, r1 in strips:
+      for i, (r0, r1) in enumerate(strips):
         upload_cols(av.slab, a_np, r0, r1, a_axes[me][1])
         ev_a.append(copy.record_event())
+        if trace: trace.mark('h2d A%d done' % i, copy)
 
     order = [(me + j) % W for j in range(W)]
 
@@ -351,12 +374,14 @@ class DotExpr(Expr):
                                         buf=gather.tensor[slot(i, me) * part:(slot(i, me) + 1) * part])
       mine.prepare_a(av.slab[r0:r1, :], 0)
       ev = main.record_event()
+      if trace: trace.mark('prep A%d done' % i, main)
       with torch.cuda.stream(push):
         push.wait_event(ev)
         dsts = [(me - j) % W for j in range(1, W)]           # ring order: the peer that needs this slot first goes first
         peer.push([gather.ptrs[d] + slot(i, me) * part for d in dsts], mine.buf.data_ptr(), mine.nbytes,
                   [peer.flag_ptr(d, f0 + slot(i, me)) for d in dsts], esrc)
         ctx.push_done = push.record_event()
+        if trace: trace.mark('push A%d done' % i, push)
       return mine
 
     # B[:, mine]: prepared once per source rank p as the rows k_p of the transposed operand
@@ -383,6 +408,7 @@ class DotExpr(Expr):
       device_ops.gemm_prepared_views_gated(views, flags, [epoch] * W, peer.status.data_ptr(), target.slab[r0:r1, :],
                                            False, precision)
       ev_c = main.record_event()
+      if trace: trace.mark('gemm %d done' % i, main)
       for c0, c1 in c_runs[me][1]:
         done.append((extent.create((r0, c0), (r1, c1), (M, N)), ev_c))
     for arr in (av, bv, target):
@@ -390,6 +416,7 @@ class DotExpr(Expr):
         if ctx.is_local(tid):
           ctx.tile(tid).valid = True
     target.block_events = done
+    target.trace = trace
     for e, v in ((ea, av), (eb, bv)):
       if e.needs_cache:
         eval_cache.set(e.expr_id, v)

@@ -512,6 +512,7 @@ class Bench(object):
         e2e = {'value': flops / ms_e / 1e6, 'unit': 'GFLOP/s', 'ms_per_step': ms_e, 'steps': steps_e, 'timeline_ms': timeline,
                'h2d_bytes_per_step': int(2 * n * n * 4 // world), 'd2h_bytes_per_step': int(out_bytes[0]),
                'max_rel_diff_vs_resident': self.maxreduce(diff / scale),
+               'numa_bound_cpus': (len(ctx.numa_cpus) if ctx.numa_cpus else None),
                'note': 'sp.dot(sp.from_numpy(a), sp.from_numpy(b)).evaluate() + read-back of C; pinned host buffers; bytes '
                        'are per rank; upload, contraction and read-back are pipelined strip by strip '
                        '(FLAGS.dot_stream_host_operands)'}

@@ -56,6 +56,7 @@ class BlobCtx(object):
     self.data_epoch = 0                       # bumped whenever an existing array may have changed in place
     self._peer = None
     self.push_done = None                     # event after the last copy-engine push of this rank
+    self.numa_cpus = None                     # CPUs this rank was pinned to (multi-rank jobs)
 
   @property
   def peer(self):
@@ -170,6 +171,43 @@ def set(ctx):
   _global_ctx[0] = ctx
 
 
+def _bind_to_gpu_numa_node(index):
+  """Pins this process to the CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI function), so that the pinned
+  host buffers it allocates from now on are first-touched on that NUMA node and H2D / D2H traffic of the ranks does not
+  all cross one socket link.  Multi-rank jobs only; SPARTAN_NUMA_BIND=0 disables.  Returns the CPU set or None."""
+  if os.environ.get('SPARTAN_NUMA_BIND', '1') == '0':
+    return None
+  try:
+    import pynvml
+    pynvml.nvmlInit()
+    visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+    phys = index
+    if visible:
+      ids = [v for v in visible.split(',') if v.strip()]
+      if index < len(ids) and ids[index].strip().isdigit():
+        phys = int(ids[index])
+    bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(phys)).busId
+    bus = bus.decode() if isinstance(bus, bytes) else bus
+    dom, rest = bus.split(':', 1)
+    path = '/sys/bus/pci/devices/%s:%s/local_cpulist' % (dom[-4:].lower(), rest.lower())
+    with open(path) as f:
+      text = f.read().strip()
+    cpus = set()
+    for part in text.split(','):
+      if '-' in part:
+        a, b = part.split('-')
+        cpus.update(range(int(a), int(b) + 1))
+      elif part:
+        cpus.add(int(part))
+    cpus &= os.sched_getaffinity(0)
+    if not cpus:
+      return None
+    os.sched_setaffinity(0, cpus)
+    return cpus
+  except Exception:
+    return None
+
+
 def initialize(device=None):
   """One-time setup of this rank: picks cuda:LOCAL_RANK, joins the torch.distributed job when
   WORLD_SIZE > 1 (NCCL on GPUs, gloo on CPU) and installs the context.  Replaces
@@ -179,6 +217,8 @@ def initialize(device=None):
     device = torch.device('cuda', int(os.environ.get('LOCAL_RANK', 0)))
     torch.cuda.set_device(device)
   ctx = BlobCtx(rank, world, device)
+  if world > 1 and ctx.device.type == 'cuda':
+    ctx.numa_cpus = _bind_to_gpu_numa_node(ctx.device.index or 0)
   set(ctx)
   return ctx
 

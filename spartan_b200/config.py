@@ -10,6 +10,9 @@ class Flags(object):
     self.optimization = True            # optimize.py:1101
     self.opt_map_fusion = True          # optimize.py:1096
     self.opt_reduce_fusion = True       # optimize.py:1099
+    # optimize.py:1094 (default True there); here arrays without a tile_hint keep the reference's default tiling unless
+    # this is switched on -- results are identical either way, only placement (and NVLink traffic) changes
+    self.opt_auto_tiling = False
     self.opt_expression_cache = True    # base.py:21
     self.tile_assignment_strategy = 'round_robin'   # distarray.py:441-445 (the only strategy on one box)
     # tensor-core mode of dot(): 'bf16x3' (default: 16-bit-mantissa split, 3 bf16 passes), 'tf32x3' (22-bit),

@@ -23,6 +23,7 @@ from .map2 import (map2, outer, Map2Expr, OuterProductExpr, DeviceTileFunction, 
                    dot_outer_mapper, dot_as_join)
 from .ndarray import ndarray, NdArrayExpr
 from .optimize import optimize, MapMapFusion, ReduceMapFusion
+from .tiling import AutomaticTiling
 from .reduce import reduce, ReduceExpr, ArgReduceExpr
 from .write_array import from_numpy, WriteArrayExpr
 from .slice import SliceExpr

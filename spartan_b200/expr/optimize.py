@@ -1,8 +1,8 @@
 """Expression-graph optimisation: the two fusion passes that define "fused element-wise chain" and
 "fused map+reduce" (reference: spartan/expr/operator/optimize.py:107-227, pass order :1093-1099).
 
-Out of scope: AutomaticTiling, RotateSlice, ParakeetGeneration,
-CollapsedCachedExpressions.  A map is only fused into its consumer if its local tree can run on the
+AutomaticTiling lives in tiling.py (re-targeted to NVLink bytes; off by default: FLAGS.opt_auto_tiling).  Out of scope
+(SURVEY.md section 2.1): RotateSlice, ParakeetGeneration, CollapsedCachedExpressions.  A map is only fused into its consumer if its local tree can run on the
 device (program.tree_is_mappable); otherwise it stays a separate node, exactly like an un-fusable
 child in the reference.
 """
@@ -114,7 +114,20 @@ class ReduceMapFusion(OptimizePass):
                      tile_hint=expr.tile_hint)
 
 
-passes = [MapMapFusion, ReduceMapFusion]     # optimize.py:1093-1099 order (the in-scope passes)
+def _auto_tiling():
+  from .tiling import AutomaticTiling
+  return AutomaticTiling
+
+
+class _AutoTilingPass(object):
+  """optimize.py:1094 registers AutomaticTiling before the fusion passes; resolved lazily (tiling.py imports dot.py)."""
+  name = 'auto_tiling'
+
+  def __new__(cls):
+    return _auto_tiling()()
+
+
+passes = [_AutoTilingPass, MapMapFusion, ReduceMapFusion]     # optimize.py:1093-1099 order (the in-scope passes)
 
 
 def apply_pass(klass, dag):

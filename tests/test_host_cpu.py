@@ -446,3 +446,75 @@ def test_map2_join_extents_match_oracle_join_mapper():
       assert len(got) == len(seen)
       for a, b in zip(got, seen):
         assert [(e.ul, e.lr, tuple(e.array_shape)) for e in a] == [(e.ul, e.lr, tuple(e.array_shape)) for e in b]
+
+
+def test_automatic_tiling_minimises_nvlink_bytes():
+  """AutomaticTiling (optimize.py:459-1054) with this backend's cost -- bytes over NVLink: the chosen tilings must be a
+  global minimum of the cost model (checked against brute force), must remove avoidable traffic in the textbook cases,
+  and the rewritten DAG must carry the matching tile_hints."""
+  import itertools
+  from spartan_b200.expr import tiling
+  from spartan_b200.expr.base import Expr
+  from spartan_b200.expr.ndarray import NdArrayExpr
+  from spartan_b200.expr.dot import DotExpr
+  W = 8
+  n = 4096
+  # 1. a reduction over axis 0 of a fused chain: row tiling needs an all-reduce, column tiling does not
+  x = sp.ndarray((n, n), dtype=np.float32); y = sp.ndarray((n, n), dtype=np.float32)
+  e = (x * 2 + y).sum(axis=0)
+  p = tiling.AutomaticTiling(W)
+  p._build(e)
+  choice, cost, _ = p.solve()
+  assert cost == 0 and set(choice.values()) == {tiling.COL}
+  # ... and over axis 1 the other way round
+  p = tiling.AutomaticTiling(W); p._build((x * 2 + y).sum(axis=1))
+  choice, cost, _ = p.solve()
+  assert cost == 0 and set(choice.values()) == {tiling.ROW}
+  # 2. operands of one map end up tiled alike (an existing array fixes the choice of the free one)
+  fixed = sp.ndarray((n, n), dtype=np.float32, tile_hint=(n, n // W))
+  p = tiling.AutomaticTiling(W); p._build(fixed + x)
+  choice, cost, _ = p.solve()
+  assert cost == 0 and list(choice.values()) == [tiling.COL]
+  # 3. dot: a column-tiled C with B tiled by columns moves (W-1)|A| bytes and nothing else
+  a = sp.ndarray((n, n), dtype=np.float32); b = sp.ndarray((n, 2 * n), dtype=np.float32)
+  d = sp.dot(a, b)
+  p = tiling.AutomaticTiling(W); p._build(d)
+  choice, cost, til = p.solve()
+  assert cost == (W - 1) * n * n * 4          # |A| < |B|: gather A, keep B's columns in place
+  assert til[d.expr_id] != tiling.ROW and til[b.expr_id] != tiling.ROW
+  # 4. brute force over every assignment of a mixed DAG: the pass returns a global minimum
+  u = sp.ndarray((n, n), dtype=np.float32); v = sp.ndarray((n, n), dtype=np.float32); w = sp.ndarray((n, n), dtype=np.float32)
+  dag = (sp.dot(u, v) + sp.transpose(w)).sum(axis=1)
+  p = tiling.AutomaticTiling(W); p._build(dag)
+  free = p.free_nodes()
+  choice, cost, _ = p.solve()
+  best = min(p.evaluate(dict(zip(free, combo)))[0] for combo in itertools.product((0, 1, 2), repeat=len(free)))
+  assert cost == best
+  # coordinate descent (used beyond EXHAUSTIVE_LIMIT free nodes) must not be worse than a fixed default
+  old = tiling.EXHAUSTIVE_LIMIT
+  try:
+    tiling.EXHAUSTIVE_LIMIT = 0
+    p2 = tiling.AutomaticTiling(W); p2._build(dag)
+    _, cost2, _ = p2.solve()
+    assert cost2 <= p2.evaluate({})[0]
+  finally:
+    tiling.EXHAUSTIVE_LIMIT = old
+  # 5. the rewritten DAG carries the hints (and only free nodes change)
+  out = tiling.AutomaticTiling(W).visit((x * 2 + y).sum(axis=0))
+  hints = []
+  def walk(ex):
+    if isinstance(ex, NdArrayExpr):
+      hints.append(ex.tile_hint)
+    elif isinstance(ex, Expr):
+      for dep in ex.dependencies().values():
+        walk(dep)
+      if hasattr(ex, 'children') and ex.children is not None:
+        for c in ex.children:
+          walk(c)
+  walk(out)
+  assert hints and all(h == (n, n // W) for h in hints), hints
+  assert tiling.hint_for((100, 60), tiling.ROW, 8) == (13, 60) and tiling.hint_for((100, 60), tiling.COL, 8) == (100, 8)
+  assert tiling.hint_for((100, 60), tiling.BLOCK, 8) == (13, 8)
+  # a single rank has nothing to optimise
+  e1 = (x * 2 + y).sum(axis=0)
+  assert tiling.AutomaticTiling(1).visit(e1) is e1

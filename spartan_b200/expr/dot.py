@@ -75,6 +75,28 @@ def _regular_layout(av, bv, target, W, M, K):
   return a_axes, b_axes, c_runs
 
 
+_PUSH_BYTES_PER_S = 600e9       # copy-engine push over NVLink 5, one stream (measured: 3.76 GB in 6.1 ms)
+_DOT_FLOPS_PER_S = 480e12       # algorithmic rate of the bf16x3 contraction on one B200
+
+
+def _arrival_groups(n_segments, t_push, t_segment, max_groups=4):
+  """Positions 0..n-1 of the segment order (0 = local, j = the j-th push to land) grouped into passes: a pass takes
+  every segment expected to have arrived when the previous pass ends (at least one)."""
+  groups, t, nxt = [], 0.0, 0
+  while nxt < n_segments:
+    arrived = n_segments if t_push <= 0 else min(n_segments, int(t / t_push) + 1)
+    if arrived <= nxt:
+      arrived = nxt + 1
+      t = max(t, nxt * t_push)
+    if len(groups) == max_groups - 1:
+      arrived = n_segments
+    grp = list(range(nxt, arrived))
+    groups.append(grp)
+    t += len(grp) * t_segment
+    nxt = arrived
+  return groups
+
+
 class _Trace(object):
   """Timeline of one streamed evaluation (FLAGS.dot_trace): named CUDA events on the streams involved, reported as
   milliseconds since the evaluation began.  A diagnostic; costs a few event records."""
@@ -465,22 +487,31 @@ class DotExpr(Expr):
                 [peer.flag_ptr(d, f0 + half * W + me) for d in dsts], esrc)
       ctx.push_done = push.record_event()
     order = [(me + j) % W for j in range(W)]
+    # The kernel walks K innermost: a launch cannot finish its first tile before the last of ITS segments has landed.
+    # So the segments are contracted in a few passes, grouped by when they arrive (local first; then what the copy
+    # engines deliver while the previous pass computes), each pass accumulating into C.  The gates keep any grouping
+    # correct; the grouping only decides how much of the exchange hides behind the math (measured on 2 x B200 with the
+    # 8-rank traffic pattern: one pass over all segments 20-22 ms, the GEMM alone 15.8-17 ms, profiles/r02_peer_probe*).
+    groups = _arrival_groups(W, mine.nbytes / _PUSH_BYTES_PER_S,
+                             2.0 * M * sum(c1 - c0 for c0, c1 in c_runs[me][1]) * width / _DOT_FLOPS_PER_S)
     for (r0, r1) in c_runs[me][0]:
       for (c0, c1) in c_runs[me][1]:
-        views, flags = [], []
-        for p in order:
-          def fill(op, p=p):
-            off = 0
-            for a, b in a_axes[p][1]:
-              Bv = bv.fetch(extent.create((a, c0), (b, c1), bv.shape))       # zero-copy view of this rank's B slab
-              op.prepare_b(Bv, 0, k_offset=off)
-              off += b - a
-          pb = device_ops.cached_operand(bv, ('b_cols', c0, c1, p), c1 - c0, width, precision, fill)
-          a_ptr = mine.row_ptr(r0) if p == me else gather.local_ptr + (half * W + p) * a_bytes + r0 * rb
-          views.append((a_ptr, M * rb, pb.row_ptr(0), pb.copy_stride, Kp))
-          flags.append(0 if p == me else peer.flag_ptr(me, f0 + half * W + p))
         Cv = target.fetch(extent.create((r0, c0), (r1, c1), shape))
-        device_ops.gemm_prepared_views_gated(views, flags, [epoch] * W, peer.status.data_ptr(), Cv, False, precision)
+        for gi, grp in enumerate(groups):
+          views, flags = [], []
+          for p in [order[j] for j in grp]:
+            def fill(op, p=p):
+              off = 0
+              for a, b in a_axes[p][1]:
+                Bv = bv.fetch(extent.create((a, c0), (b, c1), bv.shape))       # zero-copy view of this rank's B slab
+                op.prepare_b(Bv, 0, k_offset=off)
+                off += b - a
+            pb = device_ops.cached_operand(bv, ('b_cols', c0, c1, p), c1 - c0, width, precision, fill)
+            a_ptr = mine.row_ptr(r0) if p == me else gather.local_ptr + (half * W + p) * a_bytes + r0 * rb
+            views.append((a_ptr, M * rb, pb.row_ptr(0), pb.copy_stride, Kp))
+            flags.append(0 if p == me else peer.flag_ptr(me, f0 + half * W + p))
+          device_ops.gemm_prepared_views_gated(views, flags, [epoch] * len(views), peer.status.data_ptr(), Cv, gi > 0,
+                                               precision)
     return True
 
   def _allgather_path(self, ctx, av, bv, target, shape, M, N, K, dtype, precision):

@@ -518,3 +518,16 @@ def test_automatic_tiling_minimises_nvlink_bytes():
   # a single rank has nothing to optimise
   e1 = (x * 2 + y).sum(axis=0)
   assert tiling.AutomaticTiling(1).visit(e1) is e1
+
+
+def test_dot_arrival_groups_cover_every_segment_once():
+  """The passes of the multi-GPU dot (segments grouped by expected arrival) must be a partition of the segment order,
+  in order, starting with the local segment alone."""
+  from spartan_b200.expr.dot import _arrival_groups
+  for n in (1, 2, 3, 4, 8):
+    for t_push, t_seg in [(0.87, 2.1), (3.6, 36.0), (3.0, 1.0), (0.0, 1.0), (1.0, 1e-9)]:
+      g = _arrival_groups(n, t_push, t_seg)
+      assert [j for grp in g for j in grp] == list(range(n))
+      assert g[0] == [0] or t_push <= 0
+      assert 1 <= len(g) <= 4
+  assert _arrival_groups(8, 0.87, 2.1) == [[0], [1, 2], [3, 4, 5, 6, 7]]

@@ -20,6 +20,7 @@ def timeit(fn, n=10):
   e1.record(); torch.cuda.synchronize()
   return e0.elapsed_time(e1) / n
 
+print(json.dumps({"map_kernel": os.environ.get("SPARTAN_MAP_KERNEL", "direct")}), flush=True)
 for hint in [(rows, cols), (rows, cols // 8)]:
   X = sp.rand(rows, cols, seed=2, dtype=np.float32, tile_hint=hint).evaluate()
   Y = sp.rand(rows, cols, seed=3, dtype=np.float32, tile_hint=hint).evaluate()

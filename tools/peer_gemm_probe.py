@@ -87,7 +87,35 @@ def make_case(nstreams, with_gemm):
       for st in streams[:nstreams]: main.wait_stream(st)
   return fn
 
+def traced(nstreams, gated):
+  """One step with events: when each pushed segment has left this rank, and when the GEMM ends (ms from the start)."""
+  comm.barrier(); torch.cuda.synchronize()
+  t0 = torch.cuda.Event(enable_timing=True); t0.record()
+  e, esrc = peer.next_epoch('probe')
+  ev = main.record_event()
+  marks = []
+  for j in range(1, S):
+    st = streams[(j - 1) % nstreams]
+    with torch.cuda.stream(st):
+      st.wait_event(ev)
+      peer.push([gather.ptrs[other] + j * a_bytes], mine.buf.data_ptr(), a_bytes, [peer.flag_ptr(other, f0 + j)], esrc)
+      m = torch.cuda.Event(enable_timing=True); m.record(st); marks.append(m)
+  launch(gated, e)
+  g = torch.cuda.Event(enable_timing=True); g.record(main)
+  for st in streams: main.wait_stream(st)
+  comm.barrier(); torch.cuda.synchronize()
+  return {'push_done_ms': [round(t0.elapsed_time(m), 2) for m in marks], 'gemm_done_ms': round(t0.elapsed_time(g), 2)}
+
+
 out = {'gemm_alone_ms': timed(case_gemm_alone)}
+for ns in (1, 2):
+  for gated in (False, True):
+    traced(ns, gated)
+    out['trace_%dstreams_%s' % (ns, 'gated' if gated else 'ungated')] = traced(ns, gated)
+lib.sp_gemm_set_round_sync(0)
+out['gemm_alone_no_round_sync_ms'] = timed(case_gemm_alone)
+out['gated_with_pushes_1stream_no_round_sync_ms'] = timed(make_case(1, True))
+lib.sp_gemm_set_round_sync(1)
 for ns in (1, 2, 4, 7):
   out['pushes_alone_%dstreams_ms' % ns] = timed(make_case(ns, False))
   out['gated_gemm_with_pushes_%dstreams_ms' % ns] = timed(make_case(ns, True))

@@ -230,6 +230,9 @@ int sp_map_reduce(const sp_program* prog, int n_in, const sp_operand* in, const 
  * ncclAllReduce with the matching op instead. */
 int sp_combine(void* dst, const void* src, int dtype, int64_t n, int reduce_op, void* stream);
 
+/* A transposed view (transpose.py:27-67) made dense: dst (R x C, ld ldd) = transpose of src (C x R, ld lds), through a
+ * shared-memory tile so both sides are coalesced.  elem_size 1, 4 or 8 bytes; C <= 65535 * 32 per call. */
+int sp_transpose_2d(void* dst, int64_t ldd, const void* src, int64_t lds, int64_t R, int64_t C, int elem_size, void* stream);
 /* Tile.merge on a partially written tile (tile.pyx:270-283): per element, dst = mask ? reducer(dst, src) : src, then
  * mask = 1.  reduce_op < 0: no reducer.  3-D strided views (strides in elements); the reduction is evaluated in the
  * NumPy result type of the two dtypes.  Pairs: equal dtypes, (f32,f64), (f64,f32), (i64,i32), (i32,i64). */

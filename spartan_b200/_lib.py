@@ -89,6 +89,7 @@ _SIGS = {
   'sp_jit_compile_check': (_i64, [ctypes.POINTER(sp_program), _int, _int]),
   'sp_combine': (_int, [_vp, _vp, _int, _i64, _int, _vp]),
   'sp_merge_masked': (_int, [_vp, _i64p, _int, _vp, _i64p, _int, _vp, _i64p, _i64p, _int, _vp]),
+  'sp_transpose_2d': (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _int, _vp]),
   'sp_copy_rect': (_int, [_vp, _i64p, _vp, _i64p, _i64p, _int, _vp]),
   'sp_gemm_set_chunk_kblocks': (_int, [_int]),
   'sp_gemm_set_variant': (_int, [_int]),

@@ -214,6 +214,25 @@ __global__ void merge_masked_kernel(DT* __restrict__ dst, int64_t ds0, int64_t d
   }
 }
 
+// dst[i][j] = src[j][i]: a transposed view (spartan/expr/operator/transpose.py:27-67) made dense through a 32 x 32
+// shared-memory tile, so that both the reads of `src` and the writes of `dst` are coalesced.
+template <typename T>
+__global__ void transpose_2d_kernel(T* __restrict__ dst, int64_t ldd, const T* __restrict__ src, int64_t lds, int64_t R,
+                                    int64_t C) {
+  __shared__ T tile[32][33];
+  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * 32;     // dst rows = src columns
+  const int64_t j0 = static_cast<int64_t>(blockIdx.y) * 32;     // dst columns = src rows
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int64_t j = j0 + r, i = i0 + threadIdx.x;
+    if (j < C && i < R) tile[r][threadIdx.x] = src[j * lds + i];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int64_t i = i0 + r, j = j0 + threadIdx.x;
+    if (i < R && j < C) dst[i * ldd + j] = tile[threadIdx.x][r];
+  }
+}
+
 static inline int grid_for(int64_t n) {
   const int64_t want = (n + 255) / 256;
   return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(num_sms()) * 16)));
@@ -405,6 +424,29 @@ extern "C" int sp_merge_masked(void* dst, const int64_t dst_stride[3], int dst_d
       return SP_ERR_UNSUPPORTED;
   }
 #undef SP_MERGE
+  SP_CUDA_CHECK(cudaGetLastError());
+  return SP_OK;
+}
+
+
+// dst (R x C, leading dimension ldd) = transpose of src (C x R, leading dimension lds); elem_size in {1, 4, 8} bytes.
+extern "C" int sp_transpose_2d(void* dst, int64_t ldd, const void* src, int64_t lds, int64_t R, int64_t C, int elem_size,
+                               void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SP_REQUIRE(R >= 0 && C >= 0 && ldd >= C && lds >= R, SP_ERR_INVALID, "sp_transpose_2d: bad shape");
+  if (R == 0 || C == 0) return SP_OK;
+  SP_REQUIRE(dst && src, SP_ERR_INVALID, "sp_transpose_2d: null pointer");
+  const int64_t gx = (R + 31) / 32, gy = (C + 31) / 32;
+  SP_REQUIRE(gy <= 65535 && gx < (1ll << 31), SP_ERR_INVALID, "sp_transpose_2d: too many columns for one launch");
+  dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(gy)), block(32, 8);
+  switch (elem_size) {
+    case 1: transpose_2d_kernel<uint8_t><<<grid, block, 0, stream>>>(static_cast<uint8_t*>(dst), ldd, static_cast<const uint8_t*>(src), lds, R, C); break;
+    case 4: transpose_2d_kernel<uint32_t><<<grid, block, 0, stream>>>(static_cast<uint32_t*>(dst), ldd, static_cast<const uint32_t*>(src), lds, R, C); break;
+    case 8: transpose_2d_kernel<uint64_t><<<grid, block, 0, stream>>>(static_cast<uint64_t*>(dst), ldd, static_cast<const uint64_t*>(src), lds, R, C); break;
+    default:
+      set_error("sp_transpose_2d: bad element size %d", elem_size);
+      return SP_ERR_INVALID;
+  }
   SP_CUDA_CHECK(cudaGetLastError());
   return SP_OK;
 }

@@ -117,6 +117,25 @@ def _set_index(prog, base, stride3):
     prog.index_stride[i] = int(stride3[i])
 
 
+_COALESCE_MIN_BYTES = 1 << 20
+
+
+def coalesced(t):
+  """A large 2-D operand whose unit stride runs along its FIRST axis (a transposed view of a row-major matrix) read as
+  is would touch one 32-byte sector per element; it is made dense once through the tiled transpose kernel instead (one
+  coalesced read + one coalesced write).  Everything else is returned unchanged."""
+  if (t.dim() != 2 or t.stride(1) in (0, 1) or t.stride(0) != 1 or t.device.type != 'cuda'
+      or t.numel() * t.element_size() < _COALESCE_MIN_BYTES or t.element_size() not in (1, 4, 8)
+      or t.shape[1] > 65535 * 32):
+    return t
+  R, C = t.shape
+  out = torch.empty((R, C), dtype=t.dtype, device=t.device)
+  check(lib.sp_transpose_2d(out.data_ptr(), C, t.data_ptr(), t.stride(1), R, C, t.element_size(), _stream()),
+        'sp_transpose_2d')
+  _count_launch()
+  return out
+
+
 def run_map(prog, inputs, out, index=None):
   """out[...] = prog(inputs...) element-wise with broadcasting; ``out`` may be a strided view.
   ``index`` = (base, per-dimension coefficients): the value SP_OP_INDEX yields for element (i_0, i_1, ...)
@@ -125,6 +144,7 @@ def run_map(prog, inputs, out, index=None):
   out_shape = tuple(out.shape)
   if out.numel() == 0:
     return
+  inputs = [coalesced(t) for t in inputs]
   strides = [broadcast_strides(t, out_shape) for t in inputs] + [list(out.stride())]
   if index is not None:
     strides.append(list(index[1]))
@@ -150,6 +170,7 @@ def run_map_reduce(prog, inputs, in_shape, axis, red_op, out, accumulate, index=
   in_shape = tuple(int(s) for s in in_shape)
   nd = len(in_shape)
   ctx = blob_ctx.get()
+  inputs = [coalesced(t) for t in inputs]
   in_strides = [broadcast_strides(t, in_shape) for t in inputs]
   n_in = len(inputs)
   if index is not None:

@@ -4,13 +4,13 @@ implementation: kmeans_map2_dist_mapper -> kmeans_count_mapper -> kmeans_center_
 One iteration = one `sp_kmeans_assign` per contiguous block of this rank's rows (distance GEMM on the tensor
 cores + label/accumulate kernel) followed by ncclAllReduce of the (k x d) sums and the k counts -- the
 cross-tile combine the reference's map2 targets were meant to do (they have no reducer and overwrite,
-SURVEY.md section 9 Q7).  Empty clusters are re-seeded on the host exactly like the reference does
-(k_means_.py:148-157) but from a seeded generator so every rank agrees."""
+SURVEY.md section 9 Q7).  The centre update and the re-seeding of empty clusters (k_means_.py:148-159) run on the
+device too (fused map kernels, counter-based generator), so an iteration never waits for the host."""
 import numpy as np
 import torch
 
 from .. import blob_ctx, comm, device_ops
-from .._lib import lib, check, SP_RED_SUM, SP_F64, SpartanError
+from .._lib import lib, check, SP_RED_SUM, SP_F64, SP_FILL_RANDN, SpartanError
 from ..array import distarray, extent
 from ..expr.base import Expr, evaluate
 
@@ -32,9 +32,8 @@ class KMeans(object):
     for ex in X.tiles:
       if ex.ul[1] != 0 or ex.lr[1] != d:
         raise SpartanError('KMeans.fit: X must be tiled by rows (k_means_.py:122)')
-    rng = np.random.RandomState(seed)
     if centers is None:
-      centers = rng.rand(k, d)                                   # k_means_.py:132
+      centers = np.random.RandomState(seed).rand(k, d)                                   # k_means_.py:132
     centers = np.ascontiguousarray(centers, dtype=np.float32)
     tile_rows = X.tile_shape()[0]
     labels = distarray.create((n,), np.int32, tile_hint=(tile_rows,))
@@ -57,7 +56,17 @@ class KMeans(object):
       xp = device_ops.cached_operand(X, ('kmeans_points', block.ul[0], block.lr[0]), m, d, 'bf16x3', fill)
       blocks.append((x, lab, m, xp))
     c_dev = torch.from_numpy(centers).to(ctx.device)
-    div = device_ops.make_program([('IN', 0), ('IN', 1), ('DIV', 0)], SP_F64)
+    # centres = sums / counts in float64, stored as float32 (k_means_.py:159); a centre that lost all its points is
+    # re-seeded with standard-normal values (:148-157).  All of it on the device -- no host round trip inside the
+    # loop: denom = counts + [counts == 0]; c = sums / denom; c += [counts == 0] * randn.  (The reference draws the
+    # re-seed values from the master's unseeded np.random; here they come from the counter-based device generator keyed
+    # by (seed, iteration), so every rank agrees and a run is reproducible.)
+    denom = torch.empty((k, 1), dtype=torch.float64, device=ctx.device)
+    rnd = torch.empty((k, d), dtype=torch.float32, device=ctx.device)
+    p_denom = device_ops.make_program([('IN', 0), ('IN', 0), ('ISZERO', 0), ('ADD', 0)], SP_F64)
+    p_div = device_ops.make_program([('IN', 0), ('IN', 1), ('DIV', 0)], SP_F64)
+    p_seed = device_ops.make_program([('IN', 0), ('IN', 1), ('ISZERO', 0), ('IN', 2), ('MUL', 0), ('ADD', 0)], SP_F64)
+    counts_col = counts.reshape(k, 1)
     for it in range(self.n_iter):
       sums.zero_(); counts.zero_()
       for x, lab, m, xp in blocks:
@@ -69,18 +78,10 @@ class KMeans(object):
         ctx.kernel_launches += 4
       comm.allreduce(sums, SP_RED_SUM)
       comm.allreduce(counts, SP_RED_SUM)
-      # Only the k counts go to the host -- to decide whether a centre lost all its points (k_means_.py:148-157); the
-      # new centres are sums / counts evaluated in float64 and stored as float32 (:159) by the map kernel, on the device.
-      counts_h = counts.cpu().numpy()
-      zcount = counts_h == 0
-      if np.any(zcount):
-        counts_f = counts_h.astype(np.float64)
-        centers_h = sums.cpu().numpy().astype(np.float64)
-        counts_f[zcount] = 1
-        centers_h[zcount, :] = rng.randn(int(np.count_nonzero(zcount)), d)
-        c_dev = torch.from_numpy((centers_h / counts_f.reshape(k, 1)).astype(np.float32)).to(ctx.device)
-      else:
-        device_ops.run_map(div, [sums, counts.reshape(k, 1)], c_dev)
+      device_ops.fill(rnd, SP_FILL_RANDN, 0.0, 1.0, seed=(int(seed) * 1000003 + it) & 0xffffffffffff)
+      device_ops.run_map(p_denom, [counts_col], denom)
+      device_ops.run_map(p_div, [sums, denom], c_dev)
+      device_ops.run_map(p_seed, [c_dev, counts_col, rnd], c_dev)
     centers = c_dev.cpu().numpy()
     for tid in labels.tiles.values():
       if ctx.is_local(tid):

@@ -57,6 +57,18 @@ typedef enum {
 
 const char* sp_last_error(void);
 int sp_version(void);
+/* Housekeeping for hosts without their own allocator / stream library (the Python host uses torch for these):
+ * sp_init selects the device and creates its context, sp_tile_alloc / sp_tile_free are stream-ordered HBM buffers
+ * (BlobCtx.create / destroy, blob_ctx.py:221-254,181-196), sp_sync waits for a stream, sp_event_* time a region. */
+int sp_init(int device);
+int sp_shutdown(void);
+int sp_tile_alloc(int64_t bytes, void** out, void* stream);
+int sp_tile_free(void* p, void* stream);
+int sp_sync(void* stream);
+int sp_event_create(void** out);
+int sp_event_record(void* event, void* stream);
+int sp_event_elapsed(void* start, void* stop, float* ms);
+int sp_event_destroy(void* event);
 /* Device properties of the current CUDA device (fails without a GPU). */
 int sp_device_info(int* n_sms, int64_t* hbm_bytes, int* cc_major, int* cc_minor);
 

@@ -67,6 +67,15 @@ _vp, _i64, _int, _dbl, _u64 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, cty
 _SIGS = {
   'sp_last_error': (ctypes.c_char_p, []),
   'sp_version': (_int, []),
+  'sp_init': (_int, [_int]),
+  'sp_shutdown': (_int, []),
+  'sp_tile_alloc': (_int, [_i64, ctypes.POINTER(_vp), _vp]),
+  'sp_tile_free': (_int, [_vp, _vp]),
+  'sp_sync': (_int, [_vp]),
+  'sp_event_create': (_int, [ctypes.POINTER(_vp)]),
+  'sp_event_record': (_int, [_vp, _vp]),
+  'sp_event_elapsed': (_int, [_vp, _vp, ctypes.POINTER(ctypes.c_float)]),
+  'sp_event_destroy': (_int, [_vp]),
   'sp_device_info': (_int, [ctypes.POINTER(_int), _i64p, ctypes.POINTER(_int), ctypes.POINTER(_int)]),
   'sp_extent_intersection': (_int, [_int, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p]),
   'sp_extent_ravelled_pos': (_i64, [_int, _i64p, _i64p]),

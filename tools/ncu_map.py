@@ -1,5 +1,5 @@
 """Workload for an ncu capture of the streaming kernel: a few launches of the fused map x*2+y and of the fused
-map+reduce (x*2+y).sum(axis=0) over 1 GiB operands (see profiles/)."""
+map+reduce (x*2+y).sum(axis=0) / .sum(axis=1) over 1 GiB operands (see profiles/)."""
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
@@ -13,4 +13,5 @@ x, y = lazify(X), lazify(Y)
 for _ in range(3):
   (x * 2 + y).optimized().evaluate()
   (x * 2 + y).sum(axis=0).optimized().evaluate()
+  (x * 2 + y).sum(axis=1).optimized().evaluate()
 torch.cuda.synchronize()

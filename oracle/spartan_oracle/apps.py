@@ -1,8 +1,12 @@
 """ORACLE (test infrastructure only) -- k-means iteration and strip SpMV.
 
-PARITY UNPINNED: the reference's tests for these two paths assert nothing (tests/test_kmeans.py:16-21 is a
-smoke test, tests/test_pagerank.py and tests/test_sparse.py contain no numeric assertion).
-What follows restates the mapper math against SciPy/NumPy directly; tolerances are stated in the tests.
+PINNED by vectors produced by running the reference's own mapper functions: oracle/ref_apps/make_app_vectors.py takes
+the definitions of kmeans_map2_dist_mapper / kmeans_count_mapper / kmeans_center_mapper (k_means_.py:61-97) and
+dot_map2_mapper (dot.py:195-217) out of the reference's files, executes them on seeded inputs and commits inputs +
+outputs as tests/golden/app_vectors.json; tests/test_oracle_reference_vectors.py checks every function below against
+them (labels, counts and partial products bit for bit).  The reference's own tests for these two paths assert nothing
+(tests/test_kmeans.py:16-21, tests/test_pagerank.py, tests/test_sparse.py), which is why the
+vectors had to be generated.
 
 k-means: spartan/examples/sklearn/cluster/k_means_.py:61-97 (mappers) and :130-160 (driver, 'map2').
 SpMV:    spartan/expr/dot.py:213-217 (`tocsr().dot(dense)` per column strip) + np.add merge.

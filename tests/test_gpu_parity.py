@@ -666,6 +666,42 @@ def test_spmv_vs_oracle(n, outlinks, strip):
 
 
 # ------------------------------------------------------------------ edge cases: 0-d, empty, ragged, tiny
+def test_kmeans_and_spmv_on_reference_generated_vectors():
+  """The device k-means iteration and the device SpMV on the inputs of tests/golden/app_vectors.json, whose outputs
+  were produced by the reference's own mapper functions (oracle/ref_apps/make_app_vectors.py): labels must be
+  identical (the points are cast to float32 first; a label may only differ where float64 distances are a near tie),
+  counts / centres and the strip products within float32 accuracy."""
+  import json, os
+  import scipy.sparse
+  with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'app_vectors.json')) as f:
+    vec = json.load(f)
+  for case in vec['kmeans']:
+    pts = np.array(case['points']); centers = np.array(case['centers']); k, n = case['k'], case['n']
+    X = sp.from_numpy(pts.astype(np.float32), tile_hint=(case['tile_rows'], case['d']))
+    new_centers, labels = sp.KMeans(n_clusters=k, n_iter=1).fit(X, centers=centers.astype(np.float32))
+    got = labels.glom()
+    want = np.array([v for t in case['tiles'] for v in t['labels']])
+    if not np.array_equal(got, want):
+      d2 = ((pts[:, None, :] - centers[None, :, :]) ** 2).sum(-1)
+      bad = np.nonzero(got != want)[0]
+      gap = d2[bad, got[bad]] - d2[bad, want[bad]]
+      assert np.all(gap <= 1e-5 * d2[bad, want[bad]]), 'labels differ away from a tie'
+    else:
+      counts = np.sum([t['counts'] for t in case['tiles']], axis=0).astype(np.float64)
+      sums = np.sum([t['sums'] for t in case['tiles']], axis=0)
+      ok = counts > 0
+      np.testing.assert_allclose(new_centers[ok], sums[ok] / counts[ok, None], rtol=2e-6)
+  for case in vec['spmv']:
+    n, strip = case['n'], case['strip']
+    m = scipy.sparse.coo_matrix((np.array(case['vals'], np.float32), (case['rows'], case['cols'])), shape=(n, n))
+    x = np.array(case['x'], np.float32).reshape(n, 1)
+    want = np.zeros(n, np.float64)
+    for s in case['strips']:
+      want += np.array(s['partial'], np.float64)
+    got = sp.dot(sp.sparse.from_scipy(m, strip_width=strip), sp.from_numpy(x, tile_hint=(strip, 1))).glom().reshape(-1)
+    np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-6)
+
+
 def test_zero_dim_and_empty_arrays():
   s = sp.from_numpy(np.array(3.0, dtype=np.float32))
   assert (s * 2 + 1).glom() == 7.0

@@ -4,6 +4,7 @@ Every test below is the Python-3 restatement of an assertion in /root/reference/
 the reference compares against NumPy, so the expected side is recomputed with NumPy here exactly as the
 reference test does.  Run on CPU (no GPU, no reference tree needed).
 """
+import os
 import random
 
 import numpy as np
@@ -340,3 +341,53 @@ def test_std_reference_cases():
     sx = expr.from_numpy(x)
     assert np.allclose(expr.std(sx, 0).glom(), np.std(x, 0))
     assert np.allclose(expr.std(sx, 1).glom(), np.std(x, 1))
+
+
+# ---- k-means and sparse dot: vectors produced by running the reference's own mapper functions
+#      (oracle/ref_apps/make_app_vectors.py executes the definitions of k_means_.py:61-97 and dot.py:195-217 taken
+#      from the reference's files; their inputs and outputs are committed as tests/golden/app_vectors.json)
+def _app_vectors():
+  import json
+  with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'app_vectors.json')) as f:
+    return json.load(f)
+
+
+def test_kmeans_mappers_match_reference_vectors():
+  from spartan_oracle import apps
+  vec = _app_vectors()
+  assert vec['kmeans'], 'no k-means vectors'
+  for case in vec['kmeans']:
+    pts, centers, k = np.array(case['points']), np.array(case['centers']), case['k']
+    for t in case['tiles']:
+      r0, r1 = t['rows']
+      labels = apps.kmeans_dist_mapper(pts[r0:r1], centers)
+      assert labels.tolist() == t['labels']
+      assert apps.kmeans_count_mapper(labels, k).tolist() == t['counts']
+      assert np.array_equal(apps.kmeans_center_mapper(pts[r0:r1], labels, k), np.array(t['sums']))
+      assert t['label_extent'] == [[r0], [r1], [case['n']]]
+    # one full iteration of the driver (k_means_.py:130-160) = the per-tile results summed (Q7) and divided
+    new_centers, labels = apps.kmeans_fit(pts, centers, 1, case['tile_rows'])
+    counts = np.sum([t['counts'] for t in case['tiles']], axis=0).astype(np.float64)
+    sums = np.sum([t['sums'] for t in case['tiles']], axis=0)
+    assert labels.tolist() == [v for t in case['tiles'] for v in t['labels']]
+    ok = counts > 0
+    assert np.allclose(new_centers[ok], sums[ok] / counts[ok, None], rtol=1e-15, atol=0)
+
+
+def test_sparse_dot_mapper_matches_reference_vectors():
+  import scipy.sparse
+  from spartan_oracle import apps
+  vec = _app_vectors()
+  assert vec['spmv'], 'no sparse-dot vectors'
+  for case in vec['spmv']:
+    n, strip = case['n'], case['strip']
+    m = scipy.sparse.coo_matrix((np.array(case['vals'], np.float32), (case['rows'], case['cols'])), shape=(n, n))
+    x = np.array(case['x'], np.float32)
+    want = np.zeros(n, np.float32)
+    for s in case['strips']:
+      c0, c1 = s['cols']
+      assert s['target_extent'] == [[0, 0], [n, 1], [n, 1]] and s['partial_dtype'] == 'float32'
+      part = scipy.sparse.csc_matrix(m)[:, c0:c1].tocsr().dot(x[c0:c1]).astype(np.float32)
+      assert np.array_equal(part, np.array(s['partial'], np.float32))     # the oracle's per-strip product, bit for bit
+      want = np.add(want, np.array(s['partial'], np.float32))              # np.add merge of the strips (tile.pyx:263-268)
+    assert np.array_equal(apps.spmv_strips(m, x, strip), want)

@@ -35,26 +35,28 @@ __global__ void row_sqnorm_kernel(const float* __restrict__ C, int64_t ldc, int 
   if (lane == 0) out[row] = s;
 }
 
-// one warp per point: label = arg min over the per-half-tile candidates the GEMM epilogue emitted
-// (part_val / part_idx [n][parts]); then sums[label] += x_i, counts[label] += 1.
-// The point's row is loaded BEFORE the label is known (its address does not depend on it), so the row loads overlap the
-// candidate loads and the shuffles; 64 resident warps per SM keep the other points' atomics in flight meanwhile.
-template <bool VEC>
-__device__ __forceinline__ void kmeans_point(const float* __restrict__ part_val, const int* __restrict__ part_idx, int parts,
-                                             const float* __restrict__ X, int64_t ldx, int64_t i, int d, int lane,
-                                             int32_t* __restrict__ labels, float* __restrict__ sums,
-                                             unsigned long long* __restrict__ counts) {
-  const float* x = X + i * ldx;
-  float4 xv[2];
-  if (VEC) {                          // d == 256: two float4 per lane cover the row
-    xv[0] = __ldcs(reinterpret_cast<const float4*>(x) + lane);
-    xv[1] = __ldcs(reinterpret_cast<const float4*>(x) + 32 + lane);
-  }
+// Candidates of one point -> its label.  parts == 8 (k = 1024): every lane reads the 8 (value, index) pairs itself
+// (uniform 16-byte loads, one transaction per warp) and picks the minimum in registers -- no shuffles; otherwise the lanes
+// split the candidates and reduce by shuffle.  Ties resolve to the smaller index, like np.argmin.
+__device__ __forceinline__ int kmeans_pick(const float* __restrict__ part_val, const int* __restrict__ part_idx, int parts,
+                                           int64_t i, int lane) {
   float best = FLT_MAX;
   int best_j = 0x7fffffff;
-  for (int j = lane; j < parts; j += 32) {
-    const float v = __ldcs(part_val + i * parts + j);
-    const int c = __ldcs(part_idx + i * parts + j);
+  if (parts == 8) {
+    const float4 v0 = __ldcs(reinterpret_cast<const float4*>(part_val + i * 8));
+    const float4 v1 = __ldcs(reinterpret_cast<const float4*>(part_val + i * 8) + 1);
+    const int4 j0 = __ldcs(reinterpret_cast<const int4*>(part_idx + i * 8));
+    const int4 j1 = __ldcs(reinterpret_cast<const int4*>(part_idx + i * 8) + 1);
+    const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    const int j[8] = {j0.x, j0.y, j0.z, j0.w, j1.x, j1.y, j1.z, j1.w};
+#pragma unroll
+    for (int p = 0; p < 8; ++p)
+      if (v[p] < best || (v[p] == best && j[p] < best_j)) { best = v[p]; best_j = j[p]; }
+    return best_j;
+  }
+  for (int p = lane; p < parts; p += 32) {
+    const float v = __ldcs(part_val + i * parts + p);
+    const int c = __ldcs(part_idx + i * parts + p);
     if (v < best || (v == best && c < best_j)) { best = v; best_j = c; }
   }
 #pragma unroll
@@ -63,21 +65,12 @@ __device__ __forceinline__ void kmeans_point(const float* __restrict__ part_val,
     const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
     if (ob < best || (ob == best && oj < best_j)) { best = ob; best_j = oj; }
   }
-  if (lane == 0) {
-    labels[i] = best_j;
-    atomicAdd(counts + best_j, 1ull);
-  }
-  float* dst = sums + static_cast<int64_t>(best_j) * d;
-  if (VEC) {
-    atomicAdd(reinterpret_cast<float4*>(dst) + lane, xv[0]);            // red.global.add.v4.f32 (sm_90+)
-    atomicAdd(reinterpret_cast<float4*>(dst) + 32 + lane, xv[1]);
-  } else if ((d & 3) == 0 && ((reinterpret_cast<uint64_t>(x) | reinterpret_cast<uint64_t>(dst)) & 15) == 0) {
-    for (int j = lane * 4; j < d; j += 128) atomicAdd(reinterpret_cast<float4*>(dst + j), *reinterpret_cast<const float4*>(x + j));
-  } else {
-    for (int j = lane; j < d; j += 32) atomicAdd(dst + j, x[j]);
-  }
+  return best_j;
 }
 
+// one warp per point, two points in flight per warp: the rows of both points are loaded before either label is known
+// (their addresses do not depend on it), then both labels are picked, then both rows go into their centroids with
+// vectorised fire-and-forget float atomics (red.global.add.v4.f32).
 template <bool VEC>
 __global__ void __launch_bounds__(256)
 kmeans_label_accumulate_kernel(const float* __restrict__ part_val, const int* __restrict__ part_idx, int parts,
@@ -85,8 +78,48 @@ kmeans_label_accumulate_kernel(const float* __restrict__ part_val, const int* __
                                int32_t* __restrict__ labels, float* __restrict__ sums, unsigned long long* __restrict__ counts) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = static_cast<int64_t>(gridDim.x) * (blockDim.x / 32);
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x / 32) + (threadIdx.x / 32); i < n; i += warps)
-    kmeans_point<VEC>(part_val, part_idx, parts, X, ldx, i, d, lane, labels, sums, counts);
+  const int64_t w = blockIdx.x * static_cast<int64_t>(blockDim.x / 32) + (threadIdx.x / 32);
+  for (int64_t i = w; i < n; i += 2 * warps) {
+    const int64_t i2 = i + warps;
+    const bool two = i2 < n;
+    float4 xa[2], xb[2];
+    if (VEC) {                          // d == 256: two float4 per lane cover a row
+      const float4* pa = reinterpret_cast<const float4*>(X + i * ldx);
+      xa[0] = __ldcs(pa + lane); xa[1] = __ldcs(pa + 32 + lane);
+      if (two) {
+        const float4* pb = reinterpret_cast<const float4*>(X + i2 * ldx);
+        xb[0] = __ldcs(pb + lane); xb[1] = __ldcs(pb + 32 + lane);
+      }
+    }
+    const int la = kmeans_pick(part_val, part_idx, parts, i, lane);
+    const int lb = two ? kmeans_pick(part_val, part_idx, parts, i2, lane) : 0;
+    if (lane == 0) {
+      labels[i] = la;
+      atomicAdd(counts + la, 1ull);
+      if (two) {
+        labels[i2] = lb;
+        atomicAdd(counts + lb, 1ull);
+      }
+    }
+    if (VEC) {
+      float4* da = reinterpret_cast<float4*>(sums + static_cast<int64_t>(la) * d);
+      atomicAdd(da + lane, xa[0]); atomicAdd(da + 32 + lane, xa[1]);
+      if (two) {
+        float4* db = reinterpret_cast<float4*>(sums + static_cast<int64_t>(lb) * d);
+        atomicAdd(db + lane, xb[0]); atomicAdd(db + 32 + lane, xb[1]);
+      }
+    } else {
+      for (int pt = 0; pt < (two ? 2 : 1); ++pt) {
+        const float* x = X + (pt ? i2 : i) * ldx;
+        float* dst = sums + static_cast<int64_t>(pt ? lb : la) * d;
+        if ((d & 3) == 0 && ((reinterpret_cast<uint64_t>(x) | reinterpret_cast<uint64_t>(dst)) & 15) == 0) {
+          for (int j = lane * 4; j < d; j += 128) atomicAdd(reinterpret_cast<float4*>(dst + j), *reinterpret_cast<const float4*>(x + j));
+        } else {
+          for (int j = lane; j < d; j += 32) atomicAdd(dst + j, x[j]);
+        }
+      }
+    }
+  }
 }
 
 // CSR SpMV: GROUP threads per row; PTR = int32_t row pointers whenever nnz < 2^31 (4 B per row instead of 8)

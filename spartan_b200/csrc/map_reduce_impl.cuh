@@ -534,15 +534,25 @@ static int launch_reduce_v(const sp_program* prog, int n_in, const sp_operand* i
     sdp.index_stride[1] = dp.index_stride[0];
     sdp.index_stride[0] = 0;
     stream::Plan plan;
-    if (plan_stream<T, NI>(sops, sd, false, kStreamReduceRows, &plan)) {
-      const int64_t sneed = static_cast<int64_t>(plan.n_panels) * dims[0] * static_cast<int64_t>(sizeof(T));
+    // MODE 2 units are rb rows over their whole length (one stage per panel); it needs one item per consumer warp per
+    // stage (rb * 4 <= 16) and rows long enough to amortise the end-of-row fold
+    if (dims[1] * static_cast<int64_t>(sizeof(T)) >= 4 * stream::kPanelBytes && plan_stream<T, NI>(sops, sd, false, 0, &plan)) {
+      if (plan.rb * stream::kSegsPerPanel > stream::kConsumerWarps) {      // one operand: 4 rows per stage, deeper ring
+        plan.rb = stream::kConsumerWarps / stream::kSegsPerPanel;
+        plan.stage_bytes = plan.n_stream * plan.rb * stream::kPanelBytes;
+        plan.n_stages = std::min(stream::kMaxStages, stream::kRingBytes / plan.stage_bytes);
+      }
+      plan.rc = plan.rb;
+      plan.n_chunks = (sd[1] + plan.rb - 1) / plan.rb;
+      plan.n_units = plan.n_chunks;
+      const int64_t sneed = dims[0] * static_cast<int64_t>(sizeof(T));
       SP_REQUIRE(scratch_bytes >= sneed, SP_ERR_INVALID, "sp_map_reduce: scratch %lld B < required %lld B",
                  (long long)scratch_bytes, (long long)sneed);
       int rc = launch_stream<T, NI, 2>(sdp, sops, plan, red_op, sc, stream, interp_ok);
       if (rc < 0) return rc;
       if (rc != kNotLaunched) {
         const int fb = static_cast<int>(std::min<int64_t>((n_out + 255) / 256, 4096));
-        finalize_kernel<T><<<fb, 256, 0, stream>>>(sc, n_out, plan.n_panels, n_out, 1, o, 1, red_op, accumulate);
+        finalize_kernel<T><<<fb, 256, 0, stream>>>(sc, n_out, 1, n_out, 1, o, 1, red_op, accumulate);
         SP_CUDA_CHECK(cudaGetLastError());
         return SP_OK;
       }

@@ -95,10 +95,150 @@ __device__ __forceinline__ void load_direct_split(const DevOperand& o, int64_t b
   }
 }
 
-// MODE 0: map (store), MODE 1: reduce over d1 (partials to scratch[chunk][d0][d2]),
-// MODE 2: reduce over d2, the vector axis (trailing-axis reductions): every (row, panel) of a unit is folded to one value
-//         -- lanes by shuffle, the panel's four segments through shared memory, in fixed order -- and written to
-//         scratch[panel][d0 * d1 rows]; finalize_kernel folds the panels of a row.
+// MODE 2 (trailing-axis reductions): reduce over d2, the vector axis.  A work unit is `rb` consecutive rows over their WHOLE
+// length: stage p of a unit carries panel p of those rows, so consumer warp w always works on the same (row w / 4, segment
+// w % 4) and keeps its V-wide accumulator in registers across the panels of the row -- the per-element cost of MODE 1 --
+// and only at the end of the unit are the lanes folded by shuffle and the row's four segment partials combined through
+// shared memory (fixed order).  One value per row goes to scratch[d0 * d1]; nothing is left for finalize to fold.
+template <typename T, int NI, typename PROG>
+__device__ __forceinline__ void row_reduce_body(const DevProgram<T>& prog, const DevOperands<NI>& ops, const Plan& plan,
+                                                const int red_op, T* __restrict__ scratch, const uint32_t smem_base,
+                                                uint8_t* smem_gen, T* red_smem, const uint32_t bar_base) {
+  constexpr int V = 32 / sizeof(T);
+  constexpr int H = V / 2;
+  constexpr int EPS = kSegBytes / sizeof(T);
+  constexpr int EPP = kPanelBytes / sizeof(T);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  const int n_stages = plan.n_stages;
+  const int stage_bytes = plan.stage_bytes;
+  const int rb = plan.rb;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t n_units = plan.d0 * plan.n_chunks;           // n_chunks = ceil(d1 / rb)
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    const int slot = lane / rb;
+    const int r_in = lane - slot * rb;
+    int my_op = -1;
+    for (int i = 0; i < NI; ++i)
+      if (i < ops.n_in && plan.stream_slot[i] == slot) my_op = i;
+    for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int64_t chunk = u % plan.n_chunks;
+      const int64_t i0 = u / plan.n_chunks;
+      const int64_t row0 = chunk * rb;
+      const int rows = static_cast<int>(min(static_cast<int64_t>(rb), plan.d1 - row0));
+      for (int panel = 0; panel < plan.n_panels; ++panel) {
+        const int64_t col0 = static_cast<int64_t>(panel) * EPP;
+        const uint32_t seg_bytes = static_cast<uint32_t>(min(static_cast<int64_t>(EPP), plan.d2 - col0) * sizeof(T));
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        if (lane == 0) mbar_expect_tx(full_bar(stage), seg_bytes * rows * plan.n_stream);
+        __syncwarp();
+        if (my_op >= 0 && slot < plan.n_stream && r_in < rows) {
+          const DevOperand& o = ops.in[my_op];
+          const T* src = static_cast<const T*>(o.ptr) + i0 * o.stride[0] + (row0 + r_in) * o.stride[1] + col0;
+          bulk_g2s(smem_base + stage * stage_bytes + (slot * rb + r_in) * kPanelBytes, src, seg_bytes, full_bar(stage));
+        }
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
+      }
+    }
+    return;
+  }
+  const int cw = warp - 1;
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+    const int64_t chunk = u % plan.n_chunks;
+    const int64_t i0 = u / plan.n_chunks;
+    const int64_t row0 = chunk * rb;
+    const int rows = static_cast<int>(min(static_cast<int64_t>(rb), plan.d1 - row0));
+    T acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = red_identity<T>(red_op);
+    for (int panel = 0; panel < plan.n_panels; ++panel) {
+      const int64_t col0 = static_cast<int64_t>(panel) * EPP;
+      const int64_t cols = min(static_cast<int64_t>(EPP), plan.d2 - col0);
+      mbar_wait(full_bar(stage), phase);
+      const uint8_t* sbase = smem_gen + stage * stage_bytes;
+      bool released = false;
+      for (int item = cw; item < rows * kSegsPerPanel; item += kConsumerWarps) {
+        const int r = item / kSegsPerPanel;
+        const int q = item % kSegsPerPanel;
+        const int64_t col_a = col0 + q * EPS + lane * H;
+        const int64_t col_b = col_a + EPS / 2;
+        const int valid_a = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(H), col0 + cols - col_a)));
+        const int valid_b = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(H), col0 + cols - col_b)));
+        T in[NI][V];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          if (i < ops.n_in) {
+            const int sl = plan.stream_slot[i];
+            if (sl >= 0) {
+              const uint8_t* seg = sbase + (sl * rb + r) * kPanelBytes + q * kSegBytes;
+              T tmp[V];
+              *reinterpret_cast<int4*>(&tmp[0]) = *reinterpret_cast<const int4*>(seg + 16 * lane);
+              *reinterpret_cast<int4*>(&tmp[H]) = *reinterpret_cast<const int4*>(seg + 512 + 16 * lane);
+#pragma unroll
+              for (int v = 0; v < V; ++v) in[i][v] = tmp[v];
+            } else {
+              const DevOperand& o = ops.in[i];
+              load_direct_split<T, V>(o, i0 * o.stride[0] + (row0 + r) * o.stride[1], col_a, col_b, valid_a, valid_b, in[i]);
+            }
+          }
+        }
+        if (item + kConsumerWarps >= rows * kSegsPerPanel) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty_bar(stage));
+          released = true;
+        }
+        T res[V], idx[V];
+        if (prog.uses_index) {
+          const long long base = prog.index_base + i0 * prog.index_stride[0] + (row0 + r) * prog.index_stride[1];
+#pragma unroll
+          for (int v = 0; v < H; ++v) {
+            idx[v] = static_cast<T>(base + (col_a + v) * prog.index_stride[2]);
+            idx[H + v] = static_cast<T>(base + (col_b + v) * prog.index_stride[2]);
+          }
+        }
+        PROG::template run<T, V, NI>(prog, in, idx, res);
+        if (valid_a == H && valid_b == H) {
+#pragma unroll
+          for (int v = 0; v < V; ++v) acc[v] = red_apply<T>(red_op, acc[v], res[v]);
+        } else {                       // the ragged end of a row: elements past it hold no data
+#pragma unroll
+          for (int v = 0; v < H; ++v) {
+            if (v < valid_a) acc[v] = red_apply<T>(red_op, acc[v], res[v]);
+            if (v < valid_b) acc[H + v] = red_apply<T>(red_op, acc[H + v], res[H + v]);
+          }
+        }
+      }
+      if (!released) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar(stage));
+      }
+      if (++stage == n_stages) { stage = 0; phase ^= 1; }
+    }
+    // end of the unit: lanes -> one value per (row, segment); segments -> one value per row
+    // (rows * 4 <= 16 items per stage: warp w owned item w of every stage, i.e. row w / 4, segment w % 4)
+    T a = acc[0];
+#pragma unroll
+    for (int v = 1; v < V; ++v) a = red_apply<T>(red_op, a, acc[v]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) a = red_apply<T>(red_op, a, shfl_down_t<T>(a, d));
+    if (lane == 0) red_smem[cw] = a;
+    consumer_bar();
+    if (cw == 0 && lane < rows) {
+      T r = red_smem[lane * kSegsPerPanel];
+#pragma unroll
+      for (int sg = 1; sg < kSegsPerPanel; ++sg) r = red_apply<T>(red_op, r, red_smem[lane * kSegsPerPanel + sg]);
+      scratch[i0 * plan.d1 + row0 + lane] = r;
+    }
+    consumer_bar();
+  }
+}
+
+// MODE 0: map (store), MODE 1: reduce over d1 (partials to scratch[chunk][d0][d2]), MODE 2: see row_reduce_body.
 template <typename T, int NI, int MODE, typename PROG>
 __global__ void __launch_bounds__(kThreads, 1)
 stream_kernel(const DevProgram<T> prog, const DevOperands<NI> ops, const Plan plan, const int red_op,
@@ -128,6 +268,10 @@ stream_kernel(const DevProgram<T> prog, const DevOperands<NI> ops, const Plan pl
   }
   __syncthreads();
 
+  if constexpr (MODE == 2) {
+    row_reduce_body<T, NI, PROG>(prog, ops, plan, red_op, scratch, smem_base, smem_gen, red_smem, bar_base);
+    return;
+  }
   const int rb = plan.rb;
   const int stages_per_unit = (plan.rc + rb - 1) / rb;
 
@@ -188,11 +332,6 @@ stream_kernel(const DevProgram<T> prog, const DevOperands<NI> ops, const Plan pl
 #pragma unroll
         for (int v = 0; v < V; ++v) acc[v] = red_identity<T>(red_op);
       }
-      if (MODE == 2) {
-        // a slot per (row of the unit, segment); rows no warp visits (ragged last unit) keep the identity
-        for (int i = threadIdx.x - 32; i < plan.rc * kSegsPerPanel; i += 32 * kConsumerWarps) red_smem[i] = red_identity<T>(red_op);
-        consumer_bar();
-      }
       for (int st = 0; st < stages_per_unit; ++st) {
         const int64_t row0 = chunk * plan.rc + static_cast<int64_t>(st) * rb;
         if (row0 >= row_end) break;
@@ -249,20 +388,9 @@ stream_kernel(const DevProgram<T> prog, const DevOperands<NI> ops, const Plan pl
             if (valid_b == H) *reinterpret_cast<int4*>(dst + col_b) = *reinterpret_cast<const int4*>(&res[H]);
             else
               for (int v = 0; v < valid_b; ++v) dst[col_b + v] = res[H + v];
-          } else if (MODE == 1) {
+          } else {
 #pragma unroll
             for (int v = 0; v < V; ++v) acc[v] = red_apply<T>(red_op, acc[v], res[v]);
-          } else {
-            // fold this lane's vector (elements past the end of the row hold no data), then the warp
-            T a = red_identity<T>(red_op);
-#pragma unroll
-            for (int v = 0; v < H; ++v) {
-              if (v < valid_a) a = red_apply<T>(red_op, a, res[v]);
-              if (v < valid_b) a = red_apply<T>(red_op, a, res[H + v]);
-            }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) a = red_apply<T>(red_op, a, shfl_down_t<T>(a, d));
-            if (lane == 0) red_smem[(st * rb + r) * kSegsPerPanel + q] = a;
           }
         }
         if (!released) {               // a warp without an item in this stage
@@ -284,18 +412,6 @@ stream_kernel(const DevProgram<T> prog, const DevOperands<NI> ops, const Plan pl
           T* dst = scratch + (chunk * plan.d0 + i0) * plan.d2;
           for (int v = 0; v < valid_a; ++v) dst[col_a + v] = acc[v];
           for (int v = 0; v < valid_b; ++v) dst[col_b + v] = acc[H + v];
-        }
-        consumer_bar();
-      }
-      if (MODE == 2) {
-        consumer_bar();
-        const int rows_in_unit = static_cast<int>(row_end - chunk * plan.rc);
-        T* dst = scratch + (static_cast<int64_t>(panel) * plan.d0 + i0) * plan.d1 + chunk * plan.rc;
-        for (int r = threadIdx.x - 32; r < rows_in_unit; r += 32 * kConsumerWarps) {
-          T a = red_smem[r * kSegsPerPanel];
-#pragma unroll
-          for (int sg = 1; sg < kSegsPerPanel; ++sg) a = red_apply<T>(red_op, a, red_smem[r * kSegsPerPanel + sg]);
-          dst[r] = a;
         }
         consumer_bar();
       }

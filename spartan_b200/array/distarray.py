@@ -264,6 +264,11 @@ class DistArrayImpl(DistArray):
       if view is not None:
         return view
     splits = list(extent.find_overlapping(self.tiles.keys(), region))
+    if dst is None and ctx.num_workers > 1:
+      remote = [ex for ex, _ in splits if self.tiles[ex].worker != me]
+      if remote:
+        raise SpartanError('fetch(%s) without dst= touches %d tile(s) owned by other ranks; remote pieces travel only in '
+                           'the collective form fetch(region, dst=rank) that every rank calls' % (region, len(remote)))
     if len(splits) == 1 and self.tiles[splits[0][0]].worker == want:
       ex, inter = splits[0]
       return ctx.get(self.tiles[ex], extent.offset_slice(ex, inter)) if want == me else None

@@ -51,6 +51,8 @@ class BlobCtx(object):
     self._next_id = [0] * self.num_workers    # per-worker id sequence, identical on every rank
     self._rr = 0
     self._scratch = {}
+    self._retired_scratch = []                # outgrown scratch buffers a captured graph may still address
+    self.graph_captures = 0                   # evaluations captured as CUDA graphs so far (replay.py)
     self._side_streams = {}
     self.kernel_launches = 0                  # launches of this library's kernels (bench.py "gpu_launches")
     self.data_epoch = 0                       # bumped whenever an existing array may have changed in place
@@ -143,6 +145,10 @@ class BlobCtx(object):
     """Grow-only device scratch buffers (reduction partials, GEMM operand copies)."""
     buf = self._scratch.get(key)
     if buf is None or buf.numel() < nbytes:
+      if buf is not None and self.graph_captures > 0:
+        # a captured CUDA graph (replay.py) may have baked this buffer's address in: keep it alive instead of handing
+        # its memory back to the allocator
+        self._retired_scratch.append(buf)
       self._scratch[key] = None
       buf = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
       self._scratch[key] = buf

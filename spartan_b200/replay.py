@@ -31,6 +31,7 @@ class Replayable(object):
     main.wait_stream(side)
     torch.cuda.synchronize(ctx.device)
     launches0 = ctx.kernel_launches
+    ctx.graph_captures += 1           # from now on outgrown scratch buffers are retired, not freed (their addresses are in the graph)
     self.graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(self.graph, stream=side):
       self.result = fn()

@@ -349,6 +349,13 @@ int sp_gemm_prepared_views_gated(int n_seg, const sp_gemm_prepared_view* segs, c
 int64_t sp_gemm_argmin_parts(int64_t N);
 int sp_gemm_prepared_argmin(int n_seg, const sp_gemm_prepared_segment* segs, int64_t M, int64_t N, const float* col_bias,
                             float* part_val, int32_t* part_idx, int precision, void* stream);
+/* The whole k-means assignment in the GEMM (k_means_.py:61-97): labels[i] = argmin_j (col_bias[j] - 2 (A.B)[i, j]),
+ * counts[labels[i]] += 1, sums[labels[i], :] += pts[i, :d].  Column tiles of a row tile are walked back to back, the running
+ * arg min stays in registers and the epilogue warps accumulate while the tensor cores work on the next row tile.
+ * d, ldp multiples of 4; pts, sums 16-byte aligned. */
+int sp_gemm_prepared_kmeans(const sp_gemm_prepared_segment* seg, int64_t M, int64_t N, const float* col_bias,
+                            const float* pts, int64_t ldp, int64_t d, int32_t* labels, float* sums, int64_t* counts,
+                            int precision, void* stream);
 int sp_gemm_f32(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
                 int64_t N, int64_t K, int accumulate, int precision, void* workspace, int64_t workspace_bytes,
                 void* stream);
@@ -377,6 +384,7 @@ int sp_kmeans_assign(const float* X, int64_t ldx, int64_t n, int64_t d, const fl
 int64_t sp_kmeans_prepared_bytes(int64_t n, int64_t d);
 int sp_kmeans_prepare_points(const float* X, int64_t ldx, int64_t n, int64_t d, void* out, int64_t out_bytes, void* stream);
 int64_t sp_kmeans_assign_workspace_bytes(int64_t n, int64_t d, int64_t k);
+int sp_kmeans_set_fused(int on); /* test hook: 1 = everything in the GEMM epilogue (default), 0 = candidates + second kernel */
 int sp_kmeans_assign_prepared(const void* Xprep, const float* X, int64_t ldx, int64_t n, int64_t d, const float* centers,
                               int64_t k, int32_t* labels, float* sums, int64_t* counts, void* workspace,
                               int64_t workspace_bytes, void* stream);

@@ -126,6 +126,7 @@ _SIGS = {
   'sp_peer_push_2d': (_int, [_int, ctypes.POINTER(_vp), _i64, _vp, _i64, _i64, _i64, ctypes.POINTER(_vp), _vp, _vp]),
   'sp_write_u32': (_int, [_vp, ctypes.c_uint32, _vp]),
   'sp_wait_u32': (_int, [_vp, ctypes.c_uint32, _i64, _vp, _vp]),
+  'sp_gemm_prepared_kmeans': (_int, [ctypes.POINTER(sp_gemm_prepared_segment), _i64, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _int, _vp]),
   'sp_gemm_argmin_parts': (_i64, [_i64]),
   'sp_gemm_prepared_argmin': (_int, [_int, ctypes.POINTER(sp_gemm_prepared_segment), _i64, _i64, _vp, _vp, _vp, _int, _vp]),
   'sp_gemm_f32_workspace_bytes': (_i64, [_i64, _i64, _int, _i64p, _int]),
@@ -136,6 +137,7 @@ _SIGS = {
   'sp_kmeans_assign': (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),
   'sp_kmeans_prepared_bytes': (_i64, [_i64, _i64]),
   'sp_kmeans_prepare_points': (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp]),
+  'sp_kmeans_set_fused': (_int, [_int]),
   'sp_kmeans_assign_workspace_bytes': (_i64, [_i64, _i64, _i64]),
   'sp_kmeans_assign_prepared': (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),
   'sp_spmv_csr': (_int, [_vp, _int, _vp, _vp, _i64, _vp, _vp, _int, _int, _vp]),

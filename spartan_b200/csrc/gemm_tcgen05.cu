@@ -50,7 +50,8 @@ constexpr int EPI_WARP0 = 4;
 constexpr int GROUP_M = 16;                  // tile rasterisation group (L2 reuse)
 constexpr int MAX_SEGMENTS = SP_GEMM_MAX_TERMS;
 constexpr int MAX_MAPS = 4 * 8;              // per launch: <= 8 segments x (A_hi, A_lo, B_hi, B_lo)
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EPI_EXCHANGE_BYTES = 2048;     // epilogue mode 2: per-row (min, arg min) of the upper column half + the 128 row labels
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_EXCHANGE_BYTES;
 constexpr int REGS_PRODUCER = 40;
 constexpr int REGS_EPILOGUE = 232;
 // CTA-pair variant (cta_group::2): the two CTAs of a cluster own one 256 x 256 tile of C.  Each CTA loads its own 128 rows
@@ -59,7 +60,7 @@ constexpr int REGS_EPILOGUE = 232;
 // of 144 KiB, and half the B bytes per MMA out of each SM's shared memory.
 constexpr int PAIR_TILE_BYTES = 128 * 128;                 // 128 rows x one 128 B swizzle row of K
 constexpr int PAIR_RING_BYTES = 12 * PAIR_TILE_BYTES;      // 192 KiB: 3 stages x 4 tiles (split modes), 6 x 2 (tf32x1)
-constexpr int PAIR_SMEM_BYTES = PAIR_RING_BYTES + 1024 + 256;
+constexpr int PAIR_SMEM_BYTES = PAIR_RING_BYTES + 1024 + 256 + EPI_EXCHANGE_BYTES;
 
 struct Segment {
   int k_blocks;
@@ -89,6 +90,16 @@ struct Params {
   unsigned int* round_sync;
   int sync_kb;           // additional check-ins every sync_kb k-blocks inside a tile (0 = only at tile starts)
   int group_m;           // tile rasterisation: tile rows per group
+  // epilogue mode 2 (k-means, fused): tiles are walked n-fastest per cluster (raster 1) so that a CTA sees every column
+  // tile of its 128 rows back to back; the running (min, arg min) stays in registers, and after the last column tile the
+  // epilogue warps write the labels and add the rows of `pts` (the points in fp32) into sums[label] / counts[label]
+  int raster;            // 0: grouped rasterisation (tile_coords), 1: all column tiles of a row tile consecutively
+  const float* pts;
+  int64_t ldp;
+  int pts_d;
+  int* labels;
+  float* sums;
+  unsigned long long* counts;
   // gated segments (multi-GPU dot): segment s may only be read once *seg_flag[s] has reached seg_flag_value[s] -- the word
   // a peer's copy engine writes after it has pushed the operand strip of that segment into this GPU's memory (peer.cu)
   const unsigned int* seg_flag[8];
@@ -283,6 +294,22 @@ __device__ __forceinline__ void tile_coords(int tile, int m_blocks, int n_blocks
   n_blk = in_group / rows_in_group;
 }
 
+// The v-th tile of this CTA / cluster, or false when it has none left.
+template <typename P>
+__device__ __forceinline__ bool tile_at(const P& p, int v, int first, int step, int m_tiles, int& m_blk, int& n_blk) {
+  if (p.raster == 1) {
+    const int mt = first + (v / p.n_blocks) * step;
+    if (mt >= m_tiles) return false;
+    m_blk = mt;
+    n_blk = v % p.n_blocks;
+    return true;
+  }
+  const int tile = first + v * step;
+  if (tile >= m_tiles * p.n_blocks) return false;
+  tile_coords(tile, m_tiles, p.n_blocks, p.group_m, m_blk, n_blk);
+  return true;
+}
+
 // One check-in of the soft round barrier: `participants` clusters pass this point; wait until all have -- for at most
 // ~100 us (in step, clusters arrive within a few us of each other).  A cluster that times out stops waiting for the rest
 // of the launch (it keeps checking in): when not every cluster of the grid is resident -- another kernel, e.g. an NCCL
@@ -401,9 +428,9 @@ gemm_kernel(const __grid_constant__ Params p) {
         unsigned int round_target = 0;
         bool round_wait = true;
         unsigned int gate_seen = 0;      // segments whose gate this CTA has passed
-        for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
-          int m_blk, n_blk;
-          tile_coords(tile, m_tiles, p.n_blocks, p.group_m, m_blk, n_blk);
+        int m_blk, n_blk;
+        for (int v = 0; tile_at(p, v, first_tile, tile_step, m_tiles, m_blk, n_blk); ++v) {
+          const int tile = first_tile + v * tile_step;      // (raster 0; the round barrier is off for raster 1)
           if constexpr (PAIR) {
             // Soft round barrier (leaders only; the peer is throttled through the ring): every cluster with a tile in
             // this round checks in, then waits -- for a bounded time, so nothing can deadlock -- until all have.
@@ -455,7 +482,8 @@ gemm_kernel(const __grid_constant__ Params p) {
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        int mma_m, mma_n;
+        for (int v = 0; tile_at(p, v, first_tile, tile_step, m_tiles, mma_m, mma_n); ++v) {
           int in_chunk = 0;          // k-blocks issued into the current TMEM chunk
           uint32_t accum = 0;
           bool chunk_open = false;
@@ -533,9 +561,10 @@ gemm_kernel(const __grid_constant__ Params p) {
     const int n_chunks = (total_kb + p.chunk_kb - 1) / p.chunk_kb;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
-      int m_blk, n_blk;
-      tile_coords(tile, m_tiles, p.n_blocks, p.group_m, m_blk, n_blk);
+    float run_best = 3.402823466e+38f;     // epilogue mode 2: minimum over the column tiles seen so far of this row tile
+    int run_best_j = 0x7fffffff;
+    int m_blk, n_blk;
+    for (int v = 0; tile_at(p, v, first_tile, tile_step, m_tiles, m_blk, n_blk); ++v) {
       if constexpr (PAIR) m_blk = m_blk * 2 + static_cast<int>(rank);     // this CTA's 128-row block
       float sum[128];
 #pragma unroll
@@ -562,7 +591,7 @@ gemm_kernel(const __grid_constant__ Params p) {
       }
       const int row = m_blk * BM + q * 32 + lane;
       const int col0 = n_blk * BN + half * 128;
-      if (p.epi_mode == 1) {
+      if (p.epi_mode != 0) {
         float best = 3.402823466e+38f;
         int best_j = 0x7fffffff;
 #pragma unroll
@@ -573,10 +602,52 @@ gemm_kernel(const __grid_constant__ Params p) {
             if (v < best) { best = v; best_j = col; }        // first minimum: ties resolve to the smallest index
           }
         }
-        if (row < p.M) {
-          const int64_t o = static_cast<int64_t>(row) * (p.n_blocks * 2) + n_blk * 2 + half;
-          p.part_val[o] = best;
-          p.part_idx[o] = best_j;
+        if (p.epi_mode == 1) {
+          if (row < p.M) {
+            const int64_t o = static_cast<int64_t>(row) * (p.n_blocks * 2) + n_blk * 2 + half;
+            p.part_val[o] = best;
+            p.part_idx[o] = best_j;
+          }
+        } else {
+          // fused k-means: keep the running minimum of this row over the column tiles (columns ascend, so a strict
+          // comparison keeps the smallest index among equal values)
+          if (best < run_best) { run_best = best; run_best_j = best_j; }
+          if (n_blk == p.n_blocks - 1) {
+            // combine the two column halves of the row (the two epilogue warpgroups), publish the labels of the CTA's
+            // 128 rows in shared memory, then all 8 epilogue warps add the rows into their centroids
+            float* ex_val = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
+            int* ex_idx = reinterpret_cast<int*>(ex_val + 128);
+            int* row_label = ex_idx + 128;
+            const int r_in = q * 32 + lane;
+            if (half == 1) { ex_val[r_in] = run_best; ex_idx[r_in] = run_best_j; }
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            if (half == 0) {
+              const float ov = ex_val[r_in];
+              const int oj = ex_idx[r_in];
+              if (ov < run_best) { run_best = ov; run_best_j = oj; }     // half 1 holds the larger indices
+              row_label[r_in] = run_best_j;
+              if (row < p.M) {
+                p.labels[row] = run_best_j;
+                atomicAdd(p.counts + run_best_j, 1ull);
+              }
+            }
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            const int ew = warp - EPI_WARP0;                 // 0..7: rows ew*16 .. ew*16+15 of the CTA's block
+            const int d4 = p.pts_d >> 2;
+#pragma unroll 4
+            for (int rr = 0; rr < 16; ++rr) {
+              const int rl = ew * 16 + rr;
+              const int64_t grow = static_cast<int64_t>(m_blk) * BM + rl;
+              if (grow < p.M) {
+                const float4* src = reinterpret_cast<const float4*>(p.pts + grow * p.ldp);
+                float4* dst = reinterpret_cast<float4*>(p.sums + static_cast<int64_t>(row_label[rl]) * p.pts_d);
+                for (int j = lane; j < d4; j += 32) atomicAdd(dst + j, __ldcs(src + j));     // red.global.add.v4.f32
+              }
+            }
+            asm volatile("bar.sync 2, 256;" ::: "memory");   // row_label is rewritten for the next row tile
+            run_best = 3.402823466e+38f;
+            run_best_j = 0x7fffffff;
+          }
         }
       } else if (row < p.M) {
         float* c_row = p.C + static_cast<int64_t>(row) * p.ldc;
@@ -880,9 +951,18 @@ struct Gates {
   uint32_t* status;                // time-out counter (device memory) or NULL
 };
 
+struct FusedKmeans {
+  const float* pts;            // the points in fp32 (rows of the A operand before preparation)
+  int64_t ldp;
+  int d;
+  int32_t* labels;
+  float* sums;
+  unsigned long long* counts;
+};
+
 static int launch_prepared(int n_seg, const sp_gemm_prepared_view* segs, float* C, int64_t ldc, int64_t M, int64_t N,
                            int accumulate, int precision, int epi_mode, const float* col_bias, float* part_val,
-                           int* part_idx, void* stream_, const Gates* gates = nullptr) {
+                           int* part_idx, void* stream_, const Gates* gates = nullptr, const FusedKmeans* fused = nullptr) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   Mode md;
   SP_REQUIRE(mode_of(precision, &md), SP_ERR_INVALID, "sp_gemm_prepared: unknown precision %d", precision);
@@ -972,6 +1052,11 @@ static int launch_prepared(int n_seg, const sp_gemm_prepared_view* segs, float* 
   p.group_m = pair ? g_group_m : 2 * g_group_m;
   p.sync_kb = g_sync_kb;
   p.epi_mode = epi_mode;
+  if (fused != nullptr) {
+    p.raster = 1;
+    p.pts = fused->pts; p.ldp = fused->ldp; p.pts_d = fused->d;
+    p.labels = fused->labels; p.sums = fused->sums; p.counts = fused->counts;
+  }
   p.col_bias = col_bias;
   p.part_val = part_val;
   p.part_idx = part_idx;
@@ -991,7 +1076,8 @@ static int launch_prepared(int n_seg, const sp_gemm_prepared_view* segs, float* 
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.gridDim = dim3(static_cast<unsigned>(2 * std::min(tiles, max_clusters)));
+    const int units = p.raster == 1 ? (p.m_blocks + 1) / 2 : tiles;      // raster 1: a cluster takes whole row tiles
+    cfg.gridDim = dim3(static_cast<unsigned>(2 * std::min(units, max_clusters)));
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = PAIR_SMEM_BYTES;
     cfg.stream = stream;
@@ -999,7 +1085,7 @@ static int launch_prepared(int n_seg, const sp_gemm_prepared_view* segs, float* 
     if (md.kind == 0) SP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<0, true>, p));
     else SP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<1, true>, p));
   } else {
-    const int tiles = p.m_blocks * p.n_blocks;
+    const int tiles = p.raster == 1 ? p.m_blocks : p.m_blocks * p.n_blocks;
     const int grid = std::min(tiles, num_sms());
     if (md.kind == 0) gemm_kernel<0, false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);
     else gemm_kernel<1, false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);
@@ -1063,6 +1149,24 @@ extern "C" int sp_gemm_prepared_argmin(int n_seg, const sp_gemm_prepared_segment
   int rc = to_views(n_seg, segs, M, N, precision, v);
   if (rc) return rc;
   return launch_prepared(n_seg, v, nullptr, 0, M, N, 0, precision, 1, col_bias, part_val, part_idx, stream_);
+}
+
+// k-means assignment fused end to end (k_means_.py:61-97): labels[i] = argmin_j (col_bias[j] - 2 (A.B)[i, j]) over ALL
+// columns, counts[labels[i]] += 1, sums[labels[i], :] += pts[i, :] -- the GEMM walks the column tiles of a row tile back to
+// back, keeps the running arg min in registers and its epilogue warps do the accumulation while the tensor cores are
+// already on the next row tile.  d must be a multiple of 4, pts / sums 16-byte aligned.
+extern "C" int sp_gemm_prepared_kmeans(const sp_gemm_prepared_segment* seg, int64_t M, int64_t N, const float* col_bias,
+                                       const float* pts, int64_t ldp, int64_t d, int32_t* labels, float* sums,
+                                       int64_t* counts, int precision, void* stream_) {
+  SP_REQUIRE(seg && col_bias && pts && labels && sums && counts, SP_ERR_INVALID, "sp_gemm_prepared_kmeans: null pointer");
+  SP_REQUIRE(d > 0 && (d & 3) == 0 && (ldp & 3) == 0 && d < (1ll << 31) &&
+             ((reinterpret_cast<uint64_t>(pts) | reinterpret_cast<uint64_t>(sums)) & 15) == 0, SP_ERR_INVALID,
+             "sp_gemm_prepared_kmeans: d / ldp must be multiples of 4 and pts / sums 16-byte aligned");
+  sp_gemm_prepared_view v[1];
+  int rc = to_views(1, seg, M, N, precision, v);
+  if (rc) return rc;
+  FusedKmeans fk{pts, ldp, static_cast<int>(d), labels, sums, reinterpret_cast<unsigned long long*>(counts)};
+  return launch_prepared(1, v, nullptr, 0, M, N, 0, precision, 2, col_bias, nullptr, nullptr, stream_, nullptr, &fk);
 }
 
 extern "C" int64_t sp_gemm_f32_workspace_bytes(int64_t M, int64_t N, int n_seg, const int64_t* seg_k, int precision) {

@@ -151,6 +151,8 @@ static void launch_spmv(int group, int blocks, const PTR* rowptr, const int32_t*
   }
 }
 
+static int g_kmeans_fused = 1;
+
 }  // namespace sp
 
 using namespace sp;
@@ -211,6 +213,10 @@ extern "C" int sp_kmeans_assign_prepared(const void* Xprep, const float* X, int6
                                                                             static_cast<int>(d), cnorm);
   sp_gemm_prepared_segment seg;
   seg.A = Xprep; seg.B = b_prep; seg.Kp = Kp;
+  const bool fused = g_kmeans_fused && (d & 3) == 0 && (ldx & 3) == 0 &&
+                     ((reinterpret_cast<uint64_t>(X) | reinterpret_cast<uint64_t>(sums)) & 15) == 0;
+  if (fused)      // labels, counts and sums straight from the GEMM's epilogue: no candidates in HBM, no second pass
+    return sp_gemm_prepared_kmeans(&seg, n, k, cnorm, X, ldx, d, labels, sums, counts, prec, stream);
   rc = sp_gemm_prepared_argmin(1, &seg, n, k, cnorm, part_val, part_idx, prec, stream);   // no n x k matrix in HBM
   if (rc) return rc;
   const int blocks = static_cast<int>(std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(num_sms()) * 8));
@@ -222,6 +228,12 @@ extern "C" int sp_kmeans_assign_prepared(const void* Xprep, const float* X, int6
     kmeans_label_accumulate_kernel<false><<<blocks, 256, 0, stream>>>(part_val, part_idx, parts, X, ldx, n, static_cast<int>(d),
                                                                       labels, sums, reinterpret_cast<unsigned long long*>(counts));
   SP_CUDA_CHECK(cudaGetLastError());
+  return SP_OK;
+}
+
+// Test / tuning hook: 1 (default) = labels / counts / sums from the GEMM's own epilogue, 0 = candidates + second kernel.
+extern "C" int sp_kmeans_set_fused(int on) {
+  g_kmeans_fused = on ? 1 : 0;
   return SP_OK;
 }
 

@@ -182,17 +182,18 @@ def run_map_reduce(prog, inputs, in_shape, axis, red_op, out, accumulate, index=
       shape, strides = [1], [[0] for _ in in_strides]
     first = True
     if len(shape) == 1 and shape[0] >= _FLAT_REDUCE_MIN and all(st[0] in (0, 1) for st in strides):
-      # A long contiguous run: fold it as rows of _FLAT_REDUCE_COLS elements down to one row (the streaming
-      # column-reduce kernel, HBM-bound), then fold that row; the ragged tail goes through the generic path below.
+      # A long contiguous run: re-viewed as rows of _FLAT_REDUCE_COLS elements and reduced along the rows (the streaming
+      # kernel's trailing-axis mode, HBM-bound), then the per-row values are folded; the ragged tail goes through the
+      # generic path below.
       cols = _FLAT_REDUCE_COLS
       rows = shape[0] // cols
-      st3 = [[0, st[0] * cols, st[0]] for st in strides]
+      st3 = [[st[0] * cols, st[0], 0] for st in strides]
       if index is not None:
         _set_index(prog, index[0], st3[n_in])
-      row = torch.empty((cols,), dtype=_TORCH_OF_COMPUTE[prog.compute_dtype], device=out.device)
-      _launch_reduce(ctx, prog, inputs, st3[:n_in], [0] * n_in, row, [0, 0, 1], 0, [1, rows, cols], red_op, False)
+      col = torch.empty((rows,), dtype=_TORCH_OF_COMPUTE[prog.compute_dtype], device=out.device)
+      _launch_reduce(ctx, prog, inputs, st3[:n_in], [0] * n_in, col, [1, 0, 0], 0, [rows, cols, 1], red_op, False)
       ident = make_program([('IN', 0)], prog.compute_dtype)
-      _launch_reduce(ctx, ident, [row], [[0, 1, 0]], [0], out, [0, 0, 0], 0, [1, cols, 1], red_op, accumulate)
+      _launch_reduce(ctx, ident, [col], [[0, 1, 0]], [0], out, [0, 0, 0], 0, [1, rows, 1], red_op, accumulate)
       first = False
       done = rows * cols
       if done == shape[0]:
@@ -235,7 +236,7 @@ def run_map_reduce(prog, inputs, in_shape, axis, red_op, out, accumulate, index=
                      offs[no] + ioffs[no], [d0, in_shape[axis], d2], red_op, accumulate)
 
 
-_FLAT_REDUCE_COLS = 8192          # elements per row when a flat reduction is re-viewed as a column reduction
+_FLAT_REDUCE_COLS = 32768         # elements per row when a flat reduction is re-viewed as a trailing-axis reduction
 _FLAT_REDUCE_MIN = 1 << 20
 _TORCH_OF_COMPUTE = {SP_F32: torch.float32, SP_F64: torch.float64, SP_I64: torch.int64}
 

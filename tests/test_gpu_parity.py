@@ -666,6 +666,34 @@ def test_spmv_vs_oracle(n, outlinks, strip):
 
 
 # ------------------------------------------------------------------ edge cases: 0-d, empty, ragged, tiny
+@pytest.mark.parametrize('n,d,k', [(5000, 32, 16), (33333, 256, 1024), (777, 64, 300), (4096, 128, 257)])
+def test_kmeans_fused_epilogue_matches_two_kernel_form(n, d, k):
+  """The assignment fused into the GEMM (running arg min across the column tiles in registers, accumulation by the
+  epilogue warps) against the candidates + second-kernel form: identical labels and counts, sums equal up to the order of
+  the float atomics; both against float64 distances."""
+  from spartan_b200._lib import lib
+  rng = np.random.default_rng(n + d + k)
+  x = rng.random((n, d), dtype=np.float32)
+  c0 = x[rng.choice(n, k, replace=False)].copy()
+  X = sp.from_numpy(x, tile_hint=(n, d)).evaluate()
+  out = {}
+  try:
+    for fused in (1, 0):
+      lib.sp_kmeans_set_fused(fused)
+      centers, labels = sp.KMeans(n_clusters=k, n_iter=1).fit(X, centers=c0)
+      out[fused] = (centers, labels.glom())
+  finally:
+    lib.sp_kmeans_set_fused(1)
+  all_eq(out[1][1], out[0][1])
+  np.testing.assert_allclose(out[1][0], out[0][0], rtol=2e-6, atol=1e-7)
+  x64, c64 = x.astype(np.float64), c0.astype(np.float64)
+  d2 = (x64 * x64).sum(1)[:, None] - 2.0 * x64 @ c64.T + (c64 * c64).sum(1)[None, :]
+  ref = d2.argmin(1)
+  bad = np.nonzero(out[1][1] != ref)[0]
+  gap = d2[bad, out[1][1][bad]] - d2[bad, ref[bad]]
+  assert np.all(gap <= 1e-5 * np.abs(d2[bad, ref[bad]])), 'labels differ away from a tie'
+
+
 def test_kmeans_and_spmv_on_reference_generated_vectors():
   """The device k-means iteration and the device SpMV on the inputs of tests/golden/app_vectors.json, whose outputs
   were produced by the reference's own mapper functions (oracle/ref_apps/make_app_vectors.py): labels must be

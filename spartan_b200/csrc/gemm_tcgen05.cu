@@ -566,6 +566,18 @@ gemm_kernel(const __grid_constant__ Params p) {
     int m_blk, n_blk;
     for (int v = 0; tile_at(p, v, first_tile, tile_step, m_tiles, m_blk, n_blk); ++v) {
       if constexpr (PAIR) m_blk = m_blk * 2 + static_cast<int>(rank);     // this CTA's 128-row block
+      if (p.epi_mode == 2 && n_blk == 0) {
+        // the fp32 rows this CTA will add into the centroids after its last column tile: pull them into L2 now
+        const int lines_per_row = (p.pts_d * 4 + 127) / 128;
+        const int t = (warp - EPI_WARP0) * 32 + lane;
+        for (int i = t; i < BM * lines_per_row; i += 32 * NUM_EPI_WARPS) {
+          const int64_t grow = static_cast<int64_t>(m_blk) * BM + i / lines_per_row;
+          if (grow < p.M) {
+            const char* ptr = reinterpret_cast<const char*>(p.pts + grow * p.ldp) + (i % lines_per_row) * 128;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+          }
+        }
+      }
       float sum[128];
 #pragma unroll
       for (int j = 0; j < 128; ++j) sum[j] = 0.0f;
@@ -634,14 +646,31 @@ gemm_kernel(const __grid_constant__ Params p) {
             asm volatile("bar.sync 2, 256;" ::: "memory");
             const int ew = warp - EPI_WARP0;                 // 0..7: rows ew*16 .. ew*16+15 of the CTA's block
             const int d4 = p.pts_d >> 2;
-#pragma unroll 4
-            for (int rr = 0; rr < 16; ++rr) {
-              const int rl = ew * 16 + rr;
-              const int64_t grow = static_cast<int64_t>(m_blk) * BM + rl;
-              if (grow < p.M) {
-                const float4* src = reinterpret_cast<const float4*>(p.pts + grow * p.ldp);
-                float4* dst = reinterpret_cast<float4*>(p.sums + static_cast<int64_t>(row_label[rl]) * p.pts_d);
-                for (int j = lane; j < d4; j += 32) atomicAdd(dst + j, __ldcs(src + j));     // red.global.add.v4.f32
+            // 8 rows at a time: all their loads first (16 independent 16-byte loads per lane in flight; the rows were
+            // prefetched into L2 when this row tile began), then their atomics -- a load directly followed by its atomic
+            // would serialise 32 memory round trips per warp and stall the tensor cores behind the epilogue
+            for (int jb = 0; jb < d4; jb += 64) {
+              const int ja = jb + lane, jc = jb + 32 + lane;
+#pragma unroll
+              for (int hb = 0; hb < 2; ++hb) {
+                float4 buf[16];
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) {
+                  const int64_t grow = static_cast<int64_t>(m_blk) * BM + ew * 16 + hb * 8 + rr;
+                  const float4* src = reinterpret_cast<const float4*>(p.pts + grow * p.ldp);
+                  buf[2 * rr] = (grow < p.M && ja < d4) ? __ldcs(src + ja) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  buf[2 * rr + 1] = (grow < p.M && jc < d4) ? __ldcs(src + jc) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) {
+                  const int rl = ew * 16 + hb * 8 + rr;
+                  const int64_t grow = static_cast<int64_t>(m_blk) * BM + rl;
+                  if (grow < p.M) {
+                    float4* dst = reinterpret_cast<float4*>(p.sums + static_cast<int64_t>(row_label[rl]) * p.pts_d);
+                    if (ja < d4) atomicAdd(dst + ja, buf[2 * rr]);                 // red.global.add.v4.f32
+                    if (jc < d4) atomicAdd(dst + jc, buf[2 * rr + 1]);
+                  }
+                }
               }
             }
             asm volatile("bar.sync 2, 256;" ::: "memory");   // row_label is rewritten for the next row tile

@@ -222,7 +222,10 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 // arrive on a barrier that lives in another CTA of the cluster (address from map_to_cta)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  // default semantics (what CUTLASS' ClusterBarrier::arrive issues): the TMEM hand-over is ordered by
+  // tcgen05.fence::before_thread_sync; an explicit .release.cluster here compiled to MEMBAR.ALL + ERRBAR + CGAERRBAR per
+  // chunk and cost the argmin epilogue ~12% of its time (ncu source view of the k-means GEMM, profiles/)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 // TMA load whose completion bytes are credited to a barrier in the pair's leader CTA
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1) {
@@ -606,12 +609,35 @@ gemm_kernel(const __grid_constant__ Params p) {
       if (p.epi_mode != 0) {
         float best = 3.402823466e+38f;
         int best_j = 0x7fffffff;
+        if (col0 + 128 <= p.N && (reinterpret_cast<uint64_t>(p.col_bias) & 15) == 0) {
+          // full half tile: 16-byte bias loads (uniform address: one transaction per warp), bias - 2*sum as one FMA (the
+          // doubling is exact, so it rounds once like FMUL + FADD), four independent (min, arg min) chains over j mod 4
+          // merged at the end -- the scalar loop below had the epilogue, not the tensor cores, bound this kernel
+          const float4* b4 = reinterpret_cast<const float4*>(p.col_bias + col0);
+          float bv[4] = {best, best, best, best};
+          int bj[4] = {best_j, best_j, best_j, best_j};
 #pragma unroll
-        for (int j = 0; j < 128; ++j) {       // fully unrolled: sum[] must stay in registers
-          const int col = col0 + j;
-          if (col < p.N) {
-            const float v = __ldg(p.col_bias + col) - 2.0f * sum[j];
-            if (v < best) { best = v; best_j = col; }        // first minimum: ties resolve to the smallest index
+          for (int j4 = 0; j4 < 32; ++j4) {     // fully unrolled: sum[] must stay in registers
+            const float4 b = __ldg(b4 + j4);
+            const float v0 = __fmaf_rn(-2.0f, sum[4 * j4], b.x), v1 = __fmaf_rn(-2.0f, sum[4 * j4 + 1], b.y);
+            const float v2 = __fmaf_rn(-2.0f, sum[4 * j4 + 2], b.z), v3 = __fmaf_rn(-2.0f, sum[4 * j4 + 3], b.w);
+            if (v0 < bv[0]) { bv[0] = v0; bj[0] = 4 * j4; }
+            if (v1 < bv[1]) { bv[1] = v1; bj[1] = 4 * j4 + 1; }
+            if (v2 < bv[2]) { bv[2] = v2; bj[2] = 4 * j4 + 2; }
+            if (v3 < bv[3]) { bv[3] = v3; bj[3] = 4 * j4 + 3; }
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c)           // ties resolve to the smallest index, like np.argmin
+            if (bv[c] < best || (bv[c] == best && bj[c] < best_j)) { best = bv[c]; best_j = bj[c]; }
+          best_j += col0;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 128; ++j) {       // fully unrolled: sum[] must stay in registers
+            const int col = col0 + j;
+            if (col < p.N) {
+              const float v = __ldg(p.col_bias + col) - 2.0f * sum[j];
+              if (v < best) { best = v; best_j = col; }        // first minimum: ties resolve to the smallest index
+            }
           }
         }
         if (p.epi_mode == 1) {

@@ -18,6 +18,7 @@
 #include "sp_common.h"
 #include <algorithm>
 #include <float.h>
+#include <stdlib.h>
 
 namespace sp {
 
@@ -151,7 +152,14 @@ static void launch_spmv(int group, int blocks, const PTR* rowptr, const int32_t*
   }
 }
 
-static int g_kmeans_fused = 1;
+static int g_kmeans_fused = -1;     // -1: from the environment (SPARTAN_KMEANS_FUSED, default 1)
+static bool kmeans_fused() {
+  if (g_kmeans_fused < 0) {
+    const char* e = getenv("SPARTAN_KMEANS_FUSED");
+    g_kmeans_fused = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_kmeans_fused == 1;
+}
 
 }  // namespace sp
 
@@ -204,7 +212,7 @@ extern "C" int sp_kmeans_assign_prepared(const void* Xprep, const float* X, int6
   const int parts = static_cast<int>(sp_gemm_argmin_parts(k));
   float* part_val = reinterpret_cast<float*>(b_prep + b_bytes);
   int32_t* part_idx = reinterpret_cast<int32_t*>(part_val + n * parts);
-  float* cnorm = reinterpret_cast<float*>(part_idx + n * parts);
+  float* cnorm = reinterpret_cast<float*>((reinterpret_cast<uint64_t>(part_idx + n * parts) + 15) & ~15ull);   // 16-byte loads
   if (Kp != (d + 3) / 4 * 4) SP_CUDA_CHECK(cudaMemsetAsync(b_prep, 0, b_bytes, stream));
   // the centres are already "B transposed" ([k, d] = [N, K]): prepare them like an A operand
   int rc = sp_gemm_prepare_a(centers, d, k, d, prec, b_prep, Kp, 0, b_bytes, stream);
@@ -213,7 +221,7 @@ extern "C" int sp_kmeans_assign_prepared(const void* Xprep, const float* X, int6
                                                                             static_cast<int>(d), cnorm);
   sp_gemm_prepared_segment seg;
   seg.A = Xprep; seg.B = b_prep; seg.Kp = Kp;
-  const bool fused = g_kmeans_fused && (d & 3) == 0 && (ldx & 3) == 0 &&
+  const bool fused = kmeans_fused() && (d & 3) == 0 && (ldx & 3) == 0 &&
                      ((reinterpret_cast<uint64_t>(X) | reinterpret_cast<uint64_t>(sums)) & 15) == 0;
   if (fused)      // labels, counts and sums straight from the GEMM's epilogue: no candidates in HBM, no second pass
     return sp_gemm_prepared_kmeans(&seg, n, k, cnorm, X, ldx, d, labels, sums, counts, prec, stream);

@@ -25,6 +25,9 @@ class Flags(object):
     self.dot_stream_min_bytes = 256 << 20
     # prepared (rounded / split / transposed) GEMM operands of unchanged arrays are kept between evaluations, up to this
     # many bytes (0 disables the cache)
+    # multi-GPU dot: 'auto' = segments contracted in passes grouped by arrival (dot.py _arrival_groups), 'single' = one
+    # gated launch over all segments (tuning aid)
+    self.dot_passes = os.environ.get('SPARTAN_DOT_PASSES', 'auto')
     self.dot_trace = False              # record a CUDA-event timeline of streamed multi-GPU dots (diagnostic)
     self.dot_prepared_cache = True
     self.dot_prepared_cache_bytes = 48 << 30

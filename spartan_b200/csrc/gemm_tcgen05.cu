@@ -569,6 +569,15 @@ gemm_kernel(const __grid_constant__ Params p) {
     int m_blk, n_blk;
     for (int v = 0; tile_at(p, v, first_tile, tile_step, m_tiles, m_blk, n_blk); ++v) {
       if constexpr (PAIR) m_blk = m_blk * 2 + static_cast<int>(rank);     // this CTA's 128-row block
+      if (p.epi_mode == 0 && p.accumulate) {
+        // C (+)= : pull this thread's 512 bytes of the old C into L2 while the tile's K loop runs
+        const int prow = m_blk * BM + q * 32 + lane;
+        if (prow < p.M) {
+          const char* ptr = reinterpret_cast<const char*>(p.C + static_cast<int64_t>(prow) * p.ldc + n_blk * BN + half * 128);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + 128 * i));
+        }
+      }
       if (p.epi_mode == 2 && n_blk == 0) {
         // the fp32 rows this CTA will add into the centroids after its last column tile: pull them into L2 now
         const int lines_per_row = (p.pts_d * 4 + 127) / 128;
@@ -709,14 +718,26 @@ gemm_kernel(const __grid_constant__ Params p) {
         const bool vec_ok = ((reinterpret_cast<uint64_t>(p.C) & 15) == 0) && ((p.ldc & 3) == 0) && (col0 + 128 <= p.N);
         if (vec_ok) {
           float4* dst = reinterpret_cast<float4*>(c_row + col0);
+          if (p.accumulate) {
+            // C (+)= : the old values were prefetched into L2 when the tile began; read them 8 x 16 B at a time BEFORE
+            // the stores of the batch (a load directly followed by its store serialises 32 memory round trips per
+            // thread and the tensor cores end up waiting for this epilogue)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float4 v = make_float4(sum[4 * j], sum[4 * j + 1], sum[4 * j + 2], sum[4 * j + 3]);
-            if (p.accumulate) {
-              const float4 o = dst[j];
-              v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+            for (int jb = 0; jb < 32; jb += 8) {
+              float4 o[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o[j] = __ldcs(dst + jb + j);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int jj = jb + j;
+                __stcs(dst + jj, make_float4(sum[4 * jj] + o[j].x, sum[4 * jj + 1] + o[j].y, sum[4 * jj + 2] + o[j].z,
+                                             sum[4 * jj + 3] + o[j].w));
+              }
             }
-            dst[j] = v;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              dst[j] = make_float4(sum[4 * j], sum[4 * j + 1], sum[4 * j + 2], sum[4 * j + 3]);
           }
         } else {
 #pragma unroll

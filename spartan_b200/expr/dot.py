@@ -79,22 +79,27 @@ _PUSH_BYTES_PER_S = 600e9       # copy-engine push over NVLink 5, one stream (me
 _DOT_FLOPS_PER_S = 480e12       # algorithmic rate of the bf16x3 contraction on one B200
 
 
-def _arrival_groups(n_segments, t_push, t_segment, max_groups=4):
-  """Positions 0..n-1 of the segment order (0 = local, j = the j-th push to land) grouped into passes: a pass takes
-  every segment expected to have arrived when the previous pass ends (at least one)."""
-  groups, t, nxt = [], 0.0, 0
-  while nxt < n_segments:
-    arrived = n_segments if t_push <= 0 else min(n_segments, int(t / t_push) + 1)
-    if arrived <= nxt:
-      arrived = nxt + 1
-      t = max(t, nxt * t_push)
-    if len(groups) == max_groups - 1:
-      arrived = n_segments
-    grp = list(range(nxt, arrived))
-    groups.append(grp)
-    t += len(grp) * t_segment
-    nxt = arrived
-  return groups
+_PASS_BYTES_PER_S = 2.0e12      # rate at which an accumulating pass re-reads and re-writes its C block
+_PASS_FIXED_S = 0.3e-3          # ramp / tail of one more launch
+
+
+def _arrival_groups(n_segments, t_push, t_segment, t_pass=0.0, max_groups=4):
+  """Positions 0..n-1 of the segment order (0 = local, j = the j-th push to land, at j * t_push) split into contiguous
+  passes.  A pass starts when its last segment has landed and the previous pass is done, takes len * t_segment, and
+  every pass after the first pays t_pass (it accumulates into C).  Returns the split with the earliest finish; ties go
+  to fewer passes."""
+  import itertools
+  best, best_t = None, None
+  for k in range(1, min(max_groups, n_segments) + 1):
+    for cuts in itertools.combinations(range(1, n_segments), k - 1):
+      bounds = (0,) + cuts + (n_segments,)
+      t = 0.0
+      for g in range(k):
+        lo, hi = bounds[g], bounds[g + 1]
+        t = max(t, (hi - 1) * t_push) + (hi - lo) * t_segment + (t_pass if g > 0 else 0.0)
+      if best_t is None or t < best_t - 1e-12:
+        best, best_t = bounds, t
+  return [list(range(best[g], best[g + 1])) for g in range(len(best) - 1)]
 
 
 class _Trace(object):
@@ -492,8 +497,12 @@ class DotExpr(Expr):
     # engines deliver while the previous pass computes), each pass accumulating into C.  The gates keep any grouping
     # correct; the grouping only decides how much of the exchange hides behind the math (measured on 2 x B200 with the
     # 8-rank traffic pattern: one pass over all segments 20-22 ms, the GEMM alone 15.8-17 ms, profiles/r02_peer_probe*).
-    groups = _arrival_groups(W, mine.nbytes / _PUSH_BYTES_PER_S,
-                             2.0 * M * sum(c1 - c0 for c0, c1 in c_runs[me][1]) * width / _DOT_FLOPS_PER_S)
+    n_cols = sum(c1 - c0 for c0, c1 in c_runs[me][1])
+    if FLAGS.dot_passes == 'single':
+      groups = [list(range(W))]
+    else:
+      groups = _arrival_groups(W, mine.nbytes / _PUSH_BYTES_PER_S, 2.0 * M * n_cols * width / _DOT_FLOPS_PER_S,
+                               2.0 * M * n_cols * 4 / _PASS_BYTES_PER_S + _PASS_FIXED_S)
     for (r0, r1) in c_runs[me][0]:
       for (c0, c1) in c_runs[me][1]:
         Cv = target.fetch(extent.create((r0, c0), (r1, c1), shape))

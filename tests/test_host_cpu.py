@@ -522,12 +522,17 @@ def test_automatic_tiling_minimises_nvlink_bytes():
 
 def test_dot_arrival_groups_cover_every_segment_once():
   """The passes of the multi-GPU dot (segments grouped by expected arrival) must be a partition of the segment order,
-  in order, starting with the local segment alone."""
+  in order; with free passes the local segment goes alone, with expensive passes everything is one launch."""
   from spartan_b200.expr.dot import _arrival_groups
   for n in (1, 2, 3, 4, 8):
-    for t_push, t_seg in [(0.87, 2.1), (3.6, 36.0), (3.0, 1.0), (0.0, 1.0), (1.0, 1e-9)]:
-      g = _arrival_groups(n, t_push, t_seg)
+    for t_push, t_seg, t_pass in [(0.87, 2.1, 0.0), (0.87, 2.1, 0.5), (3.6, 36.0, 2.4), (3.0, 1.0, 0.1), (0.0, 1.0, 0.2),
+                                  (1.0, 1e-9, 0.0), (0.87, 2.1, 50.0)]:
+      g = _arrival_groups(n, t_push, t_seg, t_pass)
       assert [j for grp in g for j in grp] == list(range(n))
-      assert g[0] == [0] or t_push <= 0
       assert 1 <= len(g) <= 4
-  assert _arrival_groups(8, 0.87, 2.1) == [[0], [1, 2], [3, 4, 5, 6, 7]]
+      if t_pass >= 50.0:
+        assert len(g) == 1
+  assert _arrival_groups(8, 0.87, 2.1, 0.0)[0] == [0]
+  assert _arrival_groups(8, 0.87, 2.1, 0.6) == [[0], [1, 2], [3, 4, 5, 6, 7]]
+  assert _arrival_groups(2, 3.6, 36.0, 5.0) == [[0, 1]]          # a pass dearer than the stall it avoids
+  assert _arrival_groups(2, 3.6, 36.0, 2.4) == [[0], [1]]

@@ -7,7 +7,7 @@ full-length partial y that is np.add-merged on the owners.
 
 Here a strip is a CSR triple resident in the HBM of its owner (placement = the reference's round-robin over
 column strips), a strip's product is one `sp_spmv_csr` launch accumulating into a rank-local y, and the merge
-is one ncclAllReduce(sum) of y.  Sparse *tiles* as a general array type stay out of scope: only this
+is one ncclReduceScatter(sum) of y into the owners' row blocks (ncclAllReduce for irregular result tilings).  Sparse *tiles* as a general array type stay out of scope: only this
 operation is provided."""
 import numpy as np
 import scipy.sparse as sp_sparse
@@ -173,9 +173,28 @@ class SpMVExpr(Expr):
                             n_rows, xs.data_ptr(), y.data_ptr(), 1, max(1, -(-nnz // max(1, n_rows))), ctx.stream_ptr()),
             'sp_spmv_csr')
       ctx.kernel_launches += 1
-    comm.allreduce(y, SP_RED_SUM)                # the np.add merge of the strips' partial y (tile.pyx:263-268)
     out_shape = self.compute_shape()
     out = distarray.create(out_shape, np.float32, reducer=np.add, tile_hint=self.tile_hint)
+    W = ctx.num_workers
+    # The np.add merge of the strips' partial y (tile.pyx:263-268).  When rank r owns exactly the r-th of W equal row
+    # blocks of the result (the default tiling), a reduce-scatter straight into its slab moves half the bytes of an
+    # all-reduce; otherwise all-reduce and let every rank copy out the tiles it owns.
+    rows_per = n_rows // W if W > 0 else n_rows
+    regular = (W > 1 and ctx.device.type == 'cuda' and n_rows % W == 0 and out.slab is not None
+               and out.slab.is_contiguous() and out.slab.numel() == rows_per)
+    if regular:
+      for ex, tid in out.tiles.items():
+        if not (tid.worker * rows_per <= ex.ul[0] and ex.lr[0] <= (tid.worker + 1) * rows_per):
+          regular = False
+          break
+    if regular:
+      import torch.distributed as dist
+      dist.reduce_scatter_tensor(out.slab.reshape(-1), y, op=dist.ReduceOp.SUM)
+      for tid in out.tiles.values():
+        if ctx.is_local(tid):
+          ctx.tile(tid).valid = True
+      return out
+    comm.allreduce(y, SP_RED_SUM)
     yv = y if len(out_shape) == 1 else y.reshape(n_rows, 1)
     for ex, tid in out.tiles.items():
       if ctx.is_local(tid):

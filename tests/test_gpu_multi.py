@@ -75,6 +75,27 @@ def _worker(rank, world, port, q, use_peer):
       assert np.array_equal(got, x.max(axis=1))
     xi = rng.integers(-50, 50, size=(333, 77)).astype(np.int64)
     assert sp.from_numpy(xi).sum().glom() == xi.sum()
+    # sparse column strips x vector: partial y of every rank combined by reduce-scatter (default result tiling) or
+    # all-reduce (any other tiling); k-means: rows sharded, sums / counts all-reduced
+    import scipy.sparse
+    for n_, strip, hint_y in [(4000, 500, None), (4000, 1000, (1333, 1)), (3001, 700, None)]:
+      nnz = 6 * n_
+      m = scipy.sparse.coo_matrix((rng.random(nnz, dtype=np.float32), (rng.integers(0, n_, nnz), rng.integers(0, n_, nnz))),
+                                  shape=(n_, n_))
+      xv = rng.random((n_, 1), dtype=np.float32)
+      got = sp.dot(sp.sparse.from_scipy(m, strip_width=strip), sp.from_numpy(xv, tile_hint=(strip, 1)), tile_hint=hint_y).glom()
+      want = m.tocsr().astype(np.float64).dot(xv.astype(np.float64))
+      np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-6)
+    pts = rng.random((6000, 64), dtype=np.float32)
+    c_init = pts[:10].copy()
+    cen, lab = sp.KMeans(n_clusters=10, n_iter=2).fit(sp.from_numpy(pts, tile_hint=(1500, 64)), centers=c_init)
+    c64 = c_init.astype(np.float64)
+    for _ in range(2):
+      d2 = ((pts[:, None, :].astype(np.float64) - c64[None]) ** 2).sum(-1)
+      l64 = d2.argmin(1)
+      c64 = np.stack([pts[l64 == j].astype(np.float64).mean(0) for j in range(10)])
+    assert (lab.glom() == l64).mean() > 0.999
+    np.testing.assert_allclose(cen, c64, rtol=1e-4, atol=1e-5)
     # operands with different tilings: pieces travel point-to-point to the owner of each output tile
     got = (sp.from_numpy(x, tile_hint=(128, 2048)) + sp.from_numpy(y, tile_hint=(1024, 256))).glom()
     assert np.array_equal(got, x + y)

@@ -123,9 +123,11 @@ static const char* type_name(int dtype) {
 // "sp::stream::stream_kernel<float, 2, 1, sp::StaticProgram<65536, ...> >"
 static std::string kernel_expr(int dtype, int ni, int mode, const uint8_t* op, const uint8_t* src, const uint8_t* arg, int n) {
   // modes 0-2: the ring kernel (map / reduce leading axis / reduce trailing axis); mode 3: the direct map kernel
-  std::string s = mode == 3 ? "sp::stream::direct_map_kernel<" : "sp::stream::stream_kernel<";
+  // mode 4: the direct reduce kernel (leading axis)
+  std::string s = mode == 3 ? "sp::stream::direct_map_kernel<" : mode == 4 ? "sp::stream::direct_reduce_kernel<"
+                                                                             : "sp::stream::stream_kernel<";
   s += type_name(dtype);
-  s += ", " + std::to_string(ni) + (mode == 3 ? std::string("") : ", " + std::to_string(mode)) + ", sp::StaticProgram<";
+  s += ", " + std::to_string(ni) + (mode >= 3 ? std::string("") : ", " + std::to_string(mode)) + ", sp::StaticProgram<";
   for (int i = 0; i < n; ++i) {
     if (i) s += ", ";
     s += std::to_string((static_cast<int>(op[i]) << 16) | (static_cast<int>(src[i]) << 8) | arg[i]);
@@ -253,10 +255,10 @@ extern "C" const char* sp_jit_last_log(void) {
 }
 
 // Compiles (does not load or run) the specialisation of `prog` for `n_in` operands: the build-time check that the
-// run-time path works on a machine without a GPU.  mode 0 = map, 1 = map+reduce over the leading axis, 2 = map+reduce over the trailing axis, 3 = the direct (non-ring) map kernel.  Returns the cubin size.
+// run-time path works on a machine without a GPU.  mode 0 = map, 1 = map+reduce over the leading axis, 2 = map+reduce over the trailing axis, 3 = the direct (non-ring) map kernel, 4 = the direct reduce kernel (leading axis).  Returns the cubin size.
 namespace sp { int lower_for_jit(const sp_program* prog, uint8_t* op, uint8_t* src, uint8_t* arg, int* n); }
 extern "C" int64_t sp_jit_compile_check(const sp_program* prog, int n_in, int mode) {
-  SP_REQUIRE(prog != nullptr && n_in >= 0 && n_in <= SP_MAX_OPERANDS && (mode >= 0 && mode <= 3), SP_ERR_INVALID,
+  SP_REQUIRE(prog != nullptr && n_in >= 0 && n_in <= SP_MAX_OPERANDS && (mode >= 0 && mode <= 4), SP_ERR_INVALID,
              "sp_jit_compile_check: bad arguments");
   uint8_t op[SP_MAX_PROGRAM], src[SP_MAX_PROGRAM], arg[SP_MAX_PROGRAM];
   int n = 0;

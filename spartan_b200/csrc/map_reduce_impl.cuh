@@ -363,6 +363,55 @@ static int launch_direct(const DevProgram<T>& dp, const DevOperands<NI>& ops, co
   return kNotLaunched;
 }
 
+static int g_reduce_kernel = -1;  // 0 = ring, 1 = direct; env SPARTAN_REDUCE_KERNEL=ring|direct, default direct
+static bool use_direct_reduce() {
+  if (g_reduce_kernel < 0) {
+    const char* e = getenv("SPARTAN_REDUCE_KERNEL");
+    g_reduce_kernel = (e && e[0] == 'r') ? 0 : 1;
+  }
+  return g_reduce_kernel == 1;
+}
+
+template <typename T, int NI, typename PROG>
+static int launch_direct_reduce_as(const DevProgram<T>& dp, const DevOperands<NI>& ops, const stream::Plan& plan, int red_op,
+                                   T* scratch, int64_t blocks, cudaStream_t stream_) {
+  stream::direct_reduce_kernel<T, NI, PROG><<<static_cast<unsigned>(blocks), stream::kDirectThreads, 0, stream_>>>(
+      dp, ops, plan, red_op, scratch);
+  SP_CUDA_CHECK(cudaGetLastError());
+  return SP_OK;
+}
+
+// Leading-axis reduction on the direct kernel.  `plan` must have been made with rc = stream::kDirectRows (one partial row
+// per chunk, like MODE 1).  SP_OK when launched, kNotLaunched without a compiled instance of the program.
+template <typename T, int NI>
+static int launch_direct_reduce(const DevProgram<T>& dp, const DevOperands<NI>& ops, const stream::Plan& plan, int red_op,
+                                T* scratch, cudaStream_t stream_) {
+  constexpr int VEC = 16 / sizeof(T);
+  if (plan.d2 % VEC != 0 || plan.rc != stream::kDirectRows) return kNotLaunched;
+  for (int i = 0; i < ops.n_in; ++i)
+    if (ops.in[i].kind == kGeneric) return kNotLaunched;
+  const int64_t row_vecs = plan.d2 / VEC;
+  const int64_t blocks = plan.d0 * plan.n_chunks * ((row_vecs + stream::kDirectThreads - 1) / stream::kDirectThreads);
+  if (blocks <= 0 || blocks >= (1ll << 31)) return kNotLaunched;
+  if constexpr (NI == 2 && !std::is_same<T, long long>::value) {
+    switch (match_static<T>(dp)) {
+#define SP_LAUNCH(IDX, TYPE) case IDX: return launch_direct_reduce_as<T, NI, TYPE>(dp, ops, plan, red_op, scratch, blocks, stream_);
+      SP_STATIC_PROGRAMS(SP_LAUNCH)
+#undef SP_LAUNCH
+      default: break;
+    }
+  }
+  if (plan.d0 * plan.d1 * plan.d2 * static_cast<int64_t>(sizeof(T)) >= kJitMinBytes) {
+    int red = red_op;
+    void* params[] = {const_cast<DevProgram<T>*>(&dp), const_cast<DevOperands<NI>*>(&ops), const_cast<stream::Plan*>(&plan),
+                      &red, &scratch};
+    const int rc = jit::launch_stream_specialised(TypeTag<T>::dtype, NI, 4, dp.op, dp.src, dp.arg, dp.n_ops, params,
+                                                  static_cast<int>(blocks), stream::kDirectThreads, 0, stream_);
+    if (rc != 0) return rc < 0 ? rc : SP_OK;
+  }
+  return kNotLaunched;
+}
+
 #ifndef SP_FLAT_ROW_BYTES
 #define SP_FLAT_ROW_BYTES 16384
 #endif
@@ -507,7 +556,8 @@ static int launch_reduce_v(const sp_program* prog, int n_in, const sp_operand* i
       const int64_t sneed = plan.n_chunks * dims[0] * dims[2] * static_cast<int64_t>(sizeof(T));
       SP_REQUIRE(scratch_bytes >= sneed, SP_ERR_INVALID, "sp_map_reduce: scratch %lld B < required %lld B",
                  (long long)scratch_bytes, (long long)sneed);
-      int rc = launch_stream<T, NI, 1>(dp, ops, plan, red_op, sc, stream, interp_ok);
+      int rc = use_direct_reduce() ? launch_direct_reduce<T, NI>(dp, ops, plan, red_op, sc, stream) : kNotLaunched;
+      if (rc == kNotLaunched) rc = launch_stream<T, NI, 1>(dp, ops, plan, red_op, sc, stream, interp_ok);
       if (rc < 0) return rc;
       if (rc != kNotLaunched) {
         const int fb = static_cast<int>(std::min<int64_t>((n_out + 255) / 256, 4096));

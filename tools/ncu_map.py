@@ -14,4 +14,5 @@ for _ in range(3):
   (x * 2 + y).optimized().evaluate()
   (x * 2 + y).sum(axis=0).optimized().evaluate()
   (x * 2 + y).sum(axis=1).optimized().evaluate()
+  (sp.abs(x - y) * x + sp.maximum(y, 0.5)).sum(axis=0).optimized().evaluate()     # outside the catalogue: NVRTC
 torch.cuda.synchronize()

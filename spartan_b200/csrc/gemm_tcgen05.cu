@@ -807,8 +807,28 @@ __global__ void prep_a_kernel(const float* __restrict__ A, int64_t lda, int M, i
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] = (k + j < K) ? A[m * lda + k + j] : 0.0f;
     }
+    // four consecutive k of one row: one 8-byte (bf16) or 16-byte (tf32) store per copy (Kp and k are multiples of 4
+    // and the operand buffers are 128-byte aligned, so the stores are aligned)
+    const int64_t o = m * Kp + k;
+    if constexpr (SPLIT == 2) {
+      __nv_bfloat16 h[4], l[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) split_store<SPLIT>(v[j], hi, lo, m * Kp + k + j);
+      for (int j = 0; j < 4; ++j) {
+        h[j] = __float2bfloat16_rn(v[j]);
+        l[j] = __float2bfloat16_rn(v[j] - __bfloat162float(h[j]));
+      }
+      *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(hi) + o) = *reinterpret_cast<const uint2*>(h);
+      *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(lo) + o) = *reinterpret_cast<const uint2*>(l);
+    } else {
+      float h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        h[j] = rn_tf32(v[j]);
+        l[j] = rn_tf32(v[j] - h[j]);
+      }
+      *reinterpret_cast<float4*>(static_cast<float*>(hi) + o) = make_float4(h[0], h[1], h[2], h[3]);
+      if constexpr (SPLIT == 1) *reinterpret_cast<float4*>(static_cast<float*>(lo) + o) = make_float4(l[0], l[1], l[2], l[3]);
+    }
   }
 }
 

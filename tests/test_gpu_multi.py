@@ -96,6 +96,17 @@ def _worker(rank, world, port, q, use_peer):
       c64 = np.stack([pts[l64 == j].astype(np.float64).mean(0) for j in range(10)])
     assert (lab.glom() == l64).mean() > 0.999
     np.testing.assert_allclose(cen, c64, rtol=1e-4, atol=1e-5)
+    # AutomaticTiling (tile_hints chosen to minimise NVLink bytes) must not change any value: the device generator is
+    # indexed by global element position, so the arrays are the same under any tiling
+    outs = []
+    for auto in (False, True):
+      sp.FLAGS.opt_auto_tiling = auto
+      e1 = (sp.rand(384, 640, seed=21, dtype=np.float32) * 2 + sp.rand(384, 640, seed=22, dtype=np.float32)).sum(axis=0)
+      e2 = sp.dot(sp.rand(256, 384, seed=23, dtype=np.float32), sp.rand(384, 512, seed=24, dtype=np.float32))
+      outs.append((e1.optimized().glom(), e2.optimized().glom()))
+    sp.FLAGS.opt_auto_tiling = False
+    np.testing.assert_allclose(outs[0][0], outs[1][0], rtol=1e-6)
+    np.testing.assert_allclose(outs[0][1], outs[1][1], rtol=1e-5, atol=1e-5)
     # operands with different tilings: pieces travel point-to-point to the owner of each output tile
     got = (sp.from_numpy(x, tile_hint=(128, 2048)) + sp.from_numpy(y, tile_hint=(1024, 256))).glom()
     assert np.array_equal(got, x + y)

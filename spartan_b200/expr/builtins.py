@@ -6,6 +6,7 @@ reference's names; they are never *called* on the host -- each carries the spec 
 needs (a bytecode lowering for map functions, a (reduce-op, post-ops) pair for local reducers, a fill
 kernel for location functions).
 """
+import builtins as _py
 import numpy as np
 
 from .. import blob_ctx, device_ops
@@ -124,7 +125,8 @@ def _fill_by_global_index(out, ex, kind, a=0.0, b=0.0, seed=0):
   spans the full trailing dimensions, one 2-D launch per leading index otherwise."""
   shape = ex.array_shape
   nd = len(shape)
-  if out.is_contiguous() and (nd <= 1 or all(ex.shape[d] == shape[d] for d in range(1, nd))):
+  # (`all` is this module's reduction builder -- the Python builtin is _py.all)
+  if out.is_contiguous() and (nd <= 1 or _py.all(ex.shape[d] == shape[d] for d in range(1, nd))):
     device_ops.fill(out.reshape(-1), kind, a, b, seed=seed, offset=extent.ravelled_pos(ex.ul, shape))
     return
   pitch = int(np.prod(shape[nd - 1:]))          # elements per step of the second-to-last index
@@ -270,7 +272,7 @@ def _true_divide_handler(node, operands, analyse):
   in_dt = program.legacy_result_type([(a.dtype, a.weak, a.value) for a in args])
   if in_dt.kind in 'biu':
     in_dt = np.dtype(np.float64)
-  return program._Typed('DIV', args, in_dt, weak=all(a.weak for a in args), in_dtype=in_dt)
+  return program._Typed('DIV', args, in_dt, weak=_py.all(a.weak for a in args), in_dtype=in_dt)
 
 
 program.register_special(_true_divide, _true_divide_handler)

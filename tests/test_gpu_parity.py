@@ -246,6 +246,8 @@ def test_rand_properties():
   """Device RNG (Philox): uniform [0,1), deterministic per seed, independent of the tiling."""
   a = sp.rand(512, 256, seed=7, dtype=np.float32).glom()
   b = sp.rand(512, 256, seed=7, dtype=np.float32, tile_hint=(64, 64)).glom()
+  all_eq(a, sp.rand(512, 256, seed=7, dtype=np.float32, tile_hint=(512, 64)).glom())     # full-height column tiles
+  all_eq(a, sp.rand(512, 256, seed=7, dtype=np.float32, tile_hint=(100, 256)).glom())    # full-width row tiles
   c = sp.rand(512, 256, seed=8, dtype=np.float32).glom()
   assert a.dtype == np.float32 and a.min() >= 0.0 and a.max() < 1.0
   all_eq(a, b)

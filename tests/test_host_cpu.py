@@ -536,3 +536,28 @@ def test_dot_arrival_groups_cover_every_segment_once():
   assert _arrival_groups(8, 0.87, 2.1, 0.6) == [[0], [1, 2], [3, 4, 5, 6, 7]]
   assert _arrival_groups(2, 3.6, 36.0, 5.0) == [[0, 1]]          # a pass dearer than the stall it avoids
   assert _arrival_groups(2, 3.6, 36.0, 2.4) == [[0], [1]]
+
+
+def test_location_fill_uses_global_positions_for_every_tiling(monkeypatch):
+  """rand / arange tiles are filled from the element's GLOBAL position: a tile that spans full rows is one flat fill at
+  its offset, any other tile (column blocks included) a 2-D fill with the array's row pitch.  (A full-height column tile
+  once took the flat path because the module's own `all` shadowed the builtin.)"""
+  import torch
+  from spartan_b200 import device_ops, blob_ctx
+  old = blob_ctx.get()
+  try:
+    blob_ctx.set(blob_ctx.BlobCtx(1, 2, torch.device('cpu')))      # pose as rank 1 of 2; nothing is launched
+    calls = []
+    monkeypatch.setattr(device_ops, 'fill', lambda t, kind, a=0.0, b=0.0, seed=0, offset=0: calls.append(('flat', tuple(t.shape), offset)))
+    monkeypatch.setattr(device_ops, 'fill2d', lambda t, kind, a=0.0, b=0.0, seed=0, offset=0, pitch=0:
+                        calls.append(('2d', tuple(t.shape), offset, pitch)))
+    sp.rand(384, 640, seed=1, dtype=np.float32).evaluate()
+    assert calls == [('flat', (192 * 640,), 192 * 640)]
+    del calls[:]
+    sp.rand(384, 640, seed=1, dtype=np.float32, tile_hint=(384, 320)).evaluate()
+    assert calls == [('2d', (384, 320), 320, 640)]
+    del calls[:]
+    sp.arange((384, 640), dtype=np.float32, tile_hint=(96, 160)).evaluate()
+    assert calls and all(c[0] == '2d' and c[3] == 640 for c in calls)
+  finally:
+    blob_ctx.set(old)

@@ -631,7 +631,7 @@ class Bench(object):
           'elements': total, 'algorithmic_bytes': head['algorithmic_bytes'],
           'roofline': {'bound': 'hbm', 'achieved': head['value'] / world, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                        'frac': head['value'] / world / peaks['hbm_gbs'],
-                       'traffic': measured_traffic('stream_kernel_mapreduce_2p30') if (world == 1 and args.mr_log2 == 30) else None,
+                       'traffic': measured_traffic('direct_reduce_kernel_mapreduce_2p30') if (world == 1 and args.mr_log2 == 30) else None,
                        'peak_source': peaks['source'] + ' copy bandwidth (read+write); a read-only stream can exceed it'},
           'max_rel_err_vs_fp64': head['max_rel_err'], 'tolerance': TOL, 'variants': results}
     if self.rank == 0 and world == 1 and not args.skip_cpu:

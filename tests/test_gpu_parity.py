@@ -732,6 +732,41 @@ def test_kmeans_and_spmv_on_reference_generated_vectors():
     np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-6)
 
 
+def test_c_abi_housekeeping_and_flag_words():
+  """The self-sufficient part of the boundary: device selection, stream-ordered tile buffers, events, and the flag words
+  consumers wait on (sp_write_u32 / sp_wait_u32 incl. its bounded time-out)."""
+  import ctypes, torch
+  from spartan_b200._lib import lib, check
+  check(lib.sp_init(0), 'sp_init')
+  stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+  p = ctypes.c_void_p()
+  check(lib.sp_tile_alloc(1 << 20, ctypes.byref(p), stream), 'sp_tile_alloc')
+  assert p.value
+  e0, e1 = ctypes.c_void_p(), ctypes.c_void_p()
+  check(lib.sp_event_create(ctypes.byref(e0)), 'ev'); check(lib.sp_event_create(ctypes.byref(e1)), 'ev')
+  check(lib.sp_event_record(e0, stream), 'rec')
+  check(lib.sp_fill(p, 0, (1 << 20) // 4, 0, 3.0, 0.0, 0, 0, stream), 'sp_fill')          # float32 constant fill
+  check(lib.sp_write_u32(p, 7, stream), 'sp_write_u32')
+  status = torch.zeros(1, dtype=torch.int32, device='cuda')
+  check(lib.sp_wait_u32(p, 7, 1000, ctypes.c_void_p(status.data_ptr()), stream), 'sp_wait_u32')      # already satisfied
+  check(lib.sp_wait_u32(p, 8, 20, ctypes.c_void_p(status.data_ptr()), stream), 'sp_wait_u32')        # never: times out
+  check(lib.sp_event_record(e1, stream), 'rec')
+  ms = ctypes.c_float()
+  check(lib.sp_event_elapsed(e0, e1, ctypes.byref(ms)), 'elapsed')
+  check(lib.sp_sync(stream), 'sp_sync')
+  assert 15.0 <= ms.value < 500.0, ms.value            # the 20 ms time-out is inside the timed region
+  assert int(status.item()) == 1
+  host = torch.empty(4, dtype=torch.float32)
+  torch.cuda.synchronize()
+  view = (ctypes.c_float * 4).from_address(host.data_ptr())
+  check(lib.sp_download_2d(ctypes.c_void_p(host.data_ptr()), 16, p, 16, 16, 1, stream), 'download')
+  check(lib.sp_sync(stream), 'sp_sync')
+  assert host[1].item() == 3.0 and np.frombuffer(host.numpy().tobytes(), np.uint32)[0] == 7
+  check(lib.sp_tile_free(p, stream), 'free')
+  check(lib.sp_event_destroy(e0), 'd'); check(lib.sp_event_destroy(e1), 'd')
+  check(lib.sp_shutdown(), 'sp_shutdown')
+
+
 def test_zero_dim_and_empty_arrays():
   s = sp.from_numpy(np.array(3.0, dtype=np.float32))
   assert (s * 2 + 1).glom() == 7.0

@@ -141,6 +141,55 @@ spmv_csr_kernel(const PTR* __restrict__ rowptr, const int32_t* __restrict__ col,
   }
 }
 
+// CSR SpMV, non-zero-parallel: a warp owns 32 consecutive rows and walks THEIR non-zeros 32 at a time, so val / col are
+// read with perfectly coalesced 128-byte accesses whatever the row lengths (the row-parallel kernel above touches every
+// 32-byte sector of val / col about twice: once per 8-lane row group and again for rows longer than the group).  Each lane
+// finds the row of its non-zero by a shuffle binary search over the warp's 33 row pointers, the products are combined by
+// a segmented shuffle scan, and the last lane of every row segment adds its sum to the row's slot in shared memory.  What
+// remains is the gather of x[col] -- one sector per non-zero -- which bounds SpMV on random columns (L1 tag stage).
+template <typename PTR>
+__global__ void __launch_bounds__(256)
+spmv_csr_stream_kernel(const PTR* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
+                       int64_t n_rows, const float* __restrict__ x, float* __restrict__ y, int accumulate) {
+  __shared__ float s_acc[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t n_blocks = (n_rows + 31) / 32;
+  for (int64_t rb = blockIdx.x * 8ll + w; rb < n_blocks; rb += gridDim.x * 8ll) {
+    const int64_t row0 = rb * 32;
+    const int64_t my_row = row0 + lane;
+    const long long rp = static_cast<long long>(rowptr[min(my_row, n_rows)]);       // lanes past the end: total nnz
+    const long long lo = __shfl_sync(0xffffffffu, rp, 0);
+    const long long hi = static_cast<long long>(rowptr[min(row0 + 32, n_rows)]);
+    s_acc[w][lane] = 0.f;
+    __syncwarp();
+    for (long long p = lo; p < hi; p += 32) {
+      const long long e = p + lane;
+      const bool live = e < hi;
+      float prod = 0.f;
+      if (live) prod = __ldcs(val + e) * __ldg(x + __ldcs(col + e));
+      int r = 0;                                   // largest r with rowptr[row0 + r] <= e
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const int cand = r + step;
+        const long long v = __shfl_sync(0xffffffffu, rp, cand & 31);
+        if (cand < 32 && v <= e) r = cand;
+      }
+      if (!live) r = 32 + lane;                    // dead lanes: unique keys, never merged
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {           // segmented inclusive scan over equal rows
+        const float up = __shfl_up_sync(0xffffffffu, prod, d);
+        const int rup = __shfl_up_sync(0xffffffffu, r, d);
+        if (lane >= d && rup == r) prod += up;
+      }
+      const int rnext = __shfl_down_sync(0xffffffffu, r, 1);
+      if (live && (lane == 31 || rnext != r)) s_acc[w][r] += prod;       // segment tails: distinct rows within a batch
+      __syncwarp();
+    }
+    if (my_row < n_rows) y[my_row] = accumulate ? y[my_row] + s_acc[w][lane] : s_acc[w][lane];
+    __syncwarp();
+  }
+}
+
 template <typename PTR>
 static void launch_spmv(int group, int blocks, const PTR* rowptr, const int32_t* colidx, const float* values,
                         int64_t n_rows, const float* x, float* y, int accumulate, cudaStream_t stream) {
@@ -152,6 +201,14 @@ static void launch_spmv(int group, int blocks, const PTR* rowptr, const int32_t*
   }
 }
 
+static int g_spmv_stream = -1;      // -1: from the environment (SPARTAN_SPMV_KERNEL=rows|stream, default stream)
+static bool spmv_stream() {
+  if (g_spmv_stream < 0) {
+    const char* e = getenv("SPARTAN_SPMV_KERNEL");
+    g_spmv_stream = (e && e[0] == 'r') ? 0 : 1;
+  }
+  return g_spmv_stream == 1;
+}
 static int g_kmeans_fused = -1;     // -1: from the environment (SPARTAN_KMEANS_FUSED, default 1)
 static bool kmeans_fused() {
   if (g_kmeans_fused < 0) {
@@ -268,6 +325,16 @@ extern "C" int sp_spmv_csr(const void* rowptr, int rowptr_is_i64, const int32_t*
   if (n_rows == 0) return SP_OK;
   SP_REQUIRE(rowptr && x && y, SP_ERR_INVALID, "sp_spmv_csr: null pointer");
   // threads per row follow the average row length (passed by the caller; <= 0 means unknown -> 8)
+  if (avg_nnz_per_row >= 4 && spmv_stream()) {     // enough non-zeros per 32 rows to fill the 32-wide batches
+    const int64_t n_blocks = (n_rows + 31) / 32;
+    const int blocks = static_cast<int>(std::min<int64_t>((n_blocks + 7) / 8, static_cast<int64_t>(num_sms()) * 32));
+    if (rowptr_is_i64)
+      spmv_csr_stream_kernel<int64_t><<<blocks, 256, 0, stream>>>(static_cast<const int64_t*>(rowptr), colidx, values, n_rows, x, y, accumulate);
+    else
+      spmv_csr_stream_kernel<int32_t><<<blocks, 256, 0, stream>>>(static_cast<const int32_t*>(rowptr), colidx, values, n_rows, x, y, accumulate);
+    SP_CUDA_CHECK(cudaGetLastError());
+    return SP_OK;
+  }
   const int group = avg_nnz_per_row <= 0 ? 8 : avg_nnz_per_row <= 2 ? 2 : avg_nnz_per_row <= 4 ? 4 : avg_nnz_per_row <= 16 ? 8 : 32;
   const int64_t groups_per_block = 256 / group;
   const int blocks = static_cast<int>(std::min<int64_t>((n_rows + groups_per_block - 1) / groups_per_block,

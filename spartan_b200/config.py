@@ -21,7 +21,7 @@ class Flags(object):
     # dot(from_numpy(a), from_numpy(b)) on one GPU: pipeline the PCIe upload of host operands with the contraction
     # (row strips of A / column strips of B of this many rows / columns) when the operands are at least this large
     self.dot_stream_host_operands = True
-    self.dot_stream_strip = 4096
+    self.dot_stream_strip = 2048         # measured: 196.6 ms at 2048 vs 199-202 ms at 1024 / 3072 / 4096 (tools/e2e_strip_probe.py)
     self.dot_stream_min_bytes = 256 << 20
     # prepared (rounded / split / transposed) GEMM operands of unchanged arrays are kept between evaluations, up to this
     # many bytes (0 disables the cache)

@@ -561,3 +561,33 @@ def test_location_fill_uses_global_positions_for_every_tiling(monkeypatch):
     assert calls and all(c[0] == '2d' and c[3] == 640 for c in calls)
   finally:
     blob_ctx.set(old)
+
+
+def test_prepared_operand_cache_epochs_and_eviction():
+  """PreparedCache (device_ops): an entry is fresh only within the data epoch it was filled in; a stale entry hands its
+  buffers back for re-filling; least-recently-used entries go when the byte budget is exceeded; dropping an array's
+  serial removes all of its entries."""
+  from spartan_b200.device_ops import PreparedCache
+  old = sp.FLAGS.dot_prepared_cache_bytes
+  try:
+    sp.FLAGS.dot_prepared_cache_bytes = 100
+    c = PreparedCache()
+    assert c.lookup((1, 'a'), 0) == (None, False)
+    c.store((1, 'a'), 'A1', 40, 0)
+    assert c.lookup((1, 'a'), 0) == ('A1', True)
+    assert c.lookup((1, 'a'), 1) == ('A1', False)          # the array may have changed: same buffers, re-fill
+    c.store((1, 'a'), 'A1', 40, 1)
+    c.store((2, 'b'), 'B2', 40, 1)
+    c.store((3, 'a'), 'A3', 40, 1)                          # 120 > 100: the least recently used entry goes
+    assert (1, 'a') not in c.entries and set(c.entries) == {(2, 'b'), (3, 'a')}
+    c.lookup((2, 'b'), 1)                                   # touch: (3, 'a') is now the oldest
+    c.store((4, 'a'), 'A4', 40, 1)
+    assert set(c.entries) == {(2, 'b'), (4, 'a')}
+    c.store((4, 'b'), 'B4', 10, 1)
+    c.drop(4)
+    assert set(c.entries) == {(2, 'b')}
+    c.store((5, 'huge'), 'H', 1000, 1)                      # larger than the budget: kept alone rather than thrashing
+    assert set(c.entries) == {(5, 'huge')}
+    assert c.hits >= 2 and c.misses >= 2
+  finally:
+    sp.FLAGS.dot_prepared_cache_bytes = old

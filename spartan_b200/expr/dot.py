@@ -366,13 +366,21 @@ class DotExpr(Expr):
     copy.wait_stream(main)
     if ctx.push_done is not None:
       main.wait_event(ctx.push_done)
-    gather = peer.buffer('dot_stream_gather', 2 * S * W * part)
+    gather = peer.buffer('dot_stream_gather', 2 * (S * W * part + 1024))
     f0 = peer.flag_range('dot_stream_gather', 2048)
     epoch, esrc = peer.next_epoch('dot_stream_gather')
     half = epoch & 1
 
-    def slot(i, p):
-      return (half * S + i) * W + p
+    # The two halves of the buffer (and of the flag range) are FIXED regions, whatever the strip count of this evaluation:
+    # exchange e only ever touches half e & 1, so an evaluation with other shapes cannot land in memory a slower peer is
+    # still reading for the previous exchange.
+    half_bytes = gather.nbytes // 2 // 1024 * 1024
+
+    def slot_off(i, p):                 # byte offset of slot (strip i, source p) in this exchange's half
+      return half * half_bytes + (i * W + p) * part
+
+    def flag_idx(i, p):
+      return f0 + half * 1024 + i * W + p
 
     def upload_cols(slab, host, r0, r1, col_intervals):
       off = 0
@@ -398,15 +406,15 @@ class DotExpr(Expr):
       r0, r1 = strips[i]
       main.wait_event(ev_a[i])
       mine = device_ops.PreparedOperand(r1 - r0, ka, precision, None,
-                                        buf=gather.tensor[slot(i, me) * part:(slot(i, me) + 1) * part])
+                                        buf=gather.tensor[slot_off(i, me):slot_off(i, me) + part])
       mine.prepare_a(av.slab[r0:r1, :], 0)
       ev = main.record_event()
       if trace: trace.mark('prep A%d done' % i, main)
       with torch.cuda.stream(push):
         push.wait_event(ev)
         dsts = [(me - j) % W for j in range(1, W)]           # ring order: the peer that needs this slot first goes first
-        peer.push([gather.ptrs[d] + slot(i, me) * part for d in dsts], mine.buf.data_ptr(), mine.nbytes,
-                  [peer.flag_ptr(d, f0 + slot(i, me)) for d in dsts], esrc)
+        peer.push([gather.ptrs[d] + slot_off(i, me) for d in dsts], mine.buf.data_ptr(), mine.nbytes,
+                  [peer.flag_ptr(d, flag_idx(i, me)) for d in dsts], esrc)
         ctx.push_done = push.record_event()
         if trace: trace.mark('push A%d done' % i, push)
       return mine
@@ -429,9 +437,9 @@ class DotExpr(Expr):
       mine = mines.pop(i)
       views, flags = [], []
       for p in order:
-        a_ptr = gather.local_ptr + slot(i, p) * part
+        a_ptr = gather.local_ptr + slot_off(i, p)
         views.append((a_ptr, (r1 - r0) * rb, pbs[p].row_ptr(0), pbs[p].copy_stride, Kp))
-        flags.append(0 if p == me else peer.flag_ptr(me, f0 + slot(i, p)))
+        flags.append(0 if p == me else peer.flag_ptr(me, flag_idx(i, p)))
       device_ops.gemm_prepared_views_gated(views, flags, [epoch] * W, peer.status.data_ptr(), target.slab[r0:r1, :],
                                            False, precision)
       ev_c = main.record_event()
@@ -480,7 +488,8 @@ class DotExpr(Expr):
     if ctx.push_done is not None:
       main.wait_event(ctx.push_done)        # an earlier push may still be reading the buffer about to be re-prepared
     mine = device_ops.cached_operand(av, ('a_slab',), M, width, precision, lambda op: op.prepare_a(av.slab, 0))
-    gather = peer.buffer('dot_gather', 2 * W * a_bytes)
+    gather = peer.buffer('dot_gather', 2 * (W * a_bytes + 1024))
+    half_bytes = gather.nbytes // 2 // 1024 * 1024      # the halves are fixed regions (see _evaluate_streamed_peer)
     f0 = peer.flag_range('dot_gather', 2 * W)
     epoch, esrc = peer.next_epoch('dot_gather')
     half = epoch & 1
@@ -488,7 +497,7 @@ class DotExpr(Expr):
     with torch.cuda.stream(push):
       push.wait_event(ev)
       dsts = [(me - j) % W for j in range(1, W)]
-      peer.push([gather.ptrs[d] + (half * W + me) * a_bytes for d in dsts], mine.buf.data_ptr(), mine.nbytes,
+      peer.push([gather.ptrs[d] + half * half_bytes + me * a_bytes for d in dsts], mine.buf.data_ptr(), mine.nbytes,
                 [peer.flag_ptr(d, f0 + half * W + me) for d in dsts], esrc)
       ctx.push_done = push.record_event()
     order = [(me + j) % W for j in range(W)]
@@ -516,7 +525,7 @@ class DotExpr(Expr):
                 op.prepare_b(Bv, 0, k_offset=off)
                 off += b - a
             pb = device_ops.cached_operand(bv, ('b_cols', c0, c1, p), c1 - c0, width, precision, fill)
-            a_ptr = mine.row_ptr(r0) if p == me else gather.local_ptr + (half * W + p) * a_bytes + r0 * rb
+            a_ptr = mine.row_ptr(r0) if p == me else gather.local_ptr + half * half_bytes + p * a_bytes + r0 * rb
             views.append((a_ptr, M * rb, pb.row_ptr(0), pb.copy_stride, Kp))
             flags.append(0 if p == me else peer.flag_ptr(me, f0 + half * W + p))
           device_ops.gemm_prepared_views_gated(views, flags, [epoch] * len(views), peer.status.data_ptr(), Cv, gi > 0,

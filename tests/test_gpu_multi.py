@@ -66,6 +66,21 @@ def _worker(rank, world, port, q, use_peer):
       again = sp.dot(_lz(Ad), _lz(Bd), tile_hint=hc).glom()
       sp.FLAGS.dot_prepared_cache = True
       assert np.array_equal(again, got)
+    # exchanges of DIFFERENT shapes queued back to back with no host synchronisation in between: each exchange owns a fixed
+    # half of the symmetric buffer, so a fast rank's next push can never land in what a slow peer is still reading
+    pairs = []
+    for (M, K, N) in [(1024, 2048, 512), (256, 512, 1024), (768, 1024, 256)]:
+      a = rng.standard_normal((M, K), dtype=np.float32); b = rng.standard_normal((K, N), dtype=np.float32)
+      pairs.append((sp.from_numpy(a, tile_hint=(M, K // 2)).evaluate(), sp.from_numpy(b, tile_hint=(K, N // 2)).evaluate(),
+                    a.astype(np.float64) @ b.astype(np.float64), (M, N // 2)))
+    results = []
+    for rep in range(3):
+      for Ad, Bd, ref, hc in pairs:
+        results.append((sp.dot(_lz(Ad), _lz(Bd), tile_hint=hc).evaluate(), ref))
+    for Cd, ref in results:
+      got = Cd.glom()
+      assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+    del results, pairs
     # fused map + reduce: partials combined by ncclAllReduce
     x = rng.random((1024, 2048), dtype=np.float32); y = rng.random((1024, 2048), dtype=np.float32)
     for hint in [(128, 2048), (256, 512), None]:

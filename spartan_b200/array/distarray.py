@@ -15,6 +15,7 @@ largest_value, good_tile_shape, compute_extents) and of spartan/expr/operator/br
     are bit-identical to the reference and computed in the native shim.
 """
 import collections
+import math
 import ctypes
 import itertools
 
@@ -39,14 +40,35 @@ def good_tile_shape(shape, num_shards=-1):
   return [out[i] for i in range(n)]
 
 
+_EXTENTS_MEMO = collections.OrderedDict()      # (shape, hint, shards) -> ((extent, shard), ...); extents are immutable
+_EXTENTS_MEMO_ENTRIES = 256
+_EXTENTS_MEMO_MAX_TILES = 4096
+
+
 def compute_extents(shape, tile_hint=None, num_shards=-1):
-  """distarray.py:73-110: ordered {extent: shard index}, itertools.product order (native)."""
+  """distarray.py:73-110: ordered {extent: shard index}, itertools.product order (native).  The tiling of a shape is a
+  pure function of (shape, hint, shards), and iterative programs ask for the same few over and over: recent answers
+  are kept (the extent objects are shared, the dict is the caller's own)."""
   shape = tuple(int(s) for s in shape)
   n = len(shape)
   if n == 0:
     return collections.OrderedDict([(extent.create([], [], ()), 0)])
   if tile_hint is not None:
     require_equal(len(tile_hint), n, '#dimensions in tile hint does not match shape %s vs %s' % (tile_hint, shape))
+  key = (shape, None if tile_hint is None else tuple(int(h) for h in tile_hint), int(num_shards))
+  hit = _EXTENTS_MEMO.get(key)
+  if hit is not None:
+    _EXTENTS_MEMO.move_to_end(key)
+    return collections.OrderedDict(hit)
+  result = _compute_extents(shape, n, tile_hint, num_shards)
+  if len(result) <= _EXTENTS_MEMO_MAX_TILES:
+    _EXTENTS_MEMO[key] = tuple(result.items())
+    if len(_EXTENTS_MEMO) > _EXTENTS_MEMO_ENTRIES:
+      _EXTENTS_MEMO.popitem(last=False)
+  return result
+
+
+def _compute_extents(shape, n, tile_hint, num_shards):
   hint = None if tile_hint is None else i64arr(tile_hint)
   total = check(lib.sp_compute_extents(n, i64arr(shape), hint, int(num_shards), None, None, None), 'compute_extents')
   ul = (ctypes.c_int64 * max(1, total * n))(); lr = (ctypes.c_int64 * max(1, total * n))()
@@ -81,7 +103,7 @@ class DistArray(object):
     raise NotImplementedError
 
   def real_size(self):
-    return int(np.prod(self.shape, dtype=np.int64))
+    return math.prod(self.shape)
 
   def __len__(self):
     return self.shape[0]
@@ -153,6 +175,7 @@ class DistArrayImpl(DistArray):
     self.slab_axes = None                   # per-axis sorted (lo, hi) intervals covered by the slab
     self.block_events = None                # [(region, CUDA event)] left by a producer that finished block by block
     self.serial = next(_serials)            # identity of this array for caches of derived data (never reused)
+    self._layout_key = None
 
   def __del__(self):
     try:
@@ -238,11 +261,16 @@ class DistArrayImpl(DistArray):
     zero-copy block of the other)."""
     if not isinstance(other, DistArrayImpl) or other.shape != self.shape or len(other.tiles) != len(self.tiles):
       return False
-    for ex, tid in self.tiles.items():
-      o = other.tiles.get(ex)
-      if o is None or o.worker != tid.worker:
-        return False
-    return other.slab is not None and self.slab is not None
+    if other.slab is None or self.slab is None:
+      return False
+    return other is self or self.layout_key() == other.layout_key()
+
+  def layout_key(self):
+    """The set of (tile bounds, owner): the tile table of an array never changes after construction, so it is built
+    once."""
+    if self._layout_key is None:
+      self._layout_key = frozenset((ex.ul, ex.lr, tid.worker) for ex, tid in self.tiles.items())
+    return self._layout_key
 
   # ------------------------------------------------------------------ fetch / update / glom
   def fetch(self, region, dst=None):

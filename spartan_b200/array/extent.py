@@ -16,12 +16,13 @@ MAX_DIM = 32   # extent.pyx:20-21
 
 class TileExtent(object):
   """extent.pyx:23-136."""
-  __slots__ = ('ul', 'lr', 'array_shape')
+  __slots__ = ('ul', 'lr', 'array_shape', '_hash')
 
   def __init__(self, ul, lr, array_shape):
     self.ul = tuple(int(x) for x in ul)
     self.lr = tuple(int(x) for x in lr)
     self.array_shape = None if array_shape is None else tuple(int(x) for x in array_shape)
+    self._hash = hash(self.ul)                             # extent.pyx:93-94; extents are immutable, hashed once
 
   @property
   def shape(self):
@@ -52,7 +53,7 @@ class TileExtent(object):
     return create((self.ul[idx],), (self.lr[idx],), (self.array_shape[idx],))
 
   def __hash__(self):
-    return hash(self.ul)                                   # extent.pyx:93-94
+    return self._hash
 
   def __eq__(self, other):                                 # extent.pyx:107-110
     return isinstance(other, TileExtent) and self.ul == other.ul and self.lr == other.lr

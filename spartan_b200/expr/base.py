@@ -97,7 +97,13 @@ class Expr(object):
     raise NotShapeable
 
   def visit(self, visitor):
-    deps = dict((k, visitor.visit(getattr(self, k))) for k in self.members)
+    deps, same = {}, True
+    for k in self.members:
+      old = getattr(self, k)
+      new = deps[k] = visitor.visit(old)
+      same = same and new is old
+    if same:
+      return self            # a pass that changed nothing below this node leaves the node itself in place
     return expr_like(self, **deps)
 
   def typename(self):
@@ -307,7 +313,10 @@ class ListExpr(CollectionExpr):
     return [deps['v%d' % i] for i in range(len(self.vals))]
 
   def visit(self, visitor):
-    return ListExpr(vals=[visitor.visit(v) for v in self.vals])
+    vals = [visitor.visit(v) for v in self.vals]
+    if all(a is b for a, b in zip(vals, self.vals)):
+      return self
+    return ListExpr(vals=vals)
 
 
 class TupleExpr(CollectionExpr):
@@ -320,7 +329,10 @@ class TupleExpr(CollectionExpr):
     return tuple(deps['v%d' % i] for i in range(len(self.vals)))
 
   def visit(self, visitor):
-    return TupleExpr(vals=tuple(visitor.visit(v) for v in self.vals))
+    vals = tuple(visitor.visit(v) for v in self.vals)
+    if all(a is b for a, b in zip(vals, self.vals)):
+      return self
+    return TupleExpr(vals=vals)
 
 
 def glom(value):

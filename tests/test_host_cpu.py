@@ -591,3 +591,33 @@ def test_prepared_operand_cache_epochs_and_eviction():
     assert c.hits >= 2 and c.misses >= 2
   finally:
     sp.FLAGS.dot_prepared_cache_bytes = old
+
+
+def test_tiling_memo_hands_out_independent_tables():
+  """compute_extents keeps recent answers (the tiling is a pure function of shape / hint / shards): a caller that edits
+  the table it got must not change what the next caller sees, and the memo must not confuse hints or shard counts."""
+  a = pdist.compute_extents((64, 48), (16, 48), 4)
+  first = list(a.items())
+  a.popitem()
+  a[pex.create((0, 0), (1, 1), (64, 48))] = 99
+  b = pdist.compute_extents((64, 48), (16, 48), 4)
+  assert list(b.items()) == first and b is not a
+  assert list(pdist.compute_extents((64, 48), (16, 48), 2).values()) != [w for _, w in first] or \
+    len(set(w for _, w in first)) <= 2
+  assert len(pdist.compute_extents((64, 48), (32, 48), 4)) == 2
+  assert dict((e.to_tuple(), w) for e, w in pdist.compute_extents((64, 48), None, 4).items()) == \
+    dict((e.to_tuple(), w) for e, w in odist.compute_extents((64, 48), None, 4).items())
+  # extents hash by their upper-left corner (extent.pyx:93-94) and compare by both corners
+  e1, e2 = pex.create((0, 0), (4, 4), (8, 8)), pex.create((0, 0), (4, 8), (8, 8))
+  assert hash(e1) == hash(e2) == hash((0, 0)) and e1 != e2 and len({e1: 1, e2: 2}) == 2
+
+
+def test_passes_keep_nodes_they_do_not_change():
+  """A pass that rewrites nothing below a node returns the node itself (no copy of the DAG per pass); a fused node keeps
+  the id of the node it replaces, so cached results stay addressable (base.py:49-68)."""
+  x = sp.from_numpy(np.zeros((4, 4), np.float32))
+  d = sp.dot(x, x)
+  assert d.optimized() is d
+  e = (x * 2 + x).sum(axis=0)
+  o = e.optimized()
+  assert o is not e and o.expr_id == e.expr_id and e.optimized() is o
